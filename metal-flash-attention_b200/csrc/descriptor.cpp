@@ -1,0 +1,406 @@
+// AttentionDescriptor side of the C ABI: precision policy, B200 parameter tables, and the
+// descriptor -> kernel-descriptor heuristic.  Mirrors (does not copy) the reference's
+//   Sources/FlashAttention/Attention/AttentionDescriptor/AttentionDescriptor.swift
+//   .../AttentionDescriptor+Precisions.swift, +Parameters.swift, AttentionParameterRow.swift
+// The tables hold B200 tile shapes and on-chip residency instead of Apple register-cache choices.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "internal.h"
+
+namespace mfa {
+
+thread_local std::string g_last_error;
+
+int fail(int status, const std::string &message) {
+  g_last_error = message;
+  return status;
+}
+
+static const char *kOperandNames[MFA_OPERAND_COUNT] = {"Q",  "K",  "V",  "O",  "L", "D",  "dO",
+                                                       "dV", "dK", "dQ", "S",  "P", "dP", "dS"};
+
+// ------------------------------------------------------------------------------------------------
+// Precision policy
+// ------------------------------------------------------------------------------------------------
+
+// memoryPrecisions (AttentionDescriptor+Precisions.swift:10-146)
+int memory_precision(const mfa_attention_descriptor_t &d, int operand) {
+  const bool bf16Inputs = d.input_precision_override == MFA_BF16;
+  switch (operand) {
+    case MFA_Q: case MFA_K: case MFA_V:
+      // :13-23  FP16 when lowPrecisionInputs (extension: BF16 when overridden)
+      return d.low_precision_inputs ? (bf16Inputs ? MFA_BF16 : MFA_FP16) : MFA_FP32;
+    case MFA_dO:
+      return d.low_precision_inputs ? MFA_BF16 : MFA_FP32;  // :17,22
+    case MFA_L:
+      return d.low_precision_intermediates ? MFA_FP16 : MFA_FP32;  // :81-87
+    case MFA_D:
+      return d.low_precision_intermediates ? MFA_BF16 : MFA_FP32;
+    case MFA_O: case MFA_dV: case MFA_dK: case MFA_dQ:
+      return MFA_FP32;  // :140-143  always FP32 in memory
+    default:
+      return -1;  // S, P, dP, dS are never materialised
+  }
+}
+
+// registerPrecisions (AttentionDescriptor+Precisions.swift:149-215).  B200 has native BF16
+// conversion, so the `hasNativeBF16Casting` (Apple9) branch applies.
+int register_precision(const mfa_attention_descriptor_t &d, int operand) {
+  const bool bf16Inputs = d.input_precision_override == MFA_BF16;
+  switch (operand) {
+    case MFA_Q: case MFA_K: case MFA_V:
+      return d.low_precision_inputs ? (bf16Inputs ? MFA_BF16 : MFA_FP16) : MFA_FP32;  // :158-168
+    case MFA_dO:
+      return d.low_precision_inputs ? MFA_BF16 : MFA_FP32;
+    case MFA_L:
+      return d.low_precision_intermediates ? MFA_FP16 : MFA_FP32;  // :171-177
+    case MFA_D:
+      return d.low_precision_intermediates ? MFA_BF16 : MFA_FP32;
+    case MFA_S:
+      // :197  S accumulates in FP16 only when both flags are set.  B200 tensor cores always
+      // accumulate S in FP32 in TMEM, which is the more accurate of the two; report FP32.
+      return MFA_FP32;
+    case MFA_P:
+      // :198  P is a 16-bit MMA operand under lowPrecisionIntermediates; on the tcgen05 path P is
+      // always rounded to the input element type (it is the A operand of O += P V).
+      if (d.low_precision_intermediates) return bf16Inputs ? MFA_BF16 : MFA_FP16;
+      return MFA_FP32;
+    case MFA_dP:
+      return MFA_FP32;  // :199
+    case MFA_dS:
+      return d.low_precision_intermediates ? MFA_BF16 : MFA_FP32;  // :200
+    case MFA_O: case MFA_dV: case MFA_dK: case MFA_dQ:
+      return MFA_FP32;  // :209-212  all outputs accumulate in FP32
+    default:
+      return -1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// B200 parameter tables.  Same text format as the reference's "parameter file"
+// (AttentionDescriptor+Parameters.swift:106-285):
+//     | max head dimension | parallelization | traversal | head block | resident operands |
+// First row with D <= max wins (:41-66); past the end, the last row applies.
+//   * tcgen05 family: parallelization = Q (or K/V) rows per CTA (two 128-row tcgen05 M-tiles for the
+//     forward ping-pong), traversal = keys per pipeline stage, head block = the whole padded head
+//     dimension (TMEM holds the accumulators, no D-blocking needed up to 256), resident = operands that
+//     stay in SMEM/TMEM for the entire traversal.
+//   * SIMT family: 64 x 64 blocks, 32-wide head chunks, accumulators resident in registers.
+// ------------------------------------------------------------------------------------------------
+static const char *kForwardTcgen05 =
+    "| 64  | 256 | 128 | 64  | Q, O |\n"
+    "| 128 | 256 | 128 | 128 | Q, O |\n"
+    "| 256 | 128 | 128 | 256 | Q, O |\n"
+    "\n";
+static const char *kBackwardQueryTcgen05 =
+    "| 64  | 128 | 128 | 64  | Q, dO, dQ |\n"
+    "| 128 | 128 | 128 | 128 | Q, dO, dQ |\n"
+    "\n";
+static const char *kBackwardKeyValueTcgen05 =
+    "| 64  | 128 | 128 | 64  | K, V, dV, dK |\n"
+    "| 128 | 128 | 128 | 128 | K, V, dV, dK |\n"
+    "\n";
+static const char *kForwardSimt =
+    "| 512 | 64 | 64 | 32 | O |\n"
+    "\n";
+static const char *kBackwardQuerySimt =
+    "| 512 | 64 | 64 | 32 | dQ |\n"
+    "\n";
+static const char *kBackwardKeyValueSimt =
+    "| 256 | 64 | 64 | 32 | dV, dK |\n"
+    "| 512 | 64 | 64 | 32 |        |\n"
+    "\n";
+
+// Which kernel family can serve this descriptor.  The tcgen05 family needs 16-bit row-major operands
+// whose row pitch is a multiple of 16 bytes (TMA global-stride rule), i.e. D % 8 == 0.
+int select_backend(const mfa_attention_descriptor_t &d, int type) {
+  if (!d.low_precision_inputs) return MFA_BACKEND_SIMT_FP32;
+  if (d.transpose_Q || d.transpose_K || d.transpose_V || d.transpose_O) return MFA_BACKEND_SIMT_FP32;
+  if (d.head % 8 != 0 || d.head == 0) return MFA_BACKEND_SIMT_FP32;
+  const uint32_t maxHead = (type == MFA_FORWARD) ? tcgen05_forward_max_head() : tcgen05_backward_max_head();
+  if (d.head > maxHead) return MFA_BACKEND_SIMT_FP32;
+  // the tcgen05 backward kernels consume dO through the same 16-bit MMA path as Q/K/V: the two
+  // element types must match (reference policy FP16 Q/K/V + BF16 dO goes to the SIMT family).
+  if (type != MFA_FORWARD && memory_precision(d, MFA_dO) != memory_precision(d, MFA_Q))
+    return MFA_BACKEND_SIMT_FP32;
+  return MFA_BACKEND_TCGEN05;
+}
+
+const char *parameter_file(const mfa_attention_descriptor_t &d, int type) {
+  const bool tc = select_backend(d, type) == MFA_BACKEND_TCGEN05;
+  switch (type) {
+    case MFA_FORWARD: return tc ? kForwardTcgen05 : kForwardSimt;
+    case MFA_BACKWARD_QUERY: return tc ? kBackwardQueryTcgen05 : kBackwardQuerySimt;
+    default: return tc ? kBackwardKeyValueTcgen05 : kBackwardKeyValueSimt;
+  }
+}
+
+// AttentionParameterRow (AttentionParameterRow.swift:8-19)
+struct ParameterRow {
+  unsigned maximumHeadDimension = 0;
+  std::string parallelization, traversal, head, cachedOperands;
+};
+
+static std::string strip_spaces(const std::string &s) {
+  std::string out;
+  for (char c : s)
+    if (c != ' ') out.push_back(c);  // AttentionParameterRow.swift:39-41 removes 0x20 only
+  return out;
+}
+
+// parseTable (AttentionParameterRow.swift:22-74)
+static int parse_table(const char *file, std::vector<ParameterRow> &rows) {
+  std::string text(file);
+  size_t pos = 0;
+  while (pos < text.size()) {
+    size_t eol = text.find('\n', pos);
+    if (eol == std::string::npos) eol = text.size();
+    std::string line = text.substr(pos, eol - pos);
+    pos = eol + 1;
+    if (line.empty()) continue;  // Swift's split(separator:) omits empty subsequences
+    std::vector<std::string> segments;
+    size_t p = 0;
+    bool lineEndsWithBar = false;
+    while (p <= line.size()) {
+      size_t bar = line.find('|', p);
+      if (bar == std::string::npos) bar = line.size();
+      std::string seg = line.substr(p, bar - p);
+      if (!seg.empty()) segments.push_back(strip_spaces(seg));
+      lineEndsWithBar = (bar < line.size());
+      p = bar + 1;
+    }
+    (void)lineEndsWithBar;
+    if (segments.size() != 5)
+      return fail(MFA_ERROR_INVALID_ARGUMENT, "Number of segments was invalid: " + std::to_string(segments.size()));
+    ParameterRow row;
+    char *end = nullptr;
+    unsigned long maxHead = strtoul(segments[0].c_str(), &end, 10);
+    if (segments[0].empty() || *end != '\0' || maxHead > 65535)
+      return fail(MFA_ERROR_INVALID_ARGUMENT, "Could not extract maximum head dimension.");
+    row.maximumHeadDimension = static_cast<unsigned>(maxHead);
+    row.parallelization = segments[1];
+    row.traversal = segments[2];
+    row.head = segments[3];
+    row.cachedOperands = segments[4];
+    rows.push_back(row);
+  }
+  return MFA_SUCCESS;
+}
+
+// parseOperands (AttentionParameterRow.swift:76-106)
+static int parse_operands(const std::string &text, std::vector<int> &operands) {
+  static const int accepted[] = {MFA_Q, MFA_K, MFA_V, MFA_O, MFA_dO, MFA_dV, MFA_dK, MFA_dQ};
+  size_t p = 0;
+  while (p <= text.size()) {
+    size_t comma = text.find(',', p);
+    if (comma == std::string::npos) comma = text.size();
+    std::string name = text.substr(p, comma - p);
+    p = comma + 1;
+    if (name.empty()) continue;
+    int matched = -1;
+    for (int op : accepted)
+      if (name == kOperandNames[op]) matched = op;
+    if (matched < 0) return fail(MFA_ERROR_INVALID_ARGUMENT, "Could not find match for " + name + ".");
+    operands.push_back(matched);
+  }
+  return MFA_SUCCESS;
+}
+
+static bool parse_u16(const std::string &s, uint16_t &out) {
+  if (s.empty()) return false;
+  char *end = nullptr;
+  unsigned long v = strtoul(s.c_str(), &end, 10);
+  if (*end != '\0' || v > 65535) return false;
+  out = static_cast<uint16_t>(v);
+  return true;
+}
+
+// kernelDescriptor(type:)  (AttentionDescriptor.swift:33-130)
+int kernel_descriptor(const mfa_attention_descriptor_t &d, int type, mfa_attention_kernel_descriptor_t &out) {
+  if (type < MFA_FORWARD || type > MFA_BACKWARD_KEY_VALUE)
+    return fail(MFA_ERROR_INVALID_ARGUMENT, "Unrecognized kernel type.");
+  // createHeadDimension / createTransposeState guard clauses (:88-111)
+  if (!d.has_matrix_dimensions || !d.has_transpose_state)
+    return fail(MFA_ERROR_INCOMPLETE_DESCRIPTOR, "Descriptor was incomplete.");
+
+  // Fetch the kernel-specific parameters (:36-39).
+  std::vector<ParameterRow> table;
+  int status = parse_table(parameter_file(d, type), table);
+  if (status != MFA_SUCCESS) return status;
+  // row(table:)  (AttentionDescriptor+Parameters.swift:41-66): first row with D <= max, else the last.
+  const ParameterRow *row = &table.back();
+  for (const ParameterRow &candidate : table) {
+    if (d.head <= candidate.maximumHeadDimension) {
+      row = &candidate;
+      break;
+    }
+  }
+
+  mfa_attention_kernel_descriptor_init(&out);
+
+  // createBlockDimensions (:41-54): head block <= pad8(D)
+  uint16_t parallelization, traversal, originalHead;
+  if (!parse_u16(row->parallelization, parallelization) || !parse_u16(row->traversal, traversal) ||
+      !parse_u16(row->head, originalHead))
+    return fail(MFA_ERROR_INVALID_ARGUMENT, "Could not decode block dimensions.");
+  const uint16_t paddedHeadDimension = static_cast<uint16_t>((d.head + 7) / 8 * 8);
+  out.has_block_dimensions = 1;
+  out.block_parallelization = parallelization;
+  out.block_traversal = traversal;
+  out.block_head = originalHead < paddedHeadDimension ? originalHead : paddedHeadDimension;
+
+  // createCacheState (:56-86)
+  uint16_t expected = 0;
+  switch (type) {
+    case MFA_FORWARD: expected = (1u << MFA_Q) | (1u << MFA_O); break;
+    case MFA_BACKWARD_QUERY: expected = (1u << MFA_Q) | (1u << MFA_dO) | (1u << MFA_dQ); break;
+    default: expected = (1u << MFA_K) | (1u << MFA_V) | (1u << MFA_dV) | (1u << MFA_dK); break;
+  }
+  std::vector<int> cached;
+  status = parse_operands(row->cachedOperands, cached);
+  if (status != MFA_SUCCESS) return status;
+  uint16_t cachedMask = 0;
+  for (int operand : cached) {
+    if (!(expected & (1u << operand)))
+      return fail(MFA_ERROR_UNEXPECTED_OPERAND, std::string("Unexpected operand: ") + kOperandNames[operand]);
+    cachedMask |= (1u << operand);
+  }
+  out.cache_state_valid_mask = expected;
+  out.cache_state_mask = cachedMask;
+
+  out.has_head_dimension = 1;
+  out.head_dimension = d.head;
+
+  for (int operand = 0; operand < MFA_OPERAND_COUNT; ++operand) {
+    int mem = memory_precision(d, operand);
+    int reg = register_precision(d, operand);
+    out.memory_precisions[operand] = mem < 0 ? 0xFF : static_cast<uint8_t>(mem);
+    out.register_precisions[operand] = reg < 0 ? 0xFF : static_cast<uint8_t>(reg);
+  }
+
+  out.backend = static_cast<uint8_t>(select_backend(d, type));
+  // preferAsyncCache / preferAsyncLoad (:118-124): "async" == TMA bulk-tensor copies on B200.
+  out.prefer_async_cache = out.backend == MFA_BACKEND_TCGEN05 ? 1 : 0;
+  out.prefer_async_load = out.backend == MFA_BACKEND_TCGEN05 ? 1 : 0;
+
+  // createTransposeState (:96-111): derivatives follow their forward operand.
+  uint16_t t = 0;
+  if (d.transpose_Q) t |= (1u << MFA_Q) | (1u << MFA_dQ);
+  if (d.transpose_K) t |= (1u << MFA_K) | (1u << MFA_dK);
+  if (d.transpose_V) t |= (1u << MFA_V) | (1u << MFA_dV);
+  if (d.transpose_O) t |= (1u << MFA_O) | (1u << MFA_dO);
+  out.transpose_state_valid_mask = (1u << MFA_Q) | (1u << MFA_K) | (1u << MFA_V) | (1u << MFA_O) | (1u << MFA_dO) |
+                                   (1u << MFA_dV) | (1u << MFA_dK) | (1u << MFA_dQ);
+  out.transpose_state_mask = t;
+  out.type = static_cast<uint8_t>(type);
+  return MFA_SUCCESS;
+}
+
+}  // namespace mfa
+
+// ------------------------------------------------------------------------------------------------
+// extern "C" surface
+// ------------------------------------------------------------------------------------------------
+using namespace mfa;
+
+extern "C" {
+
+const char *mfa_last_error(void) { return g_last_error.c_str(); }
+const char *mfa_version(void) { return "mfa_b200 0.1 (sm_100a; tcgen05+TMA+TMEM forward, SIMT FP32 family)"; }
+
+int mfa_precision_size(mfa_precision_t precision) { return precision == MFA_FP32 ? 4 : 2; }
+const char *mfa_precision_name(mfa_precision_t precision) {
+  switch (precision) {
+    case MFA_FP32: return "float";
+    case MFA_FP16: return "half";
+    case MFA_BF16: return "bfloat";
+  }
+  return "";
+}
+
+const char *mfa_operand_name(mfa_operand_t operand) {
+  if (operand < 0 || operand >= MFA_OPERAND_COUNT) return "";
+  return kOperandNames[operand];
+}
+int mfa_operand_buffer_binding(mfa_operand_t operand) {
+  return (operand >= 0 && operand < MFA_BUFFER_COUNT) ? static_cast<int>(operand) : -1;
+}
+
+void mfa_attention_descriptor_init(mfa_attention_descriptor_t *descriptor) {
+  if (descriptor) memset(descriptor, 0, sizeof(*descriptor));
+}
+
+int mfa_attention_descriptor_memory_precision(const mfa_attention_descriptor_t *descriptor, mfa_operand_t operand,
+                                              mfa_precision_t *out) {
+  if (!descriptor || !out) return fail(MFA_ERROR_INVALID_ARGUMENT, "NULL argument.");
+  int p = (operand >= 0 && operand < MFA_OPERAND_COUNT) ? memory_precision(*descriptor, operand) : -1;
+  if (p < 0)
+    return fail(MFA_ERROR_INVALID_ARGUMENT,
+                std::string("Precision of operand ") + mfa_operand_name(operand) + " was not specified.");
+  *out = static_cast<mfa_precision_t>(p);
+  return MFA_SUCCESS;
+}
+
+int mfa_attention_descriptor_register_precision(const mfa_attention_descriptor_t *descriptor, mfa_operand_t operand,
+                                                mfa_precision_t *out) {
+  if (!descriptor || !out) return fail(MFA_ERROR_INVALID_ARGUMENT, "NULL argument.");
+  int p = (operand >= 0 && operand < MFA_OPERAND_COUNT) ? register_precision(*descriptor, operand) : -1;
+  if (p < 0)
+    return fail(MFA_ERROR_INVALID_ARGUMENT,
+                std::string("Precision of operand ") + mfa_operand_name(operand) + " was not specified.");
+  *out = static_cast<mfa_precision_t>(p);
+  return MFA_SUCCESS;
+}
+
+void mfa_attention_kernel_descriptor_init(mfa_attention_kernel_descriptor_t *kd) {
+  if (!kd) return;
+  memset(kd, 0, sizeof(*kd));
+  memset(kd->memory_precisions, 0xFF, sizeof(kd->memory_precisions));
+  memset(kd->register_precisions, 0xFF, sizeof(kd->register_precisions));
+  kd->prefer_async_cache = 0xFF;
+  kd->prefer_async_load = 0xFF;
+  kd->type = 0xFF;
+}
+
+int mfa_attention_descriptor_kernel_descriptor(const mfa_attention_descriptor_t *descriptor, mfa_kernel_type_t type,
+                                               mfa_attention_kernel_descriptor_t *out) {
+  if (!descriptor || !out) return fail(MFA_ERROR_INVALID_ARGUMENT, "NULL argument.");
+  return kernel_descriptor(*descriptor, type, *out);
+}
+
+const char *mfa_attention_descriptor_parameter_file(const mfa_attention_descriptor_t *descriptor,
+                                                    mfa_kernel_type_t type) {
+  if (!descriptor) return "";
+  return parameter_file(*descriptor, type);
+}
+
+int mfa_attention_descriptor_set_function_constants(const mfa_attention_descriptor_t *descriptor,
+                                                    mfa_function_constants_t *constants) {
+  if (!descriptor || !constants) return fail(MFA_ERROR_INVALID_ARGUMENT, "NULL argument.");
+  if (!descriptor->has_matrix_dimensions) return fail(MFA_ERROR_INCOMPLETE_DESCRIPTOR, "Descriptor was incomplete.");
+  constants->row = descriptor->row;
+  constants->column = descriptor->column;
+  constants->batch_count = descriptor->batch_count;
+  return MFA_SUCCESS;
+}
+
+int mfa_attention_descriptor_operand_elements(const mfa_attention_descriptor_t *descriptor, mfa_operand_t operand,
+                                              size_t *out) {
+  if (!descriptor || !out) return fail(MFA_ERROR_INVALID_ARGUMENT, "NULL argument.");
+  if (!descriptor->has_matrix_dimensions) return fail(MFA_ERROR_INCOMPLETE_DESCRIPTOR, "Descriptor was incomplete.");
+  const size_t batch = descriptor->batch_count ? descriptor->batch_count : 1;
+  size_t n;
+  switch (operand) {
+    case MFA_Q: case MFA_O: case MFA_dO: case MFA_dQ: n = static_cast<size_t>(descriptor->row) * descriptor->head; break;
+    case MFA_K: case MFA_V: case MFA_dK: case MFA_dV: n = static_cast<size_t>(descriptor->column) * descriptor->head; break;
+    case MFA_L: case MFA_D: n = descriptor->row; break;
+    default: return fail(MFA_ERROR_INVALID_ARGUMENT, "Operand has no buffer.");
+  }
+  *out = n * batch;
+  return MFA_SUCCESS;
+}
+
+}  // extern "C"

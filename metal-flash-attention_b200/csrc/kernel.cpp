@@ -1,0 +1,343 @@
+// AttentionKernel side of the C ABI: handle creation/validation, launch geometry, and encode()
+// -- the compile + bind + dispatch the reference leaves to its caller
+// (Tests/FlashAttentionTests/Attention/SquareAttentionTest.swift:240-372).
+// Mirrors Sources/FlashAttention/Attention/AttentionKernel/AttentionKernel.swift.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "internal.h"
+
+struct mfa_attention_kernel {
+  mfa_attention_kernel_descriptor_t descriptor;
+  int type;
+  int backend;
+  uint32_t threads, smem_bytes, par, trav, head;
+  std::string source_name;
+};
+
+namespace mfa {
+
+// loadFunction / storeFunction legality (AttentionKernel.swift:81-139): a 16-bit memory format may
+// only be widened to FP32 or kept as is; FP32 memory can only be FP32 in registers.
+static bool precision_pair_valid(int memory, int reg) {
+  if (memory == MFA_FP16) return reg == MFA_FP16 || reg == MFA_FP32;
+  if (memory == MFA_BF16) return reg == MFA_BF16 || reg == MFA_FP32;
+  if (memory == MFA_FP32) return reg == MFA_FP32;
+  return false;
+}
+
+static const int *operands_of(int type, int *count) {
+  static const int fwd[] = {MFA_Q, MFA_K, MFA_V, MFA_O, MFA_L};
+  static const int dq[] = {MFA_Q, MFA_K, MFA_V, MFA_O, MFA_L, MFA_D, MFA_dO, MFA_dQ};
+  static const int dkv[] = {MFA_Q, MFA_K, MFA_V, MFA_L, MFA_D, MFA_dO, MFA_dV, MFA_dK};
+  switch (type) {
+    case MFA_FORWARD: *count = 5; return fwd;
+    case MFA_BACKWARD_QUERY: *count = 8; return dq;
+    default: *count = 8; return dkv;
+  }
+}
+
+static int check_device() {
+  int device = 0;
+  cudaError_t e = cudaGetDevice(&device);
+  if (e != cudaSuccess)
+    return fail(MFA_ERROR_NO_DEVICE, std::string("No CUDA device: ") + cudaGetErrorString(e) +
+                                         " (this library has no CPU fallback).");
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+  if (e != cudaSuccess) return fail(MFA_ERROR_NO_DEVICE, std::string("cudaDeviceGetAttribute: ") + cudaGetErrorString(e));
+  if (major != 10)
+    return fail(MFA_ERROR_NO_DEVICE, "Device is not sm_100 (compute capability " + std::to_string(major) +
+                                         ".x); these kernels are built for sm_100a only.");
+  return MFA_SUCCESS;
+}
+
+static int build_params(const mfa_attention_kernel *k, const mfa_function_constants_t *c, void *const buffers[],
+                        AttentionParams &p) {
+  if (c->row == 0 || c->column == 0) return fail(MFA_ERROR_INVALID_ARGUMENT, "R and C must be at least 1.");
+  p.R = c->row;
+  p.C = c->column;
+  p.D = k->descriptor.head_dimension;
+  p.batch = c->batch_count ? c->batch_count : 1;
+  for (int s = 0; s < kSlots; ++s) {
+    p.buf[s] = buffers[s];
+    uint8_t mp = k->descriptor.memory_precisions[s];
+    p.prec[s] = mp == 0xFF ? 0 : mp;
+    p.transposed[s] = (k->descriptor.transpose_state_mask >> s) & 1;
+  }
+  // dotProductScale (AttentionKernel+Softmax.swift:17-26)
+  p.scale = 1.0f / std::sqrt(static_cast<float>(p.D));
+  p.scale_log2 = 1.442695041f * p.scale;
+  int n = 0;
+  const int *ops = operands_of(k->type, &n);
+  for (int i = 0; i < n; ++i)
+    if (buffers[ops[i]] == nullptr)
+      return fail(MFA_ERROR_INVALID_ARGUMENT, std::string("Buffer ") + mfa_operand_name((mfa_operand_t)ops[i]) +
+                                                  " (binding " + std::to_string(ops[i]) + ") is NULL.");
+  return MFA_SUCCESS;
+}
+
+}  // namespace mfa
+
+using namespace mfa;
+
+extern "C" {
+
+int mfa_attention_kernel_create(const mfa_attention_kernel_descriptor_t *kd, mfa_attention_kernel_t **out) {
+  if (!kd || !out) return fail(MFA_ERROR_INVALID_ARGUMENT, "NULL argument.");
+  // guard let ... else fatalError("Descriptor was incomplete.")  (AttentionKernel.swift:28-34)
+  if (!kd->has_block_dimensions || !kd->has_head_dimension || kd->prefer_async_cache == 0xFF ||
+      kd->prefer_async_load == 0xFF || kd->type == 0xFF)
+    return fail(MFA_ERROR_INCOMPLETE_DESCRIPTOR, "Descriptor was incomplete.");
+  if (kd->type > MFA_BACKWARD_KEY_VALUE) return fail(MFA_ERROR_INVALID_ARGUMENT, "Unrecognized kernel type.");
+  if (kd->head_dimension == 0) return fail(MFA_ERROR_INVALID_ARGUMENT, "Head dimension must be at least 1.");
+
+  int n = 0;
+  const int *ops = operands_of(kd->type, &n);
+  for (int i = 0; i < n; ++i) {
+    int op = ops[i];
+    uint8_t mem = kd->memory_precisions[op], reg = kd->register_precisions[op];
+    if (mem == 0xFF || reg == 0xFF)
+      return fail(MFA_ERROR_INCOMPLETE_DESCRIPTOR,
+                  std::string("Precision of ") + mfa_operand_name((mfa_operand_t)op) + " was not specified.");
+    if (!precision_pair_valid(mem, reg)) return fail(MFA_ERROR_INVALID_PRECISIONS, "Invalid precisions.");
+    if (op != MFA_L && op != MFA_D && !((kd->transpose_state_valid_mask >> op) & 1))
+      return fail(MFA_ERROR_INCOMPLETE_DESCRIPTOR,
+                  std::string("Transpose state of ") + mfa_operand_name((mfa_operand_t)op) + " was not specified.");
+  }
+
+  mfa_attention_kernel *k = new mfa_attention_kernel();
+  k->descriptor = *kd;
+  k->type = kd->type;
+  k->backend = kd->backend;
+  const uint32_t D = kd->head_dimension;
+
+  if (k->backend == MFA_BACKEND_TCGEN05) {
+    // The tcgen05 kernels only exist for 16-bit row-major operands; reject descriptors edited into
+    // something they cannot serve instead of silently computing something else.
+    const uint8_t pq = kd->memory_precisions[MFA_Q];
+    bool ok = (pq == MFA_FP16 || pq == MFA_BF16) && kd->memory_precisions[MFA_K] == pq &&
+              kd->memory_precisions[MFA_V] == pq && D % 8 == 0 &&
+              D <= (k->type == MFA_FORWARD ? tcgen05_forward_max_head() : tcgen05_backward_max_head());
+    for (int i = 0; i < n; ++i)
+      if ((kd->transpose_state_mask >> ops[i]) & 1) ok = false;
+    if (k->type != MFA_FORWARD && kd->memory_precisions[MFA_dO] != pq) ok = false;
+    if (!ok) {
+      delete k;
+      return fail(MFA_ERROR_UNSUPPORTED,
+                  "MFA_BACKEND_TCGEN05 needs FP16/BF16 row-major Q,K,V (and dO of the same type), head % 8 == 0 "
+                  "and head <= the compiled maximum; use MFA_BACKEND_SIMT_FP32 for this descriptor.");
+    }
+    if (k->type == MFA_FORWARD)
+      tcgen05_forward_geometry(D, &k->threads, &k->smem_bytes, &k->par, &k->trav, &k->head);
+    else
+      tcgen05_backward_geometry(k->type, D, &k->threads, &k->smem_bytes, &k->par, &k->trav, &k->head);
+  } else if (k->backend == MFA_BACKEND_SIMT_FP32) {
+    if (D > 512) {
+      delete k;
+      return fail(MFA_ERROR_UNSUPPORTED, "Head dimension " + std::to_string(D) + " exceeds 512.");
+    }
+    simt_geometry(k->type, D, &k->threads, &k->smem_bytes, &k->par, &k->trav, &k->head);
+  } else {
+    delete k;
+    return fail(MFA_ERROR_INVALID_ARGUMENT, "Unrecognized backend.");
+  }
+  // The kernel object reports the tile shape the compiled kernel really uses; a descriptor whose
+  // block dimensions were edited away from a compiled configuration is rejected.
+  if (kd->block_parallelization != k->par || kd->block_traversal != k->trav) {
+    std::string msg = "Block dimensions " + std::to_string(kd->block_parallelization) + "x" +
+                      std::to_string(kd->block_traversal) + " have no compiled sm_100a kernel (available: " +
+                      std::to_string(k->par) + "x" + std::to_string(k->trav) + ").";
+    delete k;
+    return fail(MFA_ERROR_UNSUPPORTED, msg);
+  }
+  static const char *typeNames[] = {"forward", "backward_query", "backward_key_value"};
+  k->source_name = std::string("attention_") + typeNames[k->type] +
+                   (k->backend == MFA_BACKEND_TCGEN05 ? "_tcgen05" : "_simt_fp32") + "<D=" + std::to_string(D) + ">";
+  *out = k;
+  return MFA_SUCCESS;
+}
+
+void mfa_attention_kernel_destroy(mfa_attention_kernel_t *kernel) { delete kernel; }
+
+int mfa_attention_kernel_block_dimensions(const mfa_attention_kernel_t *kernel, uint16_t out[3]) {
+  if (!kernel || !out) return fail(MFA_ERROR_INVALID_ARGUMENT, "NULL argument.");
+  out[0] = static_cast<uint16_t>(kernel->par);
+  out[1] = static_cast<uint16_t>(kernel->trav);
+  out[2] = static_cast<uint16_t>(kernel->head);
+  return MFA_SUCCESS;
+}
+
+int mfa_attention_kernel_threadgroup_size(const mfa_attention_kernel_t *kernel, uint32_t *out) {
+  if (!kernel || !out) return fail(MFA_ERROR_INVALID_ARGUMENT, "NULL argument.");
+  *out = kernel->threads;
+  return MFA_SUCCESS;
+}
+
+int mfa_attention_kernel_threadgroup_memory_allocation(const mfa_attention_kernel_t *kernel, uint32_t *out) {
+  if (!kernel || !out) return fail(MFA_ERROR_INVALID_ARGUMENT, "NULL argument.");
+  *out = kernel->smem_bytes;
+  return MFA_SUCCESS;
+}
+
+int mfa_attention_kernel_grid_size(const mfa_attention_kernel_t *kernel, const mfa_function_constants_t *c,
+                                   uint32_t *out) {
+  if (!kernel || !c || !out) return fail(MFA_ERROR_INVALID_ARGUMENT, "NULL argument.");
+  // parallelization dimension: R for forward / backwardQuery, C for backwardKeyValue
+  // (AttentionKernel.swift:197-204; dispatch: SquareAttentionTest.swift:328-339)
+  const uint32_t dim = kernel->type == MFA_BACKWARD_KEY_VALUE ? c->column : c->row;
+  const uint32_t batch = c->batch_count ? c->batch_count : 1;
+  *out = ((dim + kernel->par - 1) / kernel->par) * batch;
+  return MFA_SUCCESS;
+}
+
+const char *mfa_attention_kernel_source_name(const mfa_attention_kernel_t *kernel) {
+  return kernel ? kernel->source_name.c_str() : "";
+}
+
+int mfa_attention_kernel_launch_count(const mfa_attention_kernel_t *kernel, const mfa_function_constants_t *c,
+                                      uint32_t *out) {
+  if (!kernel || !c || !out) return fail(MFA_ERROR_INVALID_ARGUMENT, "NULL argument.");
+  *out = 1;
+  return MFA_SUCCESS;
+}
+
+int mfa_attention_kernel_encode(const mfa_attention_kernel_t *kernel, const mfa_function_constants_t *constants,
+                                void *const buffers[MFA_BUFFER_COUNT], void *cuda_stream) {
+  if (!kernel || !constants || !buffers) return fail(MFA_ERROR_INVALID_ARGUMENT, "NULL argument.");
+  int status = check_device();
+  if (status != MFA_SUCCESS) return status;
+  AttentionParams p;
+  status = build_params(kernel, constants, buffers, p);
+  if (status != MFA_SUCCESS) return status;
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+
+  cudaError_t e = cudaSuccess;
+  if (kernel->backend == MFA_BACKEND_TCGEN05) {
+    switch (kernel->type) {
+      case MFA_FORWARD: e = launch_tcgen05_forward(p, stream); break;
+      case MFA_BACKWARD_QUERY: e = launch_tcgen05_backward_query(p, stream); break;
+      default: e = launch_tcgen05_backward_key_value(p, stream); break;
+    }
+  } else {
+    switch (kernel->type) {
+      case MFA_FORWARD: e = launch_simt_forward(p, stream); break;
+      case MFA_BACKWARD_QUERY: e = launch_simt_backward_query(p, stream); break;
+      default: e = launch_simt_backward_key_value(p, stream); break;
+    }
+  }
+  if (e != cudaSuccess)
+    return fail(MFA_ERROR_CUDA, std::string("launch of ") + kernel->source_name + " failed: " + cudaGetErrorString(e) +
+                                    " " + last_launch_detail());
+  return MFA_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host-buffer path: H2D -> kernels -> D2H (the end-to-end call bench.py times as `e2e`).
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Scratch {
+  void *ptr[MFA_BUFFER_COUNT] = {};
+  size_t bytes[MFA_BUFFER_COUNT] = {};
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  ~Scratch() {
+    // Process teardown: the CUDA context may already be gone; leaking here is deliberate.
+  }
+};
+thread_local Scratch g_scratch;
+}  // namespace
+
+int mfa_attention_run_host(const mfa_attention_descriptor_t *descriptor, uint32_t run_mask,
+                           void *const host_buffers[MFA_BUFFER_COUNT], int device) {
+  if (!descriptor || !host_buffers) return fail(MFA_ERROR_INVALID_ARGUMENT, "NULL argument.");
+  if (!(run_mask & 7u)) return fail(MFA_ERROR_INVALID_ARGUMENT, "run_mask selects no kernel.");
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess)
+    return fail(MFA_ERROR_NO_DEVICE, std::string("cudaSetDevice: ") + cudaGetErrorString(e) +
+                                         " (this library has no CPU fallback).");
+  Scratch &s = g_scratch;
+  if (s.device != device) {
+    for (int i = 0; i < MFA_BUFFER_COUNT; ++i) {
+      s.ptr[i] = nullptr;
+      s.bytes[i] = 0;
+    }
+    s.device = device;
+    if ((e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess)
+      return fail(MFA_ERROR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+  }
+
+  // which operands each kernel reads / writes (AttentionKernelType.swift:10-22)
+  uint32_t inputs = 0, outputs = 0;
+  if (run_mask & MFA_RUN_FORWARD) {
+    inputs |= (1u << MFA_Q) | (1u << MFA_K) | (1u << MFA_V);
+    outputs |= (1u << MFA_O) | (1u << MFA_L);
+  }
+  if (run_mask & MFA_RUN_BACKWARD_QUERY) {
+    inputs |= (1u << MFA_Q) | (1u << MFA_K) | (1u << MFA_V) | (1u << MFA_dO);
+    if (!(run_mask & MFA_RUN_FORWARD)) inputs |= (1u << MFA_O) | (1u << MFA_L);
+    outputs |= (1u << MFA_D) | (1u << MFA_dQ);
+  }
+  if (run_mask & MFA_RUN_BACKWARD_KEY_VALUE) {
+    inputs |= (1u << MFA_Q) | (1u << MFA_K) | (1u << MFA_V) | (1u << MFA_dO);
+    if (!(run_mask & MFA_RUN_FORWARD)) inputs |= (1u << MFA_L);
+    if (!(run_mask & MFA_RUN_BACKWARD_QUERY)) inputs |= (1u << MFA_D);
+    outputs |= (1u << MFA_dV) | (1u << MFA_dK);
+  }
+
+  void *dev[MFA_BUFFER_COUNT] = {};
+  size_t nbytes[MFA_BUFFER_COUNT] = {};
+  for (int op = 0; op < MFA_BUFFER_COUNT; ++op) {
+    if (!((inputs | outputs) & (1u << op))) continue;
+    size_t elements = 0;
+    int status = mfa_attention_descriptor_operand_elements(descriptor, (mfa_operand_t)op, &elements);
+    if (status != MFA_SUCCESS) return status;
+    nbytes[op] = elements * (memory_precision(*descriptor, op) == MFA_FP32 ? 4 : 2);
+    if (s.bytes[op] < nbytes[op]) {
+      if (s.ptr[op]) cudaFree(s.ptr[op]);
+      s.ptr[op] = nullptr;
+      s.bytes[op] = 0;
+      if ((e = cudaMalloc(&s.ptr[op], nbytes[op])) != cudaSuccess)
+        return fail(MFA_ERROR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+      s.bytes[op] = nbytes[op];
+    }
+    dev[op] = s.ptr[op];
+    if (inputs & (1u << op)) {
+      if (!host_buffers[op])
+        return fail(MFA_ERROR_INVALID_ARGUMENT, std::string("Host buffer ") + mfa_operand_name((mfa_operand_t)op) + " is NULL.");
+      if ((e = cudaMemcpyAsync(dev[op], host_buffers[op], nbytes[op], cudaMemcpyHostToDevice, s.stream)) != cudaSuccess)
+        return fail(MFA_ERROR_CUDA, std::string("H2D copy: ") + cudaGetErrorString(e));
+    }
+  }
+
+  mfa_function_constants_t constants;
+  int status = mfa_attention_descriptor_set_function_constants(descriptor, &constants);
+  if (status != MFA_SUCCESS) return status;
+  // reference order: forward -> backwardQuery -> backwardKeyValue (SquareAttentionTest.swift:355-368)
+  for (int type = MFA_FORWARD; type <= MFA_BACKWARD_KEY_VALUE; ++type) {
+    if (!(run_mask & (1u << type))) continue;
+    mfa_attention_kernel_descriptor_t kd;
+    if ((status = mfa_attention_descriptor_kernel_descriptor(descriptor, (mfa_kernel_type_t)type, &kd)) != MFA_SUCCESS)
+      return status;
+    mfa_attention_kernel_t *kernel = nullptr;
+    if ((status = mfa_attention_kernel_create(&kd, &kernel)) != MFA_SUCCESS) return status;
+    status = mfa_attention_kernel_encode(kernel, &constants, dev, s.stream);
+    mfa_attention_kernel_destroy(kernel);
+    if (status != MFA_SUCCESS) return status;
+  }
+  for (int op = 0; op < MFA_BUFFER_COUNT; ++op) {
+    if (!(outputs & (1u << op)) || !host_buffers[op]) continue;
+    if ((e = cudaMemcpyAsync(host_buffers[op], dev[op], nbytes[op], cudaMemcpyDeviceToHost, s.stream)) != cudaSuccess)
+      return fail(MFA_ERROR_CUDA, std::string("D2H copy: ") + cudaGetErrorString(e));
+  }
+  if ((e = cudaStreamSynchronize(s.stream)) != cudaSuccess)
+    return fail(MFA_ERROR_CUDA, std::string("kernel execution failed: ") + cudaGetErrorString(e));
+  return MFA_SUCCESS;
+}
+
+}  // extern "C"

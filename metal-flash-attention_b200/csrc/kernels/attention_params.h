@@ -1,0 +1,49 @@
+// Internal launch interface between the C-ABI host layer (csrc/*.cpp) and the sm_100a kernels.
+// Not part of the public ABI (include/mfa_b200.h is).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mfa {
+
+// Buffer slots = AttentionOperand.bufferBinding
+// (/root/reference/Sources/FlashAttention/Attention/AttentionOperand.swift:52-71).
+enum Slot { sQ = 0, sK = 1, sV = 2, sO = 3, sL = 4, sD = 5, sdO = 6, sdV = 7, sdK = 8, sdQ = 9, kSlots = 10 };
+
+// Precision raw values = GEMMOperandPrecision (GEMMOperandPrecision.swift:33-37).
+enum Prec : uint8_t { FP32 = 0, FP16 = 1, BF16 = 2 };
+
+struct AttentionParams {
+  uint32_t R;      // rows of the attention matrix (output sequence length)
+  uint32_t C;      // columns (input sequence length)
+  uint32_t D;      // head dimension
+  uint32_t batch;  // independent single-head problems, >= 1
+  void *buf[kSlots];        // device pointers, by slot
+  uint8_t prec[kSlots];     // memory precision, by slot
+  uint8_t transposed[kSlots];  // 1: stored [D][seq] (leading dim = seq), 0: [seq][D]
+  float scale;       // 1/sqrt(D)          (AttentionKernel+Softmax.swift:17-26)
+  float scale_log2;  // log2(e)/sqrt(D)
+};
+
+// ---- SIMT FP32 family (any shape / layout / precision) -------------------------------------
+cudaError_t launch_simt_forward(const AttentionParams &p, cudaStream_t stream);
+cudaError_t launch_simt_backward_query(const AttentionParams &p, cudaStream_t stream);
+cudaError_t launch_simt_backward_key_value(const AttentionParams &p, cudaStream_t stream);
+void simt_geometry(int type, uint32_t D, uint32_t *threads, uint32_t *smem_bytes, uint32_t *par, uint32_t *trav,
+                   uint32_t *head);
+
+// ---- tcgen05 / TMA / TMEM family (16-bit row-major inputs, D % 8 == 0) ----------------------
+struct Tcgen05Plan;  // owns tensor maps; defined in tcgen05_common.h
+bool tcgen05_forward_supported(const AttentionParams &p);
+cudaError_t launch_tcgen05_forward(const AttentionParams &p, cudaStream_t stream);
+void tcgen05_forward_geometry(uint32_t D, uint32_t *threads, uint32_t *smem_bytes, uint32_t *par, uint32_t *trav,
+                              uint32_t *head);
+bool tcgen05_backward_supported(const AttentionParams &p);
+cudaError_t launch_tcgen05_backward_query(const AttentionParams &p, cudaStream_t stream);
+cudaError_t launch_tcgen05_backward_key_value(const AttentionParams &p, cudaStream_t stream);
+void tcgen05_backward_geometry(int type, uint32_t D, uint32_t *threads, uint32_t *smem_bytes, uint32_t *par,
+                               uint32_t *trav, uint32_t *head);
+
+const char *last_launch_detail();  // thread-local detail string for MFA_ERROR_CUDA messages
+
+}  // namespace mfa

@@ -1,0 +1,410 @@
+// FlashAttention forward for sm_100a: TMA -> shared memory -> tcgen05.mma -> TMEM.
+//
+// Replaces the reference's generated forward kernel (loopForward, AttentionKernel+Source.swift:158-200;
+// outer product S = Q K^T, +OuterProduct.swift:18-487; online softmax, +Softmax.swift:228-324,334-505;
+// accumulate O += P V, +Accumulate.swift:24-582) for 16-bit row-major operands.
+//
+// One CTA owns 256 query rows (two 128-row tcgen05 M-tiles that ping-pong on the tensor pipe) and
+// walks the keys in blocks of 128.  Warp roles (384 threads):
+//   warps 0-3   softmax for tile 0  (thread = one query row = one TMEM lane)
+//   warps 4-7   softmax for tile 1
+//   warp  8     MMA issuer (one elected thread issues every tcgen05.mma / commit); owns TMEM alloc
+//   warp  9     TMA producer (Q once, then K and V stages)
+//   warps 10-11 idle (they donate their registers via setmaxnreg)
+// On-chip residency (the reference's "cache Q, O" rows, AttentionDescriptor+Parameters.swift:109-120,
+// re-expressed for B200): Q tiles stay in SMEM for the whole traversal, O accumulators stay in TMEM,
+// S lives in TMEM and is overwritten in place by P (16-bit) which feeds the second MMA straight from TMEM.
+//   TMEM columns: [0,128) S0/P0  [128,256) S1/P1  [256,256+D) O0  [256+D,256+2D) O1
+// Softmax bookkeeping follows Appendix A of SURVEY.md (log2 domain, L = m + log2 l) with one B200-specific
+// change: the running max is only refreshed when it grows by more than 2^8 ("lazy rescale"), so the
+// O *= correction pass over TMEM is rare; results are mathematically identical.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include <mutex>
+
+#include "attention_params.h"
+#include "sm100_ptx.cuh"
+#include "tma_host.h"
+
+namespace mfa {
+namespace fwd {
+
+using namespace ptx;
+
+constexpr uint32_t kTileM = 128;         // rows per tcgen05 M-tile
+constexpr uint32_t kTilesPerCta = 2;     // ping-pong tiles
+constexpr uint32_t kBlockN = 128;        // keys per traversal block
+constexpr uint32_t kSubTileBytes = 128 * 128;  // [128 rows][64 x 16-bit] = one 128B-swizzled TMA box
+constexpr uint32_t kThreads = 384;
+constexpr uint32_t kSoftmaxRegs = 232, kOtherRegs = 40;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units
+
+template <uint32_t DPAD>
+struct Config {
+  static constexpr uint32_t kSubTiles = DPAD / 64;                 // 64-element sub-tiles along D
+  static constexpr uint32_t kTileBytes = kSubTiles * kSubTileBytes;  // one 128 x DPAD operand tile
+  static constexpr uint32_t kStages = DPAD <= 64 ? 4 : 2;
+  static constexpr uint32_t kSmemQ = 0;
+  static constexpr uint32_t kSmemK = kSmemQ + kTilesPerCta * kTileBytes;
+  static constexpr uint32_t kSmemV = kSmemK + kStages * kTileBytes;
+  static constexpr uint32_t kSmemBar = kSmemV + kStages * kTileBytes;
+  static constexpr uint32_t kNumBars = 1 + 4 * kStages + 3 * kTilesPerCta;
+  static constexpr uint32_t kSmemTmemPtr = kSmemBar + kNumBars * 8;
+  static constexpr uint32_t kSmemBytes = kSmemTmemPtr + 16 + 1024;  // + slack for manual 1024 B alignment
+  static constexpr uint32_t kTmemS = 0;
+  static constexpr uint32_t kTmemO = 256;
+  static constexpr uint32_t kTmemCols = 512;
+};
+
+struct Barriers {
+  uint64_t *q_full, *k_full, *k_empty, *v_full, *v_empty, *s_full, *p_full, *o_full;
+};
+
+template <uint32_t DPAD, bool kBF16>
+__global__ void __launch_bounds__(kThreads, 1)
+    attention_forward_tcgen05(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                              const __grid_constant__ CUtensorMap mapV, float *__restrict__ O, void *__restrict__ L,
+                              uint32_t R, uint32_t C, uint32_t D, float scale_log2, int l_is_fp16) {
+  using Cfg = Config<DPAD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t head = blockIdx.y;
+  const uint32_t q_row0 = blockIdx.x * (kTileM * kTilesPerCta);
+  const uint32_t num_blocks = (C + kBlockN - 1) / kBlockN;
+
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kSmemBar);
+  Barriers b;
+  b.q_full = bars;
+  b.k_full = bars + 1;
+  b.k_empty = b.k_full + Cfg::kStages;
+  b.v_full = b.k_empty + Cfg::kStages;
+  b.v_empty = b.v_full + Cfg::kStages;
+  b.s_full = b.v_empty + Cfg::kStages;
+  b.p_full = b.s_full + kTilesPerCta;
+  b.o_full = b.p_full + kTilesPerCta;
+  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem + Cfg::kSmemTmemPtr);
+
+  // ---------------- one-time setup ----------------
+  if (threadIdx.x == 0) {
+    mbar_init(b.q_full, 1);
+    for (uint32_t s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&b.k_full[s], 1);
+      mbar_init(&b.k_empty[s], 1);
+      mbar_init(&b.v_full[s], 1);
+      mbar_init(&b.v_empty[s], 1);
+    }
+    for (uint32_t t = 0; t < kTilesPerCta; ++t) {
+      mbar_init(&b.s_full[t], 1);
+      mbar_init(&b.p_full[t], kTileM);
+      mbar_init(&b.o_full[t], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 8) {
+    tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  if (warp == 9 && lane == 0) {
+    prefetch_tensormap(&mapQ);
+    prefetch_tensormap(&mapK);
+    prefetch_tensormap(&mapV);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp < 8) {
+    // =====================================================================================
+    // softmax warps: thread <-> query row <-> TMEM lane
+    // =====================================================================================
+    setmaxnreg_inc<kSoftmaxRegs>();
+    const uint32_t t = warp >> 2;                      // tile
+    const uint32_t row_in_tile = (warp & 3) * 32 + lane;
+    const uint32_t lane_addr = ((warp & 3) * 32) << 16;  // this warp's TMEM lane quarter
+    const uint32_t tS = tmem_base + lane_addr + Cfg::kTmemS + t * kBlockN;
+    const uint32_t tO = tmem_base + lane_addr + Cfg::kTmemO + t * DPAD;
+
+    float m = -FLT_MAX;  // running max, log2 domain   (AttentionKernel+Caching.swift:310)
+    float l = 0.f;       // running sum
+    const uint32_t tail_cols = C - (num_blocks - 1) * kBlockN;  // valid columns in the last block
+
+    for (uint32_t j = 0; j < num_blocks; ++j) {
+      mbar_wait(&b.s_full[t], j & 1);
+      tc_fence_after();
+
+      float s[kBlockN];
+#pragma unroll
+      for (uint32_t c = 0; c < kBlockN; c += 32) tmem_ld32(tS + c, *reinterpret_cast<uint32_t(*)[32]>(&s[c]));
+      tc_wait_ld();
+
+      // edge mask (maskAttentionMatrixEdge, AttentionKernel+Softmax.swift:228-260)
+      if (j == num_blocks - 1 && tail_cols < kBlockN) {
+#pragma unroll
+        for (uint32_t c = 0; c < kBlockN; ++c)
+          if (c >= tail_cols) s[c] = -INFINITY;
+      }
+
+      // online max (onlineReduceMaximum, :267-287): the whole row is in this thread's registers
+      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+#pragma unroll
+      for (uint32_t c = 4; c < kBlockN; c += 4) {
+        mx0 = fmaxf(mx0, s[c]);
+        mx1 = fmaxf(mx1, s[c + 1]);
+        mx2 = fmaxf(mx2, s[c + 2]);
+        mx3 = fmaxf(mx3, s[c + 3]);
+      }
+      const float m_cand = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2);
+
+      // lazy correction (onlineCorrectO, :290-301): refresh m only when it grew by > 2^8
+      if (__any_sync(0xffffffffu, m_cand - m > kRescaleThreshold)) {
+        if (j > 0) {
+          const float correction = ex2_approx(m - m_cand);
+          mbar_wait(&b.o_full[t], (j - 1) & 1);  // O += P V of the previous block has landed
+          tc_fence_after();
+#pragma unroll
+          for (uint32_t c = 0; c < DPAD; c += 32) {
+            uint32_t o[32];
+            tmem_ld32(tO + c, o);
+            tc_wait_ld();
+#pragma unroll
+            for (uint32_t i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * correction);
+            tmem_st32(tO + c, o);
+          }
+          l *= correction;
+        }
+        m = m_cand;
+      }
+
+      // P = exp2(S * log2e/sqrt(D) - m), rounded to the MMA input type, written over S
+      // (softmax, :409-416; onlineReduceSum, :304-324)
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+      for (uint32_t c = 0; c < kBlockN; c += 32) {
+        uint32_t packed[16];
+#pragma unroll
+        for (uint32_t i = 0; i < 16; ++i) {
+          const float p0 = ex2_approx(fmaf(s[c + 2 * i], scale_log2, -m));
+          const float p1 = ex2_approx(fmaf(s[c + 2 * i + 1], scale_log2, -m));
+          sum0 += p0;
+          sum1 += p1;
+          packed[i] = kBF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
+        }
+        tmem_st16(tS + (c >> 1), packed);
+      }
+      l += sum0 + sum1;
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&b.p_full[t]);
+    }
+
+    // ---------------- epilogue: O / l -> global (FP32), L = m + log2(l) ----------------
+    mbar_wait(&b.o_full[t], (num_blocks - 1) & 1);
+    tc_fence_after();
+    const uint32_t row = q_row0 + t * kTileM + row_in_tile;
+    const float inv_l = 1.0f / l;
+    float *o_row = O + (static_cast<size_t>(head) * R + row) * D;
+#pragma unroll
+    for (uint32_t c = 0; c < DPAD; c += 32) {
+      uint32_t o[32];
+      tmem_ld32(tO + c, o);
+      tc_wait_ld();
+      if (row < R) {
+#pragma unroll
+        for (uint32_t i = 0; i < 32; i += 4) {
+          if (c + i < D) {  // D % 8 == 0, so a float4 is either fully inside or fully outside
+            float4 v = make_float4(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l,
+                                   __uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+            *reinterpret_cast<float4 *>(o_row + c + i) = v;
+          }
+        }
+      }
+    }
+    if (row < R && L != nullptr) {
+      const float lse2 = m + log2f(l);  // AttentionKernel+Caching.swift:373-377
+      const size_t idx = static_cast<size_t>(head) * R + row;
+      if (l_is_fp16)
+        reinterpret_cast<__half *>(L)[idx] = __float2half_rn(lse2);
+      else
+        reinterpret_cast<float *>(L)[idx] = lse2;
+    }
+  } else {
+    setmaxnreg_dec<kOtherRegs>();
+    if (warp == 9) {
+      // ===================================================================================
+      // TMA producer
+      // ===================================================================================
+      if (lane == 0) {
+        mbar_arrive_expect_tx(b.q_full, kTilesPerCta * Cfg::kTileBytes);
+        for (uint32_t t = 0; t < kTilesPerCta; ++t)
+          for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
+            tma_load_3d(smem + Cfg::kSmemQ + t * Cfg::kTileBytes + ds * kSubTileBytes, &mapQ, b.q_full, ds * 64,
+                        q_row0 + t * kTileM, head);
+        for (uint32_t j = 0; j < num_blocks; ++j) {
+          const uint32_t stage = j % Cfg::kStages, phase = (j / Cfg::kStages) & 1;
+          mbar_wait(&b.k_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&b.k_full[stage], Cfg::kTileBytes);
+          for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
+            tma_load_3d(smem + Cfg::kSmemK + stage * Cfg::kTileBytes + ds * kSubTileBytes, &mapK, &b.k_full[stage],
+                        ds * 64, j * kBlockN, head);
+          mbar_wait(&b.v_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&b.v_full[stage], Cfg::kTileBytes);
+          for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
+            tma_load_3d(smem + Cfg::kSmemV + stage * Cfg::kTileBytes + ds * kSubTileBytes, &mapV, &b.v_full[stage],
+                        ds * 64, j * kBlockN, head);
+        }
+      }
+    } else if (warp == 8) {
+      // ===================================================================================
+      // MMA issuer
+      // ===================================================================================
+      if (lane == 0) {
+        constexpr uint32_t kFormat = kBF16 ? 1u : 0u;
+        // S[128 x 128] = Q[128 x D] . K[128 x D]^T : A and B both K-major
+        constexpr uint32_t idescS = make_idesc_f16(kTileM, kBlockN, kFormat, 0, 0);
+        // O[128 x DPAD] += P[128 x 128] . V[128 x DPAD] : A from TMEM, B (= V, [key][d]) is MN-major
+        constexpr uint32_t idescO = make_idesc_f16(kTileM, DPAD, kFormat, 0, 1);
+        const uint32_t sQ = smem_u32(smem + Cfg::kSmemQ), sK = smem_u32(smem + Cfg::kSmemK),
+                       sV = smem_u32(smem + Cfg::kSmemV);
+
+        auto issue_S = [&](uint32_t t, uint32_t stage) {
+          const uint32_t d_tmem = tmem_base + Cfg::kTmemS + t * kBlockN;
+#pragma unroll
+          for (uint32_t k = 0; k < DPAD / 16; ++k) {
+            const uint32_t off = (k >> 2) * kSubTileBytes + (k & 3) * 32;  // 16 elements = 32 B inside the swizzle row
+            const uint64_t a = make_smem_desc_sw128(sQ + t * Cfg::kTileBytes + off, 16, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(sK + stage * Cfg::kTileBytes + off, 16, 1024);
+            umma_ss(d_tmem, a, bdesc, idescS, k > 0);
+          }
+        };
+        auto issue_PV = [&](uint32_t t, uint32_t stage, bool accumulate) {
+          const uint32_t d_tmem = tmem_base + Cfg::kTmemO + t * DPAD;
+          const uint32_t a_tmem = tmem_base + Cfg::kTmemS + t * kBlockN;
+#pragma unroll
+          for (uint32_t k = 0; k < kBlockN / 16; ++k) {
+            // 16 keys = two 8-row groups of 1024 B; 64-wide column blocks are kSubTileBytes apart
+            const uint64_t bdesc = make_smem_desc_sw128(sV + stage * Cfg::kTileBytes + k * 2048, kSubTileBytes, 1024);
+            umma_ts(d_tmem, a_tmem + k * 8, bdesc, idescO, (accumulate || k > 0) ? 1u : 0u);
+          }
+        };
+
+        mbar_wait(b.q_full, 0);
+        mbar_wait(&b.k_full[0], 0);
+        tc_fence_after();
+        issue_S(0, 0);
+        umma_commit(&b.s_full[0]);
+        issue_S(1, 0);
+        umma_commit(&b.s_full[1]);
+        umma_commit(&b.k_empty[0]);
+
+        for (uint32_t j = 0; j < num_blocks; ++j) {
+          const uint32_t stage = j % Cfg::kStages, phase = (j / Cfg::kStages) & 1;
+          const uint32_t nstage = (j + 1) % Cfg::kStages, nphase = ((j + 1) / Cfg::kStages) & 1;
+          mbar_wait(&b.v_full[stage], phase);
+          for (uint32_t t = 0; t < kTilesPerCta; ++t) {
+            mbar_wait(&b.p_full[t], j & 1);
+            tc_fence_after();
+            issue_PV(t, stage, j > 0);
+            umma_commit(&b.o_full[t]);
+            if (t == kTilesPerCta - 1) umma_commit(&b.v_empty[stage]);
+            if (j + 1 < num_blocks) {
+              if (t == 0) {
+                mbar_wait(&b.k_full[nstage], nphase);
+                tc_fence_after();
+              }
+              issue_S(t, nstage);
+              umma_commit(&b.s_full[t]);
+              if (t == kTilesPerCta - 1) umma_commit(&b.k_empty[nstage]);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---------------- teardown ----------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <uint32_t DPAD, bool kBF16>
+cudaError_t launch(const AttentionParams &p, cudaStream_t stream) {
+  using Cfg = Config<DPAD>;
+  auto kernel = attention_forward_tcgen05<DPAD, kBF16>;
+  static std::once_flag once;
+  static cudaError_t attr_status = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_status = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  });
+  if (attr_status != cudaSuccess) return attr_status;
+
+  CUtensorMap mapQ, mapK, mapV;
+  cudaError_t e;
+  if ((e = make_tensor_map_16bit(&mapQ, p.buf[sQ], p.R, p.D, p.batch, kTileM)) != cudaSuccess) return e;
+  if ((e = make_tensor_map_16bit(&mapK, p.buf[sK], p.C, p.D, p.batch, kBlockN)) != cudaSuccess) return e;
+  if ((e = make_tensor_map_16bit(&mapV, p.buf[sV], p.C, p.D, p.batch, kBlockN)) != cudaSuccess) return e;
+
+  dim3 grid((p.R + kTileM * kTilesPerCta - 1) / (kTileM * kTilesPerCta), p.batch);
+  kernel<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mapQ, mapK, mapV, static_cast<float *>(p.buf[sO]), p.buf[sL],
+                                                      p.R, p.C, p.D, p.scale_log2, p.prec[sL] == FP16 ? 1 : 0);
+  return cudaGetLastError();
+}
+
+}  // namespace fwd
+
+uint32_t tcgen05_forward_max_head() { return 128; }
+
+bool tcgen05_forward_supported(const AttentionParams &p) {
+  return (p.prec[sQ] == FP16 || p.prec[sQ] == BF16) && p.prec[sK] == p.prec[sQ] && p.prec[sV] == p.prec[sQ] &&
+         p.prec[sO] == FP32 && p.D % 8 == 0 && p.D <= tcgen05_forward_max_head() && !p.transposed[sQ] &&
+         !p.transposed[sK] && !p.transposed[sV] && !p.transposed[sO];
+}
+
+cudaError_t launch_tcgen05_forward(const AttentionParams &p, cudaStream_t stream) {
+  if (!tcgen05_forward_supported(p)) {
+    set_launch_detail("descriptor is outside the tcgen05 forward kernel's domain");
+    return cudaErrorInvalidValue;
+  }
+  const bool bf16 = p.prec[sQ] == BF16;
+  if (p.D <= 64) return bf16 ? fwd::launch<64, true>(p, stream) : fwd::launch<64, false>(p, stream);
+  return bf16 ? fwd::launch<128, true>(p, stream) : fwd::launch<128, false>(p, stream);
+}
+
+void tcgen05_forward_geometry(uint32_t D, uint32_t *threads, uint32_t *smem_bytes, uint32_t *par, uint32_t *trav,
+                              uint32_t *head) {
+  *threads = fwd::kThreads;
+  *smem_bytes = D <= 64 ? fwd::Config<64>::kSmemBytes : fwd::Config<128>::kSmemBytes;
+  *par = fwd::kTileM * fwd::kTilesPerCta;
+  *trav = fwd::kBlockN;
+  *head = D <= 64 ? 64 : 128;
+  const uint32_t padded = (D + 7) / 8 * 8;
+  if (*head > padded) *head = padded;
+}
+
+// ---- backward tcgen05 kernels are not built yet: the heuristic never selects them --------------
+uint32_t tcgen05_backward_max_head() { return 0; }
+bool tcgen05_backward_supported(const AttentionParams &) { return false; }
+cudaError_t launch_tcgen05_backward_query(const AttentionParams &, cudaStream_t) {
+  set_launch_detail("tcgen05 backward-query kernel is not compiled in");
+  return cudaErrorNotSupported;
+}
+cudaError_t launch_tcgen05_backward_key_value(const AttentionParams &, cudaStream_t) {
+  set_launch_detail("tcgen05 backward-key-value kernel is not compiled in");
+  return cudaErrorNotSupported;
+}
+void tcgen05_backward_geometry(int, uint32_t, uint32_t *threads, uint32_t *smem_bytes, uint32_t *par, uint32_t *trav,
+                               uint32_t *head) {
+  *threads = *smem_bytes = *par = *trav = *head = 0;
+}
+
+}  // namespace mfa
