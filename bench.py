@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's headline metric on B200: giga-FMA-instructions/s (and TFLOP/s) of the
+FlashAttention forward at N=4096, D=128, bf16 in / fp32 out.
+
+One "step" = one pass of the hot path over one batch of synthetic input: H independent single-head
+(N=4096, D=128) problems per GPU, one kernel launch (the reference is single-head; independent heads
+are the only thing that scales).  Work model is the reference's:
+(2D+5)*N^2 FMA-instructions per head forward (README.md:108-124; SquareAttentionTest.swift:742-756);
+TFLOP/s counts the two GEMMs only, 4*N^2*D per head.
+
+    python bench.py --gpus 1 --steps 50 --warmup 5            # our arm
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1   # the reference's CPU path (oracle port)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.  Inputs
+for one step (Q,K,V = 192 MiB at H=64) exceed the 126 MB L2 and two buffer sets alternate between steps.
+`e2e` goes through the C ABI's host-buffer entry point (mfa_attention_run_host: pinned host Q,K,V -> device,
+kernel, O and L -> host) inside the timed region.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_SEQ, D_HEAD = 4096, 128
+FMA_PER_HEAD = (2 * D_HEAD + 5) * N_SEQ * N_SEQ          # reference's forward work model
+FLOP_PER_HEAD = 4 * N_SEQ * N_SEQ * D_HEAD               # two GEMMs
+METRIC = "giga-FMA-instr/sec forward attn N=4096 D=128 bf16"
+UNIT = "GINSTRS"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
+# (profiles/), for the default H; None until a capture exists.
+NCU_TRAFFIC_BYTES_PER_LAUNCH = None
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            peaks = json.load(f)
+        return float(peaks["bf16_tflops"]), float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])), "measured"
+    return 1590.0, 1400.0, "fallback"   # /opt/skills/guides/B200_PROFILING.md
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, device_index, period_s=0.002):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM)
+        except Exception as exc:  # NVML missing: report that instead of inventing numbers
+            self._nvml, self._error = None, repr(exc)
+        self.period = period_s
+
+    def _loop(self):
+        nv = self._nvml
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._handle, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._handle)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._handle)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def __enter__(self):
+        if self._nvml:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+
+    def summary(self):
+        if not self._nvml:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "error": self._error}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference (Swift) cannot be
+    built here, so this is the C port of its `Network` oracle (oracle/network_oracle.c), row-parallel over all
+    host threads.  Each step is a bounded sample of the workload: ONE head (N=4096, D=128) forward."""
+    if rank != 0:
+        return
+    import oracle
+    threads = oracle.max_threads()
+    net = oracle.Network(N_SEQ, N_SEQ, D_HEAD, seed=0, threads=threads)
+    for _ in range(args.warmup):
+        net.inferenceAttention()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        net.inferenceAttention()
+    dt = time.perf_counter() - t0
+    value = FMA_PER_HEAD * args.steps / dt / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "tflops": FLOP_PER_HEAD * args.steps / dt / 1e12,
+        "config": {"workload": "forward attention N=4096 D=128, 1 head per step (bounded sample of the "
+                               "H-head step), FP32, reference CPU path = C port of Tests/.../Network.swift",
+                   "seq_len": N_SEQ, "head_dim": D_HEAD, "heads_per_step": 1},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "1 head (N=4096, D=128) forward per step, rows split over all host threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--heads", type=int, default=64, help="independent single-head problems per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import mfa_b200 as mfa   # raises if libmfa_b200.so is missing: there is no fallback path
+
+    assert torch.cuda.is_available(), "bench.py (our arm) needs a B200"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    H = args.heads
+
+    # ---- descriptor -> kernel, exactly as a client of the reference API would -------------------
+    desc = mfa.AttentionDescriptor()
+    desc.lowPrecisionInputs = True
+    desc.lowPrecisionIntermediates = False
+    desc.inputPrecisionOverride = mfa.GEMMOperandPrecision.BF16
+    desc.matrixDimensions = (N_SEQ, N_SEQ, D_HEAD)
+    desc.transposeState = (False, False, False, False)
+    desc.batchCount = H
+    kernel_desc = desc.kernelDescriptor(mfa.AttentionKernelType.forward)
+    assert kernel_desc.backend == mfa.Backend.tcgen05
+    kernel = mfa.AttentionKernel(kernel_desc)
+    constants = mfa.FunctionConstantValues()
+    desc.setFunctionConstants(constants)
+    launches_per_step = kernel.launchCount(constants)
+    Op = mfa.AttentionOperand
+
+    # ---- synthetic inputs, resident in HBM; two sets so consecutive steps never share lines -----
+    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    sets = []
+    for _ in range(2):
+        q, k, v = (torch.randn(H, N_SEQ, D_HEAD, device="cuda", dtype=torch.float32, generator=gen).to(torch.bfloat16)
+                   for _ in range(3))
+        o = torch.empty(H, N_SEQ, D_HEAD, device="cuda", dtype=torch.float32)
+        lse = torch.empty(H, N_SEQ, device="cuda", dtype=torch.float32)
+        sets.append({Op.Q: q, Op.K: k, Op.V: v, Op.O: o, Op.L: lse})
+    stream = torch.cuda.current_stream()
+
+    def step(i):
+        bufs = sets[i & 1]
+        kernel.encode(constants, {op: t.data_ptr() for op, t in bufs.items()}, stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+
+    # ---- `value`: device-timed, inputs resident ------------------------------------------------
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    visible = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+    ids = [x for x in visible.split(",") if x.strip().isdigit()]
+    sampler = ClockSampler(int(ids[local_rank]) if local_rank < len(ids) else local_rank)
+    with sampler:
+        barrier()
+        start.record(stream)
+        for i in range(args.steps):
+            step(i)
+        stop.record(stream)
+        barrier()
+    elapsed_ms = start.elapsed_time(stop)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    total_heads = H * world
+    value = FMA_PER_HEAD * total_heads / (ms_per_step * 1e-3) / 1e9
+    tflops = FLOP_PER_HEAD * total_heads / (ms_per_step * 1e-3) / 1e12
+
+    # ---- `e2e`: host buffers through mfa_attention_run_host ------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host = {}
+        for op, t in sets[0].items():
+            host[op] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            if op in (Op.Q, Op.K, Op.V):
+                host[op].copy_(t)
+        host_ptrs = {op: t.data_ptr() for op, t in host.items()}
+        fwd = [mfa.AttentionKernelType.forward]
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            desc.runHost(fwd, host_ptrs, device=torch.cuda.current_device())
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            desc.runHost(fwd, host_ptrs, device=torch.cuda.current_device())   # synchronous: returns after D2H
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        h2d = sum(host[op].numel() * host[op].element_size() for op in (Op.Q, Op.K, Op.V))
+        d2h = sum(host[op].numel() * host[op].element_size() for op in (Op.O, Op.L))
+        e2e = {"value": FMA_PER_HEAD * total_heads * e2e_steps / dt / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+               "ms_per_step": dt / e2e_steps * 1e3,
+               "api": "mfa_attention_run_host (pinned host Q,K,V -> device, kernel, O,L -> host)"}
+        # spot-check that the e2e path produced the same O as the device path
+        step(0)
+        torch.cuda.synchronize()
+        assert torch.allclose(host[Op.O][0, :8], sets[0][Op.O][0, :8].cpu(), rtol=0, atol=0), "e2e != device path"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant (only) kernel -------------------------------------------------
+    peak_burst, peak_sustained, peak_kind = measured_peaks()
+    per_gpu_tflops = FLOP_PER_HEAD * H / (ms_per_step * 1e-3) / 1e12
+    roofline = {
+        "bound": "tensor", "achieved": per_gpu_tflops, "peak": peak_burst, "unit": "TFLOP/s",
+        "frac": per_gpu_tflops / peak_burst, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
+        "peak_kind": f"{peak_kind} cuBLAS bf16 burst (MEASURED_PEAKS.json)" if peak_kind == "measured"
+                     else "fallback 1590 TF/s (B200_PROFILING.md)",
+        "frac_of_sustained_peak": per_gpu_tflops / peak_sustained,
+        "kernel": kernel.sourceName(), "flops_per_launch": FLOP_PER_HEAD * H,
+        "kernel_ms": ms_per_step,
+    }
+
+    # ---- CPU baseline: the oracle port, single thread "as written", on a bounded sample ----------
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        import oracle
+        net = oracle.Network(N_SEQ, N_SEQ, D_HEAD, seed=0, threads=1)
+        t0 = time.perf_counter()
+        net.inferenceAttention()
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": FMA_PER_HEAD / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+                        "sample": f"1 of the {H} heads of one step (N=4096, D=128), single thread, "
+                                  f"loop order of Network.inferenceAttention; {dt:.1f} s"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "tflops": tflops,
+        "config": {"workload": f"forward attention, {H} independent single-head problems per GPU per step, "
+                               "N=4096 D=128, bf16 Q/K/V, fp32 O and L (BASELINE.json configs[1] x heads)",
+                   "seq_len": N_SEQ, "head_dim": D_HEAD, "heads_per_gpu_per_step": H,
+                   "parallelism": f"heads sharded over {world} GPU(s), no data-path collective",
+                   "l2": "inputs per step (192 MiB at H=64) exceed the 126 MB L2; two buffer sets alternate"},
+        "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": args.steps * launches_per_step,
+        "roofline": roofline, "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -403,7 +403,7 @@ class AttentionKernel:
 
     def __del__(self):
         handle = getattr(self, "_handle", None)
-        if handle:
+        if handle and _lib is not None:  # _lib is None during interpreter teardown
             _lib.mfa_attention_kernel_destroy(handle)
             self._handle = None
 

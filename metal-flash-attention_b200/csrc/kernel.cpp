@@ -237,6 +237,18 @@ int mfa_attention_kernel_encode(const mfa_attention_kernel_t *kernel, const mfa_
   return MFA_SUCCESS;
 }
 
+// Debug-only export (deliberately absent from include/mfa_b200.h): forward with pipeline timestamps.
+MFA_API int mfa_debug_forward_trace(const mfa_attention_kernel_t *kernel, const mfa_function_constants_t *constants,
+                                    void *const buffers[MFA_BUFFER_COUNT], void *cuda_stream, long long *trace) {
+  if (!kernel || !constants || !buffers || !trace) return fail(MFA_ERROR_INVALID_ARGUMENT, "NULL argument.");
+  AttentionParams p;
+  int status = build_params(kernel, constants, buffers, p);
+  if (status != MFA_SUCCESS) return status;
+  cudaError_t e = launch_tcgen05_forward_trace(p, static_cast<cudaStream_t>(cuda_stream), trace);
+  if (e != cudaSuccess) return fail(MFA_ERROR_CUDA, std::string("trace launch failed: ") + cudaGetErrorString(e));
+  return MFA_SUCCESS;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Host-buffer path: H2D -> kernels -> D2H (the end-to-end call bench.py times as `e2e`).
 // ------------------------------------------------------------------------------------------------

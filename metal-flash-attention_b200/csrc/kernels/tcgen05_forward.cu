@@ -40,7 +40,11 @@ constexpr uint32_t kTilesPerCta = 2;     // ping-pong tiles
 constexpr uint32_t kBlockN = 128;        // keys per traversal block
 constexpr uint32_t kSubTileBytes = 128 * 128;  // [128 rows][64 x 16-bit] = one 128B-swizzled TMA box
 constexpr uint32_t kThreads = 384;
-constexpr uint32_t kSoftmaxRegs = 232, kOtherRegs = 40;
+// setmaxnreg budget: the CTA is launched with floor(65536 / 384 / 8) * 8 = 168 registers per thread; the two
+// softmax warpgroups grow to kSoftmaxRegs after the producer warpgroup has shrunk to kOtherRegs.  The sum
+// must not exceed the launch allocation or the second setmaxnreg.inc never returns.
+constexpr uint32_t kLaunchRegs = 168, kSoftmaxRegs = 208, kOtherRegs = 88;
+static_assert(kSoftmaxRegs * 256 + kOtherRegs * 128 <= kLaunchRegs * kThreads, "setmaxnreg over-subscribed");
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 template <uint32_t DPAD>
@@ -64,11 +68,21 @@ struct Barriers {
   uint64_t *q_full, *k_full, *k_empty, *v_full, *v_empty, *s_full, *p_full, *o_full;
 };
 
-template <uint32_t DPAD, bool kBF16>
+// kTrace: debug instantiation that records clock64() at the pipeline hand-off points of CTA (0,0)
+// (scripts/trace_forward.py); the production instantiation compiles all of it away.
+constexpr uint32_t kTraceSlots = 8;  // per (role, iteration)
+#define MFA_TRACE(role, iter, slot)                                                                   \
+  do {                                                                                                \
+    if (kTrace && trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0)                \
+      trace[((role) * 64 + ((iter) & 63)) * kTraceSlots + (slot)] = clock64();                        \
+  } while (0)
+
+template <uint32_t DPAD, bool kBF16, bool kTrace = false>
 __global__ void __launch_bounds__(kThreads, 1)
     attention_forward_tcgen05(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                               const __grid_constant__ CUtensorMap mapV, float *__restrict__ O, void *__restrict__ L,
-                              uint32_t R, uint32_t C, uint32_t D, float scale_log2, int l_is_fp16) {
+                              uint32_t R, uint32_t C, uint32_t D, float scale_log2, int l_is_fp16,
+                              long long *__restrict__ trace) {
   using Cfg = Config<DPAD>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -138,11 +152,13 @@ __global__ void __launch_bounds__(kThreads, 1)
     for (uint32_t j = 0; j < num_blocks; ++j) {
       mbar_wait(&b.s_full[t], j & 1);
       tc_fence_after();
+      MFA_TRACE(warp == 0 ? 0 : (warp == 4 ? 1 : 5), j, 0);
 
       float s[kBlockN];
 #pragma unroll
       for (uint32_t c = 0; c < kBlockN; c += 32) tmem_ld32(tS + c, *reinterpret_cast<uint32_t(*)[32]>(&s[c]));
       tc_wait_ld();
+      MFA_TRACE(warp == 0 ? 0 : (warp == 4 ? 1 : 5), j, 1);
 
       // edge mask (maskAttentionMatrixEdge, AttentionKernel+Softmax.swift:228-260)
       if (j == num_blocks - 1 && tail_cols < kBlockN) {
@@ -182,6 +198,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         m = m_cand;
       }
 
+      MFA_TRACE(warp == 0 ? 0 : (warp == 4 ? 1 : 5), j, 2);
       // P = exp2(S * log2e/sqrt(D) - m), rounded to the MMA input type, written over S
       // (softmax, :409-416; onlineReduceSum, :304-324)
       float sum0 = 0.f, sum1 = 0.f;
@@ -199,9 +216,11 @@ __global__ void __launch_bounds__(kThreads, 1)
         tmem_st16(tS + (c >> 1), packed);
       }
       l += sum0 + sum1;
+      MFA_TRACE(warp == 0 ? 0 : (warp == 4 ? 1 : 5), j, 3);
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&b.p_full[t]);
+      MFA_TRACE(warp == 0 ? 0 : (warp == 4 ? 1 : 5), j, 4);
     }
 
     // ---------------- epilogue: O / l -> global (FP32), L = m + log2(l) ----------------
@@ -236,25 +255,35 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else {
     setmaxnreg_dec<kOtherRegs>();
+    // Both producer warps run their control flow warp-wide and hand exactly one elected lane to the
+    // TMA / tcgen05 instructions: operands stay in uniform registers and the issue loops are branch-free.
     if (warp == 9) {
       // ===================================================================================
       // TMA producer
       // ===================================================================================
-      if (lane == 0) {
+      if (elect_one()) {
         mbar_arrive_expect_tx(b.q_full, kTilesPerCta * Cfg::kTileBytes);
+#pragma unroll
         for (uint32_t t = 0; t < kTilesPerCta; ++t)
+#pragma unroll
           for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
             tma_load_3d(smem + Cfg::kSmemQ + t * Cfg::kTileBytes + ds * kSubTileBytes, &mapQ, b.q_full, ds * 64,
                         q_row0 + t * kTileM, head);
-        for (uint32_t j = 0; j < num_blocks; ++j) {
-          const uint32_t stage = j % Cfg::kStages, phase = (j / Cfg::kStages) & 1;
-          mbar_wait(&b.k_empty[stage], phase ^ 1);
+      }
+      for (uint32_t j = 0; j < num_blocks; ++j) {
+        const uint32_t stage = j % Cfg::kStages, phase = (j / Cfg::kStages) & 1;
+        mbar_wait(&b.k_empty[stage], phase ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&b.k_full[stage], Cfg::kTileBytes);
+#pragma unroll
           for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
             tma_load_3d(smem + Cfg::kSmemK + stage * Cfg::kTileBytes + ds * kSubTileBytes, &mapK, &b.k_full[stage],
                         ds * 64, j * kBlockN, head);
-          mbar_wait(&b.v_empty[stage], phase ^ 1);
+        }
+        mbar_wait(&b.v_empty[stage], phase ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&b.v_full[stage], Cfg::kTileBytes);
+#pragma unroll
           for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
             tma_load_3d(smem + Cfg::kSmemV + stage * Cfg::kTileBytes + ds * kSubTileBytes, &mapV, &b.v_full[stage],
                         ds * 64, j * kBlockN, head);
@@ -264,69 +293,79 @@ __global__ void __launch_bounds__(kThreads, 1)
       // ===================================================================================
       // MMA issuer
       // ===================================================================================
-      if (lane == 0) {
-        constexpr uint32_t kFormat = kBF16 ? 1u : 0u;
-        // S[128 x 128] = Q[128 x D] . K[128 x D]^T : A and B both K-major
-        constexpr uint32_t idescS = make_idesc_f16(kTileM, kBlockN, kFormat, 0, 0);
-        // O[128 x DPAD] += P[128 x 128] . V[128 x DPAD] : A from TMEM, B (= V, [key][d]) is MN-major
-        constexpr uint32_t idescO = make_idesc_f16(kTileM, DPAD, kFormat, 0, 1);
-        const uint32_t sQ = smem_u32(smem + Cfg::kSmemQ), sK = smem_u32(smem + Cfg::kSmemK),
-                       sV = smem_u32(smem + Cfg::kSmemV);
+      constexpr uint32_t kFormat = kBF16 ? 1u : 0u;
+      // S[128 x 128] = Q[128 x D] . K[128 x D]^T : A and B both K-major
+      constexpr uint32_t idescS = make_idesc_f16(kTileM, kBlockN, kFormat, 0, 0);
+      // O[128 x DPAD] += P[128 x 128] . V[128 x DPAD] : A from TMEM, B (= V, [key][d]) is MN-major
+      constexpr uint32_t idescO = make_idesc_f16(kTileM, DPAD, kFormat, 0, 1);
+      // Descriptors differ only in the 14-bit start-address field; build each once and add (bytes >> 4).
+      const uint64_t descQ = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemQ), 16, 1024);
+      const uint64_t descK = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemK), 16, 1024);
+      const uint64_t descV = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemV), kSubTileBytes, 1024);
 
-        auto issue_S = [&](uint32_t t, uint32_t stage) {
-          const uint32_t d_tmem = tmem_base + Cfg::kTmemS + t * kBlockN;
+      // every tcgen05.mma / commit below is issued by the one elected lane
+      auto issue_S = [&](uint32_t t, uint32_t stage) {
+        const uint32_t d_tmem = tmem_base + Cfg::kTmemS + t * kBlockN;
+        const uint64_t a0 = descQ + ((t * Cfg::kTileBytes) >> 4);
+        const uint64_t b0 = descK + ((stage * Cfg::kTileBytes) >> 4);
 #pragma unroll
-          for (uint32_t k = 0; k < DPAD / 16; ++k) {
-            const uint32_t off = (k >> 2) * kSubTileBytes + (k & 3) * 32;  // 16 elements = 32 B inside the swizzle row
-            const uint64_t a = make_smem_desc_sw128(sQ + t * Cfg::kTileBytes + off, 16, 1024);
-            const uint64_t bdesc = make_smem_desc_sw128(sK + stage * Cfg::kTileBytes + off, 16, 1024);
-            umma_ss(d_tmem, a, bdesc, idescS, k > 0);
-          }
-        };
-        auto issue_PV = [&](uint32_t t, uint32_t stage, bool accumulate) {
-          const uint32_t d_tmem = tmem_base + Cfg::kTmemO + t * DPAD;
-          const uint32_t a_tmem = tmem_base + Cfg::kTmemS + t * kBlockN;
+        for (uint32_t k = 0; k < DPAD / 16; ++k) {
+          // 16 elements = 32 B inside the 128 B swizzle row; 4 k-steps per 64-element sub-tile
+          const uint32_t off = ((k >> 2) * kSubTileBytes + (k & 3) * 32) >> 4;
+          umma_ss(d_tmem, a0 + off, b0 + off, idescS, k > 0);
+        }
+      };
+      auto issue_PV = [&](uint32_t t, uint32_t stage, uint32_t accumulate) {
+        const uint32_t d_tmem = tmem_base + Cfg::kTmemO + t * DPAD;
+        const uint32_t a_tmem = tmem_base + Cfg::kTmemS + t * kBlockN;
+        const uint64_t b0 = descV + ((stage * Cfg::kTileBytes) >> 4);
 #pragma unroll
-          for (uint32_t k = 0; k < kBlockN / 16; ++k) {
-            // 16 keys = two 8-row groups of 1024 B; 64-wide column blocks are kSubTileBytes apart
-            const uint64_t bdesc = make_smem_desc_sw128(sV + stage * Cfg::kTileBytes + k * 2048, kSubTileBytes, 1024);
-            umma_ts(d_tmem, a_tmem + k * 8, bdesc, idescO, (accumulate || k > 0) ? 1u : 0u);
-          }
-        };
+        for (uint32_t k = 0; k < kBlockN / 16; ++k)
+          // 16 keys = two 8-row groups of 1024 B; 64-wide column blocks are kSubTileBytes apart (LBO)
+          umma_ts(d_tmem, a_tmem + k * 8, b0 + ((k * 2048) >> 4), idescO, k > 0 ? 1u : accumulate);
+      };
 
-        mbar_wait(b.q_full, 0);
-        mbar_wait(&b.k_full[0], 0);
-        tc_fence_after();
+      mbar_wait(b.q_full, 0);
+      mbar_wait(&b.k_full[0], 0);
+      tc_fence_after();
+      if (elect_one()) {
         issue_S(0, 0);
         umma_commit(&b.s_full[0]);
         issue_S(1, 0);
         umma_commit(&b.s_full[1]);
         umma_commit(&b.k_empty[0]);
+      }
+      __syncwarp();
 
-        for (uint32_t j = 0; j < num_blocks; ++j) {
-          const uint32_t stage = j % Cfg::kStages, phase = (j / Cfg::kStages) & 1;
-          const uint32_t nstage = (j + 1) % Cfg::kStages, nphase = ((j + 1) / Cfg::kStages) & 1;
-          mbar_wait(&b.v_full[stage], phase);
-          for (uint32_t t = 0; t < kTilesPerCta; ++t) {
-            mbar_wait(&b.p_full[t], j & 1);
-            tc_fence_after();
-            issue_PV(t, stage, j > 0);
+      for (uint32_t j = 0; j < num_blocks; ++j) {
+        const uint32_t stage = j % Cfg::kStages, phase = (j / Cfg::kStages) & 1;
+        const uint32_t nstage = (j + 1) % Cfg::kStages, nphase = ((j + 1) / Cfg::kStages) & 1;
+        const bool has_next = j + 1 < num_blocks;
+        mbar_wait(&b.v_full[stage], phase);
+        MFA_TRACE(2, j, 0);
+#pragma unroll
+        for (uint32_t t = 0; t < kTilesPerCta; ++t) {
+          mbar_wait(&b.p_full[t], j & 1);
+          if (t == 0 && has_next) mbar_wait(&b.k_full[nstage], nphase);
+          tc_fence_after();
+          MFA_TRACE(2, j, 1 + 3 * t);
+          if (elect_one()) {
+            issue_PV(t, stage, j > 0 ? 1u : 0u);
             umma_commit(&b.o_full[t]);
             if (t == kTilesPerCta - 1) umma_commit(&b.v_empty[stage]);
-            if (j + 1 < num_blocks) {
-              if (t == 0) {
-                mbar_wait(&b.k_full[nstage], nphase);
-                tc_fence_after();
-              }
+            if (has_next) {
               issue_S(t, nstage);
               umma_commit(&b.s_full[t]);
               if (t == kTilesPerCta - 1) umma_commit(&b.k_empty[nstage]);
             }
           }
+          __syncwarp();
+          MFA_TRACE(2, j, 3 + 3 * t);
         }
       }
     }
   }
+
 
   // ---------------- teardown ----------------
   tc_fence_before();
@@ -337,10 +376,10 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
 }
 
-template <uint32_t DPAD, bool kBF16>
-cudaError_t launch(const AttentionParams &p, cudaStream_t stream) {
+template <uint32_t DPAD, bool kBF16, bool kTrace = false>
+cudaError_t launch(const AttentionParams &p, cudaStream_t stream, long long *trace = nullptr) {
   using Cfg = Config<DPAD>;
-  auto kernel = attention_forward_tcgen05<DPAD, kBF16>;
+  auto kernel = attention_forward_tcgen05<DPAD, kBF16, kTrace>;
   static std::once_flag once;
   static cudaError_t attr_status = cudaSuccess;
   std::call_once(once, [&] {
@@ -356,7 +395,7 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream) {
 
   dim3 grid((p.R + kTileM * kTilesPerCta - 1) / (kTileM * kTilesPerCta), p.batch);
   kernel<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mapQ, mapK, mapV, static_cast<float *>(p.buf[sO]), p.buf[sL],
-                                                      p.R, p.C, p.D, p.scale_log2, p.prec[sL] == FP16 ? 1 : 0);
+                                                      p.R, p.C, p.D, p.scale_log2, p.prec[sL] == FP16 ? 1 : 0, trace);
   return cudaGetLastError();
 }
 
@@ -378,6 +417,12 @@ cudaError_t launch_tcgen05_forward(const AttentionParams &p, cudaStream_t stream
   const bool bf16 = p.prec[sQ] == BF16;
   if (p.D <= 64) return bf16 ? fwd::launch<64, true>(p, stream) : fwd::launch<64, false>(p, stream);
   return bf16 ? fwd::launch<128, true>(p, stream) : fwd::launch<128, false>(p, stream);
+}
+
+// Debug entry (not in include/mfa_b200.h): the D=128 bf16 forward with pipeline timestamps of CTA (0,0)
+// written to `trace` (3 roles x 64 iterations x 8 slots of clock64()).  Used by scripts/trace_forward.py.
+cudaError_t launch_tcgen05_forward_trace(const AttentionParams &p, cudaStream_t stream, long long *trace) {
+  return fwd::launch<128, true, true>(p, stream, trace);
 }
 
 void tcgen05_forward_geometry(uint32_t D, uint32_t *threads, uint32_t *smem_bytes, uint32_t *par, uint32_t *trav,

@@ -24,7 +24,7 @@
  * The *_omp entry points use the same per-row arithmetic but distribute rows over OpenMP
  * threads (used to generate goldens at large N and as the "all host cores" CPU baseline).
  *
- * Build: see oracle/Makefile  (gcc -O3 -march=native -ffp-contract=off -fopenmp).
+ * Build: see oracle/Makefile  (gcc -O3 -march=x86-64-v3 -ffp-contract=off -fopenmp).
  */
 #include <math.h>
 #include <stdint.h>

@@ -1,0 +1,127 @@
+"""Parity of the tensor-core forward (TMA + tcgen05 + TMEM) with the CPU oracle.
+
+The oracle runs on the inputs AFTER rounding to the kernel's 16-bit memory format, so the comparison
+isolates the kernel's own arithmetic.  Stated tolerances (north_star: "within 1e-3 relative"):
+  O : relative RMS error  rms(O - O_ref) / rms(O_ref) <= 1e-3 for FP16 and <= 2e-3 for BF16 (P, the A operand of
+      O += P V, is rounded to the MMA input type: BF16 keeps 8 significant bits, so every product carries a
+      relative error up to 2^-9 = 1.95e-3 that the row sum does not average away relative to O), and element-wise
+      |err| <= eps_P * max|V| + 1e-5 with eps_P = 2^-8 (bf16) or 2^-10 (fp16): P is rounded to the 16-bit MMA
+      input type before O += P V, so each element carries at most half an ulp of P times the V it multiplies
+      (the bound is reached when C is tiny and nothing averages out);
+  L : |err| <= 1e-3 absolute in natural-log units (FP32 L); 7e-3 when L is stored as FP16 (reference's bar)
+and always within the reference's own mixed-precision bars O 5e-2 / L 7e-3 (SquareAttentionTest.swift:539-546)."""
+import numpy as np
+import pytest
+
+
+def _descriptor(R, C, D, bf16, lowMid=False, batch=1):
+    import mfa_b200 as mfa
+    desc = mfa.AttentionDescriptor()
+    desc.lowPrecisionInputs = True
+    desc.lowPrecisionIntermediates = lowMid
+    desc.matrixDimensions = (R, C, D)
+    desc.transposeState = (False, False, False, False)
+    desc.batchCount = batch
+    if bf16:
+        desc.inputPrecisionOverride = mfa.GEMMOperandPrecision.BF16
+    return desc
+
+
+def _run_and_check(R, C, D, bf16, seed, lowMid=False, threads=8):
+    import mfa_b200 as mfa
+    import oracle
+    from tests.attention_harness import run_attention, check
+
+    desc = _descriptor(R, C, D, bf16, lowMid)
+    kd = desc.kernelDescriptor(mfa.AttentionKernelType.forward)
+    assert kd.backend == mfa.Backend.tcgen05, "heuristic should pick the tensor-core family here"
+    net = oracle.Network(R, C, D, seed=seed, threads=threads).round_inputs(oracle.BF16 if bf16 else oracle.FP16)
+    out = run_attention(desc, net, types=[mfa.AttentionKernelType.forward])
+    O, L = net.inferenceAttention(with_L=True)
+    errO = check_O(O, out["O"], net.V, bf16)
+    errL = check(L, out["L"], 7e-3 if lowMid else 1e-3, "L")
+    return errO, errL
+
+
+def check_O(O, actual, V, bf16, name="O"):
+    from tests.attention_harness import check
+    tolO = (2.0 ** -8 if bf16 else 2.0 ** -10) * float(np.abs(V).max()) + 1e-5
+    errO = check(O, actual, min(tolO, 5e-2), name)
+    rel_rms = float(np.sqrt(np.mean((actual - O) ** 2)) / max(np.sqrt(np.mean(O ** 2)), 1e-30))
+    bound = 2e-3 if bf16 else 1e-3
+    assert rel_rms <= bound, f"{name}: relative RMS error {rel_rms:.3e} > {bound}"
+    return errO
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bf16", [True, False], ids=["bf16", "fp16"])
+@pytest.mark.parametrize("R,C,D", [
+    (256, 256, 128), (128, 128, 64), (512, 384, 128), (256, 640, 64),   # aligned
+    (200, 333, 128), (77, 129, 64), (1, 1, 8), (300, 17, 80), (129, 257, 72), (40, 500, 16),  # ragged edges
+    (1024, 1024, 128), (640, 1280, 96),
+])
+def test_forward_matches_oracle(R, C, D, bf16):
+    _run_and_check(R, C, D, bf16, seed=R * 7 + C * 3 + D)
+
+
+@pytest.mark.gpu
+def test_forward_fp16_L_storage():
+    """lowPrecisionIntermediates: L is stored as FP16 (AttentionDescriptor+Precisions.swift:81-87)."""
+    _run_and_check(256, 256, 128, True, seed=5, lowMid=True)
+    _run_and_check(192, 200, 64, False, seed=6, lowMid=True)
+
+
+@pytest.mark.gpu
+def test_config2_full_size_bf16_n4096_d128():
+    """BASELINE.json configs[1]: single-head forward bf16 N=4096 D=128, against the (row-parallel) oracle."""
+    errO, errL = _run_and_check(4096, 4096, 128, True, seed=0)
+    print(f"config2 max|dO|={errO:.3e} max|dL|={errL:.3e}")
+
+
+@pytest.mark.gpu
+def test_adversarial_growing_max_forces_rescale():
+    """Scores that keep growing along the key axis force the (normally rare) O-rescale path every block."""
+    import mfa_b200 as mfa
+    import oracle
+    from tests.attention_harness import run_attention, check
+
+    R, C, D = 256, 1024, 64
+    net = oracle.Network(R, C, D, seed=11, threads=8)
+    ramp = np.linspace(0.0, 6.0, C, dtype=np.float32)[:, None]
+    net.K = net.K + ramp * np.sign(net.Q.mean(axis=0, keepdims=True) + 1e-3)
+    net.Q = np.abs(net.Q) * np.sign(net.Q.mean(axis=0, keepdims=True) + 1e-3)
+    net.round_inputs(oracle.BF16)
+    desc = _descriptor(R, C, D, True)
+    out = run_attention(desc, net, types=[mfa.AttentionKernelType.forward])
+    O, L = net.inferenceAttention(with_L=True)
+    check_O(O, out["O"], net.V, True)
+    check(L, out["L"], 2e-3, "L")
+
+
+@pytest.mark.gpu
+def test_batched_heads_are_independent_problems():
+    """batch extension: problem b of the batch equals the single-head run on the same tensors; and the
+    softmax identity O == 1 when V == 1 holds at the full N=4096 (size-independent property)."""
+    import mfa_b200 as mfa
+    import oracle
+    from tests.attention_harness import run_attention, check
+
+    R = C = 512
+    D = 128
+    nets = [oracle.Network(R, C, D, seed=s, threads=8).round_inputs(oracle.BF16) for s in (21, 22, 23)]
+    desc = _descriptor(R, C, D, True, batch=3)
+    Op = mfa.AttentionOperand
+    inputs = {Op.Q: np.stack([n.Q for n in nets]), Op.K: np.stack([n.K for n in nets]),
+              Op.V: np.stack([n.V for n in nets])}
+    out = run_attention(desc, None, types=[mfa.AttentionKernelType.forward], inputs=inputs)
+    for b, n in enumerate(nets):
+        O, L = n.inferenceAttention(with_L=True)
+        check_O(O, out["O"][b], n.V, True, f"O[{b}]")
+        check(L, out["L"][b], 1e-3, f"L[{b}]")
+
+    N = 4096
+    big = oracle.Network(N, N, D, seed=3).round_inputs(oracle.BF16)
+    big.V = np.ones_like(big.V)
+    out = run_attention(_descriptor(N, N, D, True), big, types=[mfa.AttentionKernelType.forward])
+    # rows of P sum to 1 -> O == 1 up to the 16-bit rounding of P (relative 2^-9, averaged over the row)
+    assert np.abs(out["O"] - 1.0).max() < 2e-3
