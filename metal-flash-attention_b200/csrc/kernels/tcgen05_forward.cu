@@ -4,17 +4,19 @@
 // outer product S = Q K^T, +OuterProduct.swift:18-487; online softmax, +Softmax.swift:228-324,334-505;
 // accumulate O += P V, +Accumulate.swift:24-582) for 16-bit row-major operands.
 //
-// One CTA owns 256 query rows (two 128-row tcgen05 M-tiles that ping-pong on the tensor pipe) and
-// walks the keys in blocks of 128.  Warp roles (384 threads):
+// One CTA owns 256 query rows (two 128-row tcgen05 M-tiles) and walks the keys in blocks of 64.
+// Warp roles (384 threads):
 //   warps 0-3   softmax for tile 0  (thread = one query row = one TMEM lane)
 //   warps 4-7   softmax for tile 1
-//   warp  8     MMA issuer (one elected thread issues every tcgen05.mma / commit); owns TMEM alloc
+//   warp  8     MMA issuer (one elected lane issues every tcgen05.mma / commit); owns the TMEM allocation
 //   warp  9     TMA producer (Q once, then K and V stages)
 //   warps 10-11 idle (they donate their registers via setmaxnreg)
 // On-chip residency (the reference's "cache Q, O" rows, AttentionDescriptor+Parameters.swift:109-120,
-// re-expressed for B200): Q tiles stay in SMEM for the whole traversal, O accumulators stay in TMEM,
-// S lives in TMEM and is overwritten in place by P (16-bit) which feeds the second MMA straight from TMEM.
-//   TMEM columns: [0,128) S0/P0  [128,256) S1/P1  [256,256+D) O0  [256+D,256+2D) O1
+// re-expressed for B200): Q tiles stay in SMEM for the whole traversal, O accumulators stay in TMEM; S is
+// double-buffered in TMEM per tile and overwritten in place by P (16-bit), which feeds the second MMA
+// straight from TMEM.  Per tile t (TMEM column base 256 t):  [0,64) S/P buffer 0, [64,128) S/P buffer 1,
+// [128,128+D) O.  Because S(i+1) and S(i+2) are computed while the softmax warps work on S(i), neither the
+// tensor pipe nor the MUFU pipe waits on the other in steady state.
 // Softmax bookkeeping follows Appendix A of SURVEY.md (log2 domain, L = m + log2 l) with one B200-specific
 // change: the running max is only refreshed when it grows by more than 2^8 ("lazy rescale"), so the
 // O *= correction pass over TMEM is rare; results are mathematically identical.
@@ -35,10 +37,12 @@ namespace fwd {
 
 using namespace ptx;
 
-constexpr uint32_t kTileM = 128;         // rows per tcgen05 M-tile
-constexpr uint32_t kTilesPerCta = 2;     // ping-pong tiles
-constexpr uint32_t kBlockN = 128;        // keys per traversal block
-constexpr uint32_t kSubTileBytes = 128 * 128;  // [128 rows][64 x 16-bit] = one 128B-swizzled TMA box
+constexpr uint32_t kTileM = 128;       // rows per tcgen05 M-tile
+constexpr uint32_t kTilesPerCta = 2;   // two independent M-tiles share the SM
+constexpr uint32_t kBlockN = 64;       // keys per traversal block
+constexpr uint32_t kSBuffers = 2;      // S/P buffers per tile
+constexpr uint32_t kQSubTileBytes = kTileM * 128;    // [128 rows][64 x 16-bit]: one 128B-swizzled TMA box
+constexpr uint32_t kKVSubTileBytes = kBlockN * 128;  // [64 keys][64 x 16-bit]
 constexpr uint32_t kThreads = 384;
 // setmaxnreg budget: the CTA is launched with floor(65536 / 384 / 8) * 8 = 168 registers per thread; the two
 // softmax warpgroups grow to kSoftmaxRegs after the producer warpgroup has shrunk to kOtherRegs.  The sum
@@ -49,32 +53,32 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 template <uint32_t DPAD>
 struct Config {
-  static constexpr uint32_t kSubTiles = DPAD / 64;                 // 64-element sub-tiles along D
-  static constexpr uint32_t kTileBytes = kSubTiles * kSubTileBytes;  // one 128 x DPAD operand tile
-  static constexpr uint32_t kStages = DPAD <= 64 ? 4 : 2;
+  static constexpr uint32_t kSubTiles = DPAD / 64;                      // 64-element sub-tiles along D
+  static constexpr uint32_t kQTileBytes = kSubTiles * kQSubTileBytes;   // 128 x DPAD
+  static constexpr uint32_t kKVTileBytes = kSubTiles * kKVSubTileBytes; // 64 x DPAD
+  static constexpr uint32_t kStages = 4;
   static constexpr uint32_t kSmemQ = 0;
-  static constexpr uint32_t kSmemK = kSmemQ + kTilesPerCta * kTileBytes;
-  static constexpr uint32_t kSmemV = kSmemK + kStages * kTileBytes;
-  static constexpr uint32_t kSmemBar = kSmemV + kStages * kTileBytes;
-  static constexpr uint32_t kNumBars = 1 + 4 * kStages + 3 * kTilesPerCta;
+  static constexpr uint32_t kSmemK = kSmemQ + kTilesPerCta * kQTileBytes;
+  static constexpr uint32_t kSmemV = kSmemK + kStages * kKVTileBytes;
+  static constexpr uint32_t kSmemBar = kSmemV + kStages * kKVTileBytes;
+  static constexpr uint32_t kNumBars = 1 + 4 * kStages + kTilesPerCta * (2 * kSBuffers + 2);
   static constexpr uint32_t kSmemTmemPtr = kSmemBar + kNumBars * 8;
   static constexpr uint32_t kSmemBytes = kSmemTmemPtr + 16 + 1024;  // + slack for manual 1024 B alignment
-  static constexpr uint32_t kTmemS = 0;
-  static constexpr uint32_t kTmemO = 256;
+  static constexpr uint32_t kTmemTileStride = 256;
+  static constexpr uint32_t kTmemO = kSBuffers * kBlockN;  // O follows the two S buffers
   static constexpr uint32_t kTmemCols = 512;
-};
-
-struct Barriers {
-  uint64_t *q_full, *k_full, *k_empty, *v_full, *v_empty, *s_full, *p_full, *o_full;
+  static_assert(kTmemO + DPAD <= kTmemTileStride, "tile does not fit its TMEM slice");
 };
 
 // kTrace: debug instantiation that records clock64() at the pipeline hand-off points of CTA (0,0)
 // (scripts/trace_forward.py); the production instantiation compiles all of it away.
-constexpr uint32_t kTraceSlots = 8;  // per (role, iteration)
+constexpr uint32_t kTraceSlots = 8;    // per (role, iteration)
+constexpr uint32_t kTraceIters = 128;  // iterations recorded per role
 #define MFA_TRACE(role, iter, slot)                                                                   \
   do {                                                                                                \
-    if (kTrace && trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0)                \
-      trace[((role) * 64 + ((iter) & 63)) * kTraceSlots + (slot)] = clock64();                        \
+    if (kTrace && trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 &&             \
+        (iter) < kTraceIters)                                                                         \
+      trace[((role) * kTraceIters + (iter)) * kTraceSlots + (slot)] = clock64();                      \
   } while (0)
 
 template <uint32_t DPAD, bool kBF16, bool kTrace = false>
@@ -93,30 +97,33 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t num_blocks = (C + kBlockN - 1) / kBlockN;
 
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kSmemBar);
-  Barriers b;
-  b.q_full = bars;
-  b.k_full = bars + 1;
-  b.k_empty = b.k_full + Cfg::kStages;
-  b.v_full = b.k_empty + Cfg::kStages;
-  b.v_empty = b.v_full + Cfg::kStages;
-  b.s_full = b.v_empty + Cfg::kStages;
-  b.p_full = b.s_full + kTilesPerCta;
-  b.o_full = b.p_full + kTilesPerCta;
+  uint64_t *q_full = bars;
+  uint64_t *k_full = q_full + 1;
+  uint64_t *k_empty = k_full + Cfg::kStages;
+  uint64_t *v_full = k_empty + Cfg::kStages;
+  uint64_t *v_empty = v_full + Cfg::kStages;
+  uint64_t *s_full = v_empty + Cfg::kStages;            // [tile][buffer]
+  uint64_t *p_full = s_full + kTilesPerCta * kSBuffers;  // [tile][buffer]
+  uint64_t *o_full = p_full + kTilesPerCta * kSBuffers;  // [tile]  one phase per key block
+  uint64_t *o_final = o_full + kTilesPerCta;             // [tile]  completes once, after the last O += P V
   uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem + Cfg::kSmemTmemPtr);
 
   // ---------------- one-time setup ----------------
   if (threadIdx.x == 0) {
-    mbar_init(b.q_full, 1);
+    mbar_init(q_full, 1);
     for (uint32_t s = 0; s < Cfg::kStages; ++s) {
-      mbar_init(&b.k_full[s], 1);
-      mbar_init(&b.k_empty[s], 1);
-      mbar_init(&b.v_full[s], 1);
-      mbar_init(&b.v_empty[s], 1);
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
     }
     for (uint32_t t = 0; t < kTilesPerCta; ++t) {
-      mbar_init(&b.s_full[t], 1);
-      mbar_init(&b.p_full[t], kTileM);
-      mbar_init(&b.o_full[t], 1);
+      for (uint32_t bf = 0; bf < kSBuffers; ++bf) {
+        mbar_init(&s_full[t * kSBuffers + bf], 1);
+        mbar_init(&p_full[t * kSBuffers + bf], kTileM);
+      }
+      mbar_init(&o_full[t], 1);
+      mbar_init(&o_final[t], 1);
     }
     fence_barrier_init();
   }
@@ -139,29 +146,32 @@ __global__ void __launch_bounds__(kThreads, 1)
     // softmax warps: thread <-> query row <-> TMEM lane
     // =====================================================================================
     setmaxnreg_inc<kSoftmaxRegs>();
-    const uint32_t t = warp >> 2;                      // tile
+    const uint32_t t = warp >> 2;  // tile
     const uint32_t row_in_tile = (warp & 3) * 32 + lane;
     const uint32_t lane_addr = ((warp & 3) * 32) << 16;  // this warp's TMEM lane quarter
-    const uint32_t tS = tmem_base + lane_addr + Cfg::kTmemS + t * kBlockN;
-    const uint32_t tO = tmem_base + lane_addr + Cfg::kTmemO + t * DPAD;
+    const uint32_t tTile = tmem_base + lane_addr + t * Cfg::kTmemTileStride;
+    const uint32_t tO = tTile + Cfg::kTmemO;
+    const uint32_t trace_role = warp == 0 ? 0 : (warp == 4 ? 1 : 3);
 
     float m = -FLT_MAX;  // running max, log2 domain   (AttentionKernel+Caching.swift:310)
     float l = 0.f;       // running sum
     const uint32_t tail_cols = C - (num_blocks - 1) * kBlockN;  // valid columns in the last block
 
-    for (uint32_t j = 0; j < num_blocks; ++j) {
-      mbar_wait(&b.s_full[t], j & 1);
+    for (uint32_t i = 0; i < num_blocks; ++i) {
+      const uint32_t bf = i & 1, ph = (i >> 1) & 1;
+      const uint32_t tS = tTile + bf * kBlockN;
+      mbar_wait(&s_full[t * kSBuffers + bf], ph);
       tc_fence_after();
-      MFA_TRACE(warp == 0 ? 0 : (warp == 4 ? 1 : 5), j, 0);
+      MFA_TRACE(trace_role, i, 0);
 
       float s[kBlockN];
 #pragma unroll
       for (uint32_t c = 0; c < kBlockN; c += 32) tmem_ld32(tS + c, *reinterpret_cast<uint32_t(*)[32]>(&s[c]));
       tc_wait_ld();
-      MFA_TRACE(warp == 0 ? 0 : (warp == 4 ? 1 : 5), j, 1);
+      MFA_TRACE(trace_role, i, 1);
 
       // edge mask (maskAttentionMatrixEdge, AttentionKernel+Softmax.swift:228-260)
-      if (j == num_blocks - 1 && tail_cols < kBlockN) {
+      if (i == num_blocks - 1 && tail_cols < kBlockN) {
 #pragma unroll
         for (uint32_t c = 0; c < kBlockN; ++c)
           if (c >= tail_cols) s[c] = -INFINITY;
@@ -180,9 +190,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 
       // lazy correction (onlineCorrectO, :290-301): refresh m only when it grew by > 2^8
       if (__any_sync(0xffffffffu, m_cand - m > kRescaleThreshold)) {
-        if (j > 0) {
+        if (i > 0) {
           const float correction = ex2_approx(m - m_cand);
-          mbar_wait(&b.o_full[t], (j - 1) & 1);  // O += P V of the previous block has landed
+          mbar_wait(&o_full[t], (i - 1) & 1);  // O += P V of the previous block has landed
           tc_fence_after();
 #pragma unroll
           for (uint32_t c = 0; c < DPAD; c += 32) {
@@ -190,15 +200,15 @@ __global__ void __launch_bounds__(kThreads, 1)
             tmem_ld32(tO + c, o);
             tc_wait_ld();
 #pragma unroll
-            for (uint32_t i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * correction);
+            for (uint32_t k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * correction);
             tmem_st32(tO + c, o);
           }
           l *= correction;
         }
         m = m_cand;
       }
+      MFA_TRACE(trace_role, i, 2);
 
-      MFA_TRACE(warp == 0 ? 0 : (warp == 4 ? 1 : 5), j, 2);
       // P = exp2(S * log2e/sqrt(D) - m), rounded to the MMA input type, written over S
       // (softmax, :409-416; onlineReduceSum, :304-324)
       float sum0 = 0.f, sum1 = 0.f;
@@ -206,25 +216,26 @@ __global__ void __launch_bounds__(kThreads, 1)
       for (uint32_t c = 0; c < kBlockN; c += 32) {
         uint32_t packed[16];
 #pragma unroll
-        for (uint32_t i = 0; i < 16; ++i) {
-          const float p0 = ex2_approx(fmaf(s[c + 2 * i], scale_log2, -m));
-          const float p1 = ex2_approx(fmaf(s[c + 2 * i + 1], scale_log2, -m));
+        for (uint32_t k = 0; k < 16; ++k) {
+          const float p0 = ex2_approx(fmaf(s[c + 2 * k], scale_log2, -m));
+          const float p1 = ex2_approx(fmaf(s[c + 2 * k + 1], scale_log2, -m));
           sum0 += p0;
           sum1 += p1;
-          packed[i] = kBF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
+          packed[k] = kBF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
         }
         tmem_st16(tS + (c >> 1), packed);
       }
       l += sum0 + sum1;
-      MFA_TRACE(warp == 0 ? 0 : (warp == 4 ? 1 : 5), j, 3);
+      MFA_TRACE(trace_role, i, 3);
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(&b.p_full[t]);
-      MFA_TRACE(warp == 0 ? 0 : (warp == 4 ? 1 : 5), j, 4);
+      mbar_arrive(&p_full[t * kSBuffers + bf]);
+      MFA_TRACE(trace_role, i, 4);
     }
 
     // ---------------- epilogue: O / l -> global (FP32), L = m + log2(l) ----------------
-    mbar_wait(&b.o_full[t], (num_blocks - 1) & 1);
+    // (o_full may be up to two phases behind here, which a parity wait cannot tell apart; o_final is one-shot)
+    mbar_wait(&o_final[t], 0);
     tc_fence_after();
     const uint32_t row = q_row0 + t * kTileM + row_in_tile;
     const float inv_l = 1.0f / l;
@@ -236,11 +247,11 @@ __global__ void __launch_bounds__(kThreads, 1)
       tc_wait_ld();
       if (row < R) {
 #pragma unroll
-        for (uint32_t i = 0; i < 32; i += 4) {
-          if (c + i < D) {  // D % 8 == 0, so a float4 is either fully inside or fully outside
-            float4 v = make_float4(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l,
-                                   __uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
-            *reinterpret_cast<float4 *>(o_row + c + i) = v;
+        for (uint32_t k = 0; k < 32; k += 4) {
+          if (c + k < D) {  // D % 8 == 0, so a float4 is either fully inside or fully outside
+            float4 v = make_float4(__uint_as_float(o[k]) * inv_l, __uint_as_float(o[k + 1]) * inv_l,
+                                   __uint_as_float(o[k + 2]) * inv_l, __uint_as_float(o[k + 3]) * inv_l);
+            *reinterpret_cast<float4 *>(o_row + c + k) = v;
           }
         }
       }
@@ -262,31 +273,31 @@ __global__ void __launch_bounds__(kThreads, 1)
       // TMA producer
       // ===================================================================================
       if (elect_one()) {
-        mbar_arrive_expect_tx(b.q_full, kTilesPerCta * Cfg::kTileBytes);
+        mbar_arrive_expect_tx(q_full, kTilesPerCta * Cfg::kQTileBytes);
 #pragma unroll
         for (uint32_t t = 0; t < kTilesPerCta; ++t)
 #pragma unroll
           for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
-            tma_load_3d(smem + Cfg::kSmemQ + t * Cfg::kTileBytes + ds * kSubTileBytes, &mapQ, b.q_full, ds * 64,
+            tma_load_3d(smem + Cfg::kSmemQ + t * Cfg::kQTileBytes + ds * kQSubTileBytes, &mapQ, q_full, ds * 64,
                         q_row0 + t * kTileM, head);
       }
-      for (uint32_t j = 0; j < num_blocks; ++j) {
-        const uint32_t stage = j % Cfg::kStages, phase = (j / Cfg::kStages) & 1;
-        mbar_wait(&b.k_empty[stage], phase ^ 1);
+      for (uint32_t i = 0; i < num_blocks; ++i) {
+        const uint32_t stage = i % Cfg::kStages, phase = (i / Cfg::kStages) & 1;
+        mbar_wait(&k_empty[stage], phase ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&b.k_full[stage], Cfg::kTileBytes);
+          mbar_arrive_expect_tx(&k_full[stage], Cfg::kKVTileBytes);
 #pragma unroll
           for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
-            tma_load_3d(smem + Cfg::kSmemK + stage * Cfg::kTileBytes + ds * kSubTileBytes, &mapK, &b.k_full[stage],
-                        ds * 64, j * kBlockN, head);
+            tma_load_3d(smem + Cfg::kSmemK + stage * Cfg::kKVTileBytes + ds * kKVSubTileBytes, &mapK, &k_full[stage],
+                        ds * 64, i * kBlockN, head);
         }
-        mbar_wait(&b.v_empty[stage], phase ^ 1);
+        mbar_wait(&v_empty[stage], phase ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&b.v_full[stage], Cfg::kTileBytes);
+          mbar_arrive_expect_tx(&v_full[stage], Cfg::kKVTileBytes);
 #pragma unroll
           for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
-            tma_load_3d(smem + Cfg::kSmemV + stage * Cfg::kTileBytes + ds * kSubTileBytes, &mapV, &b.v_full[stage],
-                        ds * 64, j * kBlockN, head);
+            tma_load_3d(smem + Cfg::kSmemV + stage * Cfg::kKVTileBytes + ds * kKVSubTileBytes, &mapV, &v_full[stage],
+                        ds * 64, i * kBlockN, head);
         }
       }
     } else if (warp == 8) {
@@ -294,78 +305,85 @@ __global__ void __launch_bounds__(kThreads, 1)
       // MMA issuer
       // ===================================================================================
       constexpr uint32_t kFormat = kBF16 ? 1u : 0u;
-      // S[128 x 128] = Q[128 x D] . K[128 x D]^T : A and B both K-major
+      // S[128 x 64] = Q[128 x D] . K[64 x D]^T : A and B both K-major
       constexpr uint32_t idescS = make_idesc_f16(kTileM, kBlockN, kFormat, 0, 0);
-      // O[128 x DPAD] += P[128 x 128] . V[128 x DPAD] : A from TMEM, B (= V, [key][d]) is MN-major
+      // O[128 x DPAD] += P[128 x 64] . V[64 x DPAD] : A from TMEM, B (= V, [key][d]) is MN-major
       constexpr uint32_t idescO = make_idesc_f16(kTileM, DPAD, kFormat, 0, 1);
       // Descriptors differ only in the 14-bit start-address field; build each once and add (bytes >> 4).
       const uint64_t descQ = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemQ), 16, 1024);
       const uint64_t descK = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemK), 16, 1024);
-      const uint64_t descV = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemV), kSubTileBytes, 1024);
+      const uint64_t descV = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemV), kKVSubTileBytes, 1024);
 
       // every tcgen05.mma / commit below is issued by the one elected lane
-      auto issue_S = [&](uint32_t t, uint32_t stage) {
-        const uint32_t d_tmem = tmem_base + Cfg::kTmemS + t * kBlockN;
-        const uint64_t a0 = descQ + ((t * Cfg::kTileBytes) >> 4);
-        const uint64_t b0 = descK + ((stage * Cfg::kTileBytes) >> 4);
+      auto issue_S = [&](uint32_t t, uint32_t bf, uint32_t stage) {
+        const uint32_t d_tmem = tmem_base + t * Cfg::kTmemTileStride + bf * kBlockN;
+        const uint64_t a0 = descQ + ((t * Cfg::kQTileBytes) >> 4);
+        const uint64_t b0 = descK + ((stage * Cfg::kKVTileBytes) >> 4);
 #pragma unroll
         for (uint32_t k = 0; k < DPAD / 16; ++k) {
           // 16 elements = 32 B inside the 128 B swizzle row; 4 k-steps per 64-element sub-tile
-          const uint32_t off = ((k >> 2) * kSubTileBytes + (k & 3) * 32) >> 4;
-          umma_ss(d_tmem, a0 + off, b0 + off, idescS, k > 0);
+          const uint32_t a_off = ((k >> 2) * kQSubTileBytes + (k & 3) * 32) >> 4;
+          const uint32_t b_off = ((k >> 2) * kKVSubTileBytes + (k & 3) * 32) >> 4;
+          umma_ss(d_tmem, a0 + a_off, b0 + b_off, idescS, k > 0);
         }
       };
-      auto issue_PV = [&](uint32_t t, uint32_t stage, uint32_t accumulate) {
-        const uint32_t d_tmem = tmem_base + Cfg::kTmemO + t * DPAD;
-        const uint32_t a_tmem = tmem_base + Cfg::kTmemS + t * kBlockN;
-        const uint64_t b0 = descV + ((stage * Cfg::kTileBytes) >> 4);
+      auto issue_PV = [&](uint32_t t, uint32_t bf, uint32_t stage, uint32_t accumulate) {
+        const uint32_t d_tmem = tmem_base + t * Cfg::kTmemTileStride + Cfg::kTmemO;
+        const uint32_t a_tmem = tmem_base + t * Cfg::kTmemTileStride + bf * kBlockN;
+        const uint64_t b0 = descV + ((stage * Cfg::kKVTileBytes) >> 4);
 #pragma unroll
         for (uint32_t k = 0; k < kBlockN / 16; ++k)
-          // 16 keys = two 8-row groups of 1024 B; 64-wide column blocks are kSubTileBytes apart (LBO)
+          // 16 keys = two 8-row groups of 1024 B; 64-wide column blocks are kKVSubTileBytes apart (LBO)
           umma_ts(d_tmem, a_tmem + k * 8, b0 + ((k * 2048) >> 4), idescO, k > 0 ? 1u : accumulate);
       };
 
-      mbar_wait(b.q_full, 0);
-      mbar_wait(&b.k_full[0], 0);
-      tc_fence_after();
-      if (elect_one()) {
-        issue_S(0, 0);
-        umma_commit(&b.s_full[0]);
-        issue_S(1, 0);
-        umma_commit(&b.s_full[1]);
-        umma_commit(&b.k_empty[0]);
+      // prologue: S(0) and S(1) for both tiles
+      mbar_wait(q_full, 0);
+      for (uint32_t i = 0; i < kSBuffers && i < num_blocks; ++i) {
+        mbar_wait(&k_full[i], 0);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (uint32_t t = 0; t < kTilesPerCta; ++t) {
+            issue_S(t, i, i);
+            umma_commit(&s_full[t * kSBuffers + i]);
+          }
+          umma_commit(&k_empty[i]);
+        }
+        __syncwarp();
       }
-      __syncwarp();
 
-      for (uint32_t j = 0; j < num_blocks; ++j) {
-        const uint32_t stage = j % Cfg::kStages, phase = (j / Cfg::kStages) & 1;
-        const uint32_t nstage = (j + 1) % Cfg::kStages, nphase = ((j + 1) / Cfg::kStages) & 1;
-        const bool has_next = j + 1 < num_blocks;
-        mbar_wait(&b.v_full[stage], phase);
-        MFA_TRACE(2, j, 0);
+      for (uint32_t i = 0; i < num_blocks; ++i) {
+        const uint32_t bf = i & 1, ph = (i >> 1) & 1;
+        const uint32_t stage = i % Cfg::kStages, phase = (i / Cfg::kStages) & 1;
+        const uint32_t ni = i + kSBuffers;  // the S block that reuses this buffer
+        const uint32_t nstage = ni % Cfg::kStages, nphase = (ni / Cfg::kStages) & 1;
+        const bool has_next = ni < num_blocks;
+        mbar_wait(&v_full[stage], phase);
+        if (has_next) mbar_wait(&k_full[nstage], nphase);
+        MFA_TRACE(2, i, 0);
 #pragma unroll
         for (uint32_t t = 0; t < kTilesPerCta; ++t) {
-          mbar_wait(&b.p_full[t], j & 1);
-          if (t == 0 && has_next) mbar_wait(&b.k_full[nstage], nphase);
+          mbar_wait(&p_full[t * kSBuffers + bf], ph);
           tc_fence_after();
-          MFA_TRACE(2, j, 1 + 3 * t);
+          MFA_TRACE(2, i, 1 + 2 * t);
           if (elect_one()) {
-            issue_PV(t, stage, j > 0 ? 1u : 0u);
-            umma_commit(&b.o_full[t]);
-            if (t == kTilesPerCta - 1) umma_commit(&b.v_empty[stage]);
+            issue_PV(t, bf, stage, i > 0 ? 1u : 0u);
+            umma_commit(&o_full[t]);
+            if (i == num_blocks - 1) umma_commit(&o_final[t]);
+            if (t == kTilesPerCta - 1) umma_commit(&v_empty[stage]);
             if (has_next) {
-              issue_S(t, nstage);
-              umma_commit(&b.s_full[t]);
-              if (t == kTilesPerCta - 1) umma_commit(&b.k_empty[nstage]);
+              issue_S(t, bf, nstage);  // overwrites P(i) only after PV(i): the tensor pipe runs in order
+              umma_commit(&s_full[t * kSBuffers + bf]);
+              if (t == kTilesPerCta - 1) umma_commit(&k_empty[nstage]);
             }
           }
           __syncwarp();
-          MFA_TRACE(2, j, 3 + 3 * t);
+          MFA_TRACE(2, i, 2 + 2 * t);
         }
       }
     }
   }
-
 
   // ---------------- teardown ----------------
   tc_fence_before();
@@ -420,7 +438,7 @@ cudaError_t launch_tcgen05_forward(const AttentionParams &p, cudaStream_t stream
 }
 
 // Debug entry (not in include/mfa_b200.h): the D=128 bf16 forward with pipeline timestamps of CTA (0,0)
-// written to `trace` (3 roles x 64 iterations x 8 slots of clock64()).  Used by scripts/trace_forward.py.
+// written to `trace` (4 roles x 128 iterations x 8 slots of clock64()).  Used by scripts/trace_forward.py.
 cudaError_t launch_tcgen05_forward_trace(const AttentionParams &p, cudaStream_t stream, long long *trace) {
   return fwd::launch<128, true, true>(p, stream, trace);
 }
