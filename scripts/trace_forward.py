@@ -43,25 +43,24 @@ for _ in range(3):
     assert st == 0, lib.mfa_last_error()
     torch.cuda.synchronize()
 t = trace.cpu().numpy().reshape(4, 128, 8)
-nb = C // 64
+nb = C // 128
 t0 = t[2, 0, 0]
-print(f"R={R} H={H}: 64-key blocks; softmax slots: 0 S ready, 1 S in regs, 2 max done, 3 P computed, 4 arrived; "
-      "mma slots: 0 V/K ready, 1 p0 ready, 2 PV0+S0 issued, 3 p1 ready, 4 PV1+S1 issued")
-for j in range(4, 14):
+print(f"R={R} H={H}: 128-key blocks, two 64-key halves; softmax slots: 0 S ready, 1 S in regs, 2 max done, 3 P computed, "
+      "4 arrived; mma slots: 0 V ready, 1 p_lo ready, 2 PV_lo issued, 3 p_hi ready, 4 PV_hi issued, 5 S(i+2) issued")
+for j in range(4, 12):
     a = (t[0, j, :5] - t0).tolist()
     b = (t[1, j, :5] - t0).tolist()
-    m = (t[2, j, :5] - t0).tolist()
-    print(f"i={j:2d} sm0 {a}  sm1 {b}  mma {m}")
-lo, hi = 4, nb - 4
+    m = (t[2, j, :6] - t0).tolist()
+    print(f"i={j:2d} lo {a}  hi {b}  mma {m}")
+lo, hi = 4, nb - 3
 per_iter = np.diff(t[2, lo:hi, 1]).mean()
-print(f"steady-state period per 64-key block: {per_iter:.0f} cycles = {2*per_iter:.0f} per 128 keys "
-      "(floors per 128 keys: 2048 MUFU, 2048-2560 tensor)")
+print(f"steady-state period per 128-key block: {per_iter:.0f} cycles (floors: ~1000 tensor, 1024 MUFU)")
 for role in (0, 1):
     sm = t[role, lo:hi]
-    print(f"softmax tile{role}: wait S {np.mean(sm[1:,0]-sm[:-1,4]):.0f}, S->regs {np.mean(sm[:,1]-sm[:,0]):.0f}, "
+    print(f"softmax half{role}: wait S {np.mean(sm[1:,0]-sm[:-1,4]):.0f}, S->regs {np.mean(sm[:,1]-sm[:,0]):.0f}, "
           f"max {np.mean(sm[:,2]-sm[:,1]):.0f}, exp+pack+st {np.mean(sm[:,3]-sm[:,2]):.0f}, "
           f"wait_st+arrive {np.mean(sm[:,4]-sm[:,3]):.0f}")
 mm = t[2, lo:hi]
-print(f"mma: waits(V,K) {np.mean(mm[:,0]-np.roll(mm[:,4],1)[0:len(mm)])*0:.0f}; wait p0 {np.mean(mm[:,1]-mm[:,0]):.0f}; issue t0 {np.mean(mm[:,2]-mm[:,1]):.0f}; "
-      f"wait p1 {np.mean(mm[:,3]-mm[:,2]):.0f}; issue t1 {np.mean(mm[:,4]-mm[:,3]):.0f}; "
-      f"next V/K wait {np.mean(mm[1:,0]-mm[:-1,4]):.0f}")
+print(f"mma: wait p_lo {np.mean(mm[:,1]-mm[:,0]):.0f}; issue PV_lo {np.mean(mm[:,2]-mm[:,1]):.0f}; "
+      f"wait p_hi {np.mean(mm[:,3]-mm[:,2]):.0f}; issue PV_hi {np.mean(mm[:,4]-mm[:,3]):.0f}; "
+      f"K wait + issue S {np.mean(mm[:,5]-mm[:,4]):.0f}; V wait {np.mean(mm[1:,0]-mm[:-1,5]):.0f}")
