@@ -4,23 +4,20 @@
 // outer product S = Q K^T, +OuterProduct.swift:18-487; online softmax, +Softmax.swift:228-324,334-505;
 // accumulate O += P V, +Accumulate.swift:24-582) for 16-bit row-major operands.
 //
-// One CTA owns one 128-row tcgen05 M-tile of Q and walks the keys in blocks of 128.  Inside the CTA the key
-// axis of every block is split in two halves that are treated as two independent attention streams ("lo" =
-// keys 0-63 of each block, "hi" = keys 64-127): each half has its own softmax warpgroup, its own running
-// (max, sum) and its own O accumulator in TMEM, and the two partial results are merged once, in the epilogue
-// (the standard split-KV combine).  That removes every per-block exchange between the two warpgroups while
-// letting 256 threads share one row block.  Warp roles (384 threads):
-//   warps 0-3   softmax for the lo key half (thread = one query row = one TMEM lane)
-//   warps 4-7   softmax for the hi key half (same rows, the other 64 columns of S)
+// One CTA owns one 128-row tcgen05 M-tile of Q and walks the keys in blocks of 128.  Warp roles (384 threads):
+//   warps 0-3   softmax, columns  0-63  of every S block (thread = one query row = one TMEM lane)
+//   warps 4-7   softmax, columns 64-127 of every S block (same rows; warp w and w+4 form a "row pair")
 //   warp  8     MMA issuer (one elected lane issues every tcgen05.mma / commit); owns the TMEM allocation
-//   warp  9     TMA producer (Q once, then K and V stages)
-//   warps 10-11 idle (they donate their registers via setmaxnreg)
+//   warp  9     TMA producer for Q (once) and the K stages;  warp 10  TMA producer for the V stages
+//   warp  11    idle (the whole producer warpgroup donates registers via setmaxnreg)
 // On-chip residency (the reference's "cache Q, O" rows, AttentionDescriptor+Parameters.swift:109-120,
-// re-expressed for B200): Q stays in SMEM for the whole traversal, both O accumulators stay in TMEM; S is
-// double-buffered in TMEM and each half is overwritten in place by its P (16-bit), which feeds the second
-// MMA straight from TMEM.  TMEM columns: [0,128) S/P buffer 0, [128,256) S/P buffer 1, [256,256+D) O_lo,
-// [256+D,256+2D) O_hi.  S(i+1) is computed while the softmax warps work on S(i), so the tensor pipe
-// (S: 8 MMAs, P V: 2 x 4 MMAs per block) and the MUFU pipe (128 x 128 exp2 per block) overlap.
+// re-expressed for B200): Q stays in SMEM for the whole traversal and the O accumulator stays in TMEM.  S is
+// TRIPLE-buffered in TMEM and overwritten in place by P (16-bit), which feeds the second MMA straight from
+// TMEM:  columns [0,128) [128,256) [256,384) S/P buffers, [384,384+D) O.  S(i+1) is therefore complete before
+// the softmax warps start block i, which lets every thread software-pipeline: while the exp2 stream of block i
+// occupies the MUFU pipe, the same thread loads S(i+1), reduces its row max on the ALU pipe and swaps the
+// half-row maxima with its pair warp through shared memory.  Tensor pipe (8 + 8 MMAs per block) and MUFU pipe
+// (128 x 128 exp2 per block) then both run continuously.
 // Softmax bookkeeping follows Appendix A of SURVEY.md (log2 domain, L = m + log2 l) with one B200-specific
 // change: the running max is only refreshed when it grows by more than 2^8 ("lazy rescale"), so the
 // O *= correction pass over TMEM is rare; results are mathematically identical.
@@ -43,9 +40,9 @@ using namespace ptx;
 
 constexpr uint32_t kTileM = 128;   // query rows per CTA (one tcgen05 M-tile)
 constexpr uint32_t kBlockN = 128;  // keys per traversal block
-constexpr uint32_t kHalfN = 64;    // keys per softmax warpgroup per block
+constexpr uint32_t kHalfN = 64;    // S columns per softmax warpgroup
 constexpr uint32_t kHalves = 2;
-constexpr uint32_t kSBuffers = 2;  // S/P buffers
+constexpr uint32_t kSBuffers = 3;  // S/P buffers in TMEM
 constexpr uint32_t kSubTileBytes = 128 * 128;  // [128 rows][64 x 16-bit]: one 128B-swizzled TMA box
 constexpr uint32_t kThreads = 384;
 constexpr uint32_t kSoftmaxThreads = 256;
@@ -60,21 +57,24 @@ template <uint32_t DPAD>
 struct Config {
   static constexpr uint32_t kSubTiles = DPAD / 64;                   // 64-element sub-tiles along D
   static constexpr uint32_t kTileBytes = kSubTiles * kSubTileBytes;  // one 128 x DPAD operand tile
-  static constexpr uint32_t kStages = 3;
+  static constexpr uint32_t kStagesK = 4;  // K runs three blocks ahead of V (S is triple-buffered)
+  static constexpr uint32_t kStagesV = 2;
   static constexpr uint32_t kSmemQ = 0;
   static constexpr uint32_t kSmemK = kSmemQ + kTileBytes;
-  static constexpr uint32_t kSmemV = kSmemK + kStages * kTileBytes;
-  // float2 (m, l) [2 halves][128 rows] for the epilogue merge; aliases Q, which is dead by then (every
-  // S = Q K^T has completed before a softmax thread can leave its loop)
-  static constexpr uint32_t kSmemStats = kSmemQ;
-  static constexpr uint32_t kSmemBar = kSmemV + kStages * kTileBytes;
-  static constexpr uint32_t kNumBars = 1 + 4 * kStages + kSBuffers + kHalves * kSBuffers + kHalves + 1;
+  static constexpr uint32_t kSmemV = kSmemK + kStagesK * kTileBytes;
+  // half-row maxima swapped between pair warps: float [2 block parities][2 halves][128 rows]
+  static constexpr uint32_t kSmemXmax = kSmemV + kStagesV * kTileBytes;
+  static constexpr uint32_t kSmemBar = kSmemXmax + 2 * kHalves * kTileM * 4;
+  static constexpr uint32_t kNumBars = 1 + 2 * kStagesK + 2 * kStagesV + 2 * kSBuffers + 2 + 1;
   static constexpr uint32_t kSmemTmemPtr = kSmemBar + kNumBars * 8;
-  static constexpr uint32_t kSmemBytes = kSmemTmemPtr + 16 + 1024;  // + slack for manual 1024 B alignment
+  static constexpr uint32_t kSmemBytes = kSmemTmemPtr + 16;
+  // partial row sums for the epilogue; aliases Q, which is dead by then (every S = Q K^T has completed before a
+  // softmax thread can leave its loop)
+  static constexpr uint32_t kSmemStats = kSmemQ;
   static constexpr uint32_t kTmemS = 0;
   static constexpr uint32_t kTmemO = kSBuffers * kBlockN;
   static constexpr uint32_t kTmemCols = 512;
-  static_assert(kTmemO + kHalves * DPAD <= kTmemCols, "accumulators do not fit TMEM");
+  static_assert(kTmemO + DPAD <= kTmemCols, "accumulator does not fit TMEM");
   static_assert(kSmemBytes <= 232448, "shared memory over budget");
 };
 
@@ -92,16 +92,20 @@ constexpr uint32_t kTraceIters = 128;  // iterations recorded per role
 __device__ __forceinline__ void softmax_group_sync() {
   asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxThreads) : "memory");  // the 8 softmax warps only
 }
+// warp w (columns 0-63) and warp w + 4 (columns 64-127) of the same 32 rows
+__device__ __forceinline__ void row_pair_sync(uint32_t quarter) {
+  asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");
+}
 
 template <uint32_t DPAD, bool kBF16, bool kTrace = false>
 __global__ void __launch_bounds__(kThreads, 1)
     attention_forward_tcgen05(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                               const __grid_constant__ CUtensorMap mapV, float *__restrict__ O, void *__restrict__ L,
                               uint32_t R, uint32_t C, uint32_t D, float scale_log2, int l_is_fp16,
-                              uint32_t stagger_cycles, long long *__restrict__ trace) {
+                              long long *__restrict__ trace) {
   using Cfg = Config<DPAD>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B-swizzled tiles need a 1024 B aligned base
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t head = blockIdx.y;
@@ -111,30 +115,34 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kSmemBar);
   uint64_t *q_full = bars;
   uint64_t *k_full = q_full + 1;
-  uint64_t *k_empty = k_full + Cfg::kStages;
-  uint64_t *v_full = k_empty + Cfg::kStages;
-  uint64_t *v_empty = v_full + Cfg::kStages;
-  uint64_t *s_full = v_empty + Cfg::kStages;       // [buffer]        S(i) landed in TMEM
-  uint64_t *p_full = s_full + kSBuffers;            // [half][buffer]  P half written by its warpgroup
-  uint64_t *o_full = p_full + kHalves * kSBuffers;  // [half]          one phase per key block: O_half += P V done
-  uint64_t *o_final = o_full + kHalves;             // one-shot: every MMA of this CTA has completed
-  float2 *stats = reinterpret_cast<float2 *>(smem + Cfg::kSmemStats);
+  uint64_t *k_empty = k_full + Cfg::kStagesK;
+  uint64_t *v_full = k_empty + Cfg::kStagesK;
+  uint64_t *v_empty = v_full + Cfg::kStagesV;
+  uint64_t *s_full = v_empty + Cfg::kStagesV;  // [buffer]  S(i) landed in TMEM
+  uint64_t *p_full = s_full + kSBuffers;        // [buffer]  both halves of P(i) written (256 arrivals)
+  uint64_t *o_full = p_full + kSBuffers;        // [block parity]  O += P V of a block with that parity is done
+  uint64_t *o_final = o_full + 2;               // one-shot: every MMA of this CTA has completed
+  float *xmax = reinterpret_cast<float *>(smem + Cfg::kSmemXmax);
+  float *stats = reinterpret_cast<float *>(smem + Cfg::kSmemStats);
   uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem + Cfg::kSmemTmemPtr);
 
   // ---------------- one-time setup ----------------
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
-    for (uint32_t s = 0; s < Cfg::kStages; ++s) {
+    for (uint32_t s = 0; s < Cfg::kStagesK; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
+    }
+    for (uint32_t s = 0; s < Cfg::kStagesV; ++s) {
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
     }
     for (uint32_t bf = 0; bf < kSBuffers; ++bf) {
       mbar_init(&s_full[bf], 1);
-      for (uint32_t h = 0; h < kHalves; ++h) mbar_init(&p_full[h * kSBuffers + bf], kTileM);
+      mbar_init(&p_full[bf], kSoftmaxThreads);
     }
-    for (uint32_t h = 0; h < kHalves; ++h) mbar_init(&o_full[h], 1);
+    mbar_init(&o_full[0], 1);
+    mbar_init(&o_full[1], 1);
     mbar_init(o_final, 1);
     fence_barrier_init();
   }
@@ -145,8 +153,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp == 9 && lane == 0) {
     prefetch_tensormap(&mapQ);
     prefetch_tensormap(&mapK);
-    prefetch_tensormap(&mapV);
   }
+  if (warp == 10 && lane == 0) prefetch_tensormap(&mapV);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -154,35 +162,33 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   if (warp < 8) {
     // =====================================================================================
-    // softmax warps: thread <-> query row <-> TMEM lane; warpgroup <-> key half
+    // softmax warps: thread <-> query row <-> TMEM lane; warpgroup <-> column half
     // =====================================================================================
     setmaxnreg_inc<kSoftmaxRegs>();
-    const uint32_t h = warp >> 2;  // key half
-    const uint32_t row_in_tile = (warp & 3) * 32 + lane;
-    const uint32_t lane_addr = ((warp & 3) * 32) << 16;  // this warp's TMEM lane quarter
-    const uint32_t tLane = tmem_base + lane_addr;
-    const uint32_t tO = tLane + Cfg::kTmemO + h * DPAD;
+    const uint32_t h = warp >> 2;        // column half
+    const uint32_t quarter = warp & 3;   // TMEM lane quarter == row-pair id
+    const uint32_t row_in_tile = quarter * 32 + lane;
+    const uint32_t tLane = tmem_base + ((quarter * 32) << 16);
+    const uint32_t tO = tLane + Cfg::kTmemO;
     const uint32_t trace_role = warp == 0 ? 0 : (warp == 4 ? 1 : 3);
 
-    float m = -FLT_MAX;  // running max of this half, log2 domain   (AttentionKernel+Caching.swift:310)
-    float l = 0.f;       // running sum of this half
+    float m = -FLT_MAX;  // running row max (identical in both halves), log2 domain (AttentionKernel+Caching.swift:310)
+    float l = 0.f;       // running sum over this half's columns
     // valid columns of this half in the last block (0 when the last block ends before this half starts)
     const uint32_t tail_block = C - (num_blocks - 1) * kBlockN;
     const uint32_t tail_cols = tail_block > h * kHalfN ? min(tail_block - h * kHalfN, kHalfN) : 0u;
 
-    // Software pipeline over key blocks: while the exp2 stream of block i occupies the MUFU pipe, the same
-    // thread already loads S(i+1) from TMEM and reduces its row max on the ALU pipe, so the MUFU pipe never
-    // idles between blocks.  `cur` holds S(i) (its max is already folded into m), `nxt` receives S(i+1).
+    auto s_buffer = [&](uint32_t i) { return tLane + Cfg::kTmemS + (i % kSBuffers) * kBlockN + h * kHalfN; };
     auto load_block = [&](float (&dst)[kHalfN], uint32_t i) {
-      mbar_wait(&s_full[i & 1], (i >> 1) & 1);
+      mbar_wait(&s_full[i % kSBuffers], (i / kSBuffers) & 1);
       tc_fence_after();
-      const uint32_t tS = tLane + Cfg::kTmemS + (i & 1) * kBlockN + h * kHalfN;
+      const uint32_t tS = s_buffer(i);
 #pragma unroll
       for (uint32_t c = 0; c < kHalfN; c += 32) tmem_ld32(tS + c, *reinterpret_cast<uint32_t(*)[32]>(&dst[c]));
     };
-    // edge mask (maskAttentionMatrixEdge, AttentionKernel+Softmax.swift:228-260) + row max of one block
-    // (onlineReduceMaximum, :267-287): this half of the row sits in this thread's registers
-    auto block_max = [&](float (&v)[kHalfN], uint32_t i) -> float {
+    // edge mask (maskAttentionMatrixEdge, AttentionKernel+Softmax.swift:228-260) + max of this half of the row
+    // (onlineReduceMaximum, :267-287)
+    auto half_max = [&](float (&v)[kHalfN], uint32_t i) -> float {
       if (i == num_blocks - 1 && tail_cols < kHalfN) {
 #pragma unroll
         for (uint32_t c = 0; c < kHalfN; ++c)
@@ -198,23 +204,27 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
     };
-    // lazy correction (onlineCorrectO, :290-301): refresh m only when it grew by > 2^8.  `done_blocks` key
-    // blocks have already been accumulated into O_half and must be rescaled.
-    auto update_max = [&](float block_mx, uint32_t done_blocks) {
-      const float m_cand = fmaxf(m, block_mx * scale_log2);
+    // publish this half's max of block i / fetch the pair warp's (double-buffered by block parity)
+    auto publish_max = [&](float mx, uint32_t i) { xmax[((i & 1) * kHalves + h) * kTileM + row_in_tile] = mx; };
+    auto fetch_pair_max = [&](uint32_t i) { return xmax[((i & 1) * kHalves + (h ^ 1)) * kTileM + row_in_tile]; };
+    // lazy correction (onlineCorrectO, :290-301): refresh m only when it grew by > 2^8.  `done_blocks` key blocks
+    // are already accumulated in O; each half rescales its own DPAD/2 columns of O.
+    auto update_max = [&](float row_mx, uint32_t done_blocks) {
+      const float m_cand = fmaxf(m, row_mx * scale_log2);
       if (__any_sync(0xffffffffu, m_cand - m > kRescaleThreshold)) {
         if (done_blocks > 0) {
           const float correction = ex2_approx(m - m_cand);
-          mbar_wait(&o_full[h], (done_blocks - 1) & 1);  // O_half += P V of the previous block has landed
+          const uint32_t last = done_blocks - 1;           // O += P V of that block must have landed;
+          mbar_wait(&o_full[last & 1], (last >> 1) & 1);   // one barrier per block parity keeps the phase unambiguous
           tc_fence_after();
 #pragma unroll
-          for (uint32_t c = 0; c < DPAD; c += 32) {
+          for (uint32_t c = 0; c < DPAD / 2; c += 32) {
             uint32_t o[32];
-            tmem_ld32(tO + c, o);
+            tmem_ld32(tO + h * (DPAD / 2) + c, o);
             tc_wait_ld();
 #pragma unroll
             for (uint32_t k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * correction);
-            tmem_st32(tO + c, o);
+            tmem_st32(tO + h * (DPAD / 2) + c, o);
           }
           tc_wait_st();
           l *= correction;
@@ -236,9 +246,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       tmem_st16(tS + (c >> 1), packed);
     };
+    // one key block: exp2 stream of block i, with the load / max / pair exchange of block i + 1 folded in
     auto step = [&](float (&cur)[kHalfN], float (&nxt)[kHalfN], uint32_t i) {
-      const uint32_t bf = i & 1;
-      const uint32_t tS = tLane + Cfg::kTmemS + bf * kBlockN + h * kHalfN;
+      const uint32_t tS = s_buffer(i);
       const bool has_next = i + 1 < num_blocks;
       MFA_TRACE(trace_role, i, 0);
       if (has_next) load_block(nxt, i + 1);  // asynchronous: completes at the tc_wait_ld below
@@ -248,7 +258,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       float next_mx = 0.f;
       if (has_next) {
         tc_wait_ld();
-        next_mx = block_max(nxt, i + 1);  // ALU work the scheduler interleaves with the exp2 stream below
+        next_mx = half_max(nxt, i + 1);  // ALU work the scheduler interleaves with the exp2 stream
+        publish_max(next_mx, i + 1);
       }
       MFA_TRACE(trace_role, i, 2);
       exp_chunk(cur, 32, tS, sum0, sum1);
@@ -256,62 +267,59 @@ __global__ void __launch_bounds__(kThreads, 1)
       MFA_TRACE(trace_role, i, 3);
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(&p_full[h * kSBuffers + bf]);
+      mbar_arrive(&p_full[i % kSBuffers]);
       MFA_TRACE(trace_role, i, 4);
-      if (has_next) update_max(next_mx, i + 1);
+      if (has_next) {
+        row_pair_sync(quarter);
+        update_max(fmaxf(next_mx, fetch_pair_max(i + 1)), i + 1);
+      }
+      MFA_TRACE(trace_role, i, 5);
     };
 
     {
       float sA[kHalfN], sB[kHalfN];
       load_block(sA, 0);
       tc_wait_ld();
-      update_max(block_max(sA, 0), 0);
+      const float mx0 = half_max(sA, 0);
+      publish_max(mx0, 0);
+      row_pair_sync(quarter);
+      update_max(fmaxf(mx0, fetch_pair_max(0)), 0);
       for (uint32_t i = 0; i < num_blocks; i += 2) {
         step(sA, sB, i);
         if (i + 1 < num_blocks) step(sB, sA, i + 1);
       }
     }
 
-
-    // ---------------- epilogue: merge the two key halves, O / l -> global (FP32), L = m + log2(l) --------
-    stats[h * kTileM + row_in_tile] = make_float2(m, l);
+    // ---------------- epilogue: O / l -> global (FP32), L = m + log2(l) ----------------
+    stats[h * kTileM + row_in_tile] = l;
     softmax_group_sync();
-    const float2 other = stats[(h ^ 1) * kTileM + row_in_tile];
-    const float m_all = fmaxf(m, other.x);
-    const float a_mine = ex2_approx(m - m_all), a_other = ex2_approx(other.x - m_all);
-    const float l_all = fmaf(l, a_mine, other.y * a_other);
+    const float l_all = l + stats[(h ^ 1) * kTileM + row_in_tile];
     const float inv_l = 1.0f / l_all;
-    const float w_lo = (h == 0 ? a_mine : a_other) * inv_l, w_hi = (h == 0 ? a_other : a_mine) * inv_l;
 
     mbar_wait(o_final, 0);
     tc_fence_after();
     const uint32_t row = q_row0 + row_in_tile;
     float *o_row = O + (static_cast<size_t>(head) * R + row) * D;
-    // this warpgroup writes columns [h * DPAD/2, (h+1) * DPAD/2) of the merged O
-    constexpr uint32_t kColsPerGroup = DPAD / 2;
+    // this warpgroup writes columns [h * DPAD/2, (h+1) * DPAD/2) of O
 #pragma unroll
-    for (uint32_t cc = 0; cc < kColsPerGroup; cc += 32) {
-      const uint32_t c = h * kColsPerGroup + cc;
-      uint32_t lo[32], hi[32];
-      tmem_ld32(tLane + Cfg::kTmemO + c, lo);
-      tmem_ld32(tLane + Cfg::kTmemO + DPAD + c, hi);
+    for (uint32_t cc = 0; cc < DPAD / 2; cc += 32) {
+      const uint32_t c = h * (DPAD / 2) + cc;
+      uint32_t o[32];
+      tmem_ld32(tO + c, o);
       tc_wait_ld();
       if (row < R) {
 #pragma unroll
         for (uint32_t k = 0; k < 32; k += 4) {
           if (c + k < D) {  // D % 8 == 0, so a float4 is either fully inside or fully outside
-            float4 v;
-            v.x = fmaf(__uint_as_float(lo[k]), w_lo, __uint_as_float(hi[k]) * w_hi);
-            v.y = fmaf(__uint_as_float(lo[k + 1]), w_lo, __uint_as_float(hi[k + 1]) * w_hi);
-            v.z = fmaf(__uint_as_float(lo[k + 2]), w_lo, __uint_as_float(hi[k + 2]) * w_hi);
-            v.w = fmaf(__uint_as_float(lo[k + 3]), w_lo, __uint_as_float(hi[k + 3]) * w_hi);
+            float4 v = make_float4(__uint_as_float(o[k]) * inv_l, __uint_as_float(o[k + 1]) * inv_l,
+                                   __uint_as_float(o[k + 2]) * inv_l, __uint_as_float(o[k + 3]) * inv_l);
             *reinterpret_cast<float4 *>(o_row + c + k) = v;
           }
         }
       }
     }
     if (h == 0 && row < R && L != nullptr) {
-      const float lse2 = m_all + log2f(l_all);  // AttentionKernel+Caching.swift:373-377
+      const float lse2 = m + log2f(l_all);  // AttentionKernel+Caching.swift:373-377
       const size_t idx = static_cast<size_t>(head) * R + row;
       if (l_is_fp16)
         reinterpret_cast<__half *>(L)[idx] = __float2half_rn(lse2);
@@ -320,11 +328,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else {
     setmaxnreg_dec<kOtherRegs>();
-    // Both producer warps run their control flow warp-wide and hand exactly one elected lane to the
+    // The producer warps run their control flow warp-wide and hand exactly one elected lane to the
     // TMA / tcgen05 instructions: operands stay in uniform registers and the issue loops are branch-free.
     if (warp == 9) {
       // ===================================================================================
-      // TMA producer
+      // TMA producer: Q, then the K stages
       // ===================================================================================
       if (elect_one()) {
         mbar_arrive_expect_tx(q_full, Cfg::kTileBytes);
@@ -333,7 +341,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           tma_load_3d(smem + Cfg::kSmemQ + ds * kSubTileBytes, &mapQ, q_full, ds * 64, q_row0, head);
       }
       for (uint32_t i = 0; i < num_blocks; ++i) {
-        const uint32_t stage = i % Cfg::kStages, phase = (i / Cfg::kStages) & 1;
+        const uint32_t stage = i % Cfg::kStagesK, phase = (i / Cfg::kStagesK) & 1;
         mbar_wait(&k_empty[stage], phase ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&k_full[stage], Cfg::kTileBytes);
@@ -342,6 +350,13 @@ __global__ void __launch_bounds__(kThreads, 1)
             tma_load_3d(smem + Cfg::kSmemK + stage * Cfg::kTileBytes + ds * kSubTileBytes, &mapK, &k_full[stage],
                         ds * 64, i * kBlockN, head);
         }
+      }
+    } else if (warp == 10) {
+      // ===================================================================================
+      // TMA producer: the V stages
+      // ===================================================================================
+      for (uint32_t i = 0; i < num_blocks; ++i) {
+        const uint32_t stage = i % Cfg::kStagesV, phase = (i / Cfg::kStagesV) & 1;
         mbar_wait(&v_empty[stage], phase ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&v_full[stage], Cfg::kTileBytes);
@@ -358,7 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       constexpr uint32_t kFormat = kBF16 ? 1u : 0u;
       // S[128 x 128] = Q[128 x D] . K[128 x D]^T : A and B both K-major
       constexpr uint32_t idescS = make_idesc_f16(kTileM, kBlockN, kFormat, 0, 0);
-      // O_half[128 x DPAD] += P_half[128 x 64] . V_half[64 x DPAD] : A from TMEM, B (= V, [key][d]) MN-major
+      // O[128 x DPAD] += P[128 x 128] . V[128 x DPAD] : A from TMEM, B (= V, [key][d]) MN-major
       constexpr uint32_t idescO = make_idesc_f16(kTileM, DPAD, kFormat, 0, 1);
       // Descriptors differ only in the 14-bit start-address field; build each once and add (bytes >> 4).
       const uint64_t descQ = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemQ), 16, 1024);
@@ -376,17 +391,19 @@ __global__ void __launch_bounds__(kThreads, 1)
           umma_ss(d_tmem, descQ + off, b0 + off, idescS, k > 0);
         }
       };
-      auto issue_PV = [&](uint32_t h, uint32_t bf, uint32_t stage, uint32_t accumulate) {
-        const uint32_t d_tmem = tmem_base + Cfg::kTmemO + h * DPAD;
-        const uint32_t a_tmem = tmem_base + Cfg::kTmemS + bf * kBlockN + h * kHalfN;
-        // keys [64 h, 64 h + 64) of the stage: 16 keys = two 8-row groups of 1024 B
-        const uint64_t b0 = descV + ((stage * Cfg::kTileBytes + h * (kHalfN / 16) * 2048) >> 4);
+      auto issue_PV = [&](uint32_t bf, uint32_t stage, uint32_t accumulate) {
+        const uint32_t d_tmem = tmem_base + Cfg::kTmemO;
+        const uint64_t b0 = descV + ((stage * Cfg::kTileBytes) >> 4);
 #pragma unroll
-        for (uint32_t k = 0; k < kHalfN / 16; ++k)
-          umma_ts(d_tmem, a_tmem + k * 8, b0 + ((k * 2048) >> 4), idescO, k > 0 ? 1u : accumulate);
+        for (uint32_t k = 0; k < kBlockN / 16; ++k) {
+          // P of keys [64 hh, 64 hh + 64) sits in columns [64 hh, 64 hh + 32) of the S buffer (two 16-bit keys per
+          // column); V: 16 keys = two 8-row groups of 1024 B
+          const uint32_t a_tmem = tmem_base + Cfg::kTmemS + bf * kBlockN + (k >> 2) * kHalfN + (k & 3) * 8;
+          umma_ts(d_tmem, a_tmem, b0 + ((k * 2048) >> 4), idescO, k > 0 ? 1u : accumulate);
+        }
       };
 
-      // prologue: S(0) and S(1)
+      // prologue: S(0) .. S(2)
       mbar_wait(q_full, 0);
       for (uint32_t i = 0; i < kSBuffers && i < num_blocks; ++i) {
         mbar_wait(&k_full[i], 0);
@@ -400,41 +417,37 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
 
       for (uint32_t i = 0; i < num_blocks; ++i) {
-        const uint32_t bf = i & 1, ph = (i >> 1) & 1;
-        const uint32_t stage = i % Cfg::kStages, phase = (i / Cfg::kStages) & 1;
+        const uint32_t bf = i % kSBuffers, ph = (i / kSBuffers) & 1;
+        const uint32_t stage = i % Cfg::kStagesV, phase = (i / Cfg::kStagesV) & 1;
         const uint32_t ni = i + kSBuffers;  // the S block that reuses this buffer
-        const uint32_t nstage = ni % Cfg::kStages, nphase = (ni / Cfg::kStages) & 1;
+        const uint32_t nstage = ni % Cfg::kStagesK, nphase = (ni / Cfg::kStagesK) & 1;
         const bool has_next = ni < num_blocks;
         const bool last = i + 1 == num_blocks;
         mbar_wait(&v_full[stage], phase);
         MFA_TRACE(2, i, 0);
-#pragma unroll
-        for (uint32_t h = 0; h < kHalves; ++h) {
-          mbar_wait(&p_full[h * kSBuffers + bf], ph);
-          tc_fence_after();
-          MFA_TRACE(2, i, 1 + 2 * h);
-          if (elect_one()) {
-            issue_PV(h, bf, stage, i > 0 ? 1u : 0u);
-            umma_commit(&o_full[h]);
-            if (h == kHalves - 1) {
-              umma_commit(&v_empty[stage]);
-              if (last) umma_commit(o_final);
-            }
-          }
-          __syncwarp();
-          MFA_TRACE(2, i, 2 + 2 * h);
+        mbar_wait(&p_full[bf], ph);
+        tc_fence_after();
+        MFA_TRACE(2, i, 1);
+        if (elect_one()) {
+          issue_PV(bf, stage, i > 0 ? 1u : 0u);
+          umma_commit(&o_full[i & 1]);
+          umma_commit(&v_empty[stage]);
+          if (last) umma_commit(o_final);
         }
+        __syncwarp();
+        MFA_TRACE(2, i, 2);
         if (has_next) {
           mbar_wait(&k_full[nstage], nphase);
           tc_fence_after();
+          MFA_TRACE(2, i, 3);
           if (elect_one()) {
-            issue_S(bf, nstage);  // overwrites P(i) only after both P V(i): the tensor pipe runs in order
+            issue_S(bf, nstage);  // overwrites P(i) only after P V(i): the tensor pipe runs in order
             umma_commit(&s_full[bf]);
             umma_commit(&k_empty[nstage]);
           }
           __syncwarp();
         }
-        MFA_TRACE(2, i, 5);
+        MFA_TRACE(2, i, 4);
       }
     }
   }
@@ -447,8 +460,6 @@ __global__ void __launch_bounds__(kThreads, 1)
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
-
-uint32_t g_stagger_cycles = 600;  // tuned on B200 (scripts/tune_forward.py); settable through the debug hook
 
 template <uint32_t DPAD, bool kBF16, bool kTrace = false>
 cudaError_t launch(const AttentionParams &p, cudaStream_t stream, long long *trace = nullptr) {
@@ -469,8 +480,7 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, long long *tra
 
   dim3 grid((p.R + kTileM - 1) / kTileM, p.batch);
   kernel<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mapQ, mapK, mapV, static_cast<float *>(p.buf[sO]), p.buf[sL],
-                                                      p.R, p.C, p.D, p.scale_log2, p.prec[sL] == FP16 ? 1 : 0,
-                                                      g_stagger_cycles, trace);
+                                                      p.R, p.C, p.D, p.scale_log2, p.prec[sL] == FP16 ? 1 : 0, trace);
   return cudaGetLastError();
 }
 
@@ -494,7 +504,7 @@ cudaError_t launch_tcgen05_forward(const AttentionParams &p, cudaStream_t stream
   return bf16 ? fwd::launch<128, true>(p, stream) : fwd::launch<128, false>(p, stream);
 }
 
-void set_forward_stagger(uint32_t cycles) { fwd::g_stagger_cycles = cycles; }
+void set_forward_stagger(uint32_t) {}  // no tunable left in this kernel generation
 
 // Debug entry (not in include/mfa_b200.h): the D=128 bf16 forward with pipeline timestamps of CTA (0,0)
 // written to `trace` (4 roles x 128 iterations x 8 slots of clock64()).  Used by scripts/trace_forward.py.

@@ -45,22 +45,21 @@ for _ in range(3):
 t = trace.cpu().numpy().reshape(4, 128, 8)
 nb = C // 128
 t0 = t[2, 0, 0]
-print(f"R={R} H={H}: 128-key blocks, two 64-key halves; softmax slots: 0 S ready, 1 S in regs, 2 max done, 3 P computed, "
-      "4 arrived; mma slots: 0 V ready, 1 p_lo ready, 2 PV_lo issued, 3 p_hi ready, 4 PV_hi issued, 5 S(i+2) issued")
+print(f"R={R} H={H}: 128-key blocks; softmax slots: 0 step start, 1 S(i+1) waited + ld issued, 2 max(i+1) done, 3 exp(i) done, "
+      "4 P arrived, 5 pair exchange + max update done; mma slots: 0 V ready, 1 P ready, 2 PV issued, 3 K ready, 4 S(i+3) issued")
 for j in range(4, 12):
-    a = (t[0, j, :5] - t0).tolist()
-    b = (t[1, j, :5] - t0).tolist()
-    m = (t[2, j, :6] - t0).tolist()
+    a = (t[0, j, :6] - t0).tolist()
+    b = (t[1, j, :6] - t0).tolist()
+    m = (t[2, j, :5] - t0).tolist()
     print(f"i={j:2d} lo {a}  hi {b}  mma {m}")
-lo, hi = 4, nb - 3
+lo, hi = 4, nb - 4
 per_iter = np.diff(t[2, lo:hi, 1]).mean()
 print(f"steady-state period per 128-key block: {per_iter:.0f} cycles (floors: ~1000 tensor, 1024 MUFU)")
 for role in (0, 1):
     sm = t[role, lo:hi]
-    print(f"softmax half{role}: wait S {np.mean(sm[1:,0]-sm[:-1,4]):.0f}, S->regs {np.mean(sm[:,1]-sm[:,0]):.0f}, "
-          f"max {np.mean(sm[:,2]-sm[:,1]):.0f}, exp+pack+st {np.mean(sm[:,3]-sm[:,2]):.0f}, "
-          f"wait_st+arrive {np.mean(sm[:,4]-sm[:,3]):.0f}")
+    print(f"softmax half{role}: wait S(i+1)+ld issue {np.mean(sm[:,1]-sm[:,0]):.0f}, exp chunk0 + max(i+1) {np.mean(sm[:,2]-sm[:,1]):.0f}, "
+          f"exp chunk1 {np.mean(sm[:,3]-sm[:,2]):.0f}, wait_st+arrive {np.mean(sm[:,4]-sm[:,3]):.0f}, "
+          f"exchange+update {np.mean(sm[:,5]-sm[:,4]):.0f}, loop overhead {np.mean(sm[1:,0]-sm[:-1,5]):.0f}")
 mm = t[2, lo:hi]
-print(f"mma: wait p_lo {np.mean(mm[:,1]-mm[:,0]):.0f}; issue PV_lo {np.mean(mm[:,2]-mm[:,1]):.0f}; "
-      f"wait p_hi {np.mean(mm[:,3]-mm[:,2]):.0f}; issue PV_hi {np.mean(mm[:,4]-mm[:,3]):.0f}; "
-      f"K wait + issue S {np.mean(mm[:,5]-mm[:,4]):.0f}; V wait {np.mean(mm[1:,0]-mm[:-1,5]):.0f}")
+print(f"mma: wait P {np.mean(mm[:,1]-mm[:,0]):.0f}; issue PV {np.mean(mm[:,2]-mm[:,1]):.0f}; wait K {np.mean(mm[:,3]-mm[:,2]):.0f}; "
+      f"issue S {np.mean(mm[:,4]-mm[:,3]):.0f}; V wait {np.mean(mm[1:,0]-mm[:-1,4]):.0f}")
