@@ -91,8 +91,8 @@ int register_precision(const mfa_attention_descriptor_t &d, int operand) {
 //   * SIMT family: 64 x 64 blocks, 32-wide head chunks, accumulators resident in registers.
 // ------------------------------------------------------------------------------------------------
 static const char *kForwardTcgen05 =
-    "| 64  | 128 | 128 | 64  | Q, O |\n"
-    "| 128 | 128 | 128 | 128 | Q, O |\n"
+    "| 64  | 256 | 128 | 64  | Q, O |\n"
+    "| 128 | 256 | 128 | 128 | Q, O |\n"
     "| 256 | 128 | 128 | 256 | Q, O |\n"
     "\n";
 static const char *kBackwardQueryTcgen05 =

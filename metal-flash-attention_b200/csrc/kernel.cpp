@@ -237,9 +237,7 @@ int mfa_attention_kernel_encode(const mfa_attention_kernel_t *kernel, const mfa_
   return MFA_SUCCESS;
 }
 
-// Debug-only exports (deliberately absent from include/mfa_b200.h).
-MFA_API void mfa_debug_set_forward_stagger(uint32_t cycles) { mfa::set_forward_stagger(cycles); }
-// forward with pipeline timestamps
+// Debug-only export (deliberately absent from include/mfa_b200.h): forward with pipeline timestamps.
 MFA_API int mfa_debug_forward_trace(const mfa_attention_kernel_t *kernel, const mfa_function_constants_t *constants,
                                     void *const buffers[MFA_BUFFER_COUNT], void *cuda_stream, long long *trace) {
   if (!kernel || !constants || !buffers || !trace) return fail(MFA_ERROR_INVALID_ARGUMENT, "NULL argument.");

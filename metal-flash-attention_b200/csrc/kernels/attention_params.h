@@ -45,7 +45,6 @@ void tcgen05_backward_geometry(int type, uint32_t D, uint32_t *threads, uint32_t
                                uint32_t *trav, uint32_t *head);
 
 cudaError_t launch_tcgen05_forward_trace(const AttentionParams &p, cudaStream_t stream, long long *trace);  // debug
-void set_forward_stagger(uint32_t cycles);  // debug / tuning
 const char *last_launch_detail();  // thread-local detail string for MFA_ERROR_CUDA messages
 
 }  // namespace mfa

@@ -29,7 +29,7 @@ k = torch.randn(H, C, D, device="cuda").to(torch.bfloat16)
 v = torch.randn(H, C, D, device="cuda").to(torch.bfloat16)
 o = torch.empty(H, R, D, device="cuda")
 lse = torch.empty(H, R, device="cuda")
-trace = torch.zeros(4 * 128 * 8, dtype=torch.int64, device="cuda")
+trace = torch.zeros(3 * 64 * 8, dtype=torch.int64, device="cuda")
 
 lib = mfa._lib
 lib.mfa_debug_forward_trace.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
@@ -42,24 +42,25 @@ for _ in range(3):
                                      ctypes.c_void_p(trace.data_ptr()))
     assert st == 0, lib.mfa_last_error()
     torch.cuda.synchronize()
-t = trace.cpu().numpy().reshape(4, 128, 8)
+t = trace.cpu().numpy().reshape(3, 64, 8)
 nb = C // 128
 t0 = t[2, 0, 0]
-print(f"R={R} H={H}: 128-key blocks; softmax slots: 0 step start, 1 S(i+1) waited + ld issued, 2 max(i+1) done, 3 exp(i) done, "
-      "4 P arrived, 5 pair exchange + max update done; mma slots: 0 V ready, 1 P ready, 2 PV issued, 3 K ready, 4 S(i+3) issued")
-for j in range(4, 12):
-    a = (t[0, j, :6] - t0).tolist()
-    b = (t[1, j, :6] - t0).tolist()
-    m = (t[2, j, :5] - t0).tolist()
-    print(f"i={j:2d} lo {a}  hi {b}  mma {m}")
-lo, hi = 4, nb - 4
-per_iter = np.diff(t[2, lo:hi, 1]).mean()
-print(f"steady-state period per 128-key block: {per_iter:.0f} cycles (floors: ~1000 tensor, 1024 MUFU)")
-for role in (0, 1):
-    sm = t[role, lo:hi]
-    print(f"softmax half{role}: wait S(i+1)+ld issue {np.mean(sm[:,1]-sm[:,0]):.0f}, exp chunk0 + max(i+1) {np.mean(sm[:,2]-sm[:,1]):.0f}, "
-          f"exp chunk1 {np.mean(sm[:,3]-sm[:,2]):.0f}, wait_st+arrive {np.mean(sm[:,4]-sm[:,3]):.0f}, "
-          f"exchange+update {np.mean(sm[:,5]-sm[:,4]):.0f}, loop overhead {np.mean(sm[1:,0]-sm[:-1,5]):.0f}")
-mm = t[2, lo:hi]
-print(f"mma: wait P {np.mean(mm[:,1]-mm[:,0]):.0f}; issue PV {np.mean(mm[:,2]-mm[:,1]):.0f}; wait K {np.mean(mm[:,3]-mm[:,2]):.0f}; "
-      f"issue S {np.mean(mm[:,4]-mm[:,3]):.0f}; V wait {np.mean(mm[1:,0]-mm[:-1,4]):.0f}")
+print(f"R={R} H={H}: cycles relative to MMA warp's first V wait; softmax slots: 0 S ready, 1 S in regs, 2 max done, "
+      "3 P computed, 4 arrived; mma slots: 0 V ready, 1 p0 ready, 2 PV0 issued, 3 S0 issued, 4 p1 ready, 5 PV1 issued, 6 S1 issued")
+for j in range(min(nb, 12)):
+    a = (t[0, j, :5] - t0).tolist()
+    b = (t[1, j, :5] - t0).tolist()
+    m = (t[2, j, :7] - t0).tolist()
+    print(f"j={j:2d} sm0 {a}  sm1 {b}  mma {m}")
+per_iter = np.diff(t[2, 2:nb - 1, 1]).mean()
+sm = t[0, 2:nb - 1]
+print(f"steady-state period per key block: {per_iter:.0f} cycles (ideal 2048 tensor / 2048 MUFU)")
+print(f"softmax tile0: wait-for-S->S-in-regs {np.mean(sm[:,1]-sm[:,0]):.0f}, max {np.mean(sm[:,2]-sm[:,1]):.0f}, "
+      f"exp+pack+st {np.mean(sm[:,3]-sm[:,2]):.0f}, wait_st+arrive {np.mean(sm[:,4]-sm[:,3]):.0f}, "
+      f"arrive->next S ready {np.mean(sm[1:,0]-sm[:-1,4]):.0f}")
+mm = t[2, 2:nb - 1]
+print(f"mma: p0 ready->PV0+S0 issued {np.mean(mm[:,3]-mm[:,1]):.0f}; S0 issued->p1 ready {np.mean(mm[:,4]-mm[:,3]):.0f}; "
+      f"p1 ready->issued {np.mean(mm[:,6]-mm[:,4]):.0f}; S1 issued -> next p0 ready {np.mean(mm[1:,1]-mm[:-1,6]):.0f}")
+# MMA latency: time from S0 issue (slot 3 of iter j) to softmax0 seeing S ready (slot 0 of iter j+1)
+print(f"S0 issue -> softmax0 sees S(j+1): {np.mean(t[0,3:nb-1,0]-t[2,2:nb-2,3]):.0f} cycles; "
+      f"softmax0 arrive(j) -> mma sees p0(j): {np.mean(t[2,2:nb-1,1]-t[0,2:nb-1,4]):.0f}")
