@@ -1,0 +1,184 @@
+"""Host-side logic of the C ABI (no GPU): descriptor -> kernel-descriptor heuristic, precision policy,
+parameter tables, validation / error behaviour, and that libmfa_b200.so exports every symbol the header
+declares.  Mirrors what the reference's Swift types do on the CPU
+(Sources/FlashAttention/Attention/AttentionDescriptor/*.swift, AttentionKernel.swift)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+import mfa_b200 as mfa
+from mfa_b200 import AttentionKernelType as KT
+from mfa_b200 import AttentionOperand as Op
+from mfa_b200 import GEMMOperandPrecision as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def make(row=64, column=64, head=32, lowIn=False, lowMid=False, transposes=(False,) * 4, bf16=False):
+    d = mfa.AttentionDescriptor()
+    d.lowPrecisionInputs, d.lowPrecisionIntermediates = lowIn, lowMid
+    d.matrixDimensions = (row, column, head)
+    d.transposeState = transposes
+    if bf16:
+        d.inputPrecisionOverride = P.BF16
+    return d
+
+
+def test_header_symbols_are_exported():
+    header = open(os.path.join(ROOT, "include", "mfa_b200.h")).read()
+    declared = set(re.findall(r"MFA_API\s+[\w\s\*]+?\b(mfa_\w+)\s*\(", header))
+    assert len(declared) >= 20
+    nm = subprocess.check_output(["nm", "-D", "--defined-only", mfa.library_path()], text=True)
+    exported = set(re.findall(r"\b(mfa_\w+)\b", nm))
+    missing = declared - exported
+    assert not missing, f"declared in include/mfa_b200.h but not exported: {sorted(missing)}"
+    lib = ctypes.CDLL(mfa.library_path())
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_enum_raw_values_match_reference():
+    assert (P.FP32, P.FP16, P.BF16) == (0, 1, 2)                     # GEMMOperandPrecision.swift:33-37
+    assert [P.FP32.size, P.FP16.size, P.BF16.size] == [4, 2, 2]      # :51-60
+    bindings = {Op.Q: 0, Op.K: 1, Op.V: 2, Op.O: 3, Op.L: 4, Op.D: 5, Op.dO: 6, Op.dV: 7, Op.dK: 8, Op.dQ: 9}
+    for op, slot in bindings.items():                                 # AttentionOperand.swift:52-71
+        assert op.bufferBinding == slot
+    for op in (Op.S, Op.P, Op.dP, Op.dS):
+        assert op.bufferBinding is None
+
+
+def test_memory_precisions_follow_reference_policy():
+    """AttentionDescriptor+Precisions.swift:10-146."""
+    m = make().memoryPrecisions
+    assert all(m[op] == P.FP32 for op in m)
+    m = make(lowIn=True).memoryPrecisions
+    assert (m[Op.Q], m[Op.K], m[Op.V], m[Op.dO]) == (P.FP16, P.FP16, P.FP16, P.BF16)
+    assert (m[Op.L], m[Op.D]) == (P.FP32, P.FP32)
+    m = make(lowMid=True).memoryPrecisions
+    assert (m[Op.Q], m[Op.L], m[Op.D]) == (P.FP32, P.FP16, P.BF16)
+    for flags in ((True, True), (True, False), (False, True)):
+        m = make(lowIn=flags[0], lowMid=flags[1]).memoryPrecisions
+        assert all(m[op] == P.FP32 for op in (Op.O, Op.dV, Op.dK, Op.dQ))   # :140-143 outputs always FP32
+    m = make(lowIn=True, bf16=True).memoryPrecisions                         # B200 extension
+    assert (m[Op.Q], m[Op.K], m[Op.V], m[Op.dO]) == (P.BF16,) * 4
+
+
+def test_register_precisions():
+    r = make(lowIn=True, lowMid=True).registerPrecisions
+    assert r[Op.O] == r[Op.dV] == r[Op.dK] == r[Op.dQ] == P.FP32            # :209-212
+    assert r[Op.dS] == P.BF16 and r[Op.dP] == P.FP32 and r[Op.P] == P.FP16  # :198-200 (native BF16 branch)
+    r = make().registerPrecisions
+    assert all(v == P.FP32 for v in r.values())
+
+
+def test_incomplete_descriptor_is_an_error_not_a_crash():
+    d = mfa.AttentionDescriptor()
+    with pytest.raises(mfa.MFAError, match="Descriptor was incomplete"):     # AttentionDescriptor.swift:89-91
+        d.kernelDescriptor(KT.forward)
+    d.matrixDimensions = (8, 8, 8)
+    with pytest.raises(mfa.MFAError, match="Descriptor was incomplete"):     # transposeState still nil (:96-99)
+        d.kernelDescriptor(KT.forward)
+    with pytest.raises(mfa.MFAError, match="Descriptor was incomplete"):     # AttentionKernel.swift:28-34
+        mfa.AttentionKernel(mfa.AttentionKernelDescriptor())
+
+
+def test_kernel_descriptor_fields():
+    d = make(row=300, column=200, head=77, transposes=(True, False, True, False))
+    for t in KT:
+        kd = d.kernelDescriptor(t)
+        par, trav, head = kd.blockDimensions
+        assert head <= (77 + 7) // 8 * 8                                      # AttentionDescriptor.swift:41-54
+        assert kd.headDimension == 77 and kd.type == t
+        ts = kd.transposeState                                               # :96-111 derivatives mirror inputs
+        assert ts[Op.Q] and ts[Op.dQ] and ts[Op.V] and ts[Op.dV]
+        assert not ts[Op.K] and not ts[Op.dK] and not ts[Op.O] and not ts[Op.dO]
+        assert kd.backend == mfa.Backend.simtFP32
+    expected = {KT.forward: {Op.Q, Op.O}, KT.backwardQuery: {Op.Q, Op.dO, Op.dQ},
+                KT.backwardKeyValue: {Op.K, Op.V, Op.dV, Op.dK}}                # :58-66
+    for t, ops in expected.items():
+        assert set(d.kernelDescriptor(t).cacheState) == ops
+
+
+def test_heuristic_selects_tensor_core_family_only_where_it_applies():
+    assert make(4096, 4096, 128, lowIn=True, bf16=True).kernelDescriptor(KT.forward).backend == mfa.Backend.tcgen05
+    assert make(4096, 4096, 64, lowIn=True).kernelDescriptor(KT.forward).backend == mfa.Backend.tcgen05
+    assert make(4096, 4096, 128).kernelDescriptor(KT.forward).backend == mfa.Backend.simtFP32       # FP32 inputs
+    assert make(64, 64, 77, lowIn=True).kernelDescriptor(KT.forward).backend == mfa.Backend.simtFP32  # D % 8 != 0
+    assert make(64, 64, 64, lowIn=True, transposes=(False, True, False, False)).kernelDescriptor(
+        KT.forward).backend == mfa.Backend.simtFP32                                                # transposed K
+    kd = make(4096, 4096, 128, lowIn=True, bf16=True).kernelDescriptor(KT.forward)
+    assert kd.preferAsyncLoad and kd.preferAsyncCache           # "async" == TMA on B200
+    assert kd.cacheState == {Op.Q: True, Op.O: True}             # Q resident in SMEM, O resident in TMEM
+
+
+def test_parameter_file_has_reference_format():
+    text = make(4096, 4096, 128, lowIn=True, bf16=True).parameterFile(KT.forward)
+    rows = [line for line in text.split("\n") if line.strip()]
+    assert rows and all(len([c for c in row.split("|") if c != ""]) == 5 for row in rows)   # AttentionParameterRow.swift:46-49
+    maxima = [int(row.split("|")[1]) for row in rows]
+    assert maxima == sorted(maxima)
+
+
+def test_kernel_object_reports_launch_geometry():
+    d = make(4096, 4096, 128, lowIn=True, bf16=True)
+    d.batchCount = 64
+    k = mfa.AttentionKernel(d.kernelDescriptor(KT.forward))
+    c = mfa.FunctionConstantValues()
+    d.setFunctionConstants(c)
+    assert (c.row, c.column, c.batchCount) == (4096, 4096, 64)              # AttentionDescriptor.swift:144-147
+    par, trav, head = k.blockDimensions
+    assert k.gridSize(c) == (4096 + par - 1) // par * 64                      # SquareAttentionTest.swift:328-339
+    assert k.threadgroupSize % 32 == 0 and 0 < k.threadgroupMemoryAllocation <= 232448
+    assert "tcgen05" in k.sourceName() and k.launchCount(c) >= 1
+    k2 = mfa.AttentionKernel(make(10, 10, 3).kernelDescriptor(KT.backwardKeyValue))
+    assert "simt" in k2.sourceName()
+
+
+def test_invalid_precision_pairs_are_rejected():
+    kd = make(lowIn=True).kernelDescriptor(KT.forward)
+    kd.setRegisterPrecision(Op.Q, P.BF16)                                      # FP16 memory -> BF16 register
+    with pytest.raises(mfa.MFAError, match="Invalid precisions"):             # AttentionKernel.swift:90-105
+        mfa.AttentionKernel(kd)
+    kd = make().kernelDescriptor(KT.forward)
+    kd.setMemoryPrecision(Op.K, None)
+    with pytest.raises(mfa.MFAError, match="was not specified"):
+        mfa.AttentionKernel(kd)
+
+
+def test_edited_descriptor_outside_compiled_kernels_is_rejected():
+    kd = make(lowIn=True, head=64).kernelDescriptor(KT.forward)
+    kd.blockDimensions = (32, 80, 16)                                          # an Apple tile shape
+    with pytest.raises(mfa.MFAError, match="no compiled sm_100a kernel"):
+        mfa.AttentionKernel(kd)
+    with pytest.raises(mfa.MFAError, match="exceeds 512"):
+        mfa.AttentionKernel(make(head=600).kernelDescriptor(KT.forward))
+
+
+def test_encode_without_gpu_fails_loudly_instead_of_falling_back():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    d = make(8, 8, 8)
+    k = mfa.AttentionKernel(d.kernelDescriptor(KT.forward))
+    c = mfa.FunctionConstantValues()
+    d.setFunctionConstants(c)
+    with pytest.raises(mfa.MFAError) as err:
+        k.encode(c, {Op.Q: 16, Op.K: 16, Op.V: 16, Op.O: 16, Op.L: 16})
+    assert err.value.status == -6 and "no CPU fallback" in str(err.value)      # MFA_ERROR_NO_DEVICE
+    with pytest.raises(mfa.MFAError):
+        d.runHost([KT.forward], {}, device=0)
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under the product package may import, link or call it."""
+    pkg = os.path.join(ROOT, "metal-flash-attention_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".cuh", ".h", ".hpp", ".swift")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in text.lower().replace("test infrastructure", ""), os.path.join(dirpath, f)
+    ldd = subprocess.check_output(["ldd", mfa.library_path()], text=True)
+    assert "oracle" not in ldd
