@@ -109,10 +109,12 @@ typedef struct mfa_attention_descriptor {
   uint16_t head;                       /* matrixDimensions.head   (head dimension D)         */
   uint8_t transpose_Q, transpose_K, transpose_V, transpose_O; /* transposeState :22 */
   /* ---- B200 extensions; all-zero reproduces the reference exactly ---- */
-  uint8_t input_precision_override;    /* 0: reference policy (FP16 when lowPrecisionInputs,
+  uint8_t input_precision_override;    /* 0: reference policy (Q,K,V FP16 and dO BF16 when lowPrecisionInputs,
                                           AttentionDescriptor+Precisions.swift:13-23);
-                                          MFA_BF16 (2): Q,K,V,dO are BF16 in memory (north_star asks
-                                          for bf16 inputs). Only meaningful with low_precision_inputs. */
+                                          MFA_BF16 (2): Q,K,V,dO are all BF16 in memory (north_star asks for bf16);
+                                          MFA_FP16 (1): Q,K,V,dO are all FP16 (the tensor-core backward needs one
+                                          element type: tcgen05 kind::f16 cannot mix FP16 and BF16 operands).
+                                          Only meaningful with low_precision_inputs. */
   uint8_t reserved0;
   uint32_t batch_count;                /* 0 or 1: single head (reference). N > 1: N independent
                                           single-head problems, each operand stored back to back

@@ -34,7 +34,9 @@ int memory_precision(const mfa_attention_descriptor_t &d, int operand) {
       // :13-23  FP16 when lowPrecisionInputs (extension: BF16 when overridden)
       return d.low_precision_inputs ? (bf16Inputs ? MFA_BF16 : MFA_FP16) : MFA_FP32;
     case MFA_dO:
-      return d.low_precision_inputs ? MFA_BF16 : MFA_FP32;  // :17,22
+      // :17,22  BF16 when lowPrecisionInputs (extension: FP16 when the override asks for an all-FP16 operand set,
+      // which is what the tensor-core backward needs -- tcgen05 kind::f16 cannot mix FP16 and BF16 operands)
+      return d.low_precision_inputs ? (d.input_precision_override == MFA_FP16 ? MFA_FP16 : MFA_BF16) : MFA_FP32;
     case MFA_L:
       return d.low_precision_intermediates ? MFA_FP16 : MFA_FP32;  // :81-87
     case MFA_D:
@@ -54,7 +56,7 @@ int register_precision(const mfa_attention_descriptor_t &d, int operand) {
     case MFA_Q: case MFA_K: case MFA_V:
       return d.low_precision_inputs ? (bf16Inputs ? MFA_BF16 : MFA_FP16) : MFA_FP32;  // :158-168
     case MFA_dO:
-      return d.low_precision_inputs ? MFA_BF16 : MFA_FP32;
+      return d.low_precision_inputs ? (d.input_precision_override == MFA_FP16 ? MFA_FP16 : MFA_BF16) : MFA_FP32;
     case MFA_L:
       return d.low_precision_intermediates ? MFA_FP16 : MFA_FP32;  // :171-177
     case MFA_D:

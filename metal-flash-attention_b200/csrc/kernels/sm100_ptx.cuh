@@ -143,10 +143,15 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
 // Instruction descriptor for kind::f16 (FP16/BF16 inputs, FP32 accumulate):
 //   [4,6) D format: 1 = F32   [7,10) A format, [10,13) B format: 0 = F16, 1 = BF16
 //   [15] A major, [16] B major: 0 = K-major, 1 = MN-major   [17,23) N >> 3   [24,29) M >> 4
+__host__ __device__ constexpr uint32_t make_idesc_f16_mixed(uint32_t M, uint32_t N, uint32_t a_format,
+                                                            uint32_t b_format, uint32_t a_mn_major,
+                                                            uint32_t b_mn_major) {
+  return (1u << 4) | (a_format << 7) | (b_format << 10) | (a_mn_major << 15) | (b_mn_major << 16) |
+         ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N, uint32_t ab_format, uint32_t a_mn_major,
                                                       uint32_t b_mn_major) {
-  return (1u << 4) | (ab_format << 7) | (ab_format << 10) | (a_mn_major << 15) | (b_mn_major << 16) |
-         ((N >> 3) << 17) | ((M >> 4) << 24);
+  return make_idesc_f16_mixed(M, N, ab_format, ab_format, a_mn_major, b_mn_major);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]

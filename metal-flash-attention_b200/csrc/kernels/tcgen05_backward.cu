@@ -1,0 +1,676 @@
+// FlashAttention backward for sm_100a: the reference's atomics-free split backward (README.md:11,39) as two
+// TMA + tcgen05 + TMEM kernels for 16-bit row-major operands.
+//
+//   backwardQuery     loopBackwardQuery     AttentionKernel+Source.swift:202-242, computeD +Softmax.swift:32-221
+//       per 128-row block of Q, over key blocks c:   S = Q K^T, dP = dO V^T  ->  P = exp2(s2 S - L),
+//       dS = P (s dP - D)  ->  dQ += dS K;   also writes D = rowsum(dO * O) / sqrt(D)
+//   backwardKeyValue  loopBackwardKeyValue  AttentionKernel+Source.swift:244-293
+//       per 128-row block of K/V, over query blocks r:   S^T = K Q^T, dP^T = V dO^T  ->  P^T, dS^T
+//       ->  dV += P^T dO,  dK += dS^T Q
+//
+// Shared structure (384 threads): warps 0-3 / 4-7 are two elementwise warpgroups (thread = TMEM lane = one row of
+// the 128 x 128 block; warpgroup h owns columns [64 h, 64 h + 64)); warp 8 issues every tcgen05.mma; warp 9 is the
+// TMA producer; warps 10-11 idle or load the L / D vectors.  No row reductions are needed in the backward pass
+// (L and D are inputs), so the two warpgroups never exchange anything.  All four "accumulate" GEMMs take their A
+// operand (P, dS, P^T, dS^T: 16-bit) straight from TMEM, written in place over the FP32 S / dP they came from.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include <mutex>
+
+#include "attention_params.h"
+#include "sm100_ptx.cuh"
+#include "tma_host.h"
+
+namespace mfa {
+namespace bwd {
+
+using namespace ptx;
+
+constexpr uint32_t kTile = 128;   // rows of the parallelised operand per CTA and rows per traversal block
+constexpr uint32_t kHalf = 64;    // columns per elementwise warpgroup
+constexpr uint32_t kSubTileBytes = 128 * 128;  // [128 rows][64 x 16-bit]: one 128B-swizzled TMA box
+constexpr uint32_t kThreads = 384;
+constexpr uint32_t kElemThreads = 256;
+constexpr uint32_t kLaunchRegs = 168, kElemRegs = 208, kOtherRegs = 88;
+static_assert(kElemRegs * 256 + kOtherRegs * 128 <= kLaunchRegs * kThreads, "setmaxnreg over-subscribed");
+
+template <uint32_t DPAD>
+struct Config {
+  static constexpr uint32_t kSubTiles = DPAD / 64;
+  static constexpr uint32_t kTileBytes = kSubTiles * kSubTileBytes;  // one 128 x DPAD 16-bit tile
+  static constexpr uint32_t kStages = 2;
+  // two resident tiles (Q,dO or K,V) + two staged operands x kStages
+  static constexpr uint32_t kSmemResident0 = 0;
+  static constexpr uint32_t kSmemResident1 = kTileBytes;
+  static constexpr uint32_t kSmemStage0 = 2 * kTileBytes;                       // K (dQ kernel) / Q (dK-dV kernel)
+  static constexpr uint32_t kSmemStage1 = kSmemStage0 + kStages * kTileBytes;   // V (dQ kernel) / dO (dK-dV kernel)
+  static constexpr uint32_t kSmemVec = kSmemStage1 + kStages * kTileBytes;      // float L[stages][128], D[stages][128]
+  static constexpr uint32_t kSmemBar = kSmemVec + 2 * kStages * kTile * 4;
+  static constexpr uint32_t kNumBars = 24;
+  static constexpr uint32_t kSmemTmemPtr = kSmemBar + kNumBars * 8;
+  static constexpr uint32_t kSmemBytes = kSmemTmemPtr + 16;
+  static_assert(kSmemBytes <= 232448, "shared memory over budget");
+};
+
+__device__ __forceinline__ float load_16bit(const void *p, size_t i, bool bf16) {
+  const uint16_t h = reinterpret_cast<const uint16_t *>(p)[i];
+  return bf16 ? __uint_as_float(static_cast<uint32_t>(h) << 16) : __half2float(__ushort_as_half(h));
+}
+// L is FP32 or FP16, D is FP32 or BF16 in memory (AttentionDescriptor+Precisions.swift:81-87)
+__device__ __forceinline__ float load_stat(const void *p, size_t i, int prec) {
+  if (prec == FP32) return reinterpret_cast<const float *>(p)[i];
+  const uint16_t h = reinterpret_cast<const uint16_t *>(p)[i];
+  return prec == FP16 ? __half2float(__ushort_as_half(h)) : __uint_as_float(static_cast<uint32_t>(h) << 16);
+}
+__device__ __forceinline__ void store_stat(void *p, size_t i, int prec, float v) {
+  if (prec == FP32) reinterpret_cast<float *>(p)[i] = v;
+  else if (prec == FP16) reinterpret_cast<uint16_t *>(p)[i] = __half_as_ushort(__float2half_rn(v));
+  else reinterpret_cast<uint16_t *>(p)[i] = static_cast<uint16_t>(__float_as_uint(v) >> 16);  // BF16 store truncates
+}
+
+struct BackwardArgs {
+  const void *dO;   // [batch][R][D] 16-bit (same element type as Q/K/V)
+  const float *O;   // [batch][R][D] FP32
+  const void *L;    // [batch][R]
+  void *Dterm;      // [batch][R]
+  float *dQ, *dV, *dK;  // FP32 outputs
+  uint32_t R, C, D;
+  float scale, scale_log2;
+  int l_prec, d_prec;
+};
+
+// ================================================================================================
+// backwardQuery
+//   TMEM columns: [0,128) S (single buffer, released as soon as it is in registers),
+//                 [128,256) [256,384) dP double buffer (dS is written in place over dP),  [384,384+D) dQ
+// ================================================================================================
+template <uint32_t DPAD, bool kBF16>
+__global__ void __launch_bounds__(kThreads, 1)
+    attention_backward_query_tcgen05(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapdO,
+                                     const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV,
+                                     const BackwardArgs a) {
+  using Cfg = Config<DPAD>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t head = blockIdx.y;
+  const uint32_t r0 = blockIdx.x * kTile;
+  const uint32_t num_blocks = (a.C + kTile - 1) / kTile;
+  constexpr uint32_t kTmemS = 0, kTmemdP = 128, kTmemdQ = 384, kTmemCols = 512;
+
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kSmemBar);
+  uint64_t *q_full = bars;            // Q and dO tiles landed
+  uint64_t *k_full = bars + 1;        // [2]
+  uint64_t *k_empty = bars + 3;       // [2]
+  uint64_t *v_full = bars + 5;        // [2]
+  uint64_t *v_empty = bars + 7;       // [2]
+  uint64_t *s_full = bars + 9;        // S(j) in TMEM
+  uint64_t *s_free = bars + 10;       // S(j) is in registers (256 arrivals)
+  uint64_t *dp_full = bars + 11;      // [2] dP(j) in TMEM
+  uint64_t *ds_full = bars + 13;      // [2] dS(j) written over dP(j) (256 arrivals)
+  uint64_t *dq_final = bars + 15;     // every MMA has completed
+  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem + Cfg::kSmemTmemPtr);
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (uint32_t s = 0; s < 2; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+      mbar_init(&dp_full[s], 1);
+      mbar_init(&ds_full[s], kElemThreads);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, kElemThreads);
+    mbar_init(dq_final, 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) {
+    tmem_alloc(tmem_ptr_smem, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp < 8) {
+    // ---------------- elementwise warpgroups ----------------
+    setmaxnreg_inc<kElemRegs>();
+    const uint32_t h = warp >> 2, quarter = warp & 3;
+    const uint32_t row_in_tile = quarter * 32 + lane;
+    const uint32_t row = r0 + row_in_tile;
+    const uint32_t row_c = min(row, a.R - 1);  // clamped like clampedParallelizationThreadOffset (AttentionKernel.swift:224-226)
+    const uint32_t tLane = tmem_base + ((quarter * 32) << 16);
+
+    // computeD (AttentionKernel+Softmax.swift:32-221): D = (sum_d dO * O) / sqrt(D), kept in FP32 for this kernel
+    // and stored (possibly as BF16) for the dK/dV kernel.  L arrives in log2 units from the forward kernel.
+    float Dterm;
+    {
+      const size_t base = (static_cast<size_t>(head) * a.R + row_c) * a.D;
+      float acc0 = 0.f, acc1 = 0.f;
+      for (uint32_t d = 0; d < a.D; d += 2) {
+        acc0 = fmaf(load_16bit(a.dO, base + d, kBF16), a.O[base + d], acc0);
+        acc1 = fmaf(load_16bit(a.dO, base + d + 1, kBF16), a.O[base + d + 1], acc1);
+      }
+      Dterm = (acc0 + acc1) * a.scale;
+    }
+    const size_t stat_idx = static_cast<size_t>(head) * a.R + row_c;
+    const float Lrow = load_stat(a.L, stat_idx, a.l_prec);
+    if (h == 0 && row < a.R) store_stat(a.Dterm, stat_idx, a.d_prec, Dterm);
+
+    for (uint32_t j = 0; j < num_blocks; ++j) {
+      const uint32_t bf = j & 1;
+      const uint32_t tS = tLane + kTmemS + h * kHalf;
+      const uint32_t tdP = tLane + kTmemdP + bf * kTile + h * kHalf;
+      mbar_wait(s_full, j & 1);
+      mbar_wait(&dp_full[bf], (j >> 1) & 1);
+      tc_fence_after();
+      float s[kHalf], dp[kHalf];
+#pragma unroll
+      for (uint32_t c = 0; c < kHalf; c += 32) {
+        tmem_ld32(tS + c, *reinterpret_cast<uint32_t(*)[32]>(&s[c]));
+        tmem_ld32(tdP + c, *reinterpret_cast<uint32_t(*)[32]>(&dp[c]));
+      }
+      tc_wait_ld();
+      tc_fence_before();
+      mbar_arrive(s_free);  // S(j+1) may overwrite the S buffer now
+
+      const uint32_t col0 = j * kTile + h * kHalf;
+#pragma unroll
+      for (uint32_t c = 0; c < kHalf; c += 32) {
+        uint32_t packed[16];
+#pragma unroll
+        for (uint32_t k = 0; k < 16; ++k) {
+          // P = exp2(S * log2e/sqrt(D) - L);  dS = P * (dP/sqrt(D) - D)     (+Softmax.swift:419-427)
+          float p0 = ex2_approx(fmaf(s[c + 2 * k], a.scale_log2, -Lrow));
+          float p1 = ex2_approx(fmaf(s[c + 2 * k + 1], a.scale_log2, -Lrow));
+          if (col0 + c + 2 * k >= a.C) p0 = 0.f;      // padded key columns (maskAttentionMatrixEdge)
+          if (col0 + c + 2 * k + 1 >= a.C) p1 = 0.f;
+          const float ds0 = p0 * fmaf(dp[c + 2 * k], a.scale, -Dterm);
+          const float ds1 = p1 * fmaf(dp[c + 2 * k + 1], a.scale, -Dterm);
+          packed[k] = kBF16 ? pack_bf16x2(ds0, ds1) : pack_f16x2(ds0, ds1);
+        }
+        tmem_st16(tdP + (c >> 1), packed);  // dS of keys [64h + c, +32) -> columns [64h + c/2, +16) of the dP buffer
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&ds_full[bf]);
+    }
+
+    // epilogue: dQ -> global (FP32); warpgroup h writes columns [h D/2, (h+1) D/2)
+    mbar_wait(dq_final, 0);
+    tc_fence_after();
+    float *out_row = a.dQ + (static_cast<size_t>(head) * a.R + row) * a.D;
+#pragma unroll
+    for (uint32_t cc = 0; cc < DPAD / 2; cc += 32) {
+      const uint32_t c = h * (DPAD / 2) + cc;
+      uint32_t v[32];
+      tmem_ld32(tLane + kTmemdQ + c, v);
+      tc_wait_ld();
+      if (row < a.R) {
+#pragma unroll
+        for (uint32_t k = 0; k < 32; k += 4)
+          if (c + k < a.D)
+            *reinterpret_cast<float4 *>(out_row + c + k) =
+                make_float4(__uint_as_float(v[k]), __uint_as_float(v[k + 1]), __uint_as_float(v[k + 2]),
+                            __uint_as_float(v[k + 3]));
+      }
+    }
+  } else {
+    setmaxnreg_dec<kOtherRegs>();
+    if (warp == 9) {
+      // ---------------- TMA producer ----------------
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full, 2 * Cfg::kTileBytes);
+#pragma unroll
+        for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds) {
+          tma_load_3d(smem + Cfg::kSmemResident0 + ds * kSubTileBytes, &mapQ, q_full, ds * 64, r0, head);
+          tma_load_3d(smem + Cfg::kSmemResident1 + ds * kSubTileBytes, &mapdO, q_full, ds * 64, r0, head);
+        }
+      }
+      for (uint32_t j = 0; j < num_blocks; ++j) {
+        const uint32_t stage = j & 1, phase = (j >> 1) & 1;
+        mbar_wait(&k_empty[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&k_full[stage], Cfg::kTileBytes);
+#pragma unroll
+          for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
+            tma_load_3d(smem + Cfg::kSmemStage0 + stage * Cfg::kTileBytes + ds * kSubTileBytes, &mapK, &k_full[stage],
+                        ds * 64, j * kTile, head);
+        }
+      }
+    } else if (warp == 10) {
+      // ---------------- TMA producer for V (dP runs two blocks ahead of dQ, so V must not queue behind K) --------
+      for (uint32_t j = 0; j < num_blocks; ++j) {
+        const uint32_t stage = j & 1, phase = (j >> 1) & 1;
+        mbar_wait(&v_empty[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&v_full[stage], Cfg::kTileBytes);
+#pragma unroll
+          for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
+            tma_load_3d(smem + Cfg::kSmemStage1 + stage * Cfg::kTileBytes + ds * kSubTileBytes, &mapV, &v_full[stage],
+                        ds * 64, j * kTile, head);
+        }
+      }
+    } else if (warp == 8) {
+      // ---------------- MMA issuer ----------------
+      constexpr uint32_t kFormat = kBF16 ? 1u : 0u;
+      constexpr uint32_t idescNT = make_idesc_f16(kTile, kTile, kFormat, 0, 0);  // [128 x D] . [128 x D]^T
+      constexpr uint32_t idescAcc = make_idesc_f16(kTile, DPAD, kFormat, 0, 1);  // TMEM A . MN-major B -> [128 x DPAD]
+      const uint64_t descQ = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemResident0), 16, 1024);
+      const uint64_t descdO = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemResident1), 16, 1024);
+      const uint64_t descK = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemStage0), 16, 1024);
+      const uint64_t descV = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemStage1), 16, 1024);
+      const uint64_t descKmn = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemStage0), kSubTileBytes, 1024);
+
+      auto issue_nt = [&](uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc) {
+#pragma unroll
+        for (uint32_t k = 0; k < DPAD / 16; ++k) {
+          const uint32_t off = ((k >> 2) * kSubTileBytes + (k & 3) * 32) >> 4;
+          umma_ss(d_tmem, a_desc + off, b_desc + off, idescNT, k > 0);
+        }
+      };
+      auto issue_dQ = [&](uint32_t bf, uint32_t stage, uint32_t accumulate) {
+        const uint64_t b0 = descKmn + ((stage * Cfg::kTileBytes) >> 4);
+#pragma unroll
+        for (uint32_t k = 0; k < kTile / 16; ++k) {
+          // dS of keys [64 hh, 64 hh + 64) sits in columns [64 hh, 64 hh + 32) of the dP buffer
+          const uint32_t a_tmem = tmem_base + kTmemdP + bf * kTile + (k >> 2) * kHalf + (k & 3) * 8;
+          umma_ts(tmem_base + kTmemdQ, a_tmem, b0 + ((k * 2048) >> 4), idescAcc, k > 0 ? 1u : accumulate);
+        }
+      };
+
+      // prologue: S(0), dP(0), dP(1)
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      mbar_wait(&v_full[0], 0);
+      tc_fence_after();
+      if (elect_one()) {
+        issue_nt(tmem_base + kTmemS, descQ, descK);
+        umma_commit(s_full);
+        issue_nt(tmem_base + kTmemdP, descdO, descV);
+        umma_commit(&dp_full[0]);
+        umma_commit(&v_empty[0]);
+      }
+      __syncwarp();
+      if (num_blocks > 1) {
+        mbar_wait(&v_full[1], 0);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_nt(tmem_base + kTmemdP + kTile, descdO, descV + (Cfg::kTileBytes >> 4));
+          umma_commit(&dp_full[1]);
+          umma_commit(&v_empty[1]);
+        }
+        __syncwarp();
+      }
+
+      for (uint32_t j = 0; j < num_blocks; ++j) {
+        const uint32_t bf = j & 1, stage = j & 1;
+        // S(j+1) as soon as S(j) has been read out
+        if (j + 1 < num_blocks) {
+          const uint32_t ns = (j + 1) & 1;
+          mbar_wait(s_free, j & 1);
+          mbar_wait(&k_full[ns], ((j + 1) >> 1) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_nt(tmem_base + kTmemS, descQ, descK + ((ns * Cfg::kTileBytes) >> 4));
+            umma_commit(s_full);
+          }
+          __syncwarp();
+        }
+        // dQ += dS(j) K(j)
+        mbar_wait(&ds_full[bf], (j >> 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_dQ(bf, stage, j > 0 ? 1u : 0u);
+          umma_commit(&k_empty[stage]);
+          if (j + 1 == num_blocks) umma_commit(dq_final);
+        }
+        __syncwarp();
+        // dP(j+2) into the buffer dS(j) just left (in-order tensor pipe: after dQ(j))
+        if (j + 2 < num_blocks) {
+          mbar_wait(&v_full[stage], ((j + 2) >> 1) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_nt(tmem_base + kTmemdP + bf * kTile, descdO, descV + ((stage * Cfg::kTileBytes) >> 4));
+            umma_commit(&dp_full[bf]);
+            umma_commit(&v_empty[stage]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ================================================================================================
+// backwardKeyValue
+//   TMEM columns: [0,128) S^T / P^T,  [128,256) dP^T / dS^T,  [256,256+D) dV,  [256+D,256+2D) dK
+// ================================================================================================
+template <uint32_t DPAD, bool kBF16>
+__global__ void __launch_bounds__(kThreads, 1)
+    attention_backward_key_value_tcgen05(const __grid_constant__ CUtensorMap mapQ,
+                                         const __grid_constant__ CUtensorMap mapdO,
+                                         const __grid_constant__ CUtensorMap mapK,
+                                         const __grid_constant__ CUtensorMap mapV, const BackwardArgs a) {
+  using Cfg = Config<DPAD>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t head = blockIdx.y;
+  const uint32_t c0 = blockIdx.x * kTile;
+  const uint32_t num_blocks = (a.R + kTile - 1) / kTile;
+  constexpr uint32_t kTmemST = 0, kTmemdPT = 128, kTmemdV = 256, kTmemdK = 256 + DPAD, kTmemCols = 512;
+
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kSmemBar);
+  uint64_t *kv_full = bars;           // K and V tiles landed
+  uint64_t *q_full = bars + 1;        // [2] Q(r) and dO(r) landed
+  uint64_t *q_empty = bars + 3;       // [2]
+  uint64_t *vec_full = bars + 5;      // [2] L(r), D(r) vectors in shared memory (32 arrivals)
+  uint64_t *vec_empty = bars + 7;     // [2] (256 arrivals)
+  uint64_t *st_full = bars + 9;       // S^T(r), dP^T(r) in TMEM
+  uint64_t *pt_full = bars + 10;      // P^T(r), dS^T(r) written (256 arrivals)
+  uint64_t *acc_final = bars + 11;
+  float *vecL = reinterpret_cast<float *>(smem + Cfg::kSmemVec);  // [stage][128]
+  float *vecD = vecL + 2 * kTile;
+  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem + Cfg::kSmemTmemPtr);
+
+  if (threadIdx.x == 0) {
+    mbar_init(kv_full, 1);
+    for (uint32_t s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 1);
+      mbar_init(&vec_full[s], 32);
+      mbar_init(&vec_empty[s], kElemThreads);
+    }
+    mbar_init(st_full, 1);
+    mbar_init(pt_full, kElemThreads);
+    mbar_init(acc_final, 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) {
+    tmem_alloc(tmem_ptr_smem, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp < 8) {
+    // ---------------- elementwise warpgroups: thread = key row, columns = queries ----------------
+    setmaxnreg_inc<kElemRegs>();
+    const uint32_t h = warp >> 2, quarter = warp & 3;
+    const uint32_t row_in_tile = quarter * 32 + lane;
+    const uint32_t tLane = tmem_base + ((quarter * 32) << 16);
+    const uint32_t tST = tLane + kTmemST + h * kHalf, tdPT = tLane + kTmemdPT + h * kHalf;
+
+    for (uint32_t r = 0; r < num_blocks; ++r) {
+      const uint32_t stage = r & 1;
+      mbar_wait(st_full, r & 1);
+      mbar_wait(&vec_full[stage], (r >> 1) & 1);
+      tc_fence_after();
+      float s[kHalf], dp[kHalf];
+#pragma unroll
+      for (uint32_t c = 0; c < kHalf; c += 32) {
+        tmem_ld32(tST + c, *reinterpret_cast<uint32_t(*)[32]>(&s[c]));
+        tmem_ld32(tdPT + c, *reinterpret_cast<uint32_t(*)[32]>(&dp[c]));
+      }
+      tc_wait_ld();
+      const float *Lq = vecL + stage * kTile + h * kHalf, *Dq = vecD + stage * kTile + h * kHalf;
+      const uint32_t q0 = r * kTile + h * kHalf;
+#pragma unroll
+      for (uint32_t c = 0; c < kHalf; c += 32) {
+        uint32_t pp[16], dd[16];
+#pragma unroll
+        for (uint32_t k = 0; k < 16; ++k) {
+          // P^T = exp2(S^T * log2e/sqrt(D) - L[r]);  dS^T = P^T * (dP^T/sqrt(D) - D[r])   (+Softmax.swift:419-427)
+          float p0 = ex2_approx(fmaf(s[c + 2 * k], a.scale_log2, -Lq[c + 2 * k]));
+          float p1 = ex2_approx(fmaf(s[c + 2 * k + 1], a.scale_log2, -Lq[c + 2 * k + 1]));
+          if (q0 + c + 2 * k >= a.R) p0 = 0.f;      // padded query rows
+          if (q0 + c + 2 * k + 1 >= a.R) p1 = 0.f;
+          const float ds0 = p0 * fmaf(dp[c + 2 * k], a.scale, -Dq[c + 2 * k]);
+          const float ds1 = p1 * fmaf(dp[c + 2 * k + 1], a.scale, -Dq[c + 2 * k + 1]);
+          pp[k] = kBF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
+          dd[k] = kBF16 ? pack_bf16x2(ds0, ds1) : pack_f16x2(ds0, ds1);
+        }
+        tmem_st16(tST + (c >> 1), pp);
+        tmem_st16(tdPT + (c >> 1), dd);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(pt_full);
+      mbar_arrive(&vec_empty[stage]);
+    }
+
+    // epilogue: dV, dK -> global (FP32); warpgroup h writes columns [h D/2, (h+1) D/2) of both
+    mbar_wait(acc_final, 0);
+    tc_fence_after();
+    const uint32_t row = c0 + row_in_tile;
+    const size_t base = (static_cast<size_t>(head) * a.C + row) * a.D;
+#pragma unroll
+    for (uint32_t which = 0; which < 2; ++which) {
+      float *out_row = (which == 0 ? a.dV : a.dK) + base;
+      const uint32_t tAcc = tLane + (which == 0 ? kTmemdV : kTmemdK);
+#pragma unroll
+      for (uint32_t cc = 0; cc < DPAD / 2; cc += 32) {
+        const uint32_t c = h * (DPAD / 2) + cc;
+        uint32_t v[32];
+        tmem_ld32(tAcc + c, v);
+        tc_wait_ld();
+        if (row < a.C) {
+#pragma unroll
+          for (uint32_t k = 0; k < 32; k += 4)
+            if (c + k < a.D)
+              *reinterpret_cast<float4 *>(out_row + c + k) =
+                  make_float4(__uint_as_float(v[k]), __uint_as_float(v[k + 1]), __uint_as_float(v[k + 2]),
+                              __uint_as_float(v[k + 3]));
+        }
+      }
+    }
+  } else {
+    setmaxnreg_dec<kOtherRegs>();
+    if (warp == 9) {
+      // ---------------- TMA producer ----------------
+      if (elect_one()) {
+        mbar_arrive_expect_tx(kv_full, 2 * Cfg::kTileBytes);
+#pragma unroll
+        for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds) {
+          tma_load_3d(smem + Cfg::kSmemResident0 + ds * kSubTileBytes, &mapK, kv_full, ds * 64, c0, head);
+          tma_load_3d(smem + Cfg::kSmemResident1 + ds * kSubTileBytes, &mapV, kv_full, ds * 64, c0, head);
+        }
+      }
+      for (uint32_t r = 0; r < num_blocks; ++r) {
+        const uint32_t stage = r & 1, phase = (r >> 1) & 1;
+        mbar_wait(&q_empty[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&q_full[stage], 2 * Cfg::kTileBytes);
+#pragma unroll
+          for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds) {
+            tma_load_3d(smem + Cfg::kSmemStage0 + stage * Cfg::kTileBytes + ds * kSubTileBytes, &mapQ, &q_full[stage],
+                        ds * 64, r * kTile, head);
+            tma_load_3d(smem + Cfg::kSmemStage1 + stage * Cfg::kTileBytes + ds * kSubTileBytes, &mapdO, &q_full[stage],
+                        ds * 64, r * kTile, head);
+          }
+        }
+      }
+    } else if (warp == 10) {
+      // ---------------- L / D vector loader (values are read back in their memory precision,
+      //                  AttentionKernel+Softmax.swift:356-404, 453-468) ----------------
+      for (uint32_t r = 0; r < num_blocks; ++r) {
+        const uint32_t stage = r & 1, phase = (r >> 1) & 1;
+        mbar_wait(&vec_empty[stage], phase ^ 1);
+#pragma unroll
+        for (uint32_t i = 0; i < kTile / 32; ++i) {
+          const uint32_t q = r * kTile + i * 32 + lane;
+          const size_t idx = static_cast<size_t>(head) * a.R + min(q, a.R - 1);
+          vecL[stage * kTile + i * 32 + lane] = load_stat(a.L, idx, a.l_prec);
+          vecD[stage * kTile + i * 32 + lane] = load_stat(a.Dterm, idx, a.d_prec);
+        }
+        mbar_arrive(&vec_full[stage]);  // release semantics order the shared-memory writes above
+      }
+    } else if (warp == 8) {
+      // ---------------- MMA issuer ----------------
+      constexpr uint32_t kFormat = kBF16 ? 1u : 0u;
+      constexpr uint32_t idescNT = make_idesc_f16(kTile, kTile, kFormat, 0, 0);
+      constexpr uint32_t idescAcc = make_idesc_f16(kTile, DPAD, kFormat, 0, 1);
+      const uint64_t descK = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemResident0), 16, 1024);
+      const uint64_t descV = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemResident1), 16, 1024);
+      const uint64_t descQ = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemStage0), 16, 1024);
+      const uint64_t descdO = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemStage1), 16, 1024);
+      const uint64_t descQmn = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemStage0), kSubTileBytes, 1024);
+      const uint64_t descdOmn = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemStage1), kSubTileBytes, 1024);
+
+      auto issue_nt = [&](uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc) {
+#pragma unroll
+        for (uint32_t k = 0; k < DPAD / 16; ++k) {
+          const uint32_t off = ((k >> 2) * kSubTileBytes + (k & 3) * 32) >> 4;
+          umma_ss(d_tmem, a_desc + off, b_desc + off, idescNT, k > 0);
+        }
+      };
+      auto issue_acc = [&](uint32_t d_tmem, uint32_t a_base, uint64_t b_desc, uint32_t accumulate) {
+#pragma unroll
+        for (uint32_t k = 0; k < kTile / 16; ++k) {
+          const uint32_t a_tmem = a_base + (k >> 2) * kHalf + (k & 3) * 8;
+          umma_ts(d_tmem, a_tmem, b_desc + ((k * 2048) >> 4), idescAcc, k > 0 ? 1u : accumulate);
+        }
+      };
+
+      mbar_wait(kv_full, 0);
+      for (uint32_t r = 0; r < num_blocks; ++r) {
+        const uint32_t stage = r & 1, phase = (r >> 1) & 1;
+        const uint32_t soff = (stage * Cfg::kTileBytes) >> 4;
+        mbar_wait(&q_full[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          // (the previous block's dV / dK MMAs read P^T / dS^T from these columns; the tensor pipe runs in order)
+          issue_nt(tmem_base + kTmemST, descK, descQ + soff);    // S^T  = K Q^T
+          issue_nt(tmem_base + kTmemdPT, descV, descdO + soff);  // dP^T = V dO^T
+          umma_commit(st_full);
+        }
+        __syncwarp();
+        mbar_wait(pt_full, r & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_acc(tmem_base + kTmemdV, tmem_base + kTmemST, descdOmn + soff, r > 0 ? 1u : 0u);  // dV += P^T dO
+          issue_acc(tmem_base + kTmemdK, tmem_base + kTmemdPT, descQmn + soff, r > 0 ? 1u : 0u);  // dK += dS^T Q
+          umma_commit(&q_empty[stage]);
+          if (r + 1 == num_blocks) umma_commit(acc_final);
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <uint32_t DPAD, bool kBF16>
+cudaError_t launch(const AttentionParams &p, cudaStream_t stream, bool key_value) {
+  using Cfg = Config<DPAD>;
+  auto kernel_q = attention_backward_query_tcgen05<DPAD, kBF16>;
+  auto kernel_kv = attention_backward_key_value_tcgen05<DPAD, kBF16>;
+  static std::once_flag once;
+  static cudaError_t attr_status = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_status = cudaFuncSetAttribute(kernel_q, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (attr_status == cudaSuccess)
+      attr_status = cudaFuncSetAttribute(kernel_kv, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  });
+  if (attr_status != cudaSuccess) return attr_status;
+
+  CUtensorMap mapQ, mapdO, mapK, mapV;
+  cudaError_t e;
+  if ((e = make_tensor_map_16bit(&mapQ, p.buf[sQ], p.R, p.D, p.batch, kTile)) != cudaSuccess) return e;
+  if ((e = make_tensor_map_16bit(&mapdO, p.buf[sdO], p.R, p.D, p.batch, kTile)) != cudaSuccess) return e;
+  if ((e = make_tensor_map_16bit(&mapK, p.buf[sK], p.C, p.D, p.batch, kTile)) != cudaSuccess) return e;
+  if ((e = make_tensor_map_16bit(&mapV, p.buf[sV], p.C, p.D, p.batch, kTile)) != cudaSuccess) return e;
+
+  BackwardArgs a;
+  a.dO = p.buf[sdO];
+  a.O = static_cast<const float *>(p.buf[sO]);
+  a.L = p.buf[sL];
+  a.Dterm = p.buf[sD];
+  a.dQ = static_cast<float *>(p.buf[sdQ]);
+  a.dV = static_cast<float *>(p.buf[sdV]);
+  a.dK = static_cast<float *>(p.buf[sdK]);
+  a.R = p.R;
+  a.C = p.C;
+  a.D = p.D;
+  a.scale = p.scale;
+  a.scale_log2 = p.scale_log2;
+  a.l_prec = p.prec[sL];
+  a.d_prec = p.prec[sD];
+  if (!key_value) {
+    dim3 grid((p.R + kTile - 1) / kTile, p.batch);
+    kernel_q<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mapQ, mapdO, mapK, mapV, a);
+  } else {
+    dim3 grid((p.C + kTile - 1) / kTile, p.batch);
+    kernel_kv<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mapQ, mapdO, mapK, mapV, a);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace bwd
+
+uint32_t tcgen05_backward_max_head() { return 128; }
+
+bool tcgen05_backward_supported(const AttentionParams &p) {
+  const bool types = (p.prec[sQ] == FP16 || p.prec[sQ] == BF16) && p.prec[sK] == p.prec[sQ] &&
+                     p.prec[sV] == p.prec[sQ] && p.prec[sdO] == p.prec[sQ] && p.prec[sO] == FP32 &&
+                     p.prec[sdQ] == FP32 && p.prec[sdK] == FP32 && p.prec[sdV] == FP32;
+  const bool layout = !p.transposed[sQ] && !p.transposed[sK] && !p.transposed[sV] && !p.transposed[sO] &&
+                      !p.transposed[sdO] && !p.transposed[sdQ] && !p.transposed[sdK] && !p.transposed[sdV];
+  return types && layout && p.D % 8 == 0 && p.D <= tcgen05_backward_max_head();
+}
+
+static cudaError_t launch_backward(const AttentionParams &p, cudaStream_t stream, bool key_value) {
+  if (!tcgen05_backward_supported(p)) {
+    set_launch_detail("descriptor is outside the tcgen05 backward kernels' domain");
+    return cudaErrorInvalidValue;
+  }
+  const bool bf16 = p.prec[sQ] == BF16;
+  if (p.D <= 64)
+    return bf16 ? bwd::launch<64, true>(p, stream, key_value) : bwd::launch<64, false>(p, stream, key_value);
+  return bf16 ? bwd::launch<128, true>(p, stream, key_value) : bwd::launch<128, false>(p, stream, key_value);
+}
+
+cudaError_t launch_tcgen05_backward_query(const AttentionParams &p, cudaStream_t stream) {
+  return launch_backward(p, stream, false);
+}
+cudaError_t launch_tcgen05_backward_key_value(const AttentionParams &p, cudaStream_t stream) {
+  return launch_backward(p, stream, true);
+}
+
+void tcgen05_backward_geometry(int /*type*/, uint32_t D, uint32_t *threads, uint32_t *smem_bytes, uint32_t *par,
+                               uint32_t *trav, uint32_t *head) {
+  *threads = bwd::kThreads;
+  *smem_bytes = D <= 64 ? bwd::Config<64>::kSmemBytes : bwd::Config<128>::kSmemBytes;
+  *par = bwd::kTile;
+  *trav = bwd::kTile;
+  *head = D <= 64 ? 64 : 128;
+  const uint32_t padded = (D + 7) / 8 * 8;
+  if (*head > padded) *head = padded;
+}
+
+}  // namespace mfa

@@ -451,20 +451,4 @@ void tcgen05_forward_geometry(uint32_t D, uint32_t *threads, uint32_t *smem_byte
   if (*head > padded) *head = padded;
 }
 
-// ---- backward tcgen05 kernels are not built yet: the heuristic never selects them --------------
-uint32_t tcgen05_backward_max_head() { return 0; }
-bool tcgen05_backward_supported(const AttentionParams &) { return false; }
-cudaError_t launch_tcgen05_backward_query(const AttentionParams &, cudaStream_t) {
-  set_launch_detail("tcgen05 backward-query kernel is not compiled in");
-  return cudaErrorNotSupported;
-}
-cudaError_t launch_tcgen05_backward_key_value(const AttentionParams &, cudaStream_t) {
-  set_launch_detail("tcgen05 backward-key-value kernel is not compiled in");
-  return cudaErrorNotSupported;
-}
-void tcgen05_backward_geometry(int, uint32_t, uint32_t *threads, uint32_t *smem_bytes, uint32_t *par, uint32_t *trav,
-                               uint32_t *head) {
-  *threads = *smem_bytes = *par = *trav = *head = 0;
-}
-
 }  // namespace mfa

@@ -9,6 +9,7 @@
 //        umma_probe.cu ../../metal-flash-attention_b200/csrc/kernels/tma_host.cpp -o _build/umma_probe
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -31,6 +32,7 @@ struct ProbeArgs {
   uint32_t b_mn_major;
   uint32_t N;                      // MMA N (and columns of D)
   uint32_t ksteps;                 // number of K=16 MMAs
+  uint32_t b_format;               // 1 = BF16 (default), 0 = FP16 (B buffer holds FP16 data): mixed A/B formats
 };
 
 // A: [128][128] bf16 (K-major rows), B: [128][128] bf16. Both arrive as two [128][64] SW128 sub-tiles.
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(128, 1)
   tc_fence_after();
 
   if (threadIdx.x == 0) {
-    const uint32_t idesc = make_idesc_f16(128, args.N, 1, 0, args.b_mn_major);
+    const uint32_t idesc = make_idesc_f16_mixed(128, args.N, 1, args.b_format, 0, args.b_mn_major);
     for (uint32_t k = 0; k < args.ksteps; ++k) {
       // K-major operands: 4 k-steps of 32 B inside a 64-element sub-tile, then the next sub-tile (16 KiB)
       const uint32_t a_off = (k >> 2) * 16384 + (k & 3) * args.a_kstep;
@@ -141,7 +143,14 @@ int main() {
   cudaMemcpy(dA, Ab.data(), M * K * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(dB, Bb.data(), N * K * 2, cudaMemcpyHostToDevice);
   CUtensorMap mapA, mapB;
+  // FP16 copy of B for the mixed-format checks
+  std::vector<__half> Bh(N * K);
+  for (int i = 0; i < N * K; ++i) Bh[i] = __float2half(B[i]);
+  __half *dBh; cudaMalloc(&dBh, N * K * 2);
+  cudaMemcpy(dBh, Bh.data(), N * K * 2, cudaMemcpyHostToDevice);
+  CUtensorMap mapBh;
   if (make_tensor_map_16bit(&mapA, dA, 128, 128, 1, 128) != cudaSuccess ||
+      make_tensor_map_16bit(&mapBh, dBh, 128, 128, 1, 128) != cudaSuccess ||
       make_tensor_map_16bit(&mapB, dB, 128, 128, 1, 128) != cudaSuccess) {
     printf("PROBE tensor map failed: %s\n", last_launch_detail());
     return 2;
@@ -151,19 +160,21 @@ int main() {
 
   struct Candidate { const char *name; ProbeArgs a; };
   std::vector<Candidate> cands = {
-      {"mode0 SS K-major x K-major (expected encoding)", {0, 16, 1024, 32, 16, 1024, 32, 0, 128, 8}},
-      {"mode1 SS K-major x MN-major lbo=16384 sbo=1024 kstep=2048 (expected)", {1, 16, 1024, 32, 16384, 1024, 2048, 1, 128, 8}},
-      {"mode2 TS TMEM-A x MN-major (expected)", {2, 16, 1024, 32, 16384, 1024, 2048, 1, 128, 8}},
-      {"mode1 N=64 (single column block)", {1, 16, 1024, 32, 16384, 1024, 2048, 1, 64, 8}},
-      {"mode2 N=64 (single column block)", {2, 16, 1024, 32, 16384, 1024, 2048, 1, 64, 8}},
-      {"mode1 alt: lbo/sbo swapped", {1, 16, 1024, 32, 1024, 16384, 2048, 1, 128, 8}},
-      {"mode2 alt: lbo/sbo swapped", {2, 16, 1024, 32, 1024, 16384, 2048, 1, 128, 8}},
+      {"mode0 SS K-major x K-major (expected encoding)", {0, 16, 1024, 32, 16, 1024, 32, 0, 128, 8, 1}},
+      {"mode1 SS K-major x MN-major lbo=16384 sbo=1024 kstep=2048 (expected)", {1, 16, 1024, 32, 16384, 1024, 2048, 1, 128, 8, 1}},
+      {"mode2 TS TMEM-A x MN-major (expected)", {2, 16, 1024, 32, 16384, 1024, 2048, 1, 128, 8, 1}},
+      {"mode1 N=64 (single column block)", {1, 16, 1024, 32, 16384, 1024, 2048, 1, 64, 8, 1}},
+      {"mode2 N=64 (single column block)", {2, 16, 1024, 32, 16384, 1024, 2048, 1, 64, 8, 1}},
+      // Measured on B200 (round 1): a_format != b_format under kind::f16 ("MIXED A=bf16 B=fp16") raises
+      // "illegal instruction" -- FP16 and BF16 operands cannot be mixed in one tcgen05.mma.  Not run by default
+      // because the fault kills the context:
+      // {"mode0 MIXED A=bf16 B=fp16 K-major", {0, 16, 1024, 32, 16, 1024, 32, 0, 128, 8, 0}},
   };
   int failures = 0;
   std::vector<float> D(M * N);
   for (auto &c : cands) {
     cudaMemset(dD, 0xFF, M * N * 4);
-    probe_kernel<<<1, 128, smem_bytes>>>(mapA, mapB, dA, dD, c.a);
+    probe_kernel<<<1, 128, smem_bytes>>>(mapA, c.a.b_format == 0 ? mapBh : mapB, dA, dD, c.a);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("PROBE %-70s CUDA ERROR %s\n", c.name, cudaGetErrorString(e)); return 3; }
     cudaMemcpy(D.data(), dD, M * N * 4, cudaMemcpyDeviceToHost);
@@ -175,9 +186,9 @@ int main() {
         if (isnan(got)) nan++; else maxerr = fmax(maxerr, fabs(got - want));
       }
     bool ok = nan == 0 && maxerr < 1e-2;
-    const bool expected = strstr(c.name, "alt") == nullptr;
+    const bool expected = strstr(c.name, "MIXED") == nullptr;
     if (expected && !ok) failures++;
-    printf("PROBE %-70s max_err=%.4g nan=%d %s\n", c.name, maxerr, nan, ok ? "OK" : (expected ? "FAIL" : "(alt mismatch, fine)"));
+    printf("PROBE %-70s max_err=%.4g nan=%d %s\n", c.name, maxerr, nan, ok ? "OK" : (expected ? "FAIL" : "(informational)"));
   }
   printf("PROBE SUMMARY failures=%d\n", failures);
   return failures ? 1 : 0;
