@@ -113,7 +113,9 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     import oracle
-    threads = oracle.max_threads()
+    # every host core this process may use (torchrun exports OMP_NUM_THREADS=1; the oracle's num_threads clause
+    # takes the explicit count, so the CPU arm is not throttled by the launcher)
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     net = oracle.Network(N_SEQ, N_SEQ, D_HEAD, seed=0, threads=threads)
     for _ in range(args.warmup):
         net.inferenceAttention()
