@@ -55,17 +55,19 @@ struct Config {
   static constexpr uint32_t kSmemQ = 0;
   static constexpr uint32_t kSmemK = kSmemQ + kTilesPerCta * kTileBytes;
   static constexpr uint32_t kSmemV = kSmemK + kStages * kTileBytes;
-  static constexpr uint32_t kSmemBar = kSmemV + kStages * kTileBytes;
-  static constexpr uint32_t kNumBars = 1 + 4 * kStages + 4 * kTilesPerCta;
+  static constexpr uint32_t kSmemScratch = kSmemV + kStages * kTileBytes;  // epilogue transpose: 8 warps x 32 x 32 floats
+  static constexpr uint32_t kSmemBar = kSmemScratch + 8 * 32 * 32 * 4;
+  static constexpr uint32_t kNumBars = 2 + 4 * kStages + 5 * kTilesPerCta;
   static constexpr uint32_t kSmemTmemPtr = kSmemBar + kNumBars * 8;
   static constexpr uint32_t kSmemBytes = kSmemTmemPtr + 16 + 1024;  // + slack for manual 1024 B alignment
+  static_assert(kSmemBytes <= 232448, "shared memory over budget");
   static constexpr uint32_t kTmemS = 0;
   static constexpr uint32_t kTmemO = 256;
   static constexpr uint32_t kTmemCols = 512;
 };
 
 struct Barriers {
-  uint64_t *q_full, *k_full, *k_empty, *v_full, *v_empty, *s_full, *p_full, *o_full;
+  uint64_t *q_full, *q_empty, *k_full, *k_empty, *v_full, *v_empty, *s_full, *p_full, *o_full, *o_free;
 };
 
 // kTrace: debug instantiation that records clock64() at the pipeline hand-off points of CTA (0,0)
@@ -73,40 +75,48 @@ struct Barriers {
 constexpr uint32_t kTraceSlots = 8;  // per (role, iteration)
 #define MFA_TRACE(role, iter, slot)                                                                   \
   do {                                                                                                \
-    if (kTrace && trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0)                \
+    if (kTrace && trace != nullptr && blockIdx.x == 0 && lane == 0)                \
       trace[((role) * 64 + ((iter) & 63)) * kTraceSlots + (slot)] = clock64();                        \
   } while (0)
+
+// item-level probes: roles 4 (tile 0 softmax), 5 (tile 1 softmax), 6 (MMA), indexed by the CTA's item counter
+#define MFA_TRACE_ITEM(role, it, slot) MFA_TRACE(role, it, slot)
 
 template <uint32_t DPAD, bool kBF16, bool kTrace = false>
 __global__ void __launch_bounds__(kThreads, 1)
     attention_forward_tcgen05(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                               const __grid_constant__ CUtensorMap mapV, float *__restrict__ O, void *__restrict__ L,
                               uint32_t R, uint32_t C, uint32_t D, float scale_log2, int l_is_fp16,
-                              long long *__restrict__ trace) {
+                              uint32_t num_items, uint32_t pairs_per_head, long long *__restrict__ trace) {
+  // Persistent CTAs: one per SM, each walking the work items (head, 256-row tile pair) blockIdx.x,
+  // blockIdx.x + gridDim.x, ...  Barrier phases are carried across items, so the producers (TMA, MMA) run ahead
+  // into the next item while the softmax warps drain the current one; TMEM alloc, barrier init and descriptor
+  // prefetch are paid once per SM instead of once per tile.
   using Cfg = Config<DPAD>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t head = blockIdx.y;
-  const uint32_t q_row0 = blockIdx.x * (kTileM * kTilesPerCta);
   const uint32_t num_blocks = (C + kBlockN - 1) / kBlockN;
 
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kSmemBar);
   Barriers b;
   b.q_full = bars;
-  b.k_full = bars + 1;
+  b.q_empty = bars + 1;                    // every S MMA of the current item has read Q
+  b.k_full = bars + 2;
   b.k_empty = b.k_full + Cfg::kStages;
   b.v_full = b.k_empty + Cfg::kStages;
   b.v_empty = b.v_full + Cfg::kStages;
   b.s_full = b.v_empty + Cfg::kStages;
   b.p_full = b.s_full + kTilesPerCta;      // [tile][column half]: P columns 0-63 / 64-127 written
   b.o_full = b.p_full + 2 * kTilesPerCta;
+  b.o_free = b.o_full + kTilesPerCta;      // [tile] the epilogue has read O out of TMEM (128 arrivals)
   uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem + Cfg::kSmemTmemPtr);
 
   // ---------------- one-time setup ----------------
   if (threadIdx.x == 0) {
     mbar_init(b.q_full, 1);
+    mbar_init(b.q_empty, 1);
     for (uint32_t s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&b.k_full[s], 1);
       mbar_init(&b.k_empty[s], 1);
@@ -118,6 +128,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&b.p_full[2 * t], kTileM);
       mbar_init(&b.p_full[2 * t + 1], kTileM);
       mbar_init(&b.o_full[t], 1);
+      mbar_init(&b.o_free[t], kTileM);
     }
     fence_barrier_init();
   }
@@ -146,12 +157,18 @@ __global__ void __launch_bounds__(kThreads, 1)
     const uint32_t tS = tmem_base + lane_addr + Cfg::kTmemS + t * kBlockN;
     const uint32_t tO = tmem_base + lane_addr + Cfg::kTmemO + t * DPAD;
 
-    float m = -FLT_MAX;  // running max, log2 domain   (AttentionKernel+Caching.swift:310)
-    float l = 0.f;       // running sum
     const uint32_t tail_cols = C - (num_blocks - 1) * kBlockN;  // valid columns in the last block
 
+    for (uint32_t item = blockIdx.x, it = 0; item < num_items; item += gridDim.x, ++it) {
+    const uint32_t head = item / pairs_per_head;
+    const uint32_t q_row0 = (item % pairs_per_head) * (kTileM * kTilesPerCta);
+    const uint32_t g0 = it * num_blocks;  // key blocks this CTA has processed before this item (barrier phases)
+    float m = -FLT_MAX;  // running max, log2 domain   (AttentionKernel+Caching.swift:310)
+    float l = 0.f;       // running sum
+    MFA_TRACE_ITEM(warp == 0 ? 4 : (warp == 4 ? 5 : 7), it, 0);
+
     for (uint32_t j = 0; j < num_blocks; ++j) {
-      mbar_wait(&b.s_full[t], j & 1);
+      mbar_wait(&b.s_full[t], (g0 + j) & 1);
       tc_fence_after();
       MFA_TRACE(warp == 0 ? 0 : (warp == 4 ? 1 : 5), j, 0);
 
@@ -183,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (__any_sync(0xffffffffu, m_cand - m > kRescaleThreshold)) {
         if (j > 0) {
           const float correction = ex2_approx(m - m_cand);
-          mbar_wait(&b.o_full[t], (j - 1) & 1);  // O += P V of the previous block has landed
+          mbar_wait(&b.o_full[t], (g0 + j - 1) & 1);  // O += P V of the previous block has landed
           tc_fence_after();
 #pragma unroll
           for (uint32_t c = 0; c < DPAD; c += 32) {
@@ -232,26 +249,47 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
 
     // ---------------- epilogue: O / l -> global (FP32), L = m + log2(l) ----------------
-    mbar_wait(&b.o_full[t], (num_blocks - 1) & 1);
+    MFA_TRACE_ITEM(warp == 0 ? 4 : (warp == 4 ? 5 : 7), it, 1);
+    mbar_wait(&b.o_full[t], (g0 + num_blocks - 1) & 1);
     tc_fence_after();
+    MFA_TRACE_ITEM(warp == 0 ? 4 : (warp == 4 ? 5 : 7), it, 2);
     const uint32_t row = q_row0 + t * kTileM + row_in_tile;
     const float inv_l = 1.0f / l;
-    float *o_row = O + (static_cast<size_t>(head) * R + row) * D;
+    // TMEM hands every thread one row; storing rows straight from registers would touch 32 different cache
+    // lines per warp store.  Each warp therefore transposes 32 x 32 chunks through a private XOR-swizzled scratch
+    // tile in shared memory (128-bit accesses, conflict-free both ways) and writes four full 128 B lines per store.
+    float4 *scratch = reinterpret_cast<float4 *>(smem + Cfg::kSmemScratch) + warp * (32 * 8);
+    const uint32_t warp_row0 = q_row0 + t * kTileM + (warp & 3) * 32;
+    float *o_base = O + (static_cast<size_t>(head) * R + warp_row0) * D;
+    const uint32_t sub_row = lane >> 3, quad = lane & 7;  // transposed view: 4 rows x 8 float4 per warp access
 #pragma unroll
     for (uint32_t c = 0; c < DPAD; c += 32) {
       uint32_t o[32];
       tmem_ld32(tO + c, o);
       tc_wait_ld();
-      if (row < R) {
 #pragma unroll
-        for (uint32_t i = 0; i < 32; i += 4) {
-          if (c + i < D) {  // D % 8 == 0, so a float4 is either fully inside or fully outside
-            float4 v = make_float4(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l,
-                                   __uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
-            *reinterpret_cast<float4 *>(o_row + c + i) = v;
-          }
+      for (uint32_t j = 0; j < 8; ++j)
+        scratch[lane * 8 + (j ^ (lane & 7))] =
+            make_float4(__uint_as_float(o[4 * j]) * inv_l, __uint_as_float(o[4 * j + 1]) * inv_l,
+                        __uint_as_float(o[4 * j + 2]) * inv_l, __uint_as_float(o[4 * j + 3]) * inv_l);
+      __syncwarp();
+      // read the whole transposed chunk into distinct registers BEFORE the first store: a store keeps its source
+      // registers busy until the data has left the SM, so reusing a handful of registers would serialise the
+      // stores on memory latency (measured: 11k cycles per tile epilogue)
+      float4 v[8];
+#pragma unroll
+      for (uint32_t i = 0; i < 8; ++i) {
+        const uint32_t r = 4 * i + sub_row;
+        v[i] = scratch[r * 8 + (quad ^ (r & 7))];
+      }
+      if (c + 4 * quad < D) {  // D % 8 == 0: a float4 is either fully inside or fully outside
+#pragma unroll
+        for (uint32_t i = 0; i < 8; ++i) {
+          const uint32_t r = 4 * i + sub_row;
+          if (warp_row0 + r < R) *reinterpret_cast<float4 *>(o_base + static_cast<size_t>(r) * D + c + 4 * quad) = v[i];
         }
       }
+      __syncwarp();
     }
     if (row < R && L != nullptr) {
       const float lse2 = m + log2f(l);  // AttentionKernel+Caching.swift:373-377
@@ -261,6 +299,11 @@ __global__ void __launch_bounds__(kThreads, 1)
       else
         reinterpret_cast<float *>(L)[idx] = lse2;
     }
+    // O of this tile is out of TMEM: the next item's first O = P V (accumulate off) may overwrite it
+    tc_fence_before();
+    mbar_arrive(&b.o_free[t]);
+    MFA_TRACE_ITEM(warp == 0 ? 4 : (warp == 4 ? 5 : 7), it, 3);
+    }  // work items
   } else {
     setmaxnreg_dec<kOtherRegs>();
     // Both producer warps run their control flow warp-wide and hand exactly one elected lane to the
@@ -269,6 +312,11 @@ __global__ void __launch_bounds__(kThreads, 1)
       // ===================================================================================
       // TMA producer
       // ===================================================================================
+      for (uint32_t item = blockIdx.x, it = 0; item < num_items; item += gridDim.x, ++it) {
+      const uint32_t head = item / pairs_per_head;
+      const uint32_t q_row0 = (item % pairs_per_head) * (kTileM * kTilesPerCta);
+      const uint32_t g0 = it * num_blocks;
+      mbar_wait(b.q_empty, (it & 1) ^ 1);  // the previous item's S MMAs are done with the Q tiles
       if (elect_one()) {
         mbar_arrive_expect_tx(b.q_full, kTilesPerCta * Cfg::kTileBytes);
 #pragma unroll
@@ -279,7 +327,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                         q_row0 + t * kTileM, head);
       }
       for (uint32_t j = 0; j < num_blocks; ++j) {
-        const uint32_t stage = j % Cfg::kStages, phase = (j / Cfg::kStages) & 1;
+        const uint32_t stage = (g0 + j) % Cfg::kStages, phase = ((g0 + j) / Cfg::kStages) & 1;
         mbar_wait(&b.k_empty[stage], phase ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&b.k_full[stage], Cfg::kTileBytes);
@@ -297,6 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                         ds * 64, j * kBlockN, head);
         }
       }
+      }  // work items
     } else if (warp == 8) {
       // ===================================================================================
       // MMA issuer
@@ -336,31 +385,44 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
       };
 
-      mbar_wait(b.q_full, 0);
-      mbar_wait(&b.k_full[0], 0);
-      tc_fence_after();
-      if (elect_one()) {
-        issue_S(0, 0);
-        umma_commit(&b.s_full[0]);
-        issue_S(1, 0);
-        umma_commit(&b.s_full[1]);
-        umma_commit(&b.k_empty[0]);
+      for (uint32_t item = blockIdx.x, it = 0; item < num_items; item += gridDim.x, ++it) {
+      const uint32_t g0 = it * num_blocks;
+      {
+        // first S of the item: overlaps the softmax warps' epilogue of the previous item (S/P regions are free
+        // once the previous item's last O += P V has been issued: the tensor pipe runs in order)
+        const uint32_t stage0 = g0 % Cfg::kStages, phase0 = (g0 / Cfg::kStages) & 1;
+        MFA_TRACE_ITEM(6, it, 0);
+        mbar_wait(b.q_full, it & 1);
+        mbar_wait(&b.k_full[stage0], phase0);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_S(0, stage0);
+          umma_commit(&b.s_full[0]);
+          issue_S(1, stage0);
+          umma_commit(&b.s_full[1]);
+          umma_commit(&b.k_empty[stage0]);
+          if (num_blocks == 1) umma_commit(b.q_empty);
+        }
+        __syncwarp();
+        MFA_TRACE_ITEM(6, it, 1);
       }
-      __syncwarp();
 
       for (uint32_t j = 0; j < num_blocks; ++j) {
-        const uint32_t stage = j % Cfg::kStages, phase = (j / Cfg::kStages) & 1;
-        const uint32_t nstage = (j + 1) % Cfg::kStages, nphase = ((j + 1) / Cfg::kStages) & 1;
+        const uint32_t g = g0 + j;
+        const uint32_t stage = g % Cfg::kStages, phase = (g / Cfg::kStages) & 1;
+        const uint32_t nstage = (g + 1) % Cfg::kStages, nphase = ((g + 1) / Cfg::kStages) & 1;
         const bool has_next = j + 1 < num_blocks;
         mbar_wait(&b.v_full[stage], phase);
         MFA_TRACE(2, j, 0);
 #pragma unroll
         for (uint32_t t = 0; t < kTilesPerCta; ++t) {
-          mbar_wait(&b.p_full[2 * t], j & 1);
+          mbar_wait(&b.p_full[2 * t], g & 1);
+          // the previous item's epilogue must have read O out before accumulate-off overwrites it
+          if (j == 0 && it > 0) mbar_wait(&b.o_free[t], (it - 1) & 1);
           tc_fence_after();
           if (elect_one()) issue_PV(t, 0, stage, j > 0 ? 1u : 0u);
           __syncwarp();
-          mbar_wait(&b.p_full[2 * t + 1], j & 1);
+          mbar_wait(&b.p_full[2 * t + 1], g & 1);
           if (t == 0 && has_next) mbar_wait(&b.k_full[nstage], nphase);
           tc_fence_after();
           MFA_TRACE(2, j, 1 + 3 * t);
@@ -371,13 +433,18 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (has_next) {
               issue_S(t, nstage);
               umma_commit(&b.s_full[t]);
-              if (t == kTilesPerCta - 1) umma_commit(&b.k_empty[nstage]);
+              if (t == kTilesPerCta - 1) {
+                umma_commit(&b.k_empty[nstage]);
+                if (j + 2 == num_blocks) umma_commit(b.q_empty);  // that was the item's last read of Q
+              }
             }
           }
           __syncwarp();
           MFA_TRACE(2, j, 3 + 3 * t);
         }
       }
+      MFA_TRACE_ITEM(6, it, 2);
+      }  // work items
     }
   }
 
@@ -408,9 +475,18 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, long long *tra
   if ((e = make_tensor_map_16bit(&mapK, p.buf[sK], p.C, p.D, p.batch, kBlockN)) != cudaSuccess) return e;
   if ((e = make_tensor_map_16bit(&mapV, p.buf[sV], p.C, p.D, p.batch, kBlockN)) != cudaSuccess) return e;
 
-  dim3 grid((p.R + kTileM * kTilesPerCta - 1) / (kTileM * kTilesPerCta), p.batch);
+  const uint32_t pairs_per_head = (p.R + kTileM * kTilesPerCta - 1) / (kTileM * kTilesPerCta);
+  const uint32_t num_items = pairs_per_head * p.batch;
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int device = 0;
+    if ((e = cudaGetDevice(&device)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return e;
+  }
+  const uint32_t grid = num_items < static_cast<uint32_t>(sm_count) ? num_items : static_cast<uint32_t>(sm_count);
   kernel<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mapQ, mapK, mapV, static_cast<float *>(p.buf[sO]), p.buf[sL],
-                                                      p.R, p.C, p.D, p.scale_log2, p.prec[sL] == FP16 ? 1 : 0, trace);
+                                                      p.R, p.C, p.D, p.scale_log2, p.prec[sL] == FP16 ? 1 : 0,
+                                                      num_items, pairs_per_head, trace);
   return cudaGetLastError();
 }
 

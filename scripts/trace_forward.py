@@ -29,7 +29,7 @@ k = torch.randn(H, C, D, device="cuda").to(torch.bfloat16)
 v = torch.randn(H, C, D, device="cuda").to(torch.bfloat16)
 o = torch.empty(H, R, D, device="cuda")
 lse = torch.empty(H, R, device="cuda")
-trace = torch.zeros(3 * 64 * 8, dtype=torch.int64, device="cuda")
+trace = torch.zeros(8 * 64 * 8, dtype=torch.int64, device="cuda")
 
 lib = mfa._lib
 lib.mfa_debug_forward_trace.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
@@ -42,7 +42,7 @@ for _ in range(3):
                                      ctypes.c_void_p(trace.data_ptr()))
     assert st == 0, lib.mfa_last_error()
     torch.cuda.synchronize()
-t = trace.cpu().numpy().reshape(3, 64, 8)
+t = trace.cpu().numpy().reshape(8, 64, 8)
 nb = C // 128
 t0 = t[2, 0, 0]
 print(f"R={R} H={H}: cycles relative to MMA warp's first V wait; softmax slots: 0 S ready, 1 S in regs, 2 max done, "
@@ -64,3 +64,17 @@ print(f"mma: p0 ready->PV0+S0 issued {np.mean(mm[:,3]-mm[:,1]):.0f}; S0 issued->
 # MMA latency: time from S0 issue (slot 3 of iter j) to softmax0 seeing S ready (slot 0 of iter j+1)
 print(f"S0 issue -> softmax0 sees S(j+1): {np.mean(t[0,3:nb-1,0]-t[2,2:nb-2,3]):.0f} cycles; "
       f"softmax0 arrive(j) -> mma sees p0(j): {np.mean(t[2,2:nb-1,1]-t[0,2:nb-1,4]):.0f}")
+
+# ---- item-level timeline of CTA 0 (persistent kernel): roles 4/5 = softmax tile 0/1, role 6 = MMA warp
+items = int((t[4, :, 0] != 0).sum())
+base = t[6, 0, 0]
+print(f"items processed by CTA 0: {items}; per item (cycles from the MMA warp's first prologue):")
+for it in range(min(items, 8)):
+    a = (t[4, it, :4] - base).tolist(); b2 = (t[5, it, :4] - base).tolist(); mm2 = (t[6, it, :3] - base).tolist()
+    print(f" it={it} tile0 [start, loop end, O ready, epilogue end] {a}  tile1 {b2}  mma [prologue, S(0) issued, loop end] {mm2}")
+if items > 2:
+    per_item = np.diff(t[4, 1:items, 0]).mean()
+    print(f"cycles per item {per_item:.0f}; loop {np.mean(t[4,1:items,1]-t[4,1:items,0]):.0f}; wait O {np.mean(t[4,1:items,2]-t[4,1:items,1]):.0f}; "
+          f"epilogue {np.mean(t[4,1:items,3]-t[4,1:items,2]):.0f}; epilogue end -> next start {np.mean(t[4,2:items,0]-t[4,1:items-1,3]):.0f}")
+    first = t[0, 0:4, 4] - t[0, 0:4, 0]
+    print("first four blocks of the last item, S ready -> P arrived (tile 0):", first.tolist())
