@@ -221,6 +221,43 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// ---- packed FP32x2 arithmetic (Blackwell FFMA2 / FADD2: two FP32 lanes per issue slot) ----
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<const uint64_t *>(&a)), "l"(*reinterpret_cast<const uint64_t *>(&b)),
+        "l"(*reinterpret_cast<const uint64_t *>(&c)));
+  return *reinterpret_cast<float2 *>(&d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<const uint64_t *>(&a)), "l"(*reinterpret_cast<const uint64_t *>(&b)));
+  return *reinterpret_cast<float2 *>(&d);
+}
+// exp2 of two values on the FMA / ALU pipes (no MUFU): Cody-Waite split x = n + f, n = round(x), f in [-0.5, 0.5],
+// 2^f by a degree-3 minimax polynomial (max relative error 7.6e-5, below the 16-bit rounding P gets anyway), then
+// n is added to the exponent field.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  const float kMagic = 12582912.0f;  // 1.5 * 2^23: adding it leaves round(x) in the low mantissa bits
+  // clamp to the finite exponent range: -inf / very negative inputs give ~0, and an input far above the running max
+  // (stale or unset m) gives a huge finite value, which is what the caller's overflow check looks for
+  x.x = fminf(fmaxf(x.x, -126.0f), 127.0f);
+  x.y = fminf(fmaxf(x.y, -126.0f), 127.0f);
+  const float2 t = fadd2(x, make_float2(kMagic, kMagic));
+  const float2 n = fadd2(t, make_float2(-kMagic, -kMagic));
+  const float2 f = fadd2(x, make_float2(-n.x, -n.y));
+  float2 p = ffma2(make_float2(0.055168044f, 0.055168044f), f, make_float2(0.24260214f, 0.24260214f));
+  p = ffma2(p, f, make_float2(0.69326079f, 0.69326079f));
+  p = ffma2(p, f, make_float2(0.99992865f, 0.99992865f));
+  float2 r;
+  r.x = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23));
+  r.y = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23));
+  return r;
+}
+
 // pack two FP32 into one 32-bit register of 16-bit values: low half = lo, high half = hi
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;

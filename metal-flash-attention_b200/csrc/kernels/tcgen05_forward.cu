@@ -45,7 +45,8 @@ constexpr uint32_t kThreads = 384;
 // must not exceed the launch allocation or the second setmaxnreg.inc never returns.
 constexpr uint32_t kLaunchRegs = 168, kSoftmaxRegs = 208, kOtherRegs = 88;
 static_assert(kSoftmaxRegs * 256 + kOtherRegs * 128 <= kLaunchRegs * kThreads, "setmaxnreg over-subscribed");
-constexpr float kRescaleThreshold = 8.0f;  // log2 units
+constexpr uint32_t kPolyPairs = 2;  // of every 4 pairs, how many take exp2 on the FMA pipe (0 = all MUFU)
+constexpr float kLazySumLimit = 256.0f;  // a half-row of P summing to <= 2^8 proves every element is <= 2^8
 
 template <uint32_t DPAD>
 struct Config {
@@ -57,7 +58,7 @@ struct Config {
   static constexpr uint32_t kSmemV = kSmemK + kStages * kTileBytes;
   static constexpr uint32_t kSmemScratch = kSmemV + kStages * kTileBytes;  // epilogue transpose: 8 warps x 32 x 32 floats
   static constexpr uint32_t kSmemBar = kSmemScratch + 8 * 32 * 32 * 4;
-  static constexpr uint32_t kNumBars = 2 + 4 * kStages + 5 * kTilesPerCta;
+  static constexpr uint32_t kNumBars = 2 + 4 * kStages + 6 * kTilesPerCta;
   static constexpr uint32_t kSmemTmemPtr = kSmemBar + kNumBars * 8;
   static constexpr uint32_t kSmemBytes = kSmemTmemPtr + 16 + 1024;  // + slack for manual 1024 B alignment
   static_assert(kSmemBytes <= 232448, "shared memory over budget");
@@ -67,7 +68,7 @@ struct Config {
 };
 
 struct Barriers {
-  uint64_t *q_full, *q_empty, *k_full, *k_empty, *v_full, *v_empty, *s_full, *p_full, *o_full, *o_free;
+  uint64_t *q_full, *q_empty, *k_full, *k_empty, *v_full, *v_empty, *s_full, *p_full, *o_full, *o_free, *pv_half;
 };
 
 // kTrace: debug instantiation that records clock64() at the pipeline hand-off points of CTA (0,0)
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   b.p_full = b.s_full + kTilesPerCta;      // [tile][column half]: P columns 0-63 / 64-127 written
   b.o_full = b.p_full + 2 * kTilesPerCta;
   b.o_free = b.o_full + kTilesPerCta;      // [tile] the epilogue has read O out of TMEM (128 arrivals)
+  b.pv_half = b.o_free + kTilesPerCta;     // [tile] O += P V over the first 64 keys of the block is done
   uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem + Cfg::kSmemTmemPtr);
 
   // ---------------- one-time setup ----------------
@@ -129,6 +131,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&b.p_full[2 * t + 1], kTileM);
       mbar_init(&b.o_full[t], 1);
       mbar_init(&b.o_free[t], kTileM);
+      mbar_init(&b.pv_half[t], 1);
     }
     fence_barrier_init();
   }
@@ -185,66 +188,89 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (c >= tail_cols) s[c] = -INFINITY;
       }
 
-      // online max (onlineReduceMaximum, :267-287): the whole row is in this thread's registers
-      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+      // The reference tracks the exact running row max every block (onlineReduceMaximum / onlineCorrectO,
+      // +Softmax.swift:267-301).  Here the max is refreshed lazily: P is computed against the current (possibly
+      // stale) m straight away, and only if a half-row of P sums to more than 2^8 -- i.e. some element could
+      // exceed 2^8, or m was never set -- does the thread group fall back to the exact path: reduce the row max of
+      // that half, wait for every O += P V issued so far, rescale O and l, and recompute the half.  With m lagging
+      // the true max by at most 8 (log2), P <= 2^8 keeps full FP32 / 16-bit accuracy, and the 128-element max
+      // reduction disappears from the common path; the result is mathematically identical.
 #pragma unroll
-      for (uint32_t c = 4; c < kBlockN; c += 4) {
-        mx0 = fmaxf(mx0, s[c]);
-        mx1 = fmaxf(mx1, s[c + 1]);
-        mx2 = fmaxf(mx2, s[c + 2]);
-        mx3 = fmaxf(mx3, s[c + 3]);
-      }
-      const float m_cand = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2);
-
-      // lazy correction (onlineCorrectO, :290-301): refresh m only when it grew by > 2^8
-      if (__any_sync(0xffffffffu, m_cand - m > kRescaleThreshold)) {
-        if (j > 0) {
-          const float correction = ex2_approx(m - m_cand);
-          mbar_wait(&b.o_full[t], (g0 + j - 1) & 1);  // O += P V of the previous block has landed
-          tc_fence_after();
+      for (uint32_t half = 0; half < 2; ++half) {
+        const uint32_t c0 = half * (kBlockN / 2);
+        uint32_t packed[32];
+        // The MUFU pipe (16 ex2 / clk / SM) needs as long for a 128 x 128 block as the tensor pipe needs for its two
+        // GEMMs, so kPolyPairs of every 4 element pairs take exp2 on the FMA pipe instead (exp2_poly2).
+        float2 sum2 = make_float2(0.f, 0.f);
+        const float2 scale2 = make_float2(scale_log2, scale_log2), negm2 = make_float2(-m, -m);
 #pragma unroll
-          for (uint32_t c = 0; c < DPAD; c += 32) {
-            uint32_t o[32];
-            tmem_ld32(tO + c, o);
-            tc_wait_ld();
-#pragma unroll
-            for (uint32_t i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * correction);
-            tmem_st32(tO + c, o);
+        for (uint32_t i = 0; i < 32; ++i) {
+          const float2 x = ffma2(make_float2(s[c0 + 2 * i], s[c0 + 2 * i + 1]), scale2, negm2);
+          float2 pr;
+          if ((i & 3) < kPolyPairs) {
+            pr = exp2_poly2(x);
+          } else {
+            pr.x = ex2_approx(x.x);
+            pr.y = ex2_approx(x.y);
           }
-          l *= correction;
+          sum2 = fadd2(sum2, pr);
+          packed[i] = kBF16 ? pack_bf16x2(pr.x, pr.y) : pack_f16x2(pr.x, pr.y);
         }
-        m = m_cand;
-      }
-
-      MFA_TRACE(warp == 0 ? 0 : (warp == 4 ? 1 : 5), j, 2);
-      // P = exp2(S * log2e/sqrt(D) - m), rounded to the MMA input type, written over S
-      // (softmax, :409-416; onlineReduceSum, :304-324)
-      float sum0 = 0.f, sum1 = 0.f;
+        float sum0 = sum2.x, sum1 = sum2.y;
+        float half_sum = sum0 + sum1;
+        if (__any_sync(0xffffffffu, !(half_sum <= kLazySumLimit))) {  // also catches inf / NaN
+          // ---- exact path (rare) ----
+          float mx0 = s[c0], mx1 = s[c0 + 1], mx2 = s[c0 + 2], mx3 = s[c0 + 3];
 #pragma unroll
-      for (uint32_t c = 0; c < kBlockN; c += 32) {
-        uint32_t packed[16];
+          for (uint32_t c = 4; c < kBlockN / 2; c += 4) {
+            mx0 = fmaxf(mx0, s[c0 + c]);
+            mx1 = fmaxf(mx1, s[c0 + c + 1]);
+            mx2 = fmaxf(mx2, s[c0 + c + 2]);
+            mx3 = fmaxf(mx3, s[c0 + c + 3]);
+          }
+          const float m_new = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2);
+          if (j > 0 || half > 0) {
+            // everything already handed to the MMA warp must have been accumulated before O is rescaled:
+            // the first half of this block (pv_half) or the whole previous block (o_full)
+            if (half > 0)
+              mbar_wait(&b.pv_half[t], (g0 + j) & 1);
+            else
+              mbar_wait(&b.o_full[t], (g0 + j - 1) & 1);
+            tc_fence_after();
+            const float correction = ex2_approx(m - m_new);
 #pragma unroll
-        for (uint32_t i = 0; i < 16; ++i) {
-          const float p0 = ex2_approx(fmaf(s[c + 2 * i], scale_log2, -m));
-          const float p1 = ex2_approx(fmaf(s[c + 2 * i + 1], scale_log2, -m));
-          sum0 += p0;
-          sum1 += p1;
-          packed[i] = kBF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
+            for (uint32_t c = 0; c < DPAD; c += 32) {
+              uint32_t o[32];
+              tmem_ld32(tO + c, o);
+              tc_wait_ld();
+#pragma unroll
+              for (uint32_t i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * correction);
+              tmem_st32(tO + c, o);
+            }
+            l *= correction;
+          }
+          m = m_new;
+          sum0 = sum1 = 0.f;
+#pragma unroll
+          for (uint32_t i = 0; i < 32; ++i) {
+            const float p0 = ex2_approx(fmaf(s[c0 + 2 * i], scale_log2, -m));
+            const float p1 = ex2_approx(fmaf(s[c0 + 2 * i + 1], scale_log2, -m));
+            sum0 += p0;
+            sum1 += p1;
+            packed[i] = kBF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
+          }
+          half_sum = sum0 + sum1;
         }
-        tmem_st16(tS + (c >> 1), packed);
-        if (c == kBlockN / 2 - 32) {
-          // first 64 columns of P are in TMEM: let the MMA warp start O += P V on them while the MUFU pipe
-          // works through the other half
-          tc_wait_st();
-          tc_fence_before();
-          mbar_arrive(&b.p_full[2 * t]);
-        }
+        l += half_sum;
+        // P (16-bit) over S: keys [64 half, 64 half + 64) -> columns [32 half, 32 half + 32)
+        tmem_st32(tS + half * 32, packed);
+        tc_wait_st();
+        tc_fence_before();
+        // the first 64 columns of P are released on their own so that the MMA warp starts O += P V on them while
+        // the MUFU pipe works through the other half
+        mbar_arrive(&b.p_full[2 * t + half]);
+        MFA_TRACE(warp == 0 ? 0 : (warp == 4 ? 1 : 5), j, 2 + half);
       }
-      l += sum0 + sum1;
-      MFA_TRACE(warp == 0 ? 0 : (warp == 4 ? 1 : 5), j, 3);
-      tc_wait_st();
-      tc_fence_before();
-      mbar_arrive(&b.p_full[2 * t + 1]);
       MFA_TRACE(warp == 0 ? 0 : (warp == 4 ? 1 : 5), j, 4);
     }
 
@@ -420,7 +446,10 @@ __global__ void __launch_bounds__(kThreads, 1)
           // the previous item's epilogue must have read O out before accumulate-off overwrites it
           if (j == 0 && it > 0) mbar_wait(&b.o_free[t], (it - 1) & 1);
           tc_fence_after();
-          if (elect_one()) issue_PV(t, 0, stage, j > 0 ? 1u : 0u);
+          if (elect_one()) {
+            issue_PV(t, 0, stage, j > 0 ? 1u : 0u);
+            umma_commit(&b.pv_half[t]);
+          }
           __syncwarp();
           mbar_wait(&b.p_full[2 * t + 1], g & 1);
           if (t == 0 && has_next) mbar_wait(&b.k_full[nstage], nphase);
