@@ -38,6 +38,8 @@ bool tcgen05_forward_supported(const AttentionParams &p);
 cudaError_t launch_tcgen05_forward(const AttentionParams &p, cudaStream_t stream);
 void tcgen05_forward_geometry(uint32_t D, uint32_t *threads, uint32_t *smem_bytes, uint32_t *par, uint32_t *trav,
                               uint32_t *head);
+cudaError_t launch_tcgen05_forward_d256(const AttentionParams &p, cudaStream_t stream);  // 128 < D <= 256
+void tcgen05_forward_d256_geometry(uint32_t *threads, uint32_t *smem_bytes, uint32_t *par, uint32_t *trav);
 bool tcgen05_backward_supported(const AttentionParams &p);
 cudaError_t launch_tcgen05_backward_query(const AttentionParams &p, cudaStream_t stream);
 cudaError_t launch_tcgen05_backward_key_value(const AttentionParams &p, cudaStream_t stream);

@@ -521,7 +521,7 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, long long *tra
 
 }  // namespace fwd
 
-uint32_t tcgen05_forward_max_head() { return 128; }
+uint32_t tcgen05_forward_max_head() { return 256; }
 
 bool tcgen05_forward_supported(const AttentionParams &p) {
   return (p.prec[sQ] == FP16 || p.prec[sQ] == BF16) && p.prec[sK] == p.prec[sQ] && p.prec[sV] == p.prec[sQ] &&
@@ -535,6 +535,7 @@ cudaError_t launch_tcgen05_forward(const AttentionParams &p, cudaStream_t stream
     return cudaErrorInvalidValue;
   }
   const bool bf16 = p.prec[sQ] == BF16;
+  if (p.D > 128) return launch_tcgen05_forward_d256(p, stream);  // tcgen05_forward_d256.cu
   if (p.D <= 64) return bf16 ? fwd::launch<64, true>(p, stream) : fwd::launch<64, false>(p, stream);
   return bf16 ? fwd::launch<128, true>(p, stream) : fwd::launch<128, false>(p, stream);
 }
@@ -547,6 +548,11 @@ cudaError_t launch_tcgen05_forward_trace(const AttentionParams &p, cudaStream_t 
 
 void tcgen05_forward_geometry(uint32_t D, uint32_t *threads, uint32_t *smem_bytes, uint32_t *par, uint32_t *trav,
                               uint32_t *head) {
+  if (D > 128) {
+    tcgen05_forward_d256_geometry(threads, smem_bytes, par, trav);
+    *head = 256 < (D + 7) / 8 * 8 ? 256 : (D + 7) / 8 * 8;
+    return;
+  }
   *threads = fwd::kThreads;
   *smem_bytes = D <= 64 ? fwd::Config<64>::kSmemBytes : fwd::Config<128>::kSmemBytes;
   *par = fwd::kTileM * fwd::kTilesPerCta;

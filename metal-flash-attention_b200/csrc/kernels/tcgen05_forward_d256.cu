@@ -1,0 +1,429 @@
+// FlashAttention forward for sm_100a, large head dimensions (128 < D <= 256): the reference's "nothing cached /
+// intentional spill" regime (AttentionDescriptor+Parameters.swift:113,120: the 384 rows) re-expressed for B200.
+//
+// At D = 256 one query tile's O accumulator alone takes 256 of the 512 TMEM columns and a 128-key K or V tile takes
+// 64 KB of shared memory, so the residency choices change relative to tcgen05_forward.cu:
+//   * one 128-row tcgen05 M-tile per CTA (not two), O resident in TMEM columns [128, 384);
+//   * keys are walked in blocks of 64 so that K and V can still be double-buffered next to the resident Q tile
+//     (Q 64 KB + 2 x 32 KB K + 2 x 32 KB V);
+//   * S is double-buffered in TMEM (2 x 64 columns), so S(i+1) = Q K^T runs while the softmax warps work on S(i);
+//     P (16-bit) overwrites S in place and feeds O += P V straight from TMEM.
+// Warp roles (384 threads): warps 0-3 softmax (thread = query row = TMEM lane), warp 8 MMA issuer, warp 9 TMA
+// producer, the rest idle.  The tensor pipe dominates at this head dimension (16 + 4 MMAs of N = 64 / 256 per 64 keys
+// against 64 exp2 per thread), so one softmax warpgroup is enough.  Softmax conventions are those of
+// tcgen05_forward.cu (log2 domain, lazy rescale, L = m + log2 l).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include <mutex>
+
+#include "attention_params.h"
+#include "sm100_ptx.cuh"
+#include "tma_host.h"
+
+namespace mfa {
+namespace fwd256 {
+
+using namespace ptx;
+
+constexpr uint32_t kTileM = 128;       // rows per tcgen05 M-tile
+constexpr uint32_t kTilesPerCta = 1;   // one M-tile per CTA
+constexpr uint32_t kBlockN = 64;       // keys per traversal block
+constexpr uint32_t kSBuffers = 2;      // S/P buffers per tile
+constexpr uint32_t kQSubTileBytes = kTileM * 128;    // [128 rows][64 x 16-bit]: one 128B-swizzled TMA box
+constexpr uint32_t kKVSubTileBytes = kBlockN * 128;  // [64 keys][64 x 16-bit]
+constexpr uint32_t kThreads = 384;
+// setmaxnreg budget: the CTA is launched with floor(65536 / 384 / 8) * 8 = 168 registers per thread; the two
+// softmax warpgroups grow to kSoftmaxRegs after the producer warpgroup has shrunk to kOtherRegs.  The sum
+// must not exceed the launch allocation or the second setmaxnreg.inc never returns.
+constexpr uint32_t kLaunchRegs = 168, kSoftmaxRegs = 208, kOtherRegs = 88;
+static_assert(kSoftmaxRegs * 256 + kOtherRegs * 128 <= kLaunchRegs * kThreads, "setmaxnreg over-subscribed");
+constexpr float kRescaleThreshold = 8.0f;  // log2 units
+
+template <uint32_t DPAD>
+struct Config {
+  static constexpr uint32_t kSubTiles = DPAD / 64;                      // 64-element sub-tiles along D
+  static constexpr uint32_t kQTileBytes = kSubTiles * kQSubTileBytes;   // 128 x DPAD
+  static constexpr uint32_t kKVTileBytes = kSubTiles * kKVSubTileBytes; // 64 x DPAD
+  static constexpr uint32_t kStages = 2;
+  static constexpr uint32_t kSmemQ = 0;
+  static constexpr uint32_t kSmemK = kSmemQ + kTilesPerCta * kQTileBytes;
+  static constexpr uint32_t kSmemV = kSmemK + kStages * kKVTileBytes;
+  static constexpr uint32_t kSmemBar = kSmemV + kStages * kKVTileBytes;
+  static constexpr uint32_t kNumBars = 1 + 4 * kStages + kTilesPerCta * (2 * kSBuffers + 2);
+  static constexpr uint32_t kSmemTmemPtr = kSmemBar + kNumBars * 8;
+  static constexpr uint32_t kSmemBytes = kSmemTmemPtr + 16 + 1024;  // + slack for manual 1024 B alignment
+  static constexpr uint32_t kTmemTileStride = 512;
+  static constexpr uint32_t kTmemO = kSBuffers * kBlockN;  // O follows the two S buffers
+  static constexpr uint32_t kTmemCols = 512;
+  static_assert(kTmemO + DPAD <= kTmemTileStride, "tile does not fit its TMEM slice");
+};
+
+// kTrace: debug instantiation that records clock64() at the pipeline hand-off points of CTA (0,0)
+// (scripts/trace_forward.py); the production instantiation compiles all of it away.
+constexpr uint32_t kTraceSlots = 8;    // per (role, iteration)
+constexpr uint32_t kTraceIters = 128;  // iterations recorded per role
+#define MFA_TRACE(role, iter, slot)                                                                   \
+  do {                                                                                                \
+    if (kTrace && trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 &&             \
+        (iter) < kTraceIters)                                                                         \
+      trace[((role) * kTraceIters + (iter)) * kTraceSlots + (slot)] = clock64();                      \
+  } while (0)
+
+template <uint32_t DPAD, bool kBF16, bool kTrace = false>
+__global__ void __launch_bounds__(kThreads, 1)
+    attention_forward_d256_tcgen05(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                              const __grid_constant__ CUtensorMap mapV, float *__restrict__ O, void *__restrict__ L,
+                              uint32_t R, uint32_t C, uint32_t D, float scale_log2, int l_is_fp16,
+                              long long *__restrict__ trace) {
+  using Cfg = Config<DPAD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t head = blockIdx.y;
+  const uint32_t q_row0 = blockIdx.x * (kTileM * kTilesPerCta);
+  const uint32_t num_blocks = (C + kBlockN - 1) / kBlockN;
+
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kSmemBar);
+  uint64_t *q_full = bars;
+  uint64_t *k_full = q_full + 1;
+  uint64_t *k_empty = k_full + Cfg::kStages;
+  uint64_t *v_full = k_empty + Cfg::kStages;
+  uint64_t *v_empty = v_full + Cfg::kStages;
+  uint64_t *s_full = v_empty + Cfg::kStages;            // [tile][buffer]
+  uint64_t *p_full = s_full + kTilesPerCta * kSBuffers;  // [tile][buffer]
+  uint64_t *o_full = p_full + kTilesPerCta * kSBuffers;  // [tile]  one phase per key block
+  uint64_t *o_final = o_full + kTilesPerCta;             // [tile]  completes once, after the last O += P V
+  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem + Cfg::kSmemTmemPtr);
+
+  // ---------------- one-time setup ----------------
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (uint32_t s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    for (uint32_t t = 0; t < kTilesPerCta; ++t) {
+      for (uint32_t bf = 0; bf < kSBuffers; ++bf) {
+        mbar_init(&s_full[t * kSBuffers + bf], 1);
+        mbar_init(&p_full[t * kSBuffers + bf], kTileM);
+      }
+      mbar_init(&o_full[t], 1);
+      mbar_init(&o_final[t], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 8) {
+    tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  if (warp == 9 && lane == 0) {
+    prefetch_tensormap(&mapQ);
+    prefetch_tensormap(&mapK);
+    prefetch_tensormap(&mapV);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp < 4) {
+    // =====================================================================================
+    // softmax warps: thread <-> query row <-> TMEM lane
+    // =====================================================================================
+    setmaxnreg_inc<kSoftmaxRegs>();
+    const uint32_t t = 0;  // single tile
+    const uint32_t row_in_tile = (warp & 3) * 32 + lane;
+    const uint32_t lane_addr = ((warp & 3) * 32) << 16;  // this warp's TMEM lane quarter
+    const uint32_t tTile = tmem_base + lane_addr + t * Cfg::kTmemTileStride;
+    const uint32_t tO = tTile + Cfg::kTmemO;
+    const uint32_t trace_role = warp == 0 ? 0 : (warp == 4 ? 1 : 3);
+
+    float m = -FLT_MAX;  // running max, log2 domain   (AttentionKernel+Caching.swift:310)
+    float l = 0.f;       // running sum
+    const uint32_t tail_cols = C - (num_blocks - 1) * kBlockN;  // valid columns in the last block
+
+    for (uint32_t i = 0; i < num_blocks; ++i) {
+      const uint32_t bf = i & 1, ph = (i >> 1) & 1;
+      const uint32_t tS = tTile + bf * kBlockN;
+      mbar_wait(&s_full[t * kSBuffers + bf], ph);
+      tc_fence_after();
+      MFA_TRACE(trace_role, i, 0);
+
+      float s[kBlockN];
+#pragma unroll
+      for (uint32_t c = 0; c < kBlockN; c += 32) tmem_ld32(tS + c, *reinterpret_cast<uint32_t(*)[32]>(&s[c]));
+      tc_wait_ld();
+      MFA_TRACE(trace_role, i, 1);
+
+      // edge mask (maskAttentionMatrixEdge, AttentionKernel+Softmax.swift:228-260)
+      if (i == num_blocks - 1 && tail_cols < kBlockN) {
+#pragma unroll
+        for (uint32_t c = 0; c < kBlockN; ++c)
+          if (c >= tail_cols) s[c] = -INFINITY;
+      }
+
+      // online max (onlineReduceMaximum, :267-287): the whole row is in this thread's registers
+      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+#pragma unroll
+      for (uint32_t c = 4; c < kBlockN; c += 4) {
+        mx0 = fmaxf(mx0, s[c]);
+        mx1 = fmaxf(mx1, s[c + 1]);
+        mx2 = fmaxf(mx2, s[c + 2]);
+        mx3 = fmaxf(mx3, s[c + 3]);
+      }
+      const float m_cand = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2);
+
+      // lazy correction (onlineCorrectO, :290-301): refresh m only when it grew by > 2^8
+      if (__any_sync(0xffffffffu, m_cand - m > kRescaleThreshold)) {
+        if (i > 0) {
+          const float correction = ex2_approx(m - m_cand);
+          mbar_wait(&o_full[t], (i - 1) & 1);  // O += P V of the previous block has landed
+          tc_fence_after();
+#pragma unroll
+          for (uint32_t c = 0; c < DPAD; c += 32) {
+            uint32_t o[32];
+            tmem_ld32(tO + c, o);
+            tc_wait_ld();
+#pragma unroll
+            for (uint32_t k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * correction);
+            tmem_st32(tO + c, o);
+          }
+          l *= correction;
+        }
+        m = m_cand;
+      }
+      MFA_TRACE(trace_role, i, 2);
+
+      // P = exp2(S * log2e/sqrt(D) - m), rounded to the MMA input type, written over S
+      // (softmax, :409-416; onlineReduceSum, :304-324)
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+      for (uint32_t c = 0; c < kBlockN; c += 32) {
+        uint32_t packed[16];
+#pragma unroll
+        for (uint32_t k = 0; k < 16; ++k) {
+          const float p0 = ex2_approx(fmaf(s[c + 2 * k], scale_log2, -m));
+          const float p1 = ex2_approx(fmaf(s[c + 2 * k + 1], scale_log2, -m));
+          sum0 += p0;
+          sum1 += p1;
+          packed[k] = kBF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
+        }
+        tmem_st16(tS + (c >> 1), packed);
+      }
+      l += sum0 + sum1;
+      MFA_TRACE(trace_role, i, 3);
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&p_full[t * kSBuffers + bf]);
+      MFA_TRACE(trace_role, i, 4);
+    }
+
+    // ---------------- epilogue: O / l -> global (FP32), L = m + log2(l) ----------------
+    // (o_full may be up to two phases behind here, which a parity wait cannot tell apart; o_final is one-shot)
+    mbar_wait(&o_final[t], 0);
+    tc_fence_after();
+    const uint32_t row = q_row0 + t * kTileM + row_in_tile;
+    const float inv_l = 1.0f / l;
+    float *o_row = O + (static_cast<size_t>(head) * R + row) * D;
+#pragma unroll
+    for (uint32_t c = 0; c < DPAD; c += 32) {
+      uint32_t o[32];
+      tmem_ld32(tO + c, o);
+      tc_wait_ld();
+      if (row < R) {
+#pragma unroll
+        for (uint32_t k = 0; k < 32; k += 4) {
+          if (c + k < D) {  // D % 8 == 0, so a float4 is either fully inside or fully outside
+            float4 v = make_float4(__uint_as_float(o[k]) * inv_l, __uint_as_float(o[k + 1]) * inv_l,
+                                   __uint_as_float(o[k + 2]) * inv_l, __uint_as_float(o[k + 3]) * inv_l);
+            *reinterpret_cast<float4 *>(o_row + c + k) = v;
+          }
+        }
+      }
+    }
+    if (row < R && L != nullptr) {
+      const float lse2 = m + log2f(l);  // AttentionKernel+Caching.swift:373-377
+      const size_t idx = static_cast<size_t>(head) * R + row;
+      if (l_is_fp16)
+        reinterpret_cast<__half *>(L)[idx] = __float2half_rn(lse2);
+      else
+        reinterpret_cast<float *>(L)[idx] = lse2;
+    }
+  } else if (warp >= 8) {
+    setmaxnreg_dec<kOtherRegs>();
+    // Both producer warps run their control flow warp-wide and hand exactly one elected lane to the
+    // TMA / tcgen05 instructions: operands stay in uniform registers and the issue loops are branch-free.
+    if (warp == 9) {
+      // ===================================================================================
+      // TMA producer
+      // ===================================================================================
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full, kTilesPerCta * Cfg::kQTileBytes);
+#pragma unroll
+        for (uint32_t t = 0; t < kTilesPerCta; ++t)
+#pragma unroll
+          for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
+            tma_load_3d(smem + Cfg::kSmemQ + t * Cfg::kQTileBytes + ds * kQSubTileBytes, &mapQ, q_full, ds * 64,
+                        q_row0 + t * kTileM, head);
+      }
+      for (uint32_t i = 0; i < num_blocks; ++i) {
+        const uint32_t stage = i % Cfg::kStages, phase = (i / Cfg::kStages) & 1;
+        mbar_wait(&k_empty[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&k_full[stage], Cfg::kKVTileBytes);
+#pragma unroll
+          for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
+            tma_load_3d(smem + Cfg::kSmemK + stage * Cfg::kKVTileBytes + ds * kKVSubTileBytes, &mapK, &k_full[stage],
+                        ds * 64, i * kBlockN, head);
+        }
+        mbar_wait(&v_empty[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&v_full[stage], Cfg::kKVTileBytes);
+#pragma unroll
+          for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
+            tma_load_3d(smem + Cfg::kSmemV + stage * Cfg::kKVTileBytes + ds * kKVSubTileBytes, &mapV, &v_full[stage],
+                        ds * 64, i * kBlockN, head);
+        }
+      }
+    } else if (warp == 8) {
+      // ===================================================================================
+      // MMA issuer
+      // ===================================================================================
+      constexpr uint32_t kFormat = kBF16 ? 1u : 0u;
+      // S[128 x 64] = Q[128 x D] . K[64 x D]^T : A and B both K-major
+      constexpr uint32_t idescS = make_idesc_f16(kTileM, kBlockN, kFormat, 0, 0);
+      // O[128 x DPAD] += P[128 x 64] . V[64 x DPAD] : A from TMEM, B (= V, [key][d]) is MN-major
+      constexpr uint32_t idescO = make_idesc_f16(kTileM, DPAD, kFormat, 0, 1);
+      // Descriptors differ only in the 14-bit start-address field; build each once and add (bytes >> 4).
+      const uint64_t descQ = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemQ), 16, 1024);
+      const uint64_t descK = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemK), 16, 1024);
+      const uint64_t descV = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemV), kKVSubTileBytes, 1024);
+
+      // every tcgen05.mma / commit below is issued by the one elected lane
+      auto issue_S = [&](uint32_t t, uint32_t bf, uint32_t stage) {
+        const uint32_t d_tmem = tmem_base + t * Cfg::kTmemTileStride + bf * kBlockN;
+        const uint64_t a0 = descQ + ((t * Cfg::kQTileBytes) >> 4);
+        const uint64_t b0 = descK + ((stage * Cfg::kKVTileBytes) >> 4);
+#pragma unroll
+        for (uint32_t k = 0; k < DPAD / 16; ++k) {
+          // 16 elements = 32 B inside the 128 B swizzle row; 4 k-steps per 64-element sub-tile
+          const uint32_t a_off = ((k >> 2) * kQSubTileBytes + (k & 3) * 32) >> 4;
+          const uint32_t b_off = ((k >> 2) * kKVSubTileBytes + (k & 3) * 32) >> 4;
+          umma_ss(d_tmem, a0 + a_off, b0 + b_off, idescS, k > 0);
+        }
+      };
+      auto issue_PV = [&](uint32_t t, uint32_t bf, uint32_t stage, uint32_t accumulate) {
+        const uint32_t d_tmem = tmem_base + t * Cfg::kTmemTileStride + Cfg::kTmemO;
+        const uint32_t a_tmem = tmem_base + t * Cfg::kTmemTileStride + bf * kBlockN;
+        const uint64_t b0 = descV + ((stage * Cfg::kKVTileBytes) >> 4);
+#pragma unroll
+        for (uint32_t k = 0; k < kBlockN / 16; ++k)
+          // 16 keys = two 8-row groups of 1024 B; 64-wide column blocks are kKVSubTileBytes apart (LBO)
+          umma_ts(d_tmem, a_tmem + k * 8, b0 + ((k * 2048) >> 4), idescO, k > 0 ? 1u : accumulate);
+      };
+
+      // prologue: S(0) and S(1) for both tiles
+      mbar_wait(q_full, 0);
+      for (uint32_t i = 0; i < kSBuffers && i < num_blocks; ++i) {
+        mbar_wait(&k_full[i], 0);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (uint32_t t = 0; t < kTilesPerCta; ++t) {
+            issue_S(t, i, i);
+            umma_commit(&s_full[t * kSBuffers + i]);
+          }
+          umma_commit(&k_empty[i]);
+        }
+        __syncwarp();
+      }
+
+      for (uint32_t i = 0; i < num_blocks; ++i) {
+        const uint32_t bf = i & 1, ph = (i >> 1) & 1;
+        const uint32_t stage = i % Cfg::kStages, phase = (i / Cfg::kStages) & 1;
+        const uint32_t ni = i + kSBuffers;  // the S block that reuses this buffer
+        const uint32_t nstage = ni % Cfg::kStages, nphase = (ni / Cfg::kStages) & 1;
+        const bool has_next = ni < num_blocks;
+        mbar_wait(&v_full[stage], phase);
+        if (has_next) mbar_wait(&k_full[nstage], nphase);
+        MFA_TRACE(2, i, 0);
+#pragma unroll
+        for (uint32_t t = 0; t < kTilesPerCta; ++t) {
+          mbar_wait(&p_full[t * kSBuffers + bf], ph);
+          tc_fence_after();
+          MFA_TRACE(2, i, 1 + 2 * t);
+          if (elect_one()) {
+            issue_PV(t, bf, stage, i > 0 ? 1u : 0u);
+            umma_commit(&o_full[t]);
+            if (i == num_blocks - 1) umma_commit(&o_final[t]);
+            if (t == kTilesPerCta - 1) umma_commit(&v_empty[stage]);
+            if (has_next) {
+              issue_S(t, bf, nstage);  // overwrites P(i) only after PV(i): the tensor pipe runs in order
+              umma_commit(&s_full[t * kSBuffers + bf]);
+              if (t == kTilesPerCta - 1) umma_commit(&k_empty[nstage]);
+            }
+          }
+          __syncwarp();
+          MFA_TRACE(2, i, 2 + 2 * t);
+        }
+      }
+    }
+  }
+
+  else {
+    setmaxnreg_dec<kOtherRegs>();  // warps 4-7: idle warpgroup, donates its registers
+  }
+
+  // ---------------- teardown ----------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <uint32_t DPAD, bool kBF16, bool kTrace = false>
+cudaError_t launch(const AttentionParams &p, cudaStream_t stream, long long *trace = nullptr) {
+  using Cfg = Config<DPAD>;
+  auto kernel = attention_forward_d256_tcgen05<DPAD, kBF16, kTrace>;
+  static std::once_flag once;
+  static cudaError_t attr_status = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_status = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  });
+  if (attr_status != cudaSuccess) return attr_status;
+
+  CUtensorMap mapQ, mapK, mapV;
+  cudaError_t e;
+  if ((e = make_tensor_map_16bit(&mapQ, p.buf[sQ], p.R, p.D, p.batch, kTileM)) != cudaSuccess) return e;
+  if ((e = make_tensor_map_16bit(&mapK, p.buf[sK], p.C, p.D, p.batch, kBlockN)) != cudaSuccess) return e;
+  if ((e = make_tensor_map_16bit(&mapV, p.buf[sV], p.C, p.D, p.batch, kBlockN)) != cudaSuccess) return e;
+
+  dim3 grid((p.R + kTileM * kTilesPerCta - 1) / (kTileM * kTilesPerCta), p.batch);
+  kernel<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mapQ, mapK, mapV, static_cast<float *>(p.buf[sO]), p.buf[sL],
+                                                      p.R, p.C, p.D, p.scale_log2, p.prec[sL] == FP16 ? 1 : 0, trace);
+  return cudaGetLastError();
+}
+
+}  // namespace fwd256
+
+cudaError_t launch_tcgen05_forward_d256(const AttentionParams &p, cudaStream_t stream) {
+  return p.prec[sQ] == BF16 ? fwd256::launch<256, true>(p, stream) : fwd256::launch<256, false>(p, stream);
+}
+
+void tcgen05_forward_d256_geometry(uint32_t *threads, uint32_t *smem_bytes, uint32_t *par, uint32_t *trav) {
+  *threads = fwd256::kThreads;
+  *smem_bytes = fwd256::Config<256>::kSmemBytes;
+  *par = fwd256::kTileM;
+  *trav = fwd256::kBlockN;
+}
+
+}  // namespace mfa

@@ -59,6 +59,7 @@ def check_O(O, actual, V, bf16, name="O"):
     (256, 256, 128), (128, 128, 64), (512, 384, 128), (256, 640, 64),   # aligned
     (200, 333, 128), (77, 129, 64), (1, 1, 8), (300, 17, 80), (129, 257, 72), (40, 500, 16),  # ragged edges
     (1024, 1024, 128), (640, 1280, 96),
+    (256, 256, 256), (200, 333, 192), (384, 512, 136), (130, 70, 256), (1024, 1024, 256),   # 128 < D <= 256 kernel
 ])
 def test_forward_matches_oracle(R, C, D, bf16):
     _run_and_check(R, C, D, bf16, seed=R * 7 + C * 3 + D)
@@ -76,6 +77,13 @@ def test_config2_full_size_bf16_n4096_d128():
     """BASELINE.json configs[1]: single-head forward bf16 N=4096 D=128, against the (row-parallel) oracle."""
     errO, errL = _run_and_check(4096, 4096, 128, True, seed=0)
     print(f"config2 max|dO|={errO:.3e} max|dL|={errL:.3e}")
+
+
+@pytest.mark.gpu
+def test_config4_large_head_bf16_n8192_d256():
+    """BASELINE.json configs[3]: the large-D path, forward bf16 N=8192 D=256 (one tile per CTA, O in 256 TMEM columns)."""
+    errO, errL = _run_and_check(8192, 8192, 256, True, seed=4, threads=64)
+    print(f"config4 max|dO|={errO:.3e} max|dL|={errL:.3e}")
 
 
 @pytest.mark.gpu
