@@ -153,13 +153,36 @@ __global__ void __launch_bounds__(kThreads, 1)
     // and stored (possibly as BF16) for the dK/dV kernel.  L arrives in log2 units from the forward kernel.
     float Dterm;
     {
+      // one row of dO (16-bit) and O (FP32) per thread, read with 128-bit loads that are all issued before the first
+      // FMA (D % 8 == 0 and 16-byte aligned buffers are preconditions of this kernel family); scalar loads made this
+      // prologue a third of the kernel's run time
       const size_t base = (static_cast<size_t>(head) * a.R + row_c) * a.D;
-      float acc0 = 0.f, acc1 = 0.f;
-      for (uint32_t d = 0; d < a.D; d += 2) {
-        acc0 = fmaf(load_16bit(a.dO, base + d, kBF16), a.O[base + d], acc0);
-        acc1 = fmaf(load_16bit(a.dO, base + d + 1, kBF16), a.O[base + d + 1], acc1);
+      const uint4 *dO8 = reinterpret_cast<const uint4 *>(static_cast<const uint16_t *>(a.dO) + base);
+      const float4 *O4 = reinterpret_cast<const float4 *>(a.O + base);
+      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll 4
+      for (uint32_t d8 = 0; d8 < a.D / 8; ++d8) {
+        const uint4 g = __ldg(dO8 + d8);
+        const float4 o0 = __ldg(O4 + 2 * d8), o1 = __ldg(O4 + 2 * d8 + 1);
+        const uint32_t w[4] = {g.x, g.y, g.z, g.w};
+        float v[8];
+#pragma unroll
+        for (uint32_t k = 0; k < 4; ++k) {
+          if (kBF16) {
+            v[2 * k] = __uint_as_float(w[k] << 16);
+            v[2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
+          } else {
+            const __half2 hh = *reinterpret_cast<const __half2 *>(&w[k]);
+            v[2 * k] = __low2float(hh);
+            v[2 * k + 1] = __high2float(hh);
+          }
+        }
+        acc0 = fmaf(v[0], o0.x, acc0); acc1 = fmaf(v[1], o0.y, acc1);
+        acc2 = fmaf(v[2], o0.z, acc2); acc3 = fmaf(v[3], o0.w, acc3);
+        acc0 = fmaf(v[4], o1.x, acc0); acc1 = fmaf(v[5], o1.y, acc1);
+        acc2 = fmaf(v[6], o1.z, acc2); acc3 = fmaf(v[7], o1.w, acc3);
       }
-      Dterm = (acc0 + acc1) * a.scale;
+      Dterm = ((acc0 + acc1) + (acc2 + acc3)) * a.scale;
     }
     const size_t stat_idx = static_cast<size_t>(head) * a.R + row_c;
     const float Lrow = load_stat(a.L, stat_idx, a.l_prec);
@@ -183,16 +206,19 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_arrive(s_free);  // S(j+1) may overwrite the S buffer now
 
       const uint32_t col0 = j * kTile + h * kHalf;
+      if (j + 1 == num_blocks && col0 + kHalf > a.C) {  // padded key columns (maskAttentionMatrixEdge): P = 0 there
+#pragma unroll
+        for (uint32_t c = 0; c < kHalf; ++c)
+          if (col0 + c >= a.C) s[c] = -INFINITY;
+      }
 #pragma unroll
       for (uint32_t c = 0; c < kHalf; c += 32) {
         uint32_t packed[16];
 #pragma unroll
         for (uint32_t k = 0; k < 16; ++k) {
           // P = exp2(S * log2e/sqrt(D) - L);  dS = P * (dP/sqrt(D) - D)     (+Softmax.swift:419-427)
-          float p0 = ex2_approx(fmaf(s[c + 2 * k], a.scale_log2, -Lrow));
-          float p1 = ex2_approx(fmaf(s[c + 2 * k + 1], a.scale_log2, -Lrow));
-          if (col0 + c + 2 * k >= a.C) p0 = 0.f;      // padded key columns (maskAttentionMatrixEdge)
-          if (col0 + c + 2 * k + 1 >= a.C) p1 = 0.f;
+          const float p0 = ex2_approx(fmaf(s[c + 2 * k], a.scale_log2, -Lrow));
+          const float p1 = ex2_approx(fmaf(s[c + 2 * k + 1], a.scale_log2, -Lrow));
           const float ds0 = p0 * fmaf(dp[c + 2 * k], a.scale, -Dterm);
           const float ds1 = p1 * fmaf(dp[c + 2 * k + 1], a.scale, -Dterm);
           packed[k] = kBF16 ? pack_bf16x2(ds0, ds1) : pack_f16x2(ds0, ds1);
@@ -211,6 +237,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
     for (uint32_t cc = 0; cc < DPAD / 2; cc += 32) {
       const uint32_t c = h * (DPAD / 2) + cc;
+      // (all 32 values sit in distinct registers before the first store: a store keeps its source registers busy
+      // until the data has left the SM, so the stores must not share registers)
       uint32_t v[32];
       tmem_ld32(tLane + kTmemdQ + c, v);
       tc_wait_ld();
@@ -218,9 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
         for (uint32_t k = 0; k < 32; k += 4)
           if (c + k < a.D)
-            *reinterpret_cast<float4 *>(out_row + c + k) =
-                make_float4(__uint_as_float(v[k]), __uint_as_float(v[k + 1]), __uint_as_float(v[k + 2]),
-                            __uint_as_float(v[k + 3]));
+            *reinterpret_cast<uint4 *>(out_row + c + k) = make_uint4(v[k], v[k + 1], v[k + 2], v[k + 3]);
       }
     }
   } else {
@@ -434,16 +460,19 @@ __global__ void __launch_bounds__(kThreads, 1)
       tc_wait_ld();
       const float *Lq = vecL + stage * kTile + h * kHalf, *Dq = vecD + stage * kTile + h * kHalf;
       const uint32_t q0 = r * kTile + h * kHalf;
+      if (r + 1 == num_blocks && q0 + kHalf > a.R) {  // padded query rows: P^T = 0 there
+#pragma unroll
+        for (uint32_t c = 0; c < kHalf; ++c)
+          if (q0 + c >= a.R) s[c] = -INFINITY;
+      }
 #pragma unroll
       for (uint32_t c = 0; c < kHalf; c += 32) {
         uint32_t pp[16], dd[16];
 #pragma unroll
         for (uint32_t k = 0; k < 16; ++k) {
           // P^T = exp2(S^T * log2e/sqrt(D) - L[r]);  dS^T = P^T * (dP^T/sqrt(D) - D[r])   (+Softmax.swift:419-427)
-          float p0 = ex2_approx(fmaf(s[c + 2 * k], a.scale_log2, -Lq[c + 2 * k]));
-          float p1 = ex2_approx(fmaf(s[c + 2 * k + 1], a.scale_log2, -Lq[c + 2 * k + 1]));
-          if (q0 + c + 2 * k >= a.R) p0 = 0.f;      // padded query rows
-          if (q0 + c + 2 * k + 1 >= a.R) p1 = 0.f;
+          const float p0 = ex2_approx(fmaf(s[c + 2 * k], a.scale_log2, -Lq[c + 2 * k]));
+          const float p1 = ex2_approx(fmaf(s[c + 2 * k + 1], a.scale_log2, -Lq[c + 2 * k + 1]));
           const float ds0 = p0 * fmaf(dp[c + 2 * k], a.scale, -Dq[c + 2 * k]);
           const float ds1 = p1 * fmaf(dp[c + 2 * k + 1], a.scale, -Dq[c + 2 * k + 1]);
           pp[k] = kBF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
@@ -477,9 +506,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
           for (uint32_t k = 0; k < 32; k += 4)
             if (c + k < a.D)
-              *reinterpret_cast<float4 *>(out_row + c + k) =
-                  make_float4(__uint_as_float(v[k]), __uint_as_float(v[k + 1]), __uint_as_float(v[k + 2]),
-                              __uint_as_float(v[k + 3]));
+              *reinterpret_cast<uint4 *>(out_row + c + k) = make_uint4(v[k], v[k + 1], v[k + 2], v[k + 3]);
         }
       }
     }
