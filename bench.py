@@ -266,6 +266,34 @@ def main():
         torch.cuda.synchronize()
         assert torch.allclose(host[Op.O][0, :8], sets[0][Op.O][0, :8].cpu(), rtol=0, atol=0), "e2e != device path"
 
+    # ---- literal single-head latency (BASELINE.json configs[1] as written): one (N=4096, D=128) problem per launch;
+    #      too few tiles to fill 148 SMs, so the library splits the key axis across SMs and merges (split-KV) --------
+    single_head = None
+    if rank == 0:
+        d1 = mfa.AttentionDescriptor()
+        d1.lowPrecisionInputs = True
+        d1.inputPrecisionOverride = mfa.GEMMOperandPrecision.BF16
+        d1.matrixDimensions = (N_SEQ, N_SEQ, D_HEAD)
+        d1.transposeState = (False, False, False, False)
+        k1 = mfa.AttentionKernel(d1.kernelDescriptor(mfa.AttentionKernelType.forward))
+        c1 = mfa.FunctionConstantValues()
+        d1.setFunctionConstants(c1)
+        ptrs = {op: t[0].data_ptr() for op, t in sets[0].items()}
+        for _ in range(5):
+            k1.encode(c1, ptrs, stream.cuda_stream)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 50
+        a.record(stream)
+        for _ in range(reps):
+            k1.encode(c1, ptrs, stream.cuda_stream)
+        b.record(stream)
+        torch.cuda.synchronize()
+        ms1 = a.elapsed_time(b) / reps
+        single_head = {"ms_per_launch": ms1, "ginstrs": FMA_PER_HEAD / ms1 / 1e6, "tflops": FLOP_PER_HEAD / ms1 / 1e9,
+                       "launches_per_call": k1.launchCount(c1),
+                       "note": "one head per call, 50 back-to-back calls, inputs L2-resident (5 MB problem)"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -306,7 +334,7 @@ def main():
                    "parallelism": f"heads sharded over {world} GPU(s), no data-path collective",
                    "l2": "inputs per step (192 MiB at H=64) exceed the 126 MB L2; two buffer sets alternate"},
         "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": args.steps * launches_per_step,
-        "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "single_head": single_head,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

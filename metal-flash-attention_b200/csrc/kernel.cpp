@@ -204,6 +204,9 @@ int mfa_attention_kernel_launch_count(const mfa_attention_kernel_t *kernel, cons
                                       uint32_t *out) {
   if (!kernel || !c || !out) return fail(MFA_ERROR_INVALID_ARGUMENT, "NULL argument.");
   *out = 1;
+  if (kernel->backend == MFA_BACKEND_TCGEN05 && kernel->type == MFA_FORWARD)
+    *out = tcgen05_forward_launch_count(c->row, c->column, kernel->descriptor.head_dimension,
+                                        c->batch_count ? c->batch_count : 1);
   return MFA_SUCCESS;
 }
 

@@ -38,6 +38,7 @@ bool tcgen05_forward_supported(const AttentionParams &p);
 cudaError_t launch_tcgen05_forward(const AttentionParams &p, cudaStream_t stream);
 void tcgen05_forward_geometry(uint32_t D, uint32_t *threads, uint32_t *smem_bytes, uint32_t *par, uint32_t *trav,
                               uint32_t *head);
+uint32_t tcgen05_forward_launch_count(uint32_t R, uint32_t C, uint32_t D, uint32_t batch);
 cudaError_t launch_tcgen05_forward_d256(const AttentionParams &p, cudaStream_t stream);  // 128 < D <= 256
 void tcgen05_forward_d256_geometry(uint32_t *threads, uint32_t *smem_bytes, uint32_t *par, uint32_t *trav);
 bool tcgen05_backward_supported(const AttentionParams &p);

@@ -88,7 +88,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     attention_forward_tcgen05(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                               const __grid_constant__ CUtensorMap mapV, float *__restrict__ O, void *__restrict__ L,
                               uint32_t R, uint32_t C, uint32_t D, float scale_log2, int l_is_fp16,
-                              uint32_t num_items, uint32_t pairs_per_head, long long *__restrict__ trace) {
+                              uint32_t num_items, uint32_t pairs_per_head, uint32_t num_splits, uint32_t batch,
+                              long long *__restrict__ trace) {
   // Persistent CTAs: one per SM, each walking the work items (head, 256-row tile pair) blockIdx.x,
   // blockIdx.x + gridDim.x, ...  Barrier phases are carried across items, so the producers (TMA, MMA) run ahead
   // into the next item while the softmax warps drain the current one; TMEM alloc, barrier init and descriptor
@@ -98,7 +99,11 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t num_blocks = (C + kBlockN - 1) / kBlockN;
+  // Split-KV: when there are fewer (head, tile pair) items than SMs, the key axis of every item is cut into
+  // num_splits equal ranges that become separate work items; each writes a normalised partial O and its L as if
+  // it were a whole problem (O and L then point at scratch laid out [split][head][row]) and combine_splits merges them.
+  const uint32_t total_blocks = (C + kBlockN - 1) / kBlockN;
+  const uint32_t num_blocks = total_blocks / num_splits;  // key blocks per work item (host guarantees divisibility)
 
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kSmemBar);
   Barriers b;
@@ -160,11 +165,13 @@ __global__ void __launch_bounds__(kThreads, 1)
     const uint32_t tS = tmem_base + lane_addr + Cfg::kTmemS + t * kBlockN;
     const uint32_t tO = tmem_base + lane_addr + Cfg::kTmemO + t * DPAD;
 
-    const uint32_t tail_cols = C - (num_blocks - 1) * kBlockN;  // valid columns in the last block
+    const uint32_t tail_cols = C - (total_blocks - 1) * kBlockN;  // valid columns in the last key block
 
     for (uint32_t item = blockIdx.x, it = 0; item < num_items; item += gridDim.x, ++it) {
-    const uint32_t head = item / pairs_per_head;
-    const uint32_t q_row0 = (item % pairs_per_head) * (kTileM * kTilesPerCta);
+    const uint32_t split = item % num_splits;
+    const uint32_t head = (item / num_splits) / pairs_per_head + split * batch;  // output slot (partials: [split][head])
+    const uint32_t q_row0 = ((item / num_splits) % pairs_per_head) * (kTileM * kTilesPerCta);
+    const uint32_t key_block0 = split * num_blocks;
     const uint32_t g0 = it * num_blocks;  // key blocks this CTA has processed before this item (barrier phases)
     float m = -FLT_MAX;  // running max, log2 domain   (AttentionKernel+Caching.swift:310)
     float l = 0.f;       // running sum
@@ -182,7 +189,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       MFA_TRACE(warp == 0 ? 0 : (warp == 4 ? 1 : 5), j, 1);
 
       // edge mask (maskAttentionMatrixEdge, AttentionKernel+Softmax.swift:228-260)
-      if (j == num_blocks - 1 && tail_cols < kBlockN) {
+      if (key_block0 + j == total_blocks - 1 && tail_cols < kBlockN) {
 #pragma unroll
         for (uint32_t c = 0; c < kBlockN; ++c)
           if (c >= tail_cols) s[c] = -INFINITY;
@@ -339,8 +346,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       // TMA producer
       // ===================================================================================
       for (uint32_t item = blockIdx.x, it = 0; item < num_items; item += gridDim.x, ++it) {
-      const uint32_t head = item / pairs_per_head;
-      const uint32_t q_row0 = (item % pairs_per_head) * (kTileM * kTilesPerCta);
+      const uint32_t head = (item / num_splits) / pairs_per_head;
+      const uint32_t q_row0 = ((item / num_splits) % pairs_per_head) * (kTileM * kTilesPerCta);
+      const uint32_t key_block0 = (item % num_splits) * num_blocks;
       const uint32_t g0 = it * num_blocks;
       mbar_wait(b.q_empty, (it & 1) ^ 1);  // the previous item's S MMAs are done with the Q tiles
       if (elect_one()) {
@@ -360,7 +368,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
           for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
             tma_load_3d(smem + Cfg::kSmemK + stage * Cfg::kTileBytes + ds * kSubTileBytes, &mapK, &b.k_full[stage],
-                        ds * 64, j * kBlockN, head);
+                        ds * 64, (key_block0 + j) * kBlockN, head);
         }
         mbar_wait(&b.v_empty[stage], phase ^ 1);
         if (elect_one()) {
@@ -368,7 +376,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
           for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
             tma_load_3d(smem + Cfg::kSmemV + stage * Cfg::kTileBytes + ds * kSubTileBytes, &mapV, &b.v_full[stage],
-                        ds * 64, j * kBlockN, head);
+                        ds * 64, (key_block0 + j) * kBlockN, head);
         }
       }
       }  // work items
@@ -487,6 +495,50 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
 }
 
+// Merges the num_splits partial results of split-KV: L = log2 sum_s 2^L_s,  O = sum_s 2^(L_s - L) O_s.
+// One thread per (row, 4 columns); partials are [split][head][row][D] FP32 and [split][head][row] FP32.
+__global__ void __launch_bounds__(128)
+    combine_splits(const float *__restrict__ O_part, const float *__restrict__ L_part, float *__restrict__ O,
+                   void *__restrict__ L, uint32_t rows_total, uint32_t D, uint32_t num_splits, int l_is_fp16) {
+  const uint32_t quads_per_row = D / 4;
+  const uint64_t idx = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const uint64_t row = idx / quads_per_row;
+  const uint32_t quad = static_cast<uint32_t>(idx % quads_per_row);
+  if (row >= rows_total) return;
+  float lmax = -INFINITY;
+  for (uint32_t s = 0; s < num_splits; ++s) lmax = fmaxf(lmax, L_part[static_cast<uint64_t>(s) * rows_total + row]);
+  float denom = 0.f;
+  for (uint32_t s = 0; s < num_splits; ++s) denom += exp2f(L_part[static_cast<uint64_t>(s) * rows_total + row] - lmax);
+  const float lse = lmax + log2f(denom);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (uint32_t s = 0; s < num_splits; ++s) {
+    const float w = exp2f(L_part[static_cast<uint64_t>(s) * rows_total + row] - lse);
+    const float4 v = *reinterpret_cast<const float4 *>(O_part + (static_cast<uint64_t>(s) * rows_total + row) * D + 4 * quad);
+    acc.x = fmaf(w, v.x, acc.x);
+    acc.y = fmaf(w, v.y, acc.y);
+    acc.z = fmaf(w, v.z, acc.z);
+    acc.w = fmaf(w, v.w, acc.w);
+  }
+  *reinterpret_cast<float4 *>(O + row * D + 4 * quad) = acc;
+  if (quad == 0 && L != nullptr) {
+    if (l_is_fp16)
+      reinterpret_cast<__half *>(L)[row] = __float2half_rn(lse);
+    else
+      reinterpret_cast<float *>(L)[row] = lse;
+  }
+}
+
+// how many key ranges to cut every item into: only when the SMs would otherwise idle, only into equal ranges of at
+// least four key blocks (shorter ranges are dominated by the per-item prologue / epilogue)
+static uint32_t choose_splits(uint32_t items, uint32_t total_blocks, uint32_t sm_count) {
+  if (items * 2 > sm_count) return 1;
+  const uint32_t target = sm_count / items;
+  uint32_t best = 1;
+  for (uint32_t s = 2; s <= target && s <= 16; ++s)
+    if (total_blocks % s == 0 && total_blocks / s >= 4) best = s;
+  return best;
+}
+
 template <uint32_t DPAD, bool kBF16, bool kTrace = false>
 cudaError_t launch(const AttentionParams &p, cudaStream_t stream, long long *trace = nullptr) {
   using Cfg = Config<DPAD>;
@@ -512,11 +564,47 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, long long *tra
     if ((e = cudaGetDevice(&device)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return e;
   }
-  const uint32_t grid = num_items < static_cast<uint32_t>(sm_count) ? num_items : static_cast<uint32_t>(sm_count);
-  kernel<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mapQ, mapK, mapV, static_cast<float *>(p.buf[sO]), p.buf[sL],
-                                                      p.R, p.C, p.D, p.scale_log2, p.prec[sL] == FP16 ? 1 : 0,
-                                                      num_items, pairs_per_head, trace);
-  return cudaGetLastError();
+  const uint32_t total_blocks = (p.C + kBlockN - 1) / kBlockN;
+  const uint32_t splits = choose_splits(num_items, total_blocks, static_cast<uint32_t>(sm_count));
+  if (splits == 1) {
+    const uint32_t grid = num_items < static_cast<uint32_t>(sm_count) ? num_items : static_cast<uint32_t>(sm_count);
+    kernel<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mapQ, mapK, mapV, static_cast<float *>(p.buf[sO]), p.buf[sL],
+                                                        p.R, p.C, p.D, p.scale_log2, p.prec[sL] == FP16 ? 1 : 0,
+                                                        num_items, pairs_per_head, 1u, p.batch, trace);
+    return cudaGetLastError();
+  }
+  // split-KV: partial O / L in stream-ordered scratch, then the combine kernel
+  const uint64_t rows_total = static_cast<uint64_t>(p.batch) * p.R;
+  const size_t o_bytes = static_cast<size_t>(splits) * rows_total * p.D * sizeof(float);
+  const size_t l_bytes = static_cast<size_t>(splits) * rows_total * sizeof(float);
+  // keep freed scratch cached in the device's default memory pool instead of returning it to the OS at every
+  // synchronisation (the default release threshold is 0)
+  static std::once_flag pool_once;
+  std::call_once(pool_once, [] {
+    int device = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&device) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t threshold = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+  });
+  float *scratch = nullptr;
+  if ((e = cudaMallocAsync(reinterpret_cast<void **>(&scratch), o_bytes + l_bytes, stream)) != cudaSuccess) return e;
+  float *L_part = scratch + static_cast<size_t>(splits) * rows_total * p.D;
+  const uint32_t split_items = num_items * splits;
+  const uint32_t grid = split_items < static_cast<uint32_t>(sm_count) ? split_items : static_cast<uint32_t>(sm_count);
+  kernel<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mapQ, mapK, mapV, scratch, L_part, p.R, p.C, p.D, p.scale_log2,
+                                                      0, split_items, pairs_per_head, splits, p.batch, trace);
+  e = cudaGetLastError();
+  if (e == cudaSuccess) {
+    const uint64_t threads = rows_total * (p.D / 4);
+    combine_splits<<<static_cast<uint32_t>((threads + 127) / 128), 128, 0, stream>>>(
+        scratch, L_part, static_cast<float *>(p.buf[sO]), p.buf[sL], static_cast<uint32_t>(rows_total), p.D, splits,
+        p.prec[sL] == FP16 ? 1 : 0);
+    e = cudaGetLastError();
+  }
+  cudaError_t free_status = cudaFreeAsync(scratch, stream);
+  return e != cudaSuccess ? e : free_status;
 }
 
 }  // namespace fwd
@@ -544,6 +632,16 @@ cudaError_t launch_tcgen05_forward(const AttentionParams &p, cudaStream_t stream
 // written to `trace` (3 roles x 64 iterations x 8 slots of clock64()).  Used by scripts/trace_forward.py.
 cudaError_t launch_tcgen05_forward_trace(const AttentionParams &p, cudaStream_t stream, long long *trace) {
   return fwd::launch<128, true, true>(p, stream, trace);
+}
+
+// 1 launch, or 2 (attention + combine) when split-KV engages for this problem size
+uint32_t tcgen05_forward_launch_count(uint32_t R, uint32_t C, uint32_t D, uint32_t batch) {
+  if (D > 128) return 1;
+  int device = 0, sm_count = 148;
+  if (cudaGetDevice(&device) == cudaSuccess)
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
+  const uint32_t pairs = (R + fwd::kTileM * fwd::kTilesPerCta - 1) / (fwd::kTileM * fwd::kTilesPerCta);
+  return fwd::choose_splits(pairs * batch, (C + fwd::kBlockN - 1) / fwd::kBlockN, static_cast<uint32_t>(sm_count)) > 1 ? 2 : 1;
 }
 
 void tcgen05_forward_geometry(uint32_t D, uint32_t *threads, uint32_t *smem_bytes, uint32_t *par, uint32_t *trav,

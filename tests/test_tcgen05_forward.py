@@ -66,6 +66,20 @@ def test_forward_matches_oracle(R, C, D, bf16):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("R,C,D,bf16", [(4096, 4096, 128, True), (256, 2048, 64, False), (300, 2000, 128, True),
+                                        (512, 1536, 96, True)])
+def test_split_kv_small_grids(R, C, D, bf16):
+    """Few (head, tile pair) items: the key axis is split across SMs and merged by the combine kernel."""
+    import mfa_b200 as mfa
+    desc = _descriptor(R, C, D, bf16)
+    kernel = mfa.AttentionKernel(desc.kernelDescriptor(mfa.AttentionKernelType.forward))
+    constants = mfa.FunctionConstantValues()
+    desc.setFunctionConstants(constants)
+    assert kernel.launchCount(constants) == 2, "split-KV should engage for this grid"
+    _run_and_check(R, C, D, bf16, seed=R + C + D)
+
+
+@pytest.mark.gpu
 def test_forward_fp16_L_storage():
     """lowPrecisionIntermediates: L is stored as FP16 (AttentionDescriptor+Precisions.swift:81-87)."""
     _run_and_check(256, 256, 128, True, seed=5, lowMid=True)
