@@ -27,7 +27,7 @@ import os
 from typing import Dict, Optional, Sequence, Tuple
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "lib", "libmfa_b200.so")
+_LIB_PATH = os.environ.get("MFA_B200_LIBRARY") or os.path.join(_HERE, "lib", "libmfa_b200.so")  # override: tuning builds only
 
 MFA_OPERAND_COUNT = 14
 MFA_BUFFER_COUNT = 10

@@ -45,7 +45,10 @@ constexpr uint32_t kThreads = 384;
 // must not exceed the launch allocation or the second setmaxnreg.inc never returns.
 constexpr uint32_t kLaunchRegs = 168, kSoftmaxRegs = 208, kOtherRegs = 88;
 static_assert(kSoftmaxRegs * 256 + kOtherRegs * 128 <= kLaunchRegs * kThreads, "setmaxnreg over-subscribed");
-constexpr uint32_t kPolyPairs = 2;  // of every 4 pairs, how many take exp2 on the FMA pipe (0 = all MUFU)
+#ifndef MFA_POLY_PAIRS
+#define MFA_POLY_PAIRS 1  // swept on B200: 0 and 1 tie (1.205 PF), 2 loses 4 %, 3 loses 12 %
+#endif
+constexpr uint32_t kPolyPairs = MFA_POLY_PAIRS;  // of every 4 pairs, how many take exp2 on the FMA pipe (0 = all MUFU)
 constexpr float kLazySumLimit = 256.0f;  // a half-row of P summing to <= 2^8 proves every element is <= 2^8
 
 template <uint32_t DPAD>
@@ -214,7 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (uint32_t i = 0; i < 32; ++i) {
           const float2 x = ffma2(make_float2(s[c0 + 2 * i], s[c0 + 2 * i + 1]), scale2, negm2);
           float2 pr;
-          if ((i & 3) < kPolyPairs) {
+          if (kPolyPairs > 0 && (i & 3) < kPolyPairs) {
             pr = exp2_poly2(x);
           } else {
             pr.x = ex2_approx(x.x);
