@@ -252,6 +252,10 @@ MFA_API int mfa_debug_forward_trace(const mfa_attention_kernel_t *kernel, const 
   return MFA_SUCCESS;
 }
 
+// Debug-only export: 0 forces split-KV onto its scratch + combine fallback (tests cover both forms).
+MFA_API void mfa_debug_set_forward_cluster(int enabled) { tcgen05_forward_set_cluster(enabled); }
+MFA_API int mfa_debug_forward_max_clusters(uint32_t splits) { return tcgen05_forward_max_clusters(splits); }
+
 // ------------------------------------------------------------------------------------------------
 // Host-buffer path: H2D -> kernels -> D2H (the end-to-end call bench.py times as `e2e`).
 // ------------------------------------------------------------------------------------------------

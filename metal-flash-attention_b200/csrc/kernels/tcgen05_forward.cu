@@ -31,6 +31,13 @@
 #include "tma_host.h"
 
 namespace mfa {
+// Split-KV has two forms.  Measured on B200 (single head, N = 4096, D = 128, CUDA-graph replay): scratch + combine
+// kernel 18.5 us, cluster + distributed-shared-memory reduce 37 us -- only 15 clusters of 8 CTAs are co-resident (16
+// needed, so it falls back to clusters of 4 = 64 CTAs) and the DSMEM pull of the partials runs at ~6 B/clk/SM.  The
+// cluster form therefore stays off unless mfa_debug_set_forward_cluster(1) asks for it (tests cover both).
+static int g_forward_cluster_enabled = 0;
+void tcgen05_forward_set_cluster(int enabled) { g_forward_cluster_enabled = enabled; }
+
 namespace fwd {
 
 using namespace ptx;
@@ -60,6 +67,12 @@ struct Config {
   static constexpr uint32_t kSmemK = kSmemQ + kTilesPerCta * kTileBytes;
   static constexpr uint32_t kSmemV = kSmemK + kStages * kTileBytes;
   static constexpr uint32_t kSmemScratch = kSmemV + kStages * kTileBytes;  // epilogue transpose: 8 warps x 32 x 32 floats
+  // cluster split-KV epilogue: the raw O partial of the tile pair ([256][DPAD] FP32, 16 B slots XOR-swizzled in
+  // groups of 8) overlays the K / V stages, which are dead once the last MMA has completed; (m, l) per row
+  // goes to the head of the transpose scratch
+  static constexpr uint32_t kSmemPart = kSmemK;
+  static constexpr uint32_t kSmemML = kSmemScratch;
+  static_assert(kTilesPerCta * kTileM * DPAD * 4 <= 2 * kStages * kTileBytes, "O partial does not fit the K/V stages");
   static constexpr uint32_t kSmemBar = kSmemScratch + 8 * 32 * 32 * 4;
   static constexpr uint32_t kNumBars = 2 + 4 * kStages + 6 * kTilesPerCta;
   static constexpr uint32_t kSmemTmemPtr = kSmemBar + kNumBars * 8;
@@ -86,7 +99,7 @@ constexpr uint32_t kTraceSlots = 8;  // per (role, iteration)
 // item-level probes: roles 4 (tile 0 softmax), 5 (tile 1 softmax), 6 (MMA), indexed by the CTA's item counter
 #define MFA_TRACE_ITEM(role, it, slot) MFA_TRACE(role, it, slot)
 
-template <uint32_t DPAD, bool kBF16, bool kTrace = false>
+template <uint32_t DPAD, bool kBF16, bool kTrace = false, bool kCluster = false>
 __global__ void __launch_bounds__(kThreads, 1)
     attention_forward_tcgen05(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                               const __grid_constant__ CUtensorMap mapV, float *__restrict__ O, void *__restrict__ L,
@@ -103,8 +116,12 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Split-KV: when there are fewer (head, tile pair) items than SMs, the key axis of every item is cut into
-  // num_splits equal ranges that become separate work items; each writes a normalised partial O and its L as if
-  // it were a whole problem (O and L then point at scratch laid out [split][head][row]) and combine_splits merges them.
+  // num_splits equal ranges that become separate work items.
+  //  kCluster: the num_splits CTAs of an item form one thread-block cluster (rank = split); each leaves its raw O
+  //    partial and (m, l) in its own shared memory and, after a cluster barrier, reduces and stores a 1/num_splits
+  //    slice of the rows by reading all partials through distributed shared memory -- one launch, no HBM scratch.
+  //  otherwise (fallback): each item writes a normalised partial O and its L as if it were a whole problem (O and L
+  //    then point at scratch laid out [split][head][row]) and the combine_splits kernel merges them.
   const uint32_t total_blocks = (C + kBlockN - 1) / kBlockN;
   const uint32_t num_blocks = total_blocks / num_splits;  // key blocks per work item (host guarantees divisibility)
 
@@ -156,6 +173,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // scratch split-KV: let the combine kernel (launched with programmatic stream serialisation) be set up now; its
+  // griddepcontrol.wait still holds it until this grid has completed and flushed
+  if (!kCluster && num_splits > 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp < 8) {
     // =====================================================================================
@@ -172,7 +192,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 
     for (uint32_t item = blockIdx.x, it = 0; item < num_items; item += gridDim.x, ++it) {
     const uint32_t split = item % num_splits;
-    const uint32_t head = (item / num_splits) / pairs_per_head + split * batch;  // output slot (partials: [split][head])
+    // output slot; the scratch fallback lays partials out as [split][head]
+    const uint32_t head = (item / num_splits) / pairs_per_head + (kCluster ? 0u : split * batch);
     const uint32_t q_row0 = ((item / num_splits) % pairs_per_head) * (kTileM * kTilesPerCta);
     const uint32_t key_block0 = split * num_blocks;
     const uint32_t g0 = it * num_blocks;  // key blocks this CTA has processed before this item (barrier phases)
@@ -211,23 +232,27 @@ __global__ void __launch_bounds__(kThreads, 1)
         uint32_t packed[32];
         // The MUFU pipe (16 ex2 / clk / SM) needs as long for a 128 x 128 block as the tensor pipe needs for its two
         // GEMMs, so kPolyPairs of every 4 element pairs take exp2 on the FMA pipe instead (exp2_poly2).
-        float2 sum2 = make_float2(0.f, 0.f);
-        const float2 scale2 = make_float2(scale_log2, scale_log2), negm2 = make_float2(-m, -m);
+        float half_sum;
+        if (half == 0 && j == 0) {
+          half_sum = INFINITY;  // m is not set yet: the item's very first half goes straight to the exact path
+        } else {
+          float2 sum2 = make_float2(0.f, 0.f);
+          const float2 scale2 = make_float2(scale_log2, scale_log2), negm2 = make_float2(-m, -m);
 #pragma unroll
-        for (uint32_t i = 0; i < 32; ++i) {
-          const float2 x = ffma2(make_float2(s[c0 + 2 * i], s[c0 + 2 * i + 1]), scale2, negm2);
-          float2 pr;
-          if (kPolyPairs > 0 && (i & 3) < kPolyPairs) {
-            pr = exp2_poly2(x);
-          } else {
-            pr.x = ex2_approx(x.x);
-            pr.y = ex2_approx(x.y);
+          for (uint32_t i = 0; i < 32; ++i) {
+            const float2 x = ffma2(make_float2(s[c0 + 2 * i], s[c0 + 2 * i + 1]), scale2, negm2);
+            float2 pr;
+            if (kPolyPairs > 0 && (i & 3) < kPolyPairs) {
+              pr = exp2_poly2(x);
+            } else {
+              pr.x = ex2_approx(x.x);
+              pr.y = ex2_approx(x.y);
+            }
+            sum2 = fadd2(sum2, pr);
+            packed[i] = kBF16 ? pack_bf16x2(pr.x, pr.y) : pack_f16x2(pr.x, pr.y);
           }
-          sum2 = fadd2(sum2, pr);
-          packed[i] = kBF16 ? pack_bf16x2(pr.x, pr.y) : pack_f16x2(pr.x, pr.y);
+          half_sum = sum2.x + sum2.y;
         }
-        float sum0 = sum2.x, sum1 = sum2.y;
-        float half_sum = sum0 + sum1;
         if (__any_sync(0xffffffffu, !(half_sum <= kLazySumLimit))) {  // also catches inf / NaN
           // ---- exact path (rare) ----
           float mx0 = s[c0], mx1 = s[c0 + 1], mx2 = s[c0 + 2], mx3 = s[c0 + 3];
@@ -260,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             l *= correction;
           }
           m = m_new;
-          sum0 = sum1 = 0.f;
+          float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
           for (uint32_t i = 0; i < 32; ++i) {
             const float p0 = ex2_approx(fmaf(s[c0 + 2 * i], scale_log2, -m));
@@ -284,56 +309,149 @@ __global__ void __launch_bounds__(kThreads, 1)
       MFA_TRACE(warp == 0 ? 0 : (warp == 4 ? 1 : 5), j, 4);
     }
 
-    // ---------------- epilogue: O / l -> global (FP32), L = m + log2(l) ----------------
-    MFA_TRACE_ITEM(warp == 0 ? 4 : (warp == 4 ? 5 : 7), it, 1);
-    mbar_wait(&b.o_full[t], (g0 + num_blocks - 1) & 1);
-    tc_fence_after();
-    MFA_TRACE_ITEM(warp == 0 ? 4 : (warp == 4 ? 5 : 7), it, 2);
-    const uint32_t row = q_row0 + t * kTileM + row_in_tile;
-    const float inv_l = 1.0f / l;
-    // TMEM hands every thread one row; storing rows straight from registers would touch 32 different cache
-    // lines per warp store.  Each warp therefore transposes 32 x 32 chunks through a private XOR-swizzled scratch
-    // tile in shared memory (128-bit accesses, conflict-free both ways) and writes four full 128 B lines per store.
-    float4 *scratch = reinterpret_cast<float4 *>(smem + Cfg::kSmemScratch) + warp * (32 * 8);
-    const uint32_t warp_row0 = q_row0 + t * kTileM + (warp & 3) * 32;
-    float *o_base = O + (static_cast<size_t>(head) * R + warp_row0) * D;
-    const uint32_t sub_row = lane >> 3, quad = lane & 7;  // transposed view: 4 rows x 8 float4 per warp access
+    if constexpr (kCluster) {
+      // ---------------- cluster epilogue: reduce the splits through distributed shared memory ----------------
+      MFA_TRACE_ITEM(warp == 0 ? 4 : (warp == 4 ? 5 : 7), it, 1);
+      mbar_wait(&b.o_full[t], (g0 + num_blocks - 1) & 1);
+      // the partial overlays the K / V stages: every MMA of the CTA must be done, and tile 1's last O += P V is the
+      // last one issued (its predecessors complete in order, so this parity cannot alias an older phase)
+      mbar_wait(&b.o_full[kTilesPerCta - 1], (g0 + num_blocks - 1) & 1);
+      tc_fence_after();
+      MFA_TRACE_ITEM(warp == 0 ? 4 : (warp == 4 ? 5 : 7), it, 2);
+      constexpr uint32_t kQuadsPerRow = DPAD / 4;
+      constexpr uint32_t kPairRows = kTileM * kTilesPerCta;
+      float4 *part = reinterpret_cast<float4 *>(smem + Cfg::kSmemPart);
+      float2 *ml = reinterpret_cast<float2 *>(smem + Cfg::kSmemML);
+      {
+        const uint32_t rt = t * kTileM + row_in_tile;  // row inside the tile pair
 #pragma unroll
-    for (uint32_t c = 0; c < DPAD; c += 32) {
-      uint32_t o[32];
-      tmem_ld32(tO + c, o);
-      tc_wait_ld();
+        for (uint32_t c = 0; c < DPAD; c += 32) {
+          uint32_t o[32];
+          tmem_ld32(tO + c, o);
+          tc_wait_ld();
 #pragma unroll
-      for (uint32_t j = 0; j < 8; ++j)
-        scratch[lane * 8 + (j ^ (lane & 7))] =
-            make_float4(__uint_as_float(o[4 * j]) * inv_l, __uint_as_float(o[4 * j + 1]) * inv_l,
-                        __uint_as_float(o[4 * j + 2]) * inv_l, __uint_as_float(o[4 * j + 3]) * inv_l);
-      __syncwarp();
-      // read the whole transposed chunk into distinct registers BEFORE the first store: a store keeps its source
-      // registers busy until the data has left the SM, so reusing a handful of registers would serialise the
-      // stores on memory latency (measured: 11k cycles per tile epilogue)
-      float4 v[8];
-#pragma unroll
-      for (uint32_t i = 0; i < 8; ++i) {
-        const uint32_t r = 4 * i + sub_row;
-        v[i] = scratch[r * 8 + (quad ^ (r & 7))];
+          for (uint32_t q = 0; q < 8; ++q)
+            part[rt * kQuadsPerRow + ((c / 4 + q) ^ (rt & 7))] =
+                make_float4(__uint_as_float(o[4 * q]), __uint_as_float(o[4 * q + 1]), __uint_as_float(o[4 * q + 2]),
+                            __uint_as_float(o[4 * q + 3]));
+        }
+        ml[rt] = make_float2(m, l);
       }
-      if (c + 4 * quad < D) {  // D % 8 == 0: a float4 is either fully inside or fully outside
+      cluster_arrive_release();
+      cluster_wait_acquire();
+      MFA_TRACE_ITEM(warp == 0 ? 4 : (warp == 4 ? 5 : 7), it, 4);
+      // rank `split` owns rows [split * rows_per_rank, (split + 1) * rows_per_rank) of the pair: thread <-> (row, 16 B
+      // column slot), 32 (DPAD 128) or 16 (DPAD 64) consecutive threads per row, so global stores are full lines
+      const uint32_t rows_per_rank = (kPairRows + num_splits - 1) / num_splits;
+      const uint32_t quad = threadIdx.x % kQuadsPerRow;
+      const uint32_t part_addr = smem_u32(part), ml_addr = smem_u32(ml);
+      uint32_t part_rank[8], ml_rank[8];
 #pragma unroll
-        for (uint32_t i = 0; i < 8; ++i) {
-          const uint32_t r = 4 * i + sub_row;
-          if (warp_row0 + r < R) *reinterpret_cast<float4 *>(o_base + static_cast<size_t>(r) * D + c + 4 * quad) = v[i];
+      for (uint32_t s = 0; s < 8; ++s) {
+        // start with the own partial, then walk the ring: spreads the remote reads over the cluster
+        const uint32_t src = s < num_splits ? (split + s) % num_splits : split;
+        part_rank[s] = map_shared_rank(part_addr, src);
+        ml_rank[s] = map_shared_rank(ml_addr, src);
+      }
+      for (uint32_t r = threadIdx.x / kQuadsPerRow; r < rows_per_rank; r += (kThreads - 128) / kQuadsPerRow) {
+        const uint32_t rt = split * rows_per_rank + r;
+        if (rt >= kPairRows) break;
+        float2 mls[8];
+        float4 v[8];
+#pragma unroll
+        for (uint32_t s = 0; s < 8; ++s)
+          if (s < num_splits) {
+            mls[s] = ld_dsmem_f32x2(ml_rank[s] + rt * 8);
+            v[s] = ld_dsmem_f32x4(part_rank[s] + (rt * kQuadsPerRow + (quad ^ (rt & 7))) * 16);
+          }
+        float m_all = -FLT_MAX;
+#pragma unroll
+        for (uint32_t s = 0; s < 8; ++s)
+          if (s < num_splits) m_all = fmaxf(m_all, mls[s].x);
+        float denom = 0.f;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (uint32_t s = 0; s < 8; ++s)
+          if (s < num_splits) {
+            const float w = exp2f(mls[s].x - m_all);
+            denom = fmaf(w, mls[s].y, denom);
+            acc.x = fmaf(w, v[s].x, acc.x);
+            acc.y = fmaf(w, v[s].y, acc.y);
+            acc.z = fmaf(w, v[s].z, acc.z);
+            acc.w = fmaf(w, v[s].w, acc.w);
+          }
+        const float inv = 1.0f / denom;
+        const uint32_t row = q_row0 + rt;
+        if (row < R) {
+          if (4 * quad < D)
+            *reinterpret_cast<float4 *>(O + (static_cast<size_t>(head) * R + row) * D + 4 * quad) =
+                make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+          if (quad == 0 && L != nullptr) {
+            const float lse2 = m_all + log2f(denom);  // AttentionKernel+Caching.swift:373-377
+            const size_t idx = static_cast<size_t>(head) * R + row;
+            if (l_is_fp16)
+              reinterpret_cast<__half *>(L)[idx] = __float2half_rn(lse2);
+            else
+              reinterpret_cast<float *>(L)[idx] = lse2;
+          }
         }
       }
-      __syncwarp();
-    }
-    if (row < R && L != nullptr) {
-      const float lse2 = m + log2f(l);  // AttentionKernel+Caching.swift:373-377
-      const size_t idx = static_cast<size_t>(head) * R + row;
-      if (l_is_fp16)
-        reinterpret_cast<__half *>(L)[idx] = __float2half_rn(lse2);
-      else
-        reinterpret_cast<float *>(L)[idx] = lse2;
+      MFA_TRACE_ITEM(warp == 0 ? 4 : (warp == 4 ? 5 : 7), it, 5);
+      // no CTA may exit (or reuse its shared memory) while a peer is still reading its partial
+      cluster_arrive_release();
+      cluster_wait_acquire();
+    } else {
+      // ---------------- epilogue: O / l -> global (FP32), L = m + log2(l) ----------------
+      MFA_TRACE_ITEM(warp == 0 ? 4 : (warp == 4 ? 5 : 7), it, 1);
+      mbar_wait(&b.o_full[t], (g0 + num_blocks - 1) & 1);
+      tc_fence_after();
+      MFA_TRACE_ITEM(warp == 0 ? 4 : (warp == 4 ? 5 : 7), it, 2);
+      const uint32_t row = q_row0 + t * kTileM + row_in_tile;
+      const float inv_l = 1.0f / l;
+      // TMEM hands every thread one row; storing rows straight from registers would touch 32 different cache
+      // lines per warp store.  Each warp therefore transposes 32 x 32 chunks through a private XOR-swizzled scratch
+      // tile in shared memory (128-bit accesses, conflict-free both ways) and writes four full 128 B lines per store.
+      float4 *scratch = reinterpret_cast<float4 *>(smem + Cfg::kSmemScratch) + warp * (32 * 8);
+      const uint32_t warp_row0 = q_row0 + t * kTileM + (warp & 3) * 32;
+      float *o_base = O + (static_cast<size_t>(head) * R + warp_row0) * D;
+      const uint32_t sub_row = lane >> 3, quad = lane & 7;  // transposed view: 4 rows x 8 float4 per warp access
+  #pragma unroll
+      for (uint32_t c = 0; c < DPAD; c += 32) {
+        uint32_t o[32];
+        tmem_ld32(tO + c, o);
+        tc_wait_ld();
+  #pragma unroll
+        for (uint32_t j = 0; j < 8; ++j)
+          scratch[lane * 8 + (j ^ (lane & 7))] =
+              make_float4(__uint_as_float(o[4 * j]) * inv_l, __uint_as_float(o[4 * j + 1]) * inv_l,
+                          __uint_as_float(o[4 * j + 2]) * inv_l, __uint_as_float(o[4 * j + 3]) * inv_l);
+        __syncwarp();
+        // read the whole transposed chunk into distinct registers BEFORE the first store: a store keeps its source
+        // registers busy until the data has left the SM, so reusing a handful of registers would serialise the
+        // stores on memory latency (measured: 11k cycles per tile epilogue)
+        float4 v[8];
+  #pragma unroll
+        for (uint32_t i = 0; i < 8; ++i) {
+          const uint32_t r = 4 * i + sub_row;
+          v[i] = scratch[r * 8 + (quad ^ (r & 7))];
+        }
+        if (c + 4 * quad < D) {  // D % 8 == 0: a float4 is either fully inside or fully outside
+  #pragma unroll
+          for (uint32_t i = 0; i < 8; ++i) {
+            const uint32_t r = 4 * i + sub_row;
+            if (warp_row0 + r < R) *reinterpret_cast<float4 *>(o_base + static_cast<size_t>(r) * D + c + 4 * quad) = v[i];
+          }
+        }
+        __syncwarp();
+      }
+      if (row < R && L != nullptr) {
+        const float lse2 = m + log2f(l);  // AttentionKernel+Caching.swift:373-377
+        const size_t idx = static_cast<size_t>(head) * R + row;
+        if (l_is_fp16)
+          reinterpret_cast<__half *>(L)[idx] = __float2half_rn(lse2);
+        else
+          reinterpret_cast<float *>(L)[idx] = lse2;
+      }
     }
     // O of this tile is out of TMEM: the next item's first O = P V (accumulate off) may overwrite it
     tc_fence_before();
@@ -365,7 +483,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       for (uint32_t j = 0; j < num_blocks; ++j) {
         const uint32_t stage = (g0 + j) % Cfg::kStages, phase = ((g0 + j) / Cfg::kStages) & 1;
+        MFA_TRACE(3, j, 0);
         mbar_wait(&b.k_empty[stage], phase ^ 1);
+        MFA_TRACE(3, j, 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&b.k_full[stage], Cfg::kTileBytes);
 #pragma unroll
@@ -374,6 +494,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                         ds * 64, (key_block0 + j) * kBlockN, head);
         }
         mbar_wait(&b.v_empty[stage], phase ^ 1);
+        MFA_TRACE(3, j, 2);
         if (elect_one()) {
           mbar_arrive_expect_tx(&b.v_full[stage], Cfg::kTileBytes);
 #pragma unroll
@@ -463,6 +584,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
           __syncwarp();
           mbar_wait(&b.p_full[2 * t + 1], g & 1);
+          if (t == 0) MFA_TRACE(2, j, 2);
           if (t == 0 && has_next) mbar_wait(&b.k_full[nstage], nphase);
           tc_fence_after();
           MFA_TRACE(2, j, 1 + 3 * t);
@@ -486,6 +608,13 @@ __global__ void __launch_bounds__(kThreads, 1)
       MFA_TRACE_ITEM(6, it, 2);
       }  // work items
     }
+    if constexpr (kCluster) {
+      // the producer warpgroup takes part in the two cluster barriers of the softmax warps' epilogue
+      cluster_arrive_release();
+      cluster_wait_acquire();
+      cluster_arrive_release();
+      cluster_wait_acquire();
+    }
   }
 
 
@@ -498,32 +627,50 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
 }
 
-// Merges the num_splits partial results of split-KV: L = log2 sum_s 2^L_s,  O = sum_s 2^(L_s - L) O_s.
-// One thread per (row, 4 columns); partials are [split][head][row][D] FP32 and [split][head][row] FP32.
+// Merges the num_splits partial results of split-KV (scratch form): L = log2 sum_s 2^L_s,  O = sum_s 2^(L_s - L) O_s.
+// One thread per (row, 4 columns); partials are [split][head][row][D] FP32 and [split][head][row] FP32.  Every load of
+// a thread is issued before the first use (the partials sit in L2; a dependent chain of num_splits round trips was
+// 3x slower).  Launched with programmatic stream serialisation: the grid is set up while the attention kernel drains
+// and griddepcontrol.wait holds it until that kernel's writes are visible.
+template <uint32_t kMaxSplits>
 __global__ void __launch_bounds__(128)
     combine_splits(const float *__restrict__ O_part, const float *__restrict__ L_part, float *__restrict__ O,
                    void *__restrict__ L, uint32_t rows_total, uint32_t D, uint32_t num_splits, int l_is_fp16) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t quads_per_row = D / 4;
   const uint64_t idx = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const uint64_t row = idx / quads_per_row;
   const uint32_t quad = static_cast<uint32_t>(idx % quads_per_row);
   if (row >= rows_total) return;
-  float lmax = -INFINITY;
-  for (uint32_t s = 0; s < num_splits; ++s) lmax = fmaxf(lmax, L_part[static_cast<uint64_t>(s) * rows_total + row]);
-  float denom = 0.f;
-  for (uint32_t s = 0; s < num_splits; ++s) denom += exp2f(L_part[static_cast<uint64_t>(s) * rows_total + row] - lmax);
-  const float lse = lmax + log2f(denom);
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (uint32_t s = 0; s < num_splits; ++s) {
-    const float w = exp2f(L_part[static_cast<uint64_t>(s) * rows_total + row] - lse);
-    const float4 v = *reinterpret_cast<const float4 *>(O_part + (static_cast<uint64_t>(s) * rows_total + row) * D + 4 * quad);
-    acc.x = fmaf(w, v.x, acc.x);
-    acc.y = fmaf(w, v.y, acc.y);
-    acc.z = fmaf(w, v.z, acc.z);
-    acc.w = fmaf(w, v.w, acc.w);
+  float ls[kMaxSplits];
+  float4 v[kMaxSplits];
+#pragma unroll
+  for (uint32_t s = 0; s < kMaxSplits; ++s) {
+    ls[s] = -INFINITY;
+    v[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (s < num_splits) {
+      ls[s] = __ldcg(L_part + static_cast<uint64_t>(s) * rows_total + row);
+      v[s] = __ldcg(reinterpret_cast<const float4 *>(O_part + (static_cast<uint64_t>(s) * rows_total + row) * D) + quad);
+    }
   }
-  *reinterpret_cast<float4 *>(O + row * D + 4 * quad) = acc;
+  float lmax = ls[0];
+#pragma unroll
+  for (uint32_t s = 1; s < kMaxSplits; ++s) lmax = fmaxf(lmax, ls[s]);
+  float denom = 0.f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (uint32_t s = 0; s < kMaxSplits; ++s) {
+    const float w = exp2f(ls[s] - lmax);  // 0 for the unused slots
+    denom += w;
+    acc.x = fmaf(w, v[s].x, acc.x);
+    acc.y = fmaf(w, v[s].y, acc.y);
+    acc.z = fmaf(w, v[s].z, acc.z);
+    acc.w = fmaf(w, v[s].w, acc.w);
+  }
+  const float inv = 1.0f / denom;
+  *reinterpret_cast<float4 *>(O + row * D + 4 * quad) = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
   if (quad == 0 && L != nullptr) {
+    const float lse = lmax + log2f(denom);
     if (l_is_fp16)
       reinterpret_cast<__half *>(L)[row] = __float2half_rn(lse);
     else
@@ -533,13 +680,69 @@ __global__ void __launch_bounds__(128)
 
 // how many key ranges to cut every item into: only when the SMs would otherwise idle, only into equal ranges of at
 // least four key blocks (shorter ranges are dominated by the per-item prologue / epilogue)
-static uint32_t choose_splits(uint32_t items, uint32_t total_blocks, uint32_t sm_count) {
+static uint32_t choose_splits(uint32_t items, uint32_t total_blocks, uint32_t sm_count, uint32_t max_splits = 16) {
   if (items * 2 > sm_count) return 1;
   const uint32_t target = sm_count / items;
   uint32_t best = 1;
-  for (uint32_t s = 2; s <= target && s <= 16; ++s)
+  for (uint32_t s = 2; s <= target && s <= max_splits; ++s)
     if (total_blocks % s == 0 && total_blocks / s >= 4) best = s;
   return best;
+}
+
+constexpr uint32_t kMaxClusterSplits = 8;  // portable cluster size
+
+template <typename Kernel>
+static cudaLaunchConfig_t cluster_config(Kernel, uint32_t grid, uint32_t smem_bytes, cudaStream_t stream,
+                                         cudaLaunchAttribute *attr, uint32_t splits) {
+  cudaLaunchConfig_t config = {};
+  config.gridDim = dim3(grid, 1, 1);
+  config.blockDim = dim3(kThreads, 1, 1);
+  config.dynamicSmemBytes = smem_bytes;
+  config.stream = stream;
+  attr->id = cudaLaunchAttributeClusterDimension;
+  attr->val.clusterDim.x = splits;
+  attr->val.clusterDim.y = 1;
+  attr->val.clusterDim.z = 1;
+  config.attrs = attr;
+  config.numAttrs = 1;
+  return config;
+}
+
+// max_clusters[s]: how many clusters of s CTAs (each CTA owns a whole SM) the device can hold at once
+template <uint32_t DPAD, bool kBF16>
+static const int *cluster_occupancy() {
+  using Cfg = Config<DPAD>;
+  auto kernel = attention_forward_tcgen05<DPAD, kBF16, false, true>;
+  static std::once_flag once;
+  static int max_clusters[kMaxClusterSplits + 1] = {};
+  std::call_once(once, [&] {
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) {
+      cudaGetLastError();
+      return;
+    }
+    for (uint32_t s = 2; s <= kMaxClusterSplits; ++s) {
+      cudaLaunchAttribute attr;
+      cudaLaunchConfig_t config = cluster_config(kernel, s, Cfg::kSmemBytes, nullptr, &attr, s);
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kernel, &config) == cudaSuccess)
+        max_clusters[s] = n;
+      else
+        cudaGetLastError();
+    }
+  });
+  return max_clusters;
+}
+
+// Largest split count (<= 8) whose clusters can all be co-resident: `items` clusters of `splits` CTAs have to fit the
+// GPCs at once or the launch runs in waves.  0 = use the scratch fallback.
+template <uint32_t DPAD, bool kBF16>
+static uint32_t choose_cluster_splits(uint32_t items, uint32_t total_blocks, uint32_t sm_count) {
+  const int *max_clusters = cluster_occupancy<DPAD, kBF16>();
+  if (items * 2 > sm_count) return 0;
+  const uint32_t target = sm_count / items;
+  for (uint32_t s = target < kMaxClusterSplits ? target : kMaxClusterSplits; s >= 2; --s)
+    if (total_blocks % s == 0 && total_blocks / s >= 4 && static_cast<uint32_t>(max_clusters[s]) >= items) return s;
+  return 0;
 }
 
 template <uint32_t DPAD, bool kBF16, bool kTrace = false>
@@ -568,15 +771,40 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, long long *tra
     if ((e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return e;
   }
   const uint32_t total_blocks = (p.C + kBlockN - 1) / kBlockN;
+  const int l_is_fp16 = p.prec[sL] == FP16 ? 1 : 0;
+
+  // split-KV, preferred form: one cluster per item, reduced through distributed shared memory inside the kernel
+  {
+    const uint32_t cluster_splits =
+        g_forward_cluster_enabled ? choose_cluster_splits<DPAD, kBF16>(num_items, total_blocks, static_cast<uint32_t>(sm_count)) : 0;
+    if (cluster_splits > 1) {
+      auto cluster_kernel = attention_forward_tcgen05<DPAD, kBF16, kTrace, true>;
+      if (kTrace) {
+        static std::once_flag trace_once;
+        std::call_once(trace_once, [&] {
+          cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        });
+      }
+      cudaLaunchAttribute attr;
+      cudaLaunchConfig_t config =
+          cluster_config(cluster_kernel, num_items * cluster_splits, Cfg::kSmemBytes, stream, &attr, cluster_splits);
+      e = cudaLaunchKernelEx(&config, cluster_kernel, mapQ, mapK, mapV, static_cast<float *>(p.buf[sO]), p.buf[sL], p.R,
+                             p.C, p.D, p.scale_log2, l_is_fp16, num_items * cluster_splits, pairs_per_head,
+                             cluster_splits, p.batch, trace);
+      if (e == cudaSuccess) return cudaGetLastError();
+      cudaGetLastError();  // cluster launch refused (e.g. partitioned GPU): fall through to the scratch path
+    }
+  }
+
   const uint32_t splits = choose_splits(num_items, total_blocks, static_cast<uint32_t>(sm_count));
   if (splits == 1) {
     const uint32_t grid = num_items < static_cast<uint32_t>(sm_count) ? num_items : static_cast<uint32_t>(sm_count);
     kernel<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mapQ, mapK, mapV, static_cast<float *>(p.buf[sO]), p.buf[sL],
-                                                        p.R, p.C, p.D, p.scale_log2, p.prec[sL] == FP16 ? 1 : 0,
-                                                        num_items, pairs_per_head, 1u, p.batch, trace);
+                                                        p.R, p.C, p.D, p.scale_log2, l_is_fp16, num_items,
+                                                        pairs_per_head, 1u, p.batch, trace);
     return cudaGetLastError();
   }
-  // split-KV: partial O / L in stream-ordered scratch, then the combine kernel
+  // split-KV fallback: partial O / L in stream-ordered scratch, then the combine kernel
   const uint64_t rows_total = static_cast<uint64_t>(p.batch) * p.R;
   const size_t o_bytes = static_cast<size_t>(splits) * rows_total * p.D * sizeof(float);
   const size_t l_bytes = static_cast<size_t>(splits) * rows_total * sizeof(float);
@@ -601,10 +829,20 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, long long *tra
   e = cudaGetLastError();
   if (e == cudaSuccess) {
     const uint64_t threads = rows_total * (p.D / 4);
-    combine_splits<<<static_cast<uint32_t>((threads + 127) / 128), 128, 0, stream>>>(
-        scratch, L_part, static_cast<float *>(p.buf[sO]), p.buf[sL], static_cast<uint32_t>(rows_total), p.D, splits,
-        p.prec[sL] == FP16 ? 1 : 0);
-    e = cudaGetLastError();
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t config = {};
+    config.gridDim = dim3(static_cast<uint32_t>((threads + 127) / 128), 1, 1);
+    config.blockDim = dim3(128, 1, 1);
+    config.stream = stream;
+    config.attrs = &attr;
+    config.numAttrs = 1;
+    auto combine = splits <= 4 ? combine_splits<4> : (splits <= 8 ? combine_splits<8> : combine_splits<16>);
+    e = cudaLaunchKernelEx(&config, combine, static_cast<const float *>(scratch), static_cast<const float *>(L_part),
+                           static_cast<float *>(p.buf[sO]), p.buf[sL], static_cast<uint32_t>(rows_total), p.D, splits,
+                           l_is_fp16);
+    if (e == cudaSuccess) e = cudaGetLastError();
   }
   cudaError_t free_status = cudaFreeAsync(scratch, stream);
   return e != cudaSuccess ? e : free_status;
@@ -631,20 +869,30 @@ cudaError_t launch_tcgen05_forward(const AttentionParams &p, cudaStream_t stream
   return bf16 ? fwd::launch<128, true>(p, stream) : fwd::launch<128, false>(p, stream);
 }
 
+int tcgen05_forward_max_clusters(uint32_t splits) {
+  return splits <= fwd::kMaxClusterSplits ? fwd::cluster_occupancy<128, true>()[splits] : 0;
+}
+
 // Debug entry (not in include/mfa_b200.h): the D=128 bf16 forward with pipeline timestamps of CTA (0,0)
 // written to `trace` (3 roles x 64 iterations x 8 slots of clock64()).  Used by scripts/trace_forward.py.
 cudaError_t launch_tcgen05_forward_trace(const AttentionParams &p, cudaStream_t stream, long long *trace) {
   return fwd::launch<128, true, true>(p, stream, trace);
 }
 
-// 1 launch, or 2 (attention + combine) when split-KV engages for this problem size
+// 1 launch, or 2 (attention + combine) when the scratch form of split-KV engages for this problem size
 uint32_t tcgen05_forward_launch_count(uint32_t R, uint32_t C, uint32_t D, uint32_t batch) {
   if (D > 128) return 1;
   int device = 0, sm_count = 148;
   if (cudaGetDevice(&device) == cudaSuccess)
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
   const uint32_t pairs = (R + fwd::kTileM * fwd::kTilesPerCta - 1) / (fwd::kTileM * fwd::kTilesPerCta);
-  return fwd::choose_splits(pairs * batch, (C + fwd::kBlockN - 1) / fwd::kBlockN, static_cast<uint32_t>(sm_count)) > 1 ? 2 : 1;
+  const uint32_t blocks = (C + fwd::kBlockN - 1) / fwd::kBlockN;
+  if (g_forward_cluster_enabled) {
+    const uint32_t cs = D <= 64 ? fwd::choose_cluster_splits<64, true>(pairs * batch, blocks, static_cast<uint32_t>(sm_count))
+                                : fwd::choose_cluster_splits<128, true>(pairs * batch, blocks, static_cast<uint32_t>(sm_count));
+    if (cs > 1) return 1;  // cluster split-KV reduces inside the attention kernel
+  }
+  return fwd::choose_splits(pairs * batch, blocks, static_cast<uint32_t>(sm_count)) > 1 ? 2 : 1;
 }
 
 void tcgen05_forward_geometry(uint32_t D, uint32_t *threads, uint32_t *smem_bytes, uint32_t *par, uint32_t *trav,

@@ -20,6 +20,9 @@ desc.inputPrecisionOverride = mfa.GEMMOperandPrecision.BF16
 desc.matrixDimensions = (R, C, D)
 desc.transposeState = (False,) * 4
 desc.batchCount = H
+if os.environ.get('MFA_NO_CLUSTER'):
+    mfa._lib.mfa_debug_set_forward_cluster(0)
+print('co-resident clusters by size:', {s: mfa._lib.mfa_debug_forward_max_clusters(s) for s in range(2, 9)})
 kernel = mfa.AttentionKernel(desc.kernelDescriptor(mfa.AttentionKernelType.forward))
 constants = mfa.FunctionConstantValues()
 desc.setFunctionConstants(constants)
@@ -46,12 +49,13 @@ t = trace.cpu().numpy().reshape(8, 64, 8)
 nb = C // 128
 t0 = t[2, 0, 0]
 print(f"R={R} H={H}: cycles relative to MMA warp's first V wait; softmax slots: 0 S ready, 1 S in regs, 2 max done, "
-      "3 P computed, 4 arrived; mma slots: 0 V ready, 1 p0 ready, 2 PV0 issued, 3 S0 issued, 4 p1 ready, 5 PV1 issued, 6 S1 issued")
+      "3 P computed, 4 arrived; mma slots: 0 V ready, 1 p0 ready, 2 p1(tile 0) ready [then waits K(j+1)], 3 S0 issued, 4 p1 ready, 5 PV1 issued, 6 S1 issued")
 for j in range(min(nb, 12)):
     a = (t[0, j, :5] - t0).tolist()
     b = (t[1, j, :5] - t0).tolist()
     m = (t[2, j, :7] - t0).tolist()
-    print(f"j={j:2d} sm0 {a}  sm1 {b}  mma {m}")
+    pr = (t[3, j, :3] - t0).tolist()
+    print(f"j={j:2d} sm0 {a}  sm1 {b}  mma {m}  tma[wait k_empty, K issue, V issue] {pr}")
 per_iter = np.diff(t[2, 2:nb - 1, 1]).mean()
 sm = t[0, 2:nb - 1]
 print(f"steady-state period per key block: {per_iter:.0f} cycles (ideal 2048 tensor / 2048 MUFU)")
@@ -70,8 +74,8 @@ items = int((t[4, :, 0] != 0).sum())
 base = t[6, 0, 0]
 print(f"items processed by CTA 0: {items}; per item (cycles from the MMA warp's first prologue):")
 for it in range(min(items, 8)):
-    a = (t[4, it, :4] - base).tolist(); b2 = (t[5, it, :4] - base).tolist(); mm2 = (t[6, it, :3] - base).tolist()
-    print(f" it={it} tile0 [start, loop end, O ready, epilogue end] {a}  tile1 {b2}  mma [prologue, S(0) issued, loop end] {mm2}")
+    a = (t[4, it, :6] - base).tolist(); b2 = (t[5, it, :6] - base).tolist(); mm2 = (t[6, it, :3] - base).tolist()
+    print(f" it={it} tile0 [start, loop end, O ready, epilogue end, (cluster: partial staged + barrier, reduce done)] {a}  tile1 {b2}  mma [prologue, S(0) issued, loop end] {mm2}")
 if items > 2:
     per_item = np.diff(t[4, 1:items, 0]).mean()
     print(f"cycles per item {per_item:.0f}; loop {np.mean(t[4,1:items,1]-t[4,1:items,0]):.0f}; wait O {np.mean(t[4,1:items,2]-t[4,1:items,1]):.0f}; "

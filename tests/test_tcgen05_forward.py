@@ -65,18 +65,66 @@ def test_forward_matches_oracle(R, C, D, bf16):
     _run_and_check(R, C, D, bf16, seed=R * 7 + C * 3 + D)
 
 
+SPLIT_KV_CASES = [(4096, 4096, 128, True),   # 16 items x 8 splits: the headline single head
+                  (256, 2048, 64, False),    # 1 item x 4 splits
+                  (300, 2000, 128, True),    # ragged rows and a ragged last key block
+                  (512, 1536, 96, True),     # 12 key blocks -> 3 splits: cluster of 3, uneven row slices
+                  (1, 4096, 128, False),     # a single query row
+                  (2048, 2048, 64, True)]    # BASELINE configs[2] shape
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("R,C,D,bf16", [(4096, 4096, 128, True), (256, 2048, 64, False), (300, 2000, 128, True),
-                                        (512, 1536, 96, True)])
-def test_split_kv_small_grids(R, C, D, bf16):
-    """Few (head, tile pair) items: the key axis is split across SMs and merged by the combine kernel."""
+@pytest.mark.parametrize("cluster", [True, False], ids=["cluster-dsmem", "scratch-combine"])
+@pytest.mark.parametrize("R,C,D,bf16", SPLIT_KV_CASES)
+def test_split_kv_small_grids(R, C, D, bf16, cluster):
+    """Few (head, tile pair) items: the key axis is split across SMs.  Preferred form: the splits of an item are one
+    thread-block cluster and reduce through distributed shared memory inside the attention kernel (1 launch);
+    fallback: partials in scratch + the combine kernel (2 launches).  Both must match the oracle."""
     import mfa_b200 as mfa
     desc = _descriptor(R, C, D, bf16)
     kernel = mfa.AttentionKernel(desc.kernelDescriptor(mfa.AttentionKernelType.forward))
     constants = mfa.FunctionConstantValues()
     desc.setFunctionConstants(constants)
-    assert kernel.launchCount(constants) == 2, "split-KV should engage for this grid"
-    _run_and_check(R, C, D, bf16, seed=R + C + D)
+    mfa._lib.mfa_debug_set_forward_cluster(1 if cluster else 0)
+    try:
+        assert kernel.launchCount(constants) == (1 if cluster else 2), "split-KV should engage for this grid"
+        _run_and_check(R, C, D, bf16, seed=R + C + D)
+    finally:
+        mfa._lib.mfa_debug_set_forward_cluster(0)   # library default: the scratch form (faster on B200, see kernel source)
+
+
+@pytest.mark.gpu
+def test_split_kv_cluster_batched_heads_and_fp16_L():
+    """Cluster split-KV with several heads in one launch (item -> (head, pair) -> cluster) and FP16 L storage."""
+    import mfa_b200 as mfa
+    import oracle
+    from tests.attention_harness import run_attention, check
+    H, N, D = 3, 1024, 128
+    desc = _descriptor(N, N, D, True, lowMid=True, batch=H)
+    kernel = mfa.AttentionKernel(desc.kernelDescriptor(mfa.AttentionKernelType.forward))
+    constants = mfa.FunctionConstantValues()
+    desc.setFunctionConstants(constants)
+    mfa._lib.mfa_debug_set_forward_cluster(1)
+    try:
+        assert kernel.launchCount(constants) == 1
+        _check_batched_cluster(desc, H, N, D)
+    finally:
+        mfa._lib.mfa_debug_set_forward_cluster(0)
+
+
+def _check_batched_cluster(desc, H, N, D):
+    import mfa_b200 as mfa
+    import oracle
+    from tests.attention_harness import run_attention, check
+    nets = [oracle.Network(N, N, D, seed=100 + h, threads=8).round_inputs(oracle.BF16) for h in range(H)]
+    Op = mfa.AttentionOperand
+    inputs = {Op.Q: np.stack([n.Q for n in nets]), Op.K: np.stack([n.K for n in nets]),
+              Op.V: np.stack([n.V for n in nets])}
+    out = run_attention(desc, None, types=[mfa.AttentionKernelType.forward], inputs=inputs)
+    for h, net in enumerate(nets):
+        O, L = net.inferenceAttention(with_L=True)
+        check_O(O, out["O"][h], net.V, True, name=f"O[head {h}]")
+        check(L, out["L"][h], 7e-3, f"L[head {h}]")
 
 
 @pytest.mark.gpu
