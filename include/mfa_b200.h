@@ -112,9 +112,11 @@ typedef struct mfa_attention_descriptor {
   uint8_t input_precision_override;    /* 0: reference policy (Q,K,V FP16 and dO BF16 when lowPrecisionInputs,
                                           AttentionDescriptor+Precisions.swift:13-23);
                                           MFA_BF16 (2): Q,K,V,dO are all BF16 in memory (north_star asks for bf16);
-                                          MFA_FP16 (1): Q,K,V,dO are all FP16 (the tensor-core backward needs one
-                                          element type: tcgen05 kind::f16 cannot mix FP16 and BF16 operands).
-                                          Only meaningful with low_precision_inputs. */
+                                          MFA_FP16 (1): Q,K,V,dO are all FP16.
+                                          Only meaningful with low_precision_inputs.  All three variants run on the
+                                          tensor-core kernels (with the reference policy the backward kernels rewrite
+                                          the staged BF16 dO tiles as FP16 on chip: tcgen05 kind::f16 cannot mix
+                                          FP16 and BF16 operands in one MMA). */
   uint8_t reserved0;
   uint32_t batch_count;                /* 0 or 1: single head (reference). N > 1: N independent
                                           single-head problems, each operand stored back to back
@@ -239,6 +241,19 @@ MFA_API int mfa_attention_kernel_launch_count(const mfa_attention_kernel_t *kern
                                               const mfa_function_constants_t *constants, uint32_t *out);
 
 /* ------------------------------------------------------------------------------------------ */
+/* Kernel cache keyed by descriptor                                                            */
+/* ------------------------------------------------------------------------------------------ */
+/** The analogue of the reference's pipeline cache (GEMMKernel.register(descriptor:) / pipelineCache[descriptor],
+ *  R/GEMM/GEMMDescriptor/GEMMDescriptor+PipelineCache.swift:16-36): descriptor.kernelDescriptor(type:) +
+ *  AttentionKernel(descriptor:) run once per distinct (descriptor, type) and the validated kernel object is kept.
+ *  R, C and batch_count are launch-time constants and not part of the key.  The returned handle is owned by the
+ *  library (do NOT destroy it), is immutable, and stays valid until the process exits.  Thread-safe. */
+MFA_API int mfa_attention_kernel_cache_fetch(const mfa_attention_descriptor_t *descriptor, mfa_kernel_type_t type,
+                                             const mfa_attention_kernel_t **out);
+/** Number of kernel objects the cache currently holds. */
+MFA_API int mfa_attention_kernel_cache_size(void);
+
+/* ------------------------------------------------------------------------------------------ */
 /* Host-buffer convenience (the e2e path): H2D -> selected kernels -> D2H, synchronous.        */
 /* ------------------------------------------------------------------------------------------ */
 #define MFA_RUN_FORWARD (1u << MFA_FORWARD)
@@ -249,7 +264,10 @@ MFA_API int mfa_attention_kernel_launch_count(const mfa_attention_kernel_t *kern
  *  memoryPrecisions[operand]).  Inputs (Q,K,V, and dO for backward) are copied to the device,
  *  the kernels in `run_mask` are encoded in the reference's order fwd -> dQ -> dK/dV, and every
  *  output they produce whose host pointer is non-NULL is copied back.  Device scratch is owned
- *  by the library (grown on demand, per calling thread).  `device` = CUDA device ordinal. */
+ *  by the library (grown on demand, per calling thread).  `device` = CUDA device ordinal.
+ *  With batch_count > 1 the independent problems are processed in chunks that rotate over three
+ *  streams, so uploads, kernels and downloads of neighbouring chunks overlap (pass page-locked host
+ *  memory to get the overlap; pageable memory still works, serialised by the driver). */
 MFA_API int mfa_attention_run_host(const mfa_attention_descriptor_t *descriptor, uint32_t run_mask,
                                    void *const host_buffers[MFA_BUFFER_COUNT], int device);
 

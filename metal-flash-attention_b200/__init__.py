@@ -124,6 +124,8 @@ def _load():
                                                       c.POINTER(c.c_uint32)]
     lib.mfa_attention_kernel_encode.argtypes = [c.c_void_p, c.POINTER(_CFunctionConstants),
                                                 c.POINTER(c.c_void_p * MFA_BUFFER_COUNT), c.c_void_p]
+    lib.mfa_attention_kernel_cache_fetch.argtypes = [c.POINTER(_CDescriptor), c.c_int, c.POINTER(c.c_void_p)]
+    lib.mfa_attention_kernel_cache_size.restype = c.c_int
     lib.mfa_attention_run_host.argtypes = [c.POINTER(_CDescriptor), c.c_uint32,
                                            c.POINTER(c.c_void_p * MFA_BUFFER_COUNT), c.c_int]
     return lib
@@ -399,11 +401,27 @@ class AttentionKernel:
 
     def __init__(self, descriptor: AttentionKernelDescriptor):
         self._handle = ctypes.c_void_p()
+        self._owned = True
         _check(_lib.mfa_attention_kernel_create(ctypes.byref(descriptor._c), ctypes.byref(self._handle)))
+
+    @classmethod
+    def cached(cls, descriptor: AttentionDescriptor, type: AttentionKernelType) -> "AttentionKernel":
+        """mfa_attention_kernel_cache_fetch: the kernel object for (descriptor, type), built once per process and
+        owned by the library (the analogue of GEMMKernel.pipelineCache, GEMMDescriptor+PipelineCache.swift:16-36)."""
+        self = cls.__new__(cls)
+        self._handle = ctypes.c_void_p()
+        self._owned = False
+        c = descriptor._c()
+        _check(_lib.mfa_attention_kernel_cache_fetch(ctypes.byref(c), int(type), ctypes.byref(self._handle)))
+        return self
+
+    @staticmethod
+    def cacheSize() -> int:
+        return _lib.mfa_attention_kernel_cache_size()
 
     def __del__(self):
         handle = getattr(self, "_handle", None)
-        if handle and _lib is not None:  # _lib is None during interpreter teardown
+        if handle and getattr(self, "_owned", False) and _lib is not None:  # _lib is None during interpreter teardown
             _lib.mfa_attention_kernel_destroy(handle)
             self._handle = None
 

@@ -34,8 +34,7 @@ int memory_precision(const mfa_attention_descriptor_t &d, int operand) {
       // :13-23  FP16 when lowPrecisionInputs (extension: BF16 when overridden)
       return d.low_precision_inputs ? (bf16Inputs ? MFA_BF16 : MFA_FP16) : MFA_FP32;
     case MFA_dO:
-      // :17,22  BF16 when lowPrecisionInputs (extension: FP16 when the override asks for an all-FP16 operand set,
-      // which is what the tensor-core backward needs -- tcgen05 kind::f16 cannot mix FP16 and BF16 operands)
+      // :17,22  BF16 when lowPrecisionInputs (extension: FP16 when the override asks for an all-FP16 operand set)
       return d.low_precision_inputs ? (d.input_precision_override == MFA_FP16 ? MFA_FP16 : MFA_BF16) : MFA_FP32;
     case MFA_L:
       return d.low_precision_intermediates ? MFA_FP16 : MFA_FP32;  // :81-87
@@ -124,10 +123,8 @@ int select_backend(const mfa_attention_descriptor_t &d, int type) {
   if (d.head % 8 != 0 || d.head == 0) return MFA_BACKEND_SIMT_FP32;
   const uint32_t maxHead = (type == MFA_FORWARD) ? tcgen05_forward_max_head() : tcgen05_backward_max_head();
   if (d.head > maxHead) return MFA_BACKEND_SIMT_FP32;
-  // the tcgen05 backward kernels consume dO through the same 16-bit MMA path as Q/K/V: the two
-  // element types must match (reference policy FP16 Q/K/V + BF16 dO goes to the SIMT family).
-  if (type != MFA_FORWARD && memory_precision(d, MFA_dO) != memory_precision(d, MFA_Q))
-    return MFA_BACKEND_SIMT_FP32;
+  // (the reference's own policy, FP16 Q/K/V + BF16 dO, is served too: tcgen05 kind::f16 cannot mix element types
+  // inside one MMA, so the backward kernels rewrite the staged dO tile as FP16 in shared memory)
   return MFA_BACKEND_TCGEN05;
 }
 

@@ -126,11 +126,14 @@ int mfa_attention_kernel_create(const mfa_attention_kernel_descriptor_t *kd, mfa
               D <= (k->type == MFA_FORWARD ? tcgen05_forward_max_head() : tcgen05_backward_max_head());
     for (int i = 0; i < n; ++i)
       if ((kd->transpose_state_mask >> ops[i]) & 1) ok = false;
-    if (k->type != MFA_FORWARD && kd->memory_precisions[MFA_dO] != pq) ok = false;
+    // dO: same element type, or BF16 beside FP16 Q/K/V (the reference's policy; converted on chip)
+    if (k->type != MFA_FORWARD && kd->memory_precisions[MFA_dO] != pq &&
+        !(pq == MFA_FP16 && kd->memory_precisions[MFA_dO] == MFA_BF16))
+      ok = false;
     if (!ok) {
       delete k;
       return fail(MFA_ERROR_UNSUPPORTED,
-                  "MFA_BACKEND_TCGEN05 needs FP16/BF16 row-major Q,K,V (and dO of the same type), head % 8 == 0 "
+                  "MFA_BACKEND_TCGEN05 needs FP16/BF16 row-major Q,K,V (dO of the same type, or BF16 with FP16 Q,K,V), head % 8 == 0 "
                   "and head <= the compiled maximum; use MFA_BACKEND_SIMT_FP32 for this descriptor.");
     }
     if (k->type == MFA_FORWARD)
@@ -257,19 +260,87 @@ MFA_API void mfa_debug_set_forward_cluster(int enabled) { tcgen05_forward_set_cl
 MFA_API int mfa_debug_forward_max_clusters(uint32_t splits) { return tcgen05_forward_max_clusters(splits); }
 
 // ------------------------------------------------------------------------------------------------
-// Host-buffer path: H2D -> kernels -> D2H (the end-to-end call bench.py times as `e2e`).
+// Kernel cache keyed by descriptor -- the useful half of the reference's pipeline cache
+// (GEMMKernel.pipelineCache / register(descriptor:), GEMM/GEMMDescriptor/GEMMDescriptor+PipelineCache.swift:16-36):
+// the reference caches (kernel, MTLComputePipelineState) per problem descriptor because a Metal JIT compile costs
+// milliseconds; here the kernels are compiled ahead of time, so what is worth keeping is the validated kernel object.
+// Handles returned from the cache are owned by the library and live until process exit.
 // ------------------------------------------------------------------------------------------------
 namespace {
+struct CacheKey {
+  mfa_attention_descriptor_t descriptor;
+  int type;
+};
+std::mutex g_cache_mutex;
+std::vector<std::pair<CacheKey, mfa_attention_kernel_t *>> g_kernel_cache;
+
+bool same_descriptor(const mfa_attention_descriptor_t &a, const mfa_attention_descriptor_t &b) {
+  // field-wise (struct padding is not part of the value); the matrix dimensions R, C and the batch count are launch-time
+  // constants (setFunctionConstants), not part of the kernel -- only the head dimension is
+  return a.low_precision_inputs == b.low_precision_inputs &&
+         a.low_precision_intermediates == b.low_precision_intermediates &&
+         a.has_matrix_dimensions == b.has_matrix_dimensions && a.has_transpose_state == b.has_transpose_state &&
+         a.head == b.head && a.transpose_Q == b.transpose_Q && a.transpose_K == b.transpose_K &&
+         a.transpose_V == b.transpose_V && a.transpose_O == b.transpose_O &&
+         a.input_precision_override == b.input_precision_override;
+}
+}  // namespace
+
+int mfa_attention_kernel_cache_fetch(const mfa_attention_descriptor_t *descriptor, mfa_kernel_type_t type,
+                                     const mfa_attention_kernel_t **out) {
+  if (!descriptor || !out) return fail(MFA_ERROR_INVALID_ARGUMENT, "NULL argument.");
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
+  for (const auto &entry : g_kernel_cache)
+    if (entry.first.type == static_cast<int>(type) && same_descriptor(entry.first.descriptor, *descriptor)) {
+      *out = entry.second;
+      return MFA_SUCCESS;
+    }
+  mfa_attention_kernel_descriptor_t kd;
+  int status = mfa_attention_descriptor_kernel_descriptor(descriptor, type, &kd);
+  if (status != MFA_SUCCESS) return status;
+  mfa_attention_kernel_t *kernel = nullptr;
+  if ((status = mfa_attention_kernel_create(&kd, &kernel)) != MFA_SUCCESS) return status;
+  g_kernel_cache.push_back({CacheKey{*descriptor, static_cast<int>(type)}, kernel});
+  *out = kernel;
+  return MFA_SUCCESS;
+}
+
+int mfa_attention_kernel_cache_size(void) {
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
+  return static_cast<int>(g_kernel_cache.size());
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host-buffer path: H2D -> kernels -> D2H (the end-to-end call bench.py times as `e2e`).
+//
+// The independent single-head problems of a batch are cut into chunks that rotate over three streams, so the
+// host->device copy of chunk i+1, the kernels of chunk i and the device->host copy of chunk i-1 overlap (PCIe is full
+// duplex and the GPU has separate copy engines per direction).  With pinned host buffers the call then costs
+// max(H2D, D2H) + one chunk of fill/drain instead of H2D + kernels + D2H.
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int kHostStreams = 3;
 struct Scratch {
   void *ptr[MFA_BUFFER_COUNT] = {};
   size_t bytes[MFA_BUFFER_COUNT] = {};
   int device = -1;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream[kHostStreams] = {};
   ~Scratch() {
     // Process teardown: the CUDA context may already be gone; leaking here is deliberate.
   }
 };
 thread_local Scratch g_scratch;
+
+// heads per chunk: about eight chunks, but no chunk smaller than ~4 MB of traffic (copy launch overheads) and none at
+// all for a single problem
+uint32_t chunk_heads(uint32_t batch, size_t bytes_per_head) {
+  if (batch <= 1) return 1;
+  uint32_t heads = (batch + 7) / 8;
+  const size_t kMinChunkBytes = size_t(4) << 20;
+  if (bytes_per_head * heads < kMinChunkBytes)
+    heads = static_cast<uint32_t>((kMinChunkBytes + bytes_per_head - 1) / bytes_per_head);
+  return heads < batch ? heads : batch;
+}
 }  // namespace
 
 int mfa_attention_run_host(const mfa_attention_descriptor_t *descriptor, uint32_t run_mask,
@@ -287,8 +358,9 @@ int mfa_attention_run_host(const mfa_attention_descriptor_t *descriptor, uint32_
       s.bytes[i] = 0;
     }
     s.device = device;
-    if ((e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess)
-      return fail(MFA_ERROR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    for (int i = 0; i < kHostStreams; ++i)
+      if ((e = cudaStreamCreateWithFlags(&s.stream[i], cudaStreamNonBlocking)) != cudaSuccess)
+        return fail(MFA_ERROR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
   }
 
   // which operands each kernel reads / writes (AttentionKernelType.swift:10-22)
@@ -309,53 +381,74 @@ int mfa_attention_run_host(const mfa_attention_descriptor_t *descriptor, uint32_
     outputs |= (1u << MFA_dV) | (1u << MFA_dK);
   }
 
-  void *dev[MFA_BUFFER_COUNT] = {};
-  size_t nbytes[MFA_BUFFER_COUNT] = {};
-  for (int op = 0; op < MFA_BUFFER_COUNT; ++op) {
-    if (!((inputs | outputs) & (1u << op))) continue;
-    size_t elements = 0;
-    int status = mfa_attention_descriptor_operand_elements(descriptor, (mfa_operand_t)op, &elements);
-    if (status != MFA_SUCCESS) return status;
-    nbytes[op] = elements * (memory_precision(*descriptor, op) == MFA_FP32 ? 4 : 2);
-    if (s.bytes[op] < nbytes[op]) {
-      if (s.ptr[op]) cudaFree(s.ptr[op]);
-      s.ptr[op] = nullptr;
-      s.bytes[op] = 0;
-      if ((e = cudaMalloc(&s.ptr[op], nbytes[op])) != cudaSuccess)
-        return fail(MFA_ERROR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
-      s.bytes[op] = nbytes[op];
-    }
-    dev[op] = s.ptr[op];
-    if (inputs & (1u << op)) {
-      if (!host_buffers[op])
-        return fail(MFA_ERROR_INVALID_ARGUMENT, std::string("Host buffer ") + mfa_operand_name((mfa_operand_t)op) + " is NULL.");
-      if ((e = cudaMemcpyAsync(dev[op], host_buffers[op], nbytes[op], cudaMemcpyHostToDevice, s.stream)) != cudaSuccess)
-        return fail(MFA_ERROR_CUDA, std::string("H2D copy: ") + cudaGetErrorString(e));
-    }
-  }
-
   mfa_function_constants_t constants;
   int status = mfa_attention_descriptor_set_function_constants(descriptor, &constants);
   if (status != MFA_SUCCESS) return status;
-  // reference order: forward -> backwardQuery -> backwardKeyValue (SquareAttentionTest.swift:355-368)
-  for (int type = MFA_FORWARD; type <= MFA_BACKWARD_KEY_VALUE; ++type) {
-    if (!(run_mask & (1u << type))) continue;
-    mfa_attention_kernel_descriptor_t kd;
-    if ((status = mfa_attention_descriptor_kernel_descriptor(descriptor, (mfa_kernel_type_t)type, &kd)) != MFA_SUCCESS)
-      return status;
-    mfa_attention_kernel_t *kernel = nullptr;
-    if ((status = mfa_attention_kernel_create(&kd, &kernel)) != MFA_SUCCESS) return status;
-    status = mfa_attention_kernel_encode(kernel, &constants, dev, s.stream);
-    mfa_attention_kernel_destroy(kernel);
-    if (status != MFA_SUCCESS) return status;
-  }
+  const uint32_t batch = constants.batch_count ? constants.batch_count : 1;
+
+  void *dev[MFA_BUFFER_COUNT] = {};
+  size_t head_bytes[MFA_BUFFER_COUNT] = {};  // bytes of one single-head problem, per operand
+  size_t traffic_per_head = 0;
   for (int op = 0; op < MFA_BUFFER_COUNT; ++op) {
-    if (!(outputs & (1u << op)) || !host_buffers[op]) continue;
-    if ((e = cudaMemcpyAsync(host_buffers[op], dev[op], nbytes[op], cudaMemcpyDeviceToHost, s.stream)) != cudaSuccess)
-      return fail(MFA_ERROR_CUDA, std::string("D2H copy: ") + cudaGetErrorString(e));
+    if (!((inputs | outputs) & (1u << op))) continue;
+    size_t elements = 0;
+    status = mfa_attention_descriptor_operand_elements(descriptor, (mfa_operand_t)op, &elements);
+    if (status != MFA_SUCCESS) return status;
+    const size_t nbytes = elements * (memory_precision(*descriptor, op) == MFA_FP32 ? 4 : 2);
+    head_bytes[op] = nbytes / batch;
+    if (s.bytes[op] < nbytes) {
+      if (s.ptr[op]) cudaFree(s.ptr[op]);
+      s.ptr[op] = nullptr;
+      s.bytes[op] = 0;
+      if ((e = cudaMalloc(&s.ptr[op], nbytes)) != cudaSuccess)
+        return fail(MFA_ERROR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+      s.bytes[op] = nbytes;
+    }
+    dev[op] = s.ptr[op];
+    if ((inputs & (1u << op)) && !host_buffers[op])
+      return fail(MFA_ERROR_INVALID_ARGUMENT,
+                  std::string("Host buffer ") + mfa_operand_name((mfa_operand_t)op) + " is NULL.");
+    if ((inputs & (1u << op)) || host_buffers[op]) traffic_per_head += head_bytes[op];
   }
-  if ((e = cudaStreamSynchronize(s.stream)) != cudaSuccess)
-    return fail(MFA_ERROR_CUDA, std::string("kernel execution failed: ") + cudaGetErrorString(e));
+
+  // reference order: forward -> backwardQuery -> backwardKeyValue (SquareAttentionTest.swift:355-368)
+  const mfa_attention_kernel_t *kernels[3] = {};
+  for (int type = MFA_FORWARD; type <= MFA_BACKWARD_KEY_VALUE; ++type)
+    if (run_mask & (1u << type))
+      if ((status = mfa_attention_kernel_cache_fetch(descriptor, (mfa_kernel_type_t)type, &kernels[type])) != MFA_SUCCESS)
+        return status;
+
+  const uint32_t per_chunk = chunk_heads(batch, traffic_per_head);
+  uint32_t chunk_index = 0;
+  for (uint32_t h0 = 0; h0 < batch; h0 += per_chunk, ++chunk_index) {
+    const uint32_t heads = batch - h0 < per_chunk ? batch - h0 : per_chunk;
+    cudaStream_t stream = s.stream[chunk_index % kHostStreams];
+    void *chunk_dev[MFA_BUFFER_COUNT] = {};
+    for (int op = 0; op < MFA_BUFFER_COUNT; ++op) {
+      if (!dev[op]) continue;
+      chunk_dev[op] = static_cast<char *>(dev[op]) + head_bytes[op] * h0;
+      if (inputs & (1u << op)) {
+        const char *src = static_cast<const char *>(host_buffers[op]) + head_bytes[op] * h0;
+        if ((e = cudaMemcpyAsync(chunk_dev[op], src, head_bytes[op] * heads, cudaMemcpyHostToDevice, stream)) != cudaSuccess)
+          return fail(MFA_ERROR_CUDA, std::string("H2D copy: ") + cudaGetErrorString(e));
+      }
+    }
+    mfa_function_constants_t chunk_constants = constants;
+    chunk_constants.batch_count = heads;
+    for (int type = MFA_FORWARD; type <= MFA_BACKWARD_KEY_VALUE; ++type)
+      if (kernels[type] &&
+          (status = mfa_attention_kernel_encode(kernels[type], &chunk_constants, chunk_dev, stream)) != MFA_SUCCESS)
+        return status;
+    for (int op = 0; op < MFA_BUFFER_COUNT; ++op) {
+      if (!(outputs & (1u << op)) || !host_buffers[op]) continue;
+      char *dst = static_cast<char *>(host_buffers[op]) + head_bytes[op] * h0;
+      if ((e = cudaMemcpyAsync(dst, chunk_dev[op], head_bytes[op] * heads, cudaMemcpyDeviceToHost, stream)) != cudaSuccess)
+        return fail(MFA_ERROR_CUDA, std::string("D2H copy: ") + cudaGetErrorString(e));
+    }
+  }
+  for (int i = 0; i < kHostStreams; ++i)
+    if ((e = cudaStreamSynchronize(s.stream[i])) != cudaSuccess)
+      return fail(MFA_ERROR_CUDA, std::string("kernel execution failed: ") + cudaGetErrorString(e));
   return MFA_SUCCESS;
 }
 

@@ -72,8 +72,19 @@ __device__ __forceinline__ void store_stat(void *p, size_t i, int prec, float v)
   else reinterpret_cast<uint16_t *>(p)[i] = static_cast<uint16_t>(__float_as_uint(v) >> 16);  // BF16 store truncates
 }
 
+// dO arrives as BF16 while Q, K, V are FP16 (the reference's own low-precision policy,
+// AttentionDescriptor+Precisions.swift:13-23); tcgen05 kind::f16 cannot mix the two element types in one MMA, so the
+// staged dO tile is rewritten in place as FP16 before any MMA reads it.  BF16 -> FP16 is exact for 2^-14 <= |x| < 65504
+// (8 significant bits fit FP16's 11); gradients outside that range would not survive FP16 Q/K/V either.
+__device__ __forceinline__ uint32_t bf16x2_to_f16x2(uint32_t w) {
+  return pack_f16x2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
+}
+__device__ __forceinline__ uint4 bf16x8_to_f16x8(uint4 v) {
+  return make_uint4(bf16x2_to_f16x2(v.x), bf16x2_to_f16x2(v.y), bf16x2_to_f16x2(v.z), bf16x2_to_f16x2(v.w));
+}
+
 struct BackwardArgs {
-  const void *dO;   // [batch][R][D] 16-bit (same element type as Q/K/V)
+  const void *dO;   // [batch][R][D] 16-bit (element type of Q/K/V, or BF16 beside FP16 Q/K/V: kConvertDO)
   const float *O;   // [batch][R][D] FP32
   const void *L;    // [batch][R]
   void *Dterm;      // [batch][R]
@@ -88,7 +99,7 @@ struct BackwardArgs {
 //   TMEM columns: [0,128) S (single buffer, released as soon as it is in registers),
 //                 [128,256) [256,384) dP double buffer (dS is written in place over dP),  [384,384+D) dQ
 // ================================================================================================
-template <uint32_t DPAD, bool kBF16>
+template <uint32_t DPAD, bool kBF16, bool kConvertDO>
 __global__ void __launch_bounds__(kThreads, 1)
     attention_backward_query_tcgen05(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapdO,
                                      const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV,
@@ -114,6 +125,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t *dp_full = bars + 11;      // [2] dP(j) in TMEM
   uint64_t *ds_full = bars + 13;      // [2] dS(j) written over dP(j) (256 arrivals)
   uint64_t *dq_final = bars + 15;     // every MMA has completed
+  uint64_t *do_ready = bars + 16;     // kConvertDO: the resident dO tile has been rewritten as FP16 (256 arrivals)
+  static_assert(!(kBF16 && kConvertDO), "dO is only converted when Q, K, V are FP16");
+  constexpr bool kDOisBF16 = kBF16 || kConvertDO;  // element type of dO in global memory
   uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem + Cfg::kSmemTmemPtr);
 
   if (threadIdx.x == 0) {
@@ -129,6 +143,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     mbar_init(s_full, 1);
     mbar_init(s_free, kElemThreads);
     mbar_init(dq_final, 1);
+    mbar_init(do_ready, kElemThreads);
     fence_barrier_init();
   }
   if (warp == 8) {
@@ -149,6 +164,18 @@ __global__ void __launch_bounds__(kThreads, 1)
     const uint32_t row_c = min(row, a.R - 1);  // clamped like clampedParallelizationThreadOffset (AttentionKernel.swift:224-226)
     const uint32_t tLane = tmem_base + ((quarter * 32) << 16);
 
+    if constexpr (kConvertDO) {
+      // BF16 dO tile (TMA) -> FP16 in place; elementwise, so the 128 B swizzle is irrelevant.  Generic-proxy writes
+      // must be fenced before the tensor core (async proxy) reads them.
+      mbar_wait(q_full, 0);
+      uint4 *tile = reinterpret_cast<uint4 *>(smem + Cfg::kSmemResident1);
+#pragma unroll
+      for (uint32_t i = 0; i < Cfg::kTileBytes / (kElemThreads * 16); ++i)
+        tile[i * kElemThreads + threadIdx.x] = bf16x8_to_f16x8(tile[i * kElemThreads + threadIdx.x]);
+      fence_proxy_async_smem();
+      mbar_arrive(do_ready);
+    }
+
     // computeD (AttentionKernel+Softmax.swift:32-221): D = (sum_d dO * O) / sqrt(D), kept in FP32 for this kernel
     // and stored (possibly as BF16) for the dK/dV kernel.  L arrives in log2 units from the forward kernel.
     float Dterm;
@@ -168,7 +195,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         float v[8];
 #pragma unroll
         for (uint32_t k = 0; k < 4; ++k) {
-          if (kBF16) {
+          if (kDOisBF16) {
             v[2 * k] = __uint_as_float(w[k] << 16);
             v[2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
           } else {
@@ -316,11 +343,16 @@ __global__ void __launch_bounds__(kThreads, 1)
       // prologue: S(0), dP(0), dP(1)
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
-      mbar_wait(&v_full[0], 0);
       tc_fence_after();
       if (elect_one()) {
         issue_nt(tmem_base + kTmemS, descQ, descK);
         umma_commit(s_full);
+      }
+      __syncwarp();
+      mbar_wait(&v_full[0], 0);
+      if constexpr (kConvertDO) mbar_wait(do_ready, 0);
+      tc_fence_after();
+      if (elect_one()) {
         issue_nt(tmem_base + kTmemdP, descdO, descV);
         umma_commit(&dp_full[0]);
         umma_commit(&v_empty[0]);
@@ -387,7 +419,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 // backwardKeyValue
 //   TMEM columns: [0,128) S^T / P^T,  [128,256) dP^T / dS^T,  [256,256+D) dV,  [256+D,256+2D) dK
 // ================================================================================================
-template <uint32_t DPAD, bool kBF16>
+template <uint32_t DPAD, bool kBF16, bool kConvertDO>
 __global__ void __launch_bounds__(kThreads, 1)
     attention_backward_key_value_tcgen05(const __grid_constant__ CUtensorMap mapQ,
                                          const __grid_constant__ CUtensorMap mapdO,
@@ -412,6 +444,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t *st_full = bars + 9;       // S^T(r), dP^T(r) in TMEM
   uint64_t *pt_full = bars + 10;      // P^T(r), dS^T(r) written (256 arrivals)
   uint64_t *acc_final = bars + 11;
+  uint64_t *do_ready = bars + 12;     // [2] kConvertDO: staged dO(r) rewritten as FP16 (warps 10 and 11: 64 arrivals)
+  static_assert(!(kBF16 && kConvertDO), "dO is only converted when Q, K, V are FP16");
   float *vecL = reinterpret_cast<float *>(smem + Cfg::kSmemVec);  // [stage][128]
   float *vecD = vecL + 2 * kTile;
   uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem + Cfg::kSmemTmemPtr);
@@ -423,6 +457,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&q_empty[s], 1);
       mbar_init(&vec_full[s], 32);
       mbar_init(&vec_empty[s], kElemThreads);
+      mbar_init(&do_ready[s], 64);
     }
     mbar_init(st_full, 1);
     mbar_init(pt_full, kElemThreads);
@@ -512,6 +547,16 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else {
     setmaxnreg_dec<kOtherRegs>();
+    // kConvertDO: warps 10 and 11 each rewrite one half of the staged BF16 dO tile as FP16 once the TMA has landed it
+    // (the tile cannot be reloaded before the MMAs that wait on do_ready have retired: q_empty)
+    auto convert_dO = [&](uint32_t stage, uint32_t phase, uint32_t half) {
+      mbar_wait(&q_full[stage], phase);
+      uint4 *tile = reinterpret_cast<uint4 *>(smem + Cfg::kSmemStage1 + stage * Cfg::kTileBytes + half * (Cfg::kTileBytes / 2));
+#pragma unroll 8
+      for (uint32_t i = 0; i < Cfg::kTileBytes / 2 / 512; ++i) tile[i * 32 + lane] = bf16x8_to_f16x8(tile[i * 32 + lane]);
+      fence_proxy_async_smem();
+      mbar_arrive(&do_ready[stage]);
+    };
     if (warp == 9) {
       // ---------------- TMA producer ----------------
       if (elect_one()) {
@@ -550,7 +595,11 @@ __global__ void __launch_bounds__(kThreads, 1)
           vecD[stage * kTile + i * 32 + lane] = load_stat(a.Dterm, idx, a.d_prec);
         }
         mbar_arrive(&vec_full[stage]);  // release semantics order the shared-memory writes above
+        if constexpr (kConvertDO) convert_dO(stage, phase, 0);
       }
+    } else if (warp == 11) {
+      if constexpr (kConvertDO)
+        for (uint32_t r = 0; r < num_blocks; ++r) convert_dO(r & 1, (r >> 1) & 1, 1);
     } else if (warp == 8) {
       // ---------------- MMA issuer ----------------
       constexpr uint32_t kFormat = kBF16 ? 1u : 0u;
@@ -587,6 +636,13 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (elect_one()) {
           // (the previous block's dV / dK MMAs read P^T / dS^T from these columns; the tensor pipe runs in order)
           issue_nt(tmem_base + kTmemST, descK, descQ + soff);    // S^T  = K Q^T
+        }
+        __syncwarp();
+        if constexpr (kConvertDO) {
+          mbar_wait(&do_ready[stage], phase);
+          tc_fence_after();
+        }
+        if (elect_one()) {
           issue_nt(tmem_base + kTmemdPT, descV, descdO + soff);  // dP^T = V dO^T
           umma_commit(st_full);
         }
@@ -612,11 +668,11 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
 }
 
-template <uint32_t DPAD, bool kBF16>
+template <uint32_t DPAD, bool kBF16, bool kConvertDO = false>
 cudaError_t launch(const AttentionParams &p, cudaStream_t stream, bool key_value) {
   using Cfg = Config<DPAD>;
-  auto kernel_q = attention_backward_query_tcgen05<DPAD, kBF16>;
-  auto kernel_kv = attention_backward_key_value_tcgen05<DPAD, kBF16>;
+  auto kernel_q = attention_backward_query_tcgen05<DPAD, kBF16, kConvertDO>;
+  auto kernel_kv = attention_backward_key_value_tcgen05<DPAD, kBF16, kConvertDO>;
   static std::once_flag once;
   static cudaError_t attr_status = cudaSuccess;
   std::call_once(once, [&] {
@@ -663,8 +719,10 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, bool key_value
 uint32_t tcgen05_backward_max_head() { return 128; }
 
 bool tcgen05_backward_supported(const AttentionParams &p) {
+  // dO: the element type of Q/K/V, or BF16 beside FP16 Q/K/V (the reference's policy; converted on chip)
+  const bool dO_ok = p.prec[sdO] == p.prec[sQ] || (p.prec[sQ] == FP16 && p.prec[sdO] == BF16);
   const bool types = (p.prec[sQ] == FP16 || p.prec[sQ] == BF16) && p.prec[sK] == p.prec[sQ] &&
-                     p.prec[sV] == p.prec[sQ] && p.prec[sdO] == p.prec[sQ] && p.prec[sO] == FP32 &&
+                     p.prec[sV] == p.prec[sQ] && dO_ok && p.prec[sO] == FP32 &&
                      p.prec[sdQ] == FP32 && p.prec[sdK] == FP32 && p.prec[sdV] == FP32;
   const bool layout = !p.transposed[sQ] && !p.transposed[sK] && !p.transposed[sV] && !p.transposed[sO] &&
                       !p.transposed[sdO] && !p.transposed[sdQ] && !p.transposed[sdK] && !p.transposed[sdV];
@@ -677,8 +735,12 @@ static cudaError_t launch_backward(const AttentionParams &p, cudaStream_t stream
     return cudaErrorInvalidValue;
   }
   const bool bf16 = p.prec[sQ] == BF16;
-  if (p.D <= 64)
+  const bool convert = p.prec[sdO] != p.prec[sQ];  // FP16 Q/K/V with BF16 dO
+  if (p.D <= 64) {
+    if (convert) return bwd::launch<64, false, true>(p, stream, key_value);
     return bf16 ? bwd::launch<64, true>(p, stream, key_value) : bwd::launch<64, false>(p, stream, key_value);
+  }
+  if (convert) return bwd::launch<128, false, true>(p, stream, key_value);
   return bf16 ? bwd::launch<128, true>(p, stream, key_value) : bwd::launch<128, false>(p, stream, key_value);
 }
 

@@ -38,8 +38,42 @@ static EncodeTiledFn resolve_encode() {
   return fn;
 }
 
+// A tensor map is a pure function of (base, shape, box, type): callers that re-encode the same buffers (a training
+// loop, the benchmark's back-to-back dispatches) get the 128-byte descriptor from a small per-thread table instead of
+// a cuTensorMapEncodeTiled driver call (~1.5 us each, three or four per launch, against kernels of 15-25 us for one
+// head).  The descriptor says nothing about buffer *contents*, so a hit can never be stale.
+namespace {
+struct MapKey {
+  const void *base;
+  uint32_t seq, D, batch, boxCols, boxRows, dtype;
+  bool operator==(const MapKey &o) const {
+    return base == o.base && seq == o.seq && D == o.D && batch == o.batch && boxCols == o.boxCols &&
+           boxRows == o.boxRows && dtype == o.dtype;
+  }
+};
+struct MapEntry {
+  MapKey key;
+  CUtensorMap map;
+  bool valid = false;
+};
+constexpr uint32_t kMapCacheEntries = 32;  // direct-mapped
+thread_local MapEntry g_map_cache[kMapCacheEntries];
+uint32_t map_slot(const MapKey &k) {
+  uint64_t h = reinterpret_cast<uintptr_t>(k.base) * 0x9E3779B97F4A7C15ull;
+  h ^= (static_cast<uint64_t>(k.seq) << 32 | k.D) * 0xC2B2AE3D27D4EB4Full;
+  h ^= (static_cast<uint64_t>(k.batch) << 32 | (k.boxRows << 8) | k.dtype) * 0x165667B19E3779F9ull;
+  return static_cast<uint32_t>(h >> 40) % kMapCacheEntries;
+}
+}  // namespace
+
 static cudaError_t encode(CUtensorMap *map, CUtensorMapDataType dtype, uint32_t elemBytes, const void *base,
                           uint32_t seq, uint32_t D, uint32_t batch, uint32_t boxCols, uint32_t boxRows) {
+  const MapKey key{base, seq, D, batch, boxCols, boxRows, static_cast<uint32_t>(dtype)};
+  MapEntry &entry = g_map_cache[map_slot(key)];
+  if (entry.valid && entry.key == key) {
+    *map = entry.map;
+    return cudaSuccess;
+  }
   EncodeTiledFn fn = resolve_encode();
   if (!fn) {
     set_launch_detail("cuTensorMapEncodeTiled is not available from this driver");
@@ -60,6 +94,9 @@ static cudaError_t encode(CUtensorMap *map, CUtensorMapDataType dtype, uint32_t 
                       batch, boxCols, boxRows);
     return cudaErrorInvalidValue;
   }
+  entry.key = key;
+  entry.map = *map;
+  entry.valid = true;
   return cudaSuccess;
 }
 

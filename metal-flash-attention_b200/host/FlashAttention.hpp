@@ -89,7 +89,15 @@ struct AttentionDescriptor {  // AttentionDescriptor.swift:10-27
 class AttentionKernel {  // AttentionKernel.swift:11-50
  public:
   explicit AttentionKernel(const AttentionKernelDescriptor &descriptor) { check(mfa_attention_kernel_create(&descriptor.c, &handle_)); }
-  ~AttentionKernel() { mfa_attention_kernel_destroy(handle_); }
+  // library-owned kernel object from the descriptor-keyed cache (the analogue of GEMMKernel.pipelineCache[descriptor],
+  // GEMMDescriptor+PipelineCache.swift:16-36)
+  AttentionKernel(const AttentionDescriptor &descriptor, AttentionKernelType type) : owned_(false) {
+    mfa_attention_descriptor_t d = descriptor.c();
+    const mfa_attention_kernel_t *out = nullptr;
+    check(mfa_attention_kernel_cache_fetch(&d, static_cast<mfa_kernel_type_t>(type), &out));
+    handle_ = const_cast<mfa_attention_kernel_t *>(out);
+  }
+  ~AttentionKernel() { if (owned_) mfa_attention_kernel_destroy(handle_); }
   AttentionKernel(const AttentionKernel &) = delete;
   AttentionKernel &operator=(const AttentionKernel &) = delete;
   std::tuple<uint16_t, uint16_t, uint16_t> blockDimensions() const {
@@ -108,6 +116,7 @@ class AttentionKernel {  // AttentionKernel.swift:11-50
   }
  private:
   mfa_attention_kernel_t *handle_ = nullptr;
+  bool owned_ = true;
 };
 
 }  // namespace FlashAttention

@@ -113,14 +113,25 @@ public struct AttentionKernelDescriptor {
 /// AttentionKernel.swift:11-50, 268-363
 public final class AttentionKernel {
   let handle: OpaquePointer
+  let owned: Bool
 
   public init(descriptor: AttentionKernelDescriptor) {
     var kd = descriptor.c
     var out: OpaquePointer?
     check(mfa_attention_kernel_create(&kd, &out))
     handle = out!
+    owned = true
   }
-  deinit { mfa_attention_kernel_destroy(handle) }
+  /// Library-owned kernel object from the descriptor-keyed cache -- the analogue of
+  /// `GEMMKernel.pipelineCache[descriptor]` (GEMMDescriptor+PipelineCache.swift:16-36).
+  public init(cached descriptor: AttentionDescriptor, type: AttentionKernelType) {
+    var d = descriptor.c
+    var out: OpaquePointer?
+    check(mfa_attention_kernel_cache_fetch(&d, mfa_kernel_type_t(type.rawValue), &out))
+    handle = out!
+    owned = false
+  }
+  deinit { if owned { mfa_attention_kernel_destroy(handle) } }
 
   public var blockDimensions: (parallelization: UInt16, traversal: UInt16, head: UInt16) {
     var out: (UInt16, UInt16, UInt16) = (0, 0, 0)

@@ -17,13 +17,14 @@ KT, Op, P = mfa.AttentionKernelType, mfa.AttentionOperand, mfa.GEMMOperandPrecis
 def run(N, D, precision, H, steps=20):
     desc = mfa.AttentionDescriptor()
     desc.lowPrecisionInputs = True
-    desc.inputPrecisionOverride = precision
+    desc.inputPrecisionOverride = precision   # None = the reference's policy: FP16 Q/K/V, BF16 dO
     desc.matrixDimensions = (N, N, D)
     desc.transposeState = (False,) * 4
     desc.batchCount = H
     dt = torch.bfloat16 if precision == P.BF16 else torch.float16
+    dt_dO = torch.bfloat16 if precision is None else dt
     bufs = {Op.Q: torch.randn(H, N, D, device="cuda").to(dt), Op.K: torch.randn(H, N, D, device="cuda").to(dt),
-            Op.V: torch.randn(H, N, D, device="cuda").to(dt), Op.dO: torch.randn(H, N, D, device="cuda").to(dt),
+            Op.V: torch.randn(H, N, D, device="cuda").to(dt), Op.dO: torch.randn(H, N, D, device="cuda").to(dt_dO),
             Op.O: torch.empty(H, N, D, device="cuda"), Op.L: torch.empty(H, N, device="cuda"),
             Op.D: torch.empty(H, N, device="cuda"), Op.dQ: torch.empty(H, N, D, device="cuda"),
             Op.dK: torch.empty(H, N, D, device="cuda"), Op.dV: torch.empty(H, N, D, device="cuda")}
@@ -31,7 +32,8 @@ def run(N, D, precision, H, steps=20):
     c = mfa.FunctionConstantValues()
     desc.setFunctionConstants(c)
     stream = torch.cuda.current_stream().cuda_stream
-    out = {"N": N, "D": D, "dtype": precision.name, "heads": H}
+    out = {"N": N, "D": D, "dtype": precision.name if precision is not None else "FP16 Q/K/V + BF16 dO (reference policy)",
+           "heads": H}
     work = {KT.forward: (2 * D + 5, 4), KT.backwardQuery: (3 * D + 5, 6), KT.backwardKeyValue: (4 * D + 5, 8)}
     for t in KT:
         if D > 128 and t != KT.forward:
@@ -56,6 +58,7 @@ def run(N, D, precision, H, steps=20):
 
 if __name__ == "__main__":
     H = int(sys.argv[1]) if len(sys.argv) > 1 else 128
-    for N, D, prec, heads in ((8192, 256, P.BF16, 16), (8192, 256, P.BF16, 1), (2048, 64, P.FP16, H), (2048, 64, P.BF16, H), (4096, 128, P.BF16, 64), (4096, 64, P.BF16, 64),
+    for N, D, prec, heads in ((8192, 256, P.BF16, 16), (8192, 256, P.BF16, 1), (2048, 64, None, H), (2048, 64, P.FP16, H),
+                              (2048, 64, P.BF16, H), (4096, 128, None, 64), (4096, 128, P.BF16, 64), (4096, 64, P.BF16, 64),
                               (2048, 64, P.FP16, 1), (4096, 128, P.BF16, 1)):
         print(json.dumps(run(N, D, prec, heads)), flush=True)

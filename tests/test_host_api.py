@@ -182,3 +182,73 @@ def test_product_never_touches_the_oracle():
                 assert "oracle" not in text.lower().replace("test infrastructure", ""), os.path.join(dirpath, f)
     ldd = subprocess.check_output(["ldd", mfa.library_path()], text=True)
     assert "oracle" not in ldd
+
+
+def test_kernel_cache_returns_one_object_per_descriptor_and_type():
+    """mfa_attention_kernel_cache_fetch (the analogue of GEMMKernel.pipelineCache, GEMMDescriptor+PipelineCache.swift:
+    16-36): R, C and the batch count are launch constants, not part of the key; head, precisions, transposes are."""
+    before = mfa.AttentionKernel.cacheSize()
+    a = mfa.AttentionKernel.cached(make(4096, 4096, 120, lowIn=True, bf16=True), KT.forward)
+    b = mfa.AttentionKernel.cached(make(512, 77, 120, lowIn=True, bf16=True), KT.forward)       # other R, C: same kernel
+    assert a._handle.value == b._handle.value and mfa.AttentionKernel.cacheSize() == before + 1
+    c = mfa.AttentionKernel.cached(make(4096, 4096, 120, lowIn=True, bf16=True), KT.backwardQuery)
+    d = mfa.AttentionKernel.cached(make(4096, 4096, 120, lowIn=True), KT.forward)                 # FP16 inputs
+    e = mfa.AttentionKernel.cached(make(4096, 4096, 112, lowIn=True, bf16=True), KT.forward)      # other head dimension
+    assert len({a._handle.value, c._handle.value, d._handle.value, e._handle.value}) == 4
+    assert mfa.AttentionKernel.cacheSize() == before + 4
+    assert a.blockDimensions == mfa.AttentionKernel(make(4096, 4096, 120, lowIn=True, bf16=True).kernelDescriptor(
+        KT.forward)).blockDimensions
+    del a, b, c, d, e                                  # library-owned handles: dropping the wrappers must not free them
+    again = mfa.AttentionKernel.cached(make(4096, 4096, 120, lowIn=True, bf16=True), KT.forward)
+    assert again.threadgroupSize == 384 and mfa.AttentionKernel.cacheSize() == before + 4
+    with pytest.raises(mfa.MFAError, match="Descriptor was incomplete"):
+        mfa.AttentionKernel.cached(mfa.AttentionDescriptor(), KT.forward)
+
+
+def test_reference_low_precision_policy_maps_to_the_tensor_core_family():
+    """FP16 Q/K/V + BF16 dO (AttentionDescriptor+Precisions.swift:13-23) is served by the tcgen05 kernels for all three
+    kernel types (the backward kernels convert the staged dO tiles on chip)."""
+    for lowMid in (False, True):
+        d = make(2048, 2048, 64, lowIn=True)
+        d.lowPrecisionIntermediates = lowMid
+        assert d.memoryPrecisions[Op.dO] == mfa.GEMMOperandPrecision.BF16
+        for t in KT:
+            kd = d.kernelDescriptor(t)
+            assert kd.backend == mfa.Backend.tcgen05
+            assert "tcgen05" in mfa.AttentionKernel(kd).sourceName()
+
+
+def test_cpp_host_mirror_compiles_and_links_against_the_c_abi(tmp_path):
+    """metal-flash-attention_b200/host/FlashAttention.hpp (the compiled-language host layer standing in for the
+    reference's Swift package) builds with g++ against include/mfa_b200.h + libmfa_b200.so and reproduces the
+    descriptor -> kernel flow, including the reference's fatalError message for an incomplete descriptor."""
+    src = tmp_path / "host.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include "metal-flash-attention_b200/host/FlashAttention.hpp"
+using namespace FlashAttention;
+int main() {
+  AttentionDescriptor d;
+  d.lowPrecisionInputs = true;
+  d.matrixDimensions = MatrixDimensions{4096, 4096, 128};
+  d.transposeState = TransposeState{false, false, false, false};
+  d.inputPrecisionOverride = GEMMOperandPrecision::BF16;
+  AttentionKernel k(d.kernelDescriptor(AttentionKernelType::forward));
+  auto [par, trav, head] = k.blockDimensions();
+  AttentionKernel cached(d, AttentionKernelType::backwardKeyValue);
+  std::printf("%u %u %u %u %u\n", par, trav, head, k.threadgroupSize(), cached.threadgroupSize());
+  try {
+    AttentionDescriptor incomplete;
+    incomplete.kernelDescriptor(AttentionKernelType::forward);
+  } catch (const std::runtime_error &e) {
+    std::printf("%s\n", e.what());
+  }
+  return 0;
+}
+''')
+    exe = tmp_path / "host"
+    libdir = os.path.dirname(mfa.library_path())
+    subprocess.check_call(["g++", "-std=c++17", "-I", ROOT, str(src), "-o", str(exe), "-L", libdir, "-lmfa_b200",
+                           f"-Wl,-rpath,{libdir}"])
+    out = subprocess.check_output([str(exe)], text=True).splitlines()
+    assert out[0] == "256 128 128 384 384" and out[1] == "Descriptor was incomplete."
