@@ -261,10 +261,13 @@ def main():
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                "ms_per_step": dt / e2e_steps * 1e3,
                "api": "mfa_attention_run_host (pinned host Q,K,V -> device, kernel, O,L -> host)"}
-        # spot-check that the e2e path produced the same O as the device path
+        # spot-check that the e2e path produced the same O as the device path (the host path works through the batch in
+        # chunks of a few heads, for which the library may split the key axis across SMs and merge: same math, a
+        # different FP32 summation order, hence a tolerance of a few ulps rather than bit equality)
         step(0)
         torch.cuda.synchronize()
-        assert torch.allclose(host[Op.O][0, :8], sets[0][Op.O][0, :8].cpu(), rtol=0, atol=0), "e2e != device path"
+        assert torch.allclose(host[Op.O][0, :8], sets[0][Op.O][0, :8].cpu(), rtol=1e-4, atol=1e-6), "e2e != device path"
+        assert torch.allclose(host[Op.O][H - 1, -8:], sets[0][Op.O][H - 1, -8:].cpu(), rtol=1e-4, atol=1e-6), "e2e != device path"
 
     # ---- literal single-head latency (BASELINE.json configs[1] as written): one (N=4096, D=128) problem per launch;
     #      too few tiles to fill 148 SMs, so the library splits the key axis across SMs and merges (split-KV) --------

@@ -313,32 +313,36 @@ int mfa_attention_kernel_cache_size(void) {
 // ------------------------------------------------------------------------------------------------
 // Host-buffer path: H2D -> kernels -> D2H (the end-to-end call bench.py times as `e2e`).
 //
-// The independent single-head problems of a batch are cut into chunks that rotate over three streams, so the
-// host->device copy of chunk i+1, the kernels of chunk i and the device->host copy of chunk i-1 overlap (PCIe is full
-// duplex and the GPU has separate copy engines per direction).  With pinned host buffers the call then costs
-// max(H2D, D2H) + one chunk of fill/drain instead of H2D + kernels + D2H.
+// The independent single-head problems of a batch are cut into chunks that flow through three streams -- upload,
+// compute, download -- linked by one event pair per chunk, so the host->device copy of chunk i+1, the kernels of chunk
+// i and the device->host copy of chunk i-1 overlap (PCIe is full duplex and the GPU has a copy engine per direction) and
+// the upload stream never waits for anything.  With pinned host buffers the call then costs max(H2D, D2H) + one chunk
+// of fill/drain instead of H2D + kernels + D2H.
 // ------------------------------------------------------------------------------------------------
 namespace {
-constexpr int kHostStreams = 3;
+constexpr int kHostStreams = 3;  // 0 upload, 1 compute, 2 download
+constexpr uint32_t kMaxChunks = 32;
 struct Scratch {
   void *ptr[MFA_BUFFER_COUNT] = {};
   size_t bytes[MFA_BUFFER_COUNT] = {};
   int device = -1;
   cudaStream_t stream[kHostStreams] = {};
+  cudaEvent_t uploaded[kMaxChunks] = {}, computed[kMaxChunks] = {};
   ~Scratch() {
     // Process teardown: the CUDA context may already be gone; leaking here is deliberate.
   }
 };
 thread_local Scratch g_scratch;
 
-// heads per chunk: about eight chunks, but no chunk smaller than ~4 MB of traffic (copy launch overheads) and none at
-// all for a single problem
+// heads per chunk: about sixteen chunks (fill + drain = two chunk times), but no chunk smaller than ~4 MB of traffic
+// (copy launch overheads), at most kMaxChunks chunks, and no chunking at all for a single problem
 uint32_t chunk_heads(uint32_t batch, size_t bytes_per_head) {
   if (batch <= 1) return 1;
-  uint32_t heads = (batch + 7) / 8;
+  uint32_t heads = (batch + 15) / 16;
   const size_t kMinChunkBytes = size_t(4) << 20;
   if (bytes_per_head * heads < kMinChunkBytes)
     heads = static_cast<uint32_t>((kMinChunkBytes + bytes_per_head - 1) / bytes_per_head);
+  if ((batch + heads - 1) / heads > kMaxChunks) heads = (batch + kMaxChunks - 1) / kMaxChunks;
   return heads < batch ? heads : batch;
 }
 }  // namespace
@@ -361,6 +365,10 @@ int mfa_attention_run_host(const mfa_attention_descriptor_t *descriptor, uint32_
     for (int i = 0; i < kHostStreams; ++i)
       if ((e = cudaStreamCreateWithFlags(&s.stream[i], cudaStreamNonBlocking)) != cudaSuccess)
         return fail(MFA_ERROR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    for (uint32_t i = 0; i < kMaxChunks; ++i)
+      if ((e = cudaEventCreateWithFlags(&s.uploaded[i], cudaEventDisableTiming)) != cudaSuccess ||
+          (e = cudaEventCreateWithFlags(&s.computed[i], cudaEventDisableTiming)) != cudaSuccess)
+        return fail(MFA_ERROR_CUDA, std::string("cudaEventCreate: ") + cudaGetErrorString(e));
   }
 
   // which operands each kernel reads / writes (AttentionKernelType.swift:10-22)
@@ -419,33 +427,41 @@ int mfa_attention_run_host(const mfa_attention_descriptor_t *descriptor, uint32_
         return status;
 
   const uint32_t per_chunk = chunk_heads(batch, traffic_per_head);
+  cudaStream_t upload = s.stream[0], compute = s.stream[1], download = s.stream[2];
   uint32_t chunk_index = 0;
   for (uint32_t h0 = 0; h0 < batch; h0 += per_chunk, ++chunk_index) {
     const uint32_t heads = batch - h0 < per_chunk ? batch - h0 : per_chunk;
-    cudaStream_t stream = s.stream[chunk_index % kHostStreams];
     void *chunk_dev[MFA_BUFFER_COUNT] = {};
     for (int op = 0; op < MFA_BUFFER_COUNT; ++op) {
       if (!dev[op]) continue;
       chunk_dev[op] = static_cast<char *>(dev[op]) + head_bytes[op] * h0;
       if (inputs & (1u << op)) {
         const char *src = static_cast<const char *>(host_buffers[op]) + head_bytes[op] * h0;
-        if ((e = cudaMemcpyAsync(chunk_dev[op], src, head_bytes[op] * heads, cudaMemcpyHostToDevice, stream)) != cudaSuccess)
+        if ((e = cudaMemcpyAsync(chunk_dev[op], src, head_bytes[op] * heads, cudaMemcpyHostToDevice, upload)) != cudaSuccess)
           return fail(MFA_ERROR_CUDA, std::string("H2D copy: ") + cudaGetErrorString(e));
       }
     }
+    if ((e = cudaEventRecord(s.uploaded[chunk_index], upload)) != cudaSuccess ||
+        (e = cudaStreamWaitEvent(compute, s.uploaded[chunk_index], 0)) != cudaSuccess)
+      return fail(MFA_ERROR_CUDA, std::string("event: ") + cudaGetErrorString(e));
     mfa_function_constants_t chunk_constants = constants;
     chunk_constants.batch_count = heads;
     for (int type = MFA_FORWARD; type <= MFA_BACKWARD_KEY_VALUE; ++type)
       if (kernels[type] &&
-          (status = mfa_attention_kernel_encode(kernels[type], &chunk_constants, chunk_dev, stream)) != MFA_SUCCESS)
+          (status = mfa_attention_kernel_encode(kernels[type], &chunk_constants, chunk_dev, compute)) != MFA_SUCCESS)
         return status;
+    if ((e = cudaEventRecord(s.computed[chunk_index], compute)) != cudaSuccess ||
+        (e = cudaStreamWaitEvent(download, s.computed[chunk_index], 0)) != cudaSuccess)
+      return fail(MFA_ERROR_CUDA, std::string("event: ") + cudaGetErrorString(e));
     for (int op = 0; op < MFA_BUFFER_COUNT; ++op) {
       if (!(outputs & (1u << op)) || !host_buffers[op]) continue;
       char *dst = static_cast<char *>(host_buffers[op]) + head_bytes[op] * h0;
-      if ((e = cudaMemcpyAsync(dst, chunk_dev[op], head_bytes[op] * heads, cudaMemcpyDeviceToHost, stream)) != cudaSuccess)
+      if ((e = cudaMemcpyAsync(dst, chunk_dev[op], head_bytes[op] * heads, cudaMemcpyDeviceToHost, download)) != cudaSuccess)
         return fail(MFA_ERROR_CUDA, std::string("D2H copy: ") + cudaGetErrorString(e));
     }
   }
+  // (the device scratch is reused by the next call on this thread: every stream must have drained before returning,
+  // which the synchronous contract of this entry point requires anyway)
   for (int i = 0; i < kHostStreams; ++i)
     if ((e = cudaStreamSynchronize(s.stream[i])) != cudaSuccess)
       return fail(MFA_ERROR_CUDA, std::string("kernel execution failed: ") + cudaGetErrorString(e));

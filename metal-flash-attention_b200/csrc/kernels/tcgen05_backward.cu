@@ -83,6 +83,46 @@ __device__ __forceinline__ uint4 bf16x8_to_f16x8(uint4 v) {
   return make_uint4(bf16x2_to_f16x2(v.x), bf16x2_to_f16x2(v.y), bf16x2_to_f16x2(v.z), bf16x2_to_f16x2(v.w));
 }
 
+// Accumulator epilogue shared by both kernels: TMEM hands every thread one row, and storing rows straight from registers
+// touches 32 different cache lines per warp store.  Each warp therefore transposes 32 x 32 chunks through a private
+// XOR-swizzled 4 KB scratch tile in shared memory (128-bit accesses, conflict-free both ways) and writes four full
+// 128 B lines per store instruction -- the forward kernel's epilogue (tcgen05_forward.cu).  `scratch` overlays the
+// staged-operand ring, which is dead once the final commit has arrived.  Columns [col0, col0 + cols) of the
+// accumulator at `t_acc` go to rows [warp_row0, warp_row0 + 32) of `out` ([rows_total][D] FP32).
+__device__ __forceinline__ void store_accumulator_coalesced(uint32_t t_acc, uint32_t col0, uint32_t cols, float4 *scratch,
+                                                            float *out_base, uint32_t warp_row0, uint32_t rows_total,
+                                                            uint32_t D, uint32_t lane) {
+  const uint32_t sub_row = lane >> 3, quad = lane & 7;  // transposed view: 4 rows x 8 float4 per warp access
+  for (uint32_t cc = 0; cc < cols; cc += 32) {
+    const uint32_t c = col0 + cc;
+    uint32_t o[32];
+    tmem_ld32(t_acc + c, o);
+    tc_wait_ld();
+#pragma unroll
+    for (uint32_t j = 0; j < 8; ++j)
+      scratch[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(o[4 * j]), __uint_as_float(o[4 * j + 1]),
+                                                          __uint_as_float(o[4 * j + 2]), __uint_as_float(o[4 * j + 3]));
+    __syncwarp();
+    // all eight values in distinct registers before the first store (a store holds its source registers until the
+    // data has left the SM)
+    float4 v[8];
+#pragma unroll
+    for (uint32_t i = 0; i < 8; ++i) {
+      const uint32_t r = 4 * i + sub_row;
+      v[i] = scratch[r * 8 + (quad ^ (r & 7))];
+    }
+    if (c + 4 * quad < D) {  // D % 8 == 0: a float4 is either fully inside or fully outside
+#pragma unroll
+      for (uint32_t i = 0; i < 8; ++i) {
+        const uint32_t r = 4 * i + sub_row;
+        if (warp_row0 + r < rows_total)
+          *reinterpret_cast<float4 *>(out_base + static_cast<size_t>(r) * D + c + 4 * quad) = v[i];
+      }
+    }
+    __syncwarp();
+  }
+}
+
 struct BackwardArgs {
   const void *dO;   // [batch][R][D] 16-bit (element type of Q/K/V, or BF16 beside FP16 Q/K/V: kConvertDO)
   const float *O;   // [batch][R][D] FP32
@@ -98,13 +138,36 @@ struct BackwardArgs {
 // backwardQuery
 //   TMEM columns: [0,128) S (single buffer, released as soon as it is in registers),
 //                 [128,256) [256,384) dP double buffer (dS is written in place over dP),  [384,384+D) dQ
+//   Shared memory: Q and dO tiles resident; K in a ring of THREE stages (block j's tile is read by S(j) and, two
+//   pipeline steps later, by dQ(j): with two stages the load of K(j+1) had to wait for dQ(j-1) to retire and S(j+1)
+//   -- which the next block's elementwise pass waits for -- sat behind a TMA round trip); V in a ring of two.
+//   Tensor-pipe order per block j:  dQ(j-1)  ->  S(j+1)  ->  dP(j+1).  The elementwise warps split their pass so that
+//   the exponentials (which need only S) run while dP is still on the pipe: measured 2310 -> see DESIGN.md.
 // ================================================================================================
+template <uint32_t DPAD>
+struct QueryConfig {
+  static constexpr uint32_t kSubTiles = DPAD / 64;
+  static constexpr uint32_t kTileBytes = kSubTiles * kSubTileBytes;  // one 128 x DPAD 16-bit tile
+  static constexpr uint32_t kStagesK = 3, kStagesV = 2;
+  static constexpr uint32_t kSmemQ = 0;
+  static constexpr uint32_t kSmemdO = kTileBytes;
+  static constexpr uint32_t kSmemK = 2 * kTileBytes;
+  static constexpr uint32_t kSmemV = kSmemK + kStagesK * kTileBytes;
+  static constexpr uint32_t kSmemVec = kSmemV + kStagesV * kTileBytes;  // float D[128]: D terms, warp -> row owner
+  static constexpr uint32_t kSmemBar = kSmemVec + kTile * 4;
+  static constexpr uint32_t kNumBars = 24;
+  static constexpr uint32_t kSmemTmemPtr = kSmemBar + kNumBars * 8;
+  static constexpr uint32_t kSmemBytes = kSmemTmemPtr + 16;
+  static_assert(kSmemBytes <= 232448, "shared memory over budget");
+  static_assert(8 * 4096 <= kStagesK * kTileBytes, "epilogue scratch does not fit the K stages");
+};
+
 template <uint32_t DPAD, bool kBF16, bool kConvertDO>
 __global__ void __launch_bounds__(kThreads, 1)
     attention_backward_query_tcgen05(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapdO,
                                      const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV,
                                      const BackwardArgs a) {
-  using Cfg = Config<DPAD>;
+  using Cfg = QueryConfig<DPAD>;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
 
@@ -116,25 +179,27 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kSmemBar);
   uint64_t *q_full = bars;            // Q and dO tiles landed
-  uint64_t *k_full = bars + 1;        // [2]
-  uint64_t *k_empty = bars + 3;       // [2]
-  uint64_t *v_full = bars + 5;        // [2]
-  uint64_t *v_empty = bars + 7;       // [2]
-  uint64_t *s_full = bars + 9;        // S(j) in TMEM
-  uint64_t *s_free = bars + 10;       // S(j) is in registers (256 arrivals)
-  uint64_t *dp_full = bars + 11;      // [2] dP(j) in TMEM
-  uint64_t *ds_full = bars + 13;      // [2] dS(j) written over dP(j) (256 arrivals)
-  uint64_t *dq_final = bars + 15;     // every MMA has completed
-  uint64_t *do_ready = bars + 16;     // kConvertDO: the resident dO tile has been rewritten as FP16 (256 arrivals)
+  uint64_t *k_full = bars + 1;        // [3]
+  uint64_t *k_empty = bars + 4;       // [3]
+  uint64_t *v_full = bars + 7;        // [2]
+  uint64_t *v_empty = bars + 9;       // [2]
+  uint64_t *s_full = bars + 11;       // S(j) in TMEM
+  uint64_t *s_free = bars + 12;       // S(j) is in registers (256 arrivals)
+  uint64_t *dp_full = bars + 13;      // [2] dP(j) in TMEM
+  uint64_t *ds_full = bars + 15;      // [2] dS(j) written over dP(j) (256 arrivals)
+  uint64_t *dq_final = bars + 17;     // every MMA has completed
+  uint64_t *do_ready = bars + 18;     // kConvertDO: the resident dO tile has been rewritten as FP16 (256 arrivals)
   static_assert(!(kBF16 && kConvertDO), "dO is only converted when Q, K, V are FP16");
   constexpr bool kDOisBF16 = kBF16 || kConvertDO;  // element type of dO in global memory
   uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem + Cfg::kSmemTmemPtr);
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
-    for (uint32_t s = 0; s < 2; ++s) {
+    for (uint32_t s = 0; s < Cfg::kStagesK; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
+    }
+    for (uint32_t s = 0; s < 2; ++s) {
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
       mbar_init(&dp_full[s], 1);
@@ -168,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       // BF16 dO tile (TMA) -> FP16 in place; elementwise, so the 128 B swizzle is irrelevant.  Generic-proxy writes
       // must be fenced before the tensor core (async proxy) reads them.
       mbar_wait(q_full, 0);
-      uint4 *tile = reinterpret_cast<uint4 *>(smem + Cfg::kSmemResident1);
+      uint4 *tile = reinterpret_cast<uint4 *>(smem + Cfg::kSmemdO);
 #pragma unroll
       for (uint32_t i = 0; i < Cfg::kTileBytes / (kElemThreads * 16); ++i)
         tile[i * kElemThreads + threadIdx.x] = bf16x8_to_f16x8(tile[i * kElemThreads + threadIdx.x]);
@@ -176,40 +241,48 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_arrive(do_ready);
     }
 
-    // computeD (AttentionKernel+Softmax.swift:32-221): D = (sum_d dO * O) / sqrt(D), kept in FP32 for this kernel
-    // and stored (possibly as BF16) for the dK/dV kernel.  L arrives in log2 units from the forward kernel.
+    // computeD (AttentionKernel+Softmax.swift:32-221): D = (sum_d dO * O) / sqrt(D), kept in FP32 for this kernel and
+    // stored (possibly as BF16) for the dK/dV kernel.  A row per thread (what the MMA layout would suggest) makes every
+    // warp load touch 32 different cache lines -- the profile showed the elementwise warps spending 17 % of the kernel
+    // here -- so each warp instead takes 16 rows and spreads the columns over its lanes (one 512 B line of O per load),
+    // reduces with shuffles and hands the results to the row owners through shared memory.
     float Dterm;
     {
-      // one row of dO (16-bit) and O (FP32) per thread, read with 128-bit loads that are all issued before the first
-      // FMA (D % 8 == 0 and 16-byte aligned buffers are preconditions of this kernel family); scalar loads made this
-      // prologue a third of the kernel's run time
-      const size_t base = (static_cast<size_t>(head) * a.R + row_c) * a.D;
-      const uint4 *dO8 = reinterpret_cast<const uint4 *>(static_cast<const uint16_t *>(a.dO) + base);
-      const float4 *O4 = reinterpret_cast<const float4 *>(a.O + base);
-      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-#pragma unroll 4
-      for (uint32_t d8 = 0; d8 < a.D / 8; ++d8) {
-        const uint4 g = __ldg(dO8 + d8);
-        const float4 o0 = __ldg(O4 + 2 * d8), o1 = __ldg(O4 + 2 * d8 + 1);
-        const uint32_t w[4] = {g.x, g.y, g.z, g.w};
-        float v[8];
+      float *dvec = reinterpret_cast<float *>(smem + Cfg::kSmemVec);
+      constexpr uint32_t kRowsPerWarp = kTile / 8;
+      float4 o4[kRowsPerWarp];
+      uint2 g4[kRowsPerWarp];
+      const bool active = 4 * lane < a.D;
 #pragma unroll
-        for (uint32_t k = 0; k < 4; ++k) {
-          if (kDOisBF16) {
-            v[2 * k] = __uint_as_float(w[k] << 16);
-            v[2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
-          } else {
-            const __half2 hh = *reinterpret_cast<const __half2 *>(&w[k]);
-            v[2 * k] = __low2float(hh);
-            v[2 * k + 1] = __high2float(hh);
-          }
+      for (uint32_t i = 0; i < kRowsPerWarp; ++i) {
+        const uint32_t rr = min(r0 + warp * kRowsPerWarp + i, a.R - 1);
+        const size_t base = (static_cast<size_t>(head) * a.R + rr) * a.D + 4 * lane;
+        o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        g4[i] = make_uint2(0u, 0u);
+        if (active) {
+          o4[i] = __ldg(reinterpret_cast<const float4 *>(a.O + base));
+          g4[i] = __ldg(reinterpret_cast<const uint2 *>(static_cast<const uint16_t *>(a.dO) + base));
         }
-        acc0 = fmaf(v[0], o0.x, acc0); acc1 = fmaf(v[1], o0.y, acc1);
-        acc2 = fmaf(v[2], o0.z, acc2); acc3 = fmaf(v[3], o0.w, acc3);
-        acc0 = fmaf(v[4], o1.x, acc0); acc1 = fmaf(v[5], o1.y, acc1);
-        acc2 = fmaf(v[6], o1.z, acc2); acc3 = fmaf(v[7], o1.w, acc3);
       }
-      Dterm = ((acc0 + acc1) + (acc2 + acc3)) * a.scale;
+#pragma unroll
+      for (uint32_t i = 0; i < kRowsPerWarp; ++i) {
+        float v0, v1, v2, v3;
+        if (kDOisBF16) {
+          v0 = __uint_as_float(g4[i].x << 16);
+          v1 = __uint_as_float(g4[i].x & 0xFFFF0000u);
+          v2 = __uint_as_float(g4[i].y << 16);
+          v3 = __uint_as_float(g4[i].y & 0xFFFF0000u);
+        } else {
+          const __half2 lo = *reinterpret_cast<const __half2 *>(&g4[i].x), hi = *reinterpret_cast<const __half2 *>(&g4[i].y);
+          v0 = __low2float(lo); v1 = __high2float(lo); v2 = __low2float(hi); v3 = __high2float(hi);
+        }
+        float acc = fmaf(v0, o4[i].x, fmaf(v1, o4[i].y, fmaf(v2, o4[i].z, v3 * o4[i].w)));
+#pragma unroll
+        for (uint32_t off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane == i) dvec[warp * kRowsPerWarp + i] = acc * a.scale;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kElemThreads) : "memory");  // the eight elementwise warps only
+      Dterm = dvec[row_in_tile];
     }
     const size_t stat_idx = static_cast<size_t>(head) * a.R + row_c;
     const float Lrow = load_stat(a.L, stat_idx, a.l_prec);
@@ -219,15 +292,12 @@ __global__ void __launch_bounds__(kThreads, 1)
       const uint32_t bf = j & 1;
       const uint32_t tS = tLane + kTmemS + h * kHalf;
       const uint32_t tdP = tLane + kTmemdP + bf * kTile + h * kHalf;
+      // ---- first half of the pass: P = exp2(S * log2e/sqrt(D) - L) needs only S ----
       mbar_wait(s_full, j & 1);
-      mbar_wait(&dp_full[bf], (j >> 1) & 1);
       tc_fence_after();
-      float s[kHalf], dp[kHalf];
+      float p[kHalf];
 #pragma unroll
-      for (uint32_t c = 0; c < kHalf; c += 32) {
-        tmem_ld32(tS + c, *reinterpret_cast<uint32_t(*)[32]>(&s[c]));
-        tmem_ld32(tdP + c, *reinterpret_cast<uint32_t(*)[32]>(&dp[c]));
-      }
+      for (uint32_t c = 0; c < kHalf; c += 32) tmem_ld32(tS + c, *reinterpret_cast<uint32_t(*)[32]>(&p[c]));
       tc_wait_ld();
       tc_fence_before();
       mbar_arrive(s_free);  // S(j+1) may overwrite the S buffer now
@@ -236,18 +306,25 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (j + 1 == num_blocks && col0 + kHalf > a.C) {  // padded key columns (maskAttentionMatrixEdge): P = 0 there
 #pragma unroll
         for (uint32_t c = 0; c < kHalf; ++c)
-          if (col0 + c >= a.C) s[c] = -INFINITY;
+          if (col0 + c >= a.C) p[c] = -INFINITY;
       }
+#pragma unroll
+      for (uint32_t c = 0; c < kHalf; ++c) p[c] = ex2_approx(fmaf(p[c], a.scale_log2, -Lrow));  // (+Softmax.swift:419-427)
+
+      // ---- second half: dS = P * (dP/sqrt(D) - D), written in place over dP as the 16-bit A operand of dQ += dS K ----
+      mbar_wait(&dp_full[bf], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t dp[kHalf];
+#pragma unroll
+      for (uint32_t c = 0; c < kHalf; c += 32) tmem_ld32(tdP + c, *reinterpret_cast<uint32_t(*)[32]>(&dp[c]));
+      tc_wait_ld();
 #pragma unroll
       for (uint32_t c = 0; c < kHalf; c += 32) {
         uint32_t packed[16];
 #pragma unroll
         for (uint32_t k = 0; k < 16; ++k) {
-          // P = exp2(S * log2e/sqrt(D) - L);  dS = P * (dP/sqrt(D) - D)     (+Softmax.swift:419-427)
-          const float p0 = ex2_approx(fmaf(s[c + 2 * k], a.scale_log2, -Lrow));
-          const float p1 = ex2_approx(fmaf(s[c + 2 * k + 1], a.scale_log2, -Lrow));
-          const float ds0 = p0 * fmaf(dp[c + 2 * k], a.scale, -Dterm);
-          const float ds1 = p1 * fmaf(dp[c + 2 * k + 1], a.scale, -Dterm);
+          const float ds0 = p[c + 2 * k] * fmaf(__uint_as_float(dp[c + 2 * k]), a.scale, -Dterm);
+          const float ds1 = p[c + 2 * k + 1] * fmaf(__uint_as_float(dp[c + 2 * k + 1]), a.scale, -Dterm);
           packed[k] = kBF16 ? pack_bf16x2(ds0, ds1) : pack_f16x2(ds0, ds1);
         }
         tmem_st16(tdP + (c >> 1), packed);  // dS of keys [64h + c, +32) -> columns [64h + c/2, +16) of the dP buffer
@@ -260,47 +337,37 @@ __global__ void __launch_bounds__(kThreads, 1)
     // epilogue: dQ -> global (FP32); warpgroup h writes columns [h D/2, (h+1) D/2)
     mbar_wait(dq_final, 0);
     tc_fence_after();
-    float *out_row = a.dQ + (static_cast<size_t>(head) * a.R + row) * a.D;
-#pragma unroll
-    for (uint32_t cc = 0; cc < DPAD / 2; cc += 32) {
-      const uint32_t c = h * (DPAD / 2) + cc;
-      // (all 32 values sit in distinct registers before the first store: a store keeps its source registers busy
-      // until the data has left the SM, so the stores must not share registers)
-      uint32_t v[32];
-      tmem_ld32(tLane + kTmemdQ + c, v);
-      tc_wait_ld();
-      if (row < a.R) {
-#pragma unroll
-        for (uint32_t k = 0; k < 32; k += 4)
-          if (c + k < a.D)
-            *reinterpret_cast<uint4 *>(out_row + c + k) = make_uint4(v[k], v[k + 1], v[k + 2], v[k + 3]);
-      }
+    {
+      float4 *scratch = reinterpret_cast<float4 *>(smem + Cfg::kSmemK) + warp * 256;  // the K stages are dead now
+      const uint32_t warp_row0 = r0 + quarter * 32;
+      store_accumulator_coalesced(tLane + kTmemdQ, h * (DPAD / 2), DPAD / 2, scratch,
+                                  a.dQ + (static_cast<size_t>(head) * a.R + warp_row0) * a.D, warp_row0, a.R, a.D, lane);
     }
   } else {
     setmaxnreg_dec<kOtherRegs>();
     if (warp == 9) {
-      // ---------------- TMA producer ----------------
+      // ---------------- TMA producer: Q, dO once, then the K ring ----------------
       if (elect_one()) {
         mbar_arrive_expect_tx(q_full, 2 * Cfg::kTileBytes);
 #pragma unroll
         for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds) {
-          tma_load_3d(smem + Cfg::kSmemResident0 + ds * kSubTileBytes, &mapQ, q_full, ds * 64, r0, head);
-          tma_load_3d(smem + Cfg::kSmemResident1 + ds * kSubTileBytes, &mapdO, q_full, ds * 64, r0, head);
+          tma_load_3d(smem + Cfg::kSmemQ + ds * kSubTileBytes, &mapQ, q_full, ds * 64, r0, head);
+          tma_load_3d(smem + Cfg::kSmemdO + ds * kSubTileBytes, &mapdO, q_full, ds * 64, r0, head);
         }
       }
       for (uint32_t j = 0; j < num_blocks; ++j) {
-        const uint32_t stage = j & 1, phase = (j >> 1) & 1;
+        const uint32_t stage = j % Cfg::kStagesK, phase = (j / Cfg::kStagesK) & 1;
         mbar_wait(&k_empty[stage], phase ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&k_full[stage], Cfg::kTileBytes);
 #pragma unroll
           for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
-            tma_load_3d(smem + Cfg::kSmemStage0 + stage * Cfg::kTileBytes + ds * kSubTileBytes, &mapK, &k_full[stage],
+            tma_load_3d(smem + Cfg::kSmemK + stage * Cfg::kTileBytes + ds * kSubTileBytes, &mapK, &k_full[stage],
                         ds * 64, j * kTile, head);
         }
       }
     } else if (warp == 10) {
-      // ---------------- TMA producer for V (dP runs two blocks ahead of dQ, so V must not queue behind K) --------
+      // ---------------- TMA producer for the V ring ----------------
       for (uint32_t j = 0; j < num_blocks; ++j) {
         const uint32_t stage = j & 1, phase = (j >> 1) & 1;
         mbar_wait(&v_empty[stage], phase ^ 1);
@@ -308,7 +375,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           mbar_arrive_expect_tx(&v_full[stage], Cfg::kTileBytes);
 #pragma unroll
           for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
-            tma_load_3d(smem + Cfg::kSmemStage1 + stage * Cfg::kTileBytes + ds * kSubTileBytes, &mapV, &v_full[stage],
+            tma_load_3d(smem + Cfg::kSmemV + stage * Cfg::kTileBytes + ds * kSubTileBytes, &mapV, &v_full[stage],
                         ds * 64, j * kTile, head);
         }
       }
@@ -317,11 +384,11 @@ __global__ void __launch_bounds__(kThreads, 1)
       constexpr uint32_t kFormat = kBF16 ? 1u : 0u;
       constexpr uint32_t idescNT = make_idesc_f16(kTile, kTile, kFormat, 0, 0);  // [128 x D] . [128 x D]^T
       constexpr uint32_t idescAcc = make_idesc_f16(kTile, DPAD, kFormat, 0, 1);  // TMEM A . MN-major B -> [128 x DPAD]
-      const uint64_t descQ = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemResident0), 16, 1024);
-      const uint64_t descdO = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemResident1), 16, 1024);
-      const uint64_t descK = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemStage0), 16, 1024);
-      const uint64_t descV = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemStage1), 16, 1024);
-      const uint64_t descKmn = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemStage0), kSubTileBytes, 1024);
+      const uint64_t descQ = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemQ), 16, 1024);
+      const uint64_t descdO = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemdO), 16, 1024);
+      const uint64_t descK = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemK), 16, 1024);
+      const uint64_t descV = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemV), 16, 1024);
+      const uint64_t descKmn = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemK), kSubTileBytes, 1024);
 
       auto issue_nt = [&](uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc) {
 #pragma unroll
@@ -340,7 +407,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
       };
 
-      // prologue: S(0), dP(0), dP(1)
+      // prologue: S(0), dP(0)
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
@@ -358,51 +425,50 @@ __global__ void __launch_bounds__(kThreads, 1)
         umma_commit(&v_empty[0]);
       }
       __syncwarp();
-      if (num_blocks > 1) {
-        mbar_wait(&v_full[1], 0);
-        tc_fence_after();
-        if (elect_one()) {
-          issue_nt(tmem_base + kTmemdP + kTile, descdO, descV + (Cfg::kTileBytes >> 4));
-          umma_commit(&dp_full[1]);
-          umma_commit(&v_empty[1]);
-        }
-        __syncwarp();
-      }
 
       for (uint32_t j = 0; j < num_blocks; ++j) {
-        const uint32_t bf = j & 1, stage = j & 1;
-        // S(j+1) as soon as S(j) has been read out
-        if (j + 1 < num_blocks) {
-          const uint32_t ns = (j + 1) & 1;
-          mbar_wait(s_free, j & 1);
-          mbar_wait(&k_full[ns], ((j + 1) >> 1) & 1);
+        // (a) dQ += dS(j-1) K(j-1): frees K's stage and the dP buffer that dP(j+1) is about to overwrite
+        if (j > 0) {
+          const uint32_t pj = j - 1, ks = pj % Cfg::kStagesK;
+          mbar_wait(&ds_full[pj & 1], (pj >> 1) & 1);
           tc_fence_after();
           if (elect_one()) {
-            issue_nt(tmem_base + kTmemS, descQ, descK + ((ns * Cfg::kTileBytes) >> 4));
+            issue_dQ(pj & 1, ks, pj > 0 ? 1u : 0u);
+            umma_commit(&k_empty[ks]);
+          }
+          __syncwarp();
+        }
+        if (j + 1 < num_blocks) {
+          const uint32_t nj = j + 1, ks = nj % Cfg::kStagesK, vs = nj & 1;
+          // (b) S(j+1) as soon as S(j) has been read out: first in line for the next elementwise pass
+          mbar_wait(s_free, j & 1);
+          mbar_wait(&k_full[ks], (nj / Cfg::kStagesK) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_nt(tmem_base + kTmemS, descQ, descK + ((ks * Cfg::kTileBytes) >> 4));
             umma_commit(s_full);
           }
           __syncwarp();
-        }
-        // dQ += dS(j) K(j)
-        mbar_wait(&ds_full[bf], (j >> 1) & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          issue_dQ(bf, stage, j > 0 ? 1u : 0u);
-          umma_commit(&k_empty[stage]);
-          if (j + 1 == num_blocks) umma_commit(dq_final);
-        }
-        __syncwarp();
-        // dP(j+2) into the buffer dS(j) just left (in-order tensor pipe: after dQ(j))
-        if (j + 2 < num_blocks) {
-          mbar_wait(&v_full[stage], ((j + 2) >> 1) & 1);
+          // (c) dP(j+1) into the buffer dS(j-1) just left (in-order tensor pipe: after dQ(j-1))
+          mbar_wait(&v_full[vs], (nj >> 1) & 1);
           tc_fence_after();
           if (elect_one()) {
-            issue_nt(tmem_base + kTmemdP + bf * kTile, descdO, descV + ((stage * Cfg::kTileBytes) >> 4));
-            umma_commit(&dp_full[bf]);
-            umma_commit(&v_empty[stage]);
+            issue_nt(tmem_base + kTmemdP + vs * kTile, descdO, descV + ((vs * Cfg::kTileBytes) >> 4));
+            umma_commit(&dp_full[vs]);
+            umma_commit(&v_empty[vs]);
           }
           __syncwarp();
         }
+      }
+      {
+        const uint32_t pj = num_blocks - 1, ks = pj % Cfg::kStagesK;
+        mbar_wait(&ds_full[pj & 1], (pj >> 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_dQ(pj & 1, ks, pj > 0 ? 1u : 0u);
+          umma_commit(dq_final);
+        }
+        __syncwarp();
       }
     }
   }
@@ -525,25 +591,13 @@ __global__ void __launch_bounds__(kThreads, 1)
     // epilogue: dV, dK -> global (FP32); warpgroup h writes columns [h D/2, (h+1) D/2) of both
     mbar_wait(acc_final, 0);
     tc_fence_after();
-    const uint32_t row = c0 + row_in_tile;
-    const size_t base = (static_cast<size_t>(head) * a.C + row) * a.D;
-#pragma unroll
-    for (uint32_t which = 0; which < 2; ++which) {
-      float *out_row = (which == 0 ? a.dV : a.dK) + base;
-      const uint32_t tAcc = tLane + (which == 0 ? kTmemdV : kTmemdK);
-#pragma unroll
-      for (uint32_t cc = 0; cc < DPAD / 2; cc += 32) {
-        const uint32_t c = h * (DPAD / 2) + cc;
-        uint32_t v[32];
-        tmem_ld32(tAcc + c, v);
-        tc_wait_ld();
-        if (row < a.C) {
-#pragma unroll
-          for (uint32_t k = 0; k < 32; k += 4)
-            if (c + k < a.D)
-              *reinterpret_cast<uint4 *>(out_row + c + k) = make_uint4(v[k], v[k + 1], v[k + 2], v[k + 3]);
-        }
-      }
+    {
+      static_assert(8 * 4096 <= Cfg::kStages * Cfg::kTileBytes, "epilogue scratch does not fit the Q stages");
+      float4 *scratch = reinterpret_cast<float4 *>(smem + Cfg::kSmemStage0) + warp * 256;  // Q stages are dead now
+      const uint32_t warp_row0 = c0 + quarter * 32;
+      const size_t base = (static_cast<size_t>(head) * a.C + warp_row0) * a.D;
+      store_accumulator_coalesced(tLane + kTmemdV, h * (DPAD / 2), DPAD / 2, scratch, a.dV + base, warp_row0, a.C, a.D, lane);
+      store_accumulator_coalesced(tLane + kTmemdK, h * (DPAD / 2), DPAD / 2, scratch, a.dK + base, warp_row0, a.C, a.D, lane);
     }
   } else {
     setmaxnreg_dec<kOtherRegs>();
@@ -676,7 +730,7 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, bool key_value
   static std::once_flag once;
   static cudaError_t attr_status = cudaSuccess;
   std::call_once(once, [&] {
-    attr_status = cudaFuncSetAttribute(kernel_q, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    attr_status = cudaFuncSetAttribute(kernel_q, cudaFuncAttributeMaxDynamicSharedMemorySize, QueryConfig<DPAD>::kSmemBytes);
     if (attr_status == cudaSuccess)
       attr_status = cudaFuncSetAttribute(kernel_kv, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   });
@@ -706,7 +760,7 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, bool key_value
   a.d_prec = p.prec[sD];
   if (!key_value) {
     dim3 grid((p.R + kTile - 1) / kTile, p.batch);
-    kernel_q<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mapQ, mapdO, mapK, mapV, a);
+    kernel_q<<<grid, kThreads, QueryConfig<DPAD>::kSmemBytes, stream>>>(mapQ, mapdO, mapK, mapV, a);
   } else {
     dim3 grid((p.C + kTile - 1) / kTile, p.batch);
     kernel_kv<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mapQ, mapdO, mapK, mapV, a);
@@ -751,10 +805,13 @@ cudaError_t launch_tcgen05_backward_key_value(const AttentionParams &p, cudaStre
   return launch_backward(p, stream, true);
 }
 
-void tcgen05_backward_geometry(int /*type*/, uint32_t D, uint32_t *threads, uint32_t *smem_bytes, uint32_t *par,
+void tcgen05_backward_geometry(int type, uint32_t D, uint32_t *threads, uint32_t *smem_bytes, uint32_t *par,
                                uint32_t *trav, uint32_t *head) {
   *threads = bwd::kThreads;
-  *smem_bytes = D <= 64 ? bwd::Config<64>::kSmemBytes : bwd::Config<128>::kSmemBytes;
+  if (type == 1)  // MFA_BACKWARD_QUERY
+    *smem_bytes = D <= 64 ? bwd::QueryConfig<64>::kSmemBytes : bwd::QueryConfig<128>::kSmemBytes;
+  else
+    *smem_bytes = D <= 64 ? bwd::Config<64>::kSmemBytes : bwd::Config<128>::kSmemBytes;
   *par = bwd::kTile;
   *trav = bwd::kTile;
   *head = D <= 64 ? 64 : 128;
