@@ -261,13 +261,16 @@ def main():
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                "ms_per_step": dt / e2e_steps * 1e3,
                "api": "mfa_attention_run_host (pinned host Q,K,V -> device, kernel, O,L -> host)"}
-        # spot-check that the e2e path produced the same O as the device path (the host path works through the batch in
-        # chunks of a few heads, for which the library may split the key axis across SMs and merge: same math, a
-        # different FP32 summation order, hence a tolerance of a few ulps rather than bit equality)
+        # spot-check that the e2e path produced the same O as the device path.  The host path works through the batch in
+        # chunks of a few heads, for which the library may split the key axis across SMs and merge; each split rounds
+        # P to BF16 against its own running maximum, so the two paths agree to the kernel's accuracy (relative RMS
+        # 2e-3, tests/test_tcgen05_forward.py), not bit for bit.
         step(0)
         torch.cuda.synchronize()
-        assert torch.allclose(host[Op.O][0, :8], sets[0][Op.O][0, :8].cpu(), rtol=1e-4, atol=1e-6), "e2e != device path"
-        assert torch.allclose(host[Op.O][H - 1, -8:], sets[0][Op.O][H - 1, -8:].cpu(), rtol=1e-4, atol=1e-6), "e2e != device path"
+        for sl in ((0, slice(0, 64)), (H - 1, slice(N_SEQ - 64, N_SEQ))):
+            got, want = host[Op.O][sl].float(), sets[0][Op.O][sl].cpu().float()
+            rel = float((got - want).norm() / want.norm())
+            assert rel < 4e-3, f"e2e != device path (relative RMS {rel:.2e})"
 
     # ---- literal single-head latency (BASELINE.json configs[1] as written): one (N=4096, D=128) problem per launch;
     #      too few tiles to fill 148 SMs, so the library splits the key axis across SMs and merges (split-KV) --------

@@ -483,7 +483,15 @@ __global__ void __launch_bounds__(kThreads, 1)
 
 // ================================================================================================
 // backwardKeyValue
-//   TMEM columns: [0,128) S^T / P^T,  [128,256) dP^T / dS^T,  [256,256+D) dV,  [256+D,256+2D) dK
+//   TMEM columns: two 128-column regions X = [0,128), Y = [128,256) that swap roles every block, dV [256,256+D),
+//   dK [256+D,256+2D).  For query block r (Rs = X, Rd = Y when r is even, swapped when odd):
+//     S^T(r) (FP32) lands in Rs, dP^T(r) in Rd.  Once both warpgroups hold S^T(r) in registers, P^T(r) (16-bit) goes
+//     to Rs[0,64) and, later, dS^T(r) to Rs[64,128) -- the two 16-bit A operands share ONE region, so Rd is free the
+//     moment dP^T(r) has been read and S^T(r+1) = K Q(r+1)^T is issued into it while the warps are still computing
+//     dS^T(r).  dP^T(r+1) follows dV(r), dK(r) into Rs (in-order tensor pipe).
+//   Tensor-pipe order per block:  dV(r) [after the P half of the pass]  ->  S^T(r+1)  ->  dK(r)  ->  dP^T(r+1).
+//   The previous form (S^T, dP^T -> one elementwise pass -> dV, dK, everything serialised) left the tensor pipe
+//   idle for the whole pass: 45 % active, the elementwise warps waiting 57 % of the time (profiles/).
 // ================================================================================================
 template <uint32_t DPAD, bool kBF16, bool kConvertDO>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -499,7 +507,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t head = blockIdx.y;
   const uint32_t c0 = blockIdx.x * kTile;
   const uint32_t num_blocks = (a.R + kTile - 1) / kTile;
-  constexpr uint32_t kTmemST = 0, kTmemdPT = 128, kTmemdV = 256, kTmemdK = 256 + DPAD, kTmemCols = 512;
+  constexpr uint32_t kTmemX = 0, kTmemY = 128, kTmemdV = 256, kTmemdK = 256 + DPAD, kTmemCols = 512;
 
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kSmemBar);
   uint64_t *kv_full = bars;           // K and V tiles landed
@@ -507,10 +515,13 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t *q_empty = bars + 3;       // [2]
   uint64_t *vec_full = bars + 5;      // [2] L(r), D(r) vectors in shared memory (32 arrivals)
   uint64_t *vec_empty = bars + 7;     // [2] (256 arrivals)
-  uint64_t *st_full = bars + 9;       // S^T(r), dP^T(r) in TMEM
-  uint64_t *pt_full = bars + 10;      // P^T(r), dS^T(r) written (256 arrivals)
+  uint64_t *st_full = bars + 9;       // S^T(r) in TMEM
+  uint64_t *p_full = bars + 10;       // P^T(r) written (256 arrivals)
   uint64_t *acc_final = bars + 11;
   uint64_t *do_ready = bars + 12;     // [2] kConvertDO: staged dO(r) rewritten as FP16 (warps 10 and 11: 64 arrivals)
+  uint64_t *dpt_full = bars + 14;     // dP^T(r) in TMEM
+  uint64_t *rd_free = bars + 15;      // dP^T(r) is in registers: its region may take S^T(r+1) (256 arrivals)
+  uint64_t *ds_full = bars + 16;      // dS^T(r) written (256 arrivals)
   static_assert(!(kBF16 && kConvertDO), "dO is only converted when Q, K, V are FP16");
   float *vecL = reinterpret_cast<float *>(smem + Cfg::kSmemVec);  // [stage][128]
   float *vecD = vecL + 2 * kTile;
@@ -526,8 +537,11 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&do_ready[s], 64);
     }
     mbar_init(st_full, 1);
-    mbar_init(pt_full, kElemThreads);
+    mbar_init(p_full, kElemThreads);
     mbar_init(acc_final, 1);
+    mbar_init(dpt_full, 1);
+    mbar_init(rd_free, kElemThreads);
+    mbar_init(ds_full, kElemThreads);
     fence_barrier_init();
   }
   if (warp == 8) {
@@ -543,48 +557,67 @@ __global__ void __launch_bounds__(kThreads, 1)
     // ---------------- elementwise warpgroups: thread = key row, columns = queries ----------------
     setmaxnreg_inc<kElemRegs>();
     const uint32_t h = warp >> 2, quarter = warp & 3;
-    const uint32_t row_in_tile = quarter * 32 + lane;
     const uint32_t tLane = tmem_base + ((quarter * 32) << 16);
-    const uint32_t tST = tLane + kTmemST + h * kHalf, tdPT = tLane + kTmemdPT + h * kHalf;
 
     for (uint32_t r = 0; r < num_blocks; ++r) {
       const uint32_t stage = r & 1;
+      const uint32_t rs = (r & 1) ? kTmemY : kTmemX, rd = (r & 1) ? kTmemX : kTmemY;
+      const float *Lq = vecL + stage * kTile + h * kHalf, *Dq = vecD + stage * kTile + h * kHalf;
+      // ---- first half: P^T = exp2(S^T * log2e/sqrt(D) - L[q])   (+Softmax.swift:419-427) ----
       mbar_wait(st_full, r & 1);
       mbar_wait(&vec_full[stage], (r >> 1) & 1);
       tc_fence_after();
-      float s[kHalf], dp[kHalf];
+      float p[kHalf];
 #pragma unroll
-      for (uint32_t c = 0; c < kHalf; c += 32) {
-        tmem_ld32(tST + c, *reinterpret_cast<uint32_t(*)[32]>(&s[c]));
-        tmem_ld32(tdPT + c, *reinterpret_cast<uint32_t(*)[32]>(&dp[c]));
-      }
+      for (uint32_t c = 0; c < kHalf; c += 32) tmem_ld32(tLane + rs + h * kHalf + c, *reinterpret_cast<uint32_t(*)[32]>(&p[c]));
       tc_wait_ld();
-      const float *Lq = vecL + stage * kTile + h * kHalf, *Dq = vecD + stage * kTile + h * kHalf;
+      // both warpgroups hold S^T(r) in registers before either overwrites the region with P^T / dS^T (warpgroup 1's
+      // P^T columns [32,64) lie inside warpgroup 0's S^T columns [0,64))
+      asm volatile("bar.sync 1, %0;" ::"n"(kElemThreads) : "memory");
       const uint32_t q0 = r * kTile + h * kHalf;
       if (r + 1 == num_blocks && q0 + kHalf > a.R) {  // padded query rows: P^T = 0 there
 #pragma unroll
         for (uint32_t c = 0; c < kHalf; ++c)
-          if (q0 + c >= a.R) s[c] = -INFINITY;
+          if (q0 + c >= a.R) p[c] = -INFINITY;
       }
 #pragma unroll
       for (uint32_t c = 0; c < kHalf; c += 32) {
-        uint32_t pp[16], dd[16];
+        uint32_t pp[16];
 #pragma unroll
         for (uint32_t k = 0; k < 16; ++k) {
-          // P^T = exp2(S^T * log2e/sqrt(D) - L[r]);  dS^T = P^T * (dP^T/sqrt(D) - D[r])   (+Softmax.swift:419-427)
-          const float p0 = ex2_approx(fmaf(s[c + 2 * k], a.scale_log2, -Lq[c + 2 * k]));
-          const float p1 = ex2_approx(fmaf(s[c + 2 * k + 1], a.scale_log2, -Lq[c + 2 * k + 1]));
-          const float ds0 = p0 * fmaf(dp[c + 2 * k], a.scale, -Dq[c + 2 * k]);
-          const float ds1 = p1 * fmaf(dp[c + 2 * k + 1], a.scale, -Dq[c + 2 * k + 1]);
-          pp[k] = kBF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
-          dd[k] = kBF16 ? pack_bf16x2(ds0, ds1) : pack_f16x2(ds0, ds1);
+          p[c + 2 * k] = ex2_approx(fmaf(p[c + 2 * k], a.scale_log2, -Lq[c + 2 * k]));
+          p[c + 2 * k + 1] = ex2_approx(fmaf(p[c + 2 * k + 1], a.scale_log2, -Lq[c + 2 * k + 1]));
+          pp[k] = kBF16 ? pack_bf16x2(p[c + 2 * k], p[c + 2 * k + 1]) : pack_f16x2(p[c + 2 * k], p[c + 2 * k + 1]);
         }
-        tmem_st16(tST + (c >> 1), pp);
-        tmem_st16(tdPT + (c >> 1), dd);
+        tmem_st16(tLane + rs + h * (kHalf / 2) + (c >> 1), pp);  // P^T of queries [64h + c, +32) -> columns [32h + c/2, +16)
       }
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(pt_full);
+      mbar_arrive(p_full);
+
+      // ---- second half: dS^T = P^T * (dP^T/sqrt(D) - D[q]) ----
+      mbar_wait(dpt_full, r & 1);
+      tc_fence_after();
+      uint32_t dp[kHalf];
+#pragma unroll
+      for (uint32_t c = 0; c < kHalf; c += 32) tmem_ld32(tLane + rd + h * kHalf + c, *reinterpret_cast<uint32_t(*)[32]>(&dp[c]));
+      tc_wait_ld();
+      tc_fence_before();
+      mbar_arrive(rd_free);  // S^T(r+1) may overwrite the dP^T region now
+#pragma unroll
+      for (uint32_t c = 0; c < kHalf; c += 32) {
+        uint32_t dd[16];
+#pragma unroll
+        for (uint32_t k = 0; k < 16; ++k) {
+          const float ds0 = p[c + 2 * k] * fmaf(__uint_as_float(dp[c + 2 * k]), a.scale, -Dq[c + 2 * k]);
+          const float ds1 = p[c + 2 * k + 1] * fmaf(__uint_as_float(dp[c + 2 * k + 1]), a.scale, -Dq[c + 2 * k + 1]);
+          dd[k] = kBF16 ? pack_bf16x2(ds0, ds1) : pack_f16x2(ds0, ds1);
+        }
+        tmem_st16(tLane + rs + kHalf + h * (kHalf / 2) + (c >> 1), dd);  // dS^T -> columns [64 + 32h + c/2, +16)
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(ds_full);
       mbar_arrive(&vec_empty[stage]);
     }
 
@@ -673,43 +706,76 @@ __global__ void __launch_bounds__(kThreads, 1)
           umma_ss(d_tmem, a_desc + off, b_desc + off, idescNT, k > 0);
         }
       };
+      // A = 128 queries (K) of 16-bit values in 64 consecutive TMEM columns starting at a_base
       auto issue_acc = [&](uint32_t d_tmem, uint32_t a_base, uint64_t b_desc, uint32_t accumulate) {
 #pragma unroll
-        for (uint32_t k = 0; k < kTile / 16; ++k) {
-          const uint32_t a_tmem = a_base + (k >> 2) * kHalf + (k & 3) * 8;
-          umma_ts(d_tmem, a_tmem, b_desc + ((k * 2048) >> 4), idescAcc, k > 0 ? 1u : accumulate);
-        }
+        for (uint32_t k = 0; k < kTile / 16; ++k)
+          umma_ts(d_tmem, a_base + k * 8, b_desc + ((k * 2048) >> 4), idescAcc, k > 0 ? 1u : accumulate);
       };
 
+      // prologue: S^T(0) -> X, dP^T(0) -> Y
       mbar_wait(kv_full, 0);
+      mbar_wait(&q_full[0], 0);
+      tc_fence_after();
+      if (elect_one()) {
+        issue_nt(tmem_base + kTmemX, descK, descQ);  // S^T = K Q^T
+        umma_commit(st_full);
+      }
+      __syncwarp();
+      if constexpr (kConvertDO) {
+        mbar_wait(&do_ready[0], 0);
+        tc_fence_after();
+      }
+      if (elect_one()) {
+        issue_nt(tmem_base + kTmemY, descV, descdO);  // dP^T = V dO^T
+        umma_commit(dpt_full);
+      }
+      __syncwarp();
+
       for (uint32_t r = 0; r < num_blocks; ++r) {
-        const uint32_t stage = r & 1, phase = (r >> 1) & 1;
+        const uint32_t stage = r & 1;
         const uint32_t soff = (stage * Cfg::kTileBytes) >> 4;
-        mbar_wait(&q_full[stage], phase);
+        const uint32_t nstage = (r + 1) & 1, nphase = ((r + 1) >> 1) & 1;
+        const uint32_t nsoff = (nstage * Cfg::kTileBytes) >> 4;
+        const uint32_t rs = tmem_base + ((r & 1) ? kTmemY : kTmemX), rd = tmem_base + ((r & 1) ? kTmemX : kTmemY);
+        const bool has_next = r + 1 < num_blocks;
+        // (a) dV += P^T(r) dO(r)
+        mbar_wait(p_full, r & 1);
         tc_fence_after();
-        if (elect_one()) {
-          // (the previous block's dV / dK MMAs read P^T / dS^T from these columns; the tensor pipe runs in order)
-          issue_nt(tmem_base + kTmemST, descK, descQ + soff);    // S^T  = K Q^T
-        }
+        if (elect_one()) issue_acc(tmem_base + kTmemdV, rs, descdOmn + soff, r > 0 ? 1u : 0u);
         __syncwarp();
-        if constexpr (kConvertDO) {
-          mbar_wait(&do_ready[stage], phase);
+        // (b) S^T(r+1) = K Q(r+1)^T into the region dP^T(r) has just been read out of
+        if (has_next) {
+          mbar_wait(rd_free, r & 1);
+          mbar_wait(&q_full[nstage], nphase);
           tc_fence_after();
+          if (elect_one()) {
+            issue_nt(rd, descK, descQ + nsoff);
+            umma_commit(st_full);
+          }
+          __syncwarp();
         }
-        if (elect_one()) {
-          issue_nt(tmem_base + kTmemdPT, descV, descdO + soff);  // dP^T = V dO^T
-          umma_commit(st_full);
-        }
-        __syncwarp();
-        mbar_wait(pt_full, r & 1);
+        // (c) dK += dS^T(r) Q(r); Q(r) / dO(r) are done with after this
+        mbar_wait(ds_full, r & 1);
         tc_fence_after();
         if (elect_one()) {
-          issue_acc(tmem_base + kTmemdV, tmem_base + kTmemST, descdOmn + soff, r > 0 ? 1u : 0u);  // dV += P^T dO
-          issue_acc(tmem_base + kTmemdK, tmem_base + kTmemdPT, descQmn + soff, r > 0 ? 1u : 0u);  // dK += dS^T Q
+          issue_acc(tmem_base + kTmemdK, rs + kHalf, descQmn + soff, r > 0 ? 1u : 0u);
           umma_commit(&q_empty[stage]);
-          if (r + 1 == num_blocks) umma_commit(acc_final);
+          if (!has_next) umma_commit(acc_final);
         }
         __syncwarp();
+        // (d) dP^T(r+1) = V dO(r+1)^T into the region P^T(r) / dS^T(r) occupied (in-order pipe: after dV(r), dK(r))
+        if (has_next) {
+          if constexpr (kConvertDO) {
+            mbar_wait(&do_ready[nstage], nphase);
+            tc_fence_after();
+          }
+          if (elect_one()) {
+            issue_nt(rs, descV, descdO + nsoff);
+            umma_commit(dpt_full);
+          }
+          __syncwarp();
+        }
       }
     }
   }
