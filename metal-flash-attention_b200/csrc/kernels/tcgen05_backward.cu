@@ -38,23 +38,31 @@ constexpr uint32_t kElemThreads = 256;
 constexpr uint32_t kLaunchRegs = 168, kElemRegs = 208, kOtherRegs = 88;
 static_assert(kElemRegs * 256 + kOtherRegs * 128 <= kLaunchRegs * kThreads, "setmaxnreg over-subscribed");
 
-template <uint32_t DPAD>
-struct Config {
-  static constexpr uint32_t kSubTiles = DPAD / 64;
-  static constexpr uint32_t kTileBytes = kSubTiles * kSubTileBytes;  // one 128 x DPAD 16-bit tile
-  static constexpr uint32_t kStages = 2;
-  // two resident tiles (Q,dO or K,V) + two staged operands x kStages
-  static constexpr uint32_t kSmemResident0 = 0;
-  static constexpr uint32_t kSmemResident1 = kTileBytes;
-  static constexpr uint32_t kSmemStage0 = 2 * kTileBytes;                       // K (dQ kernel) / Q (dK-dV kernel)
-  static constexpr uint32_t kSmemStage1 = kSmemStage0 + kStages * kTileBytes;   // V (dQ kernel) / dO (dK-dV kernel)
-  static constexpr uint32_t kSmemVec = kSmemStage1 + kStages * kTileBytes;      // float L[stages][128], D[stages][128]
-  static constexpr uint32_t kSmemBar = kSmemVec + 2 * kStages * kTile * 4;
-  static constexpr uint32_t kNumBars = 24;
-  static constexpr uint32_t kSmemTmemPtr = kSmemBar + kNumBars * 8;
-  static constexpr uint32_t kSmemBytes = kSmemTmemPtr + 16;
-  static_assert(kSmemBytes <= 232448, "shared memory over budget");
-};
+// Of every 4 element pairs of P, how many take exp2 on the FMA pipe (exp2_poly2, sm100_ptx.cuh) instead of the MUFU
+// pipe.  At D = 64 a block's MMAs need 768 (dQ) / 1024 (dK/dV) tensor-pipe cycles but its 128 x 128 exponentials 1024
+// MUFU cycles (16 ex2 / clk / SM): the P half of the elementwise pass is MUFU-bound and the FMA pipe idles, so half of
+// the pairs go there.  At D = 128 the kernels are tensor-bound and the extra FMA-pipe instructions only cost issue
+// slots.  Swept on B200 (TFLOP/s, dQ | dK/dV): D=128: 0 -> 1353 | 1350, 1 -> 1288 | 1366, 2 -> 1261 | 1351,
+// 3 -> 1209 | 1301;  D=64: 0 -> 669 | 612, 1 -> 688 | 622, 2 -> 709 | 698, 3 -> 627 | 620.
+#ifdef MFA_BWD_POLY_PAIRS
+template <uint32_t DPAD> constexpr uint32_t kPolyPairs = MFA_BWD_POLY_PAIRS;
+#else
+template <uint32_t DPAD> constexpr uint32_t kPolyPairs = DPAD <= 64 ? 2 : 0;
+#endif
+
+// p0, p1 <- exp2(p * scale - l) for pair index `pair` (a compile-time constant once the caller's loop is unrolled)
+template <uint32_t kPoly>
+__device__ __forceinline__ void exp2_pair(uint32_t pair, float &p0, float &p1, float scale, float l0, float l1) {
+  const float2 x = ffma2(make_float2(p0, p1), make_float2(scale, scale), make_float2(-l0, -l1));
+  if (kPoly > 0 && (pair & 3) < kPoly) {
+    const float2 r = exp2_poly2(x);
+    p0 = r.x;
+    p1 = r.y;
+  } else {
+    p0 = ex2_approx(x.x);
+    p1 = ex2_approx(x.y);
+  }
+}
 
 __device__ __forceinline__ float load_16bit(const void *p, size_t i, bool bf16) {
   const uint16_t h = reinterpret_cast<const uint16_t *>(p)[i];
@@ -308,8 +316,9 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (uint32_t c = 0; c < kHalf; ++c)
           if (col0 + c >= a.C) p[c] = -INFINITY;
       }
+      // P = exp2(S * log2e/sqrt(D) - L)   (+Softmax.swift:419-427)
 #pragma unroll
-      for (uint32_t c = 0; c < kHalf; ++c) p[c] = ex2_approx(fmaf(p[c], a.scale_log2, -Lrow));  // (+Softmax.swift:419-427)
+      for (uint32_t i = 0; i < kHalf / 2; ++i) exp2_pair<kPolyPairs<DPAD>>(i, p[2 * i], p[2 * i + 1], a.scale_log2, Lrow, Lrow);
 
       // ---- second half: dS = P * (dP/sqrt(D) - D), written in place over dP as the 16-bit A operand of dQ += dS K ----
       mbar_wait(&dp_full[bf], (j >> 1) & 1);
@@ -493,13 +502,35 @@ __global__ void __launch_bounds__(kThreads, 1)
 //   The previous form (S^T, dP^T -> one elementwise pass -> dV, dK, everything serialised) left the tensor pipe
 //   idle for the whole pass: 45 % active, the elementwise warps waiting 57 % of the time (profiles/).
 // ================================================================================================
+template <uint32_t DPAD>
+struct KeyValueConfig {
+  static constexpr uint32_t kSubTiles = DPAD / 64;
+  static constexpr uint32_t kTileBytes = kSubTiles * kSubTileBytes;  // one 128 x DPAD 16-bit tile
+  // Q(r) is first read by S^T(r) in the middle of pass r-1 and last by dK(r) at the end of pass r, dO(r) first by
+  // dP^T(r) at the end of pass r-1 and last by dV(r) in the middle of pass r: with one shared two-stage ring the load of
+  // Q(r+1) could not start before dK(r-1) had retired and S^T(r+1) waited for a TMA round trip (22 % of the elementwise
+  // warps' time in the profile).  Separate rings, three stages of Q, two of dO.
+  static constexpr uint32_t kStagesQ = 3, kStagesdO = 2;
+  static constexpr uint32_t kSmemK = 0;
+  static constexpr uint32_t kSmemV = kTileBytes;
+  static constexpr uint32_t kSmemQ = 2 * kTileBytes;
+  static constexpr uint32_t kSmemdO = kSmemQ + kStagesQ * kTileBytes;
+  static constexpr uint32_t kSmemVec = kSmemdO + kStagesdO * kTileBytes;  // float L[2][128], D[2][128]
+  static constexpr uint32_t kSmemBar = kSmemVec + 4 * kTile * 4;
+  static constexpr uint32_t kNumBars = 24;
+  static constexpr uint32_t kSmemTmemPtr = kSmemBar + kNumBars * 8;
+  static constexpr uint32_t kSmemBytes = kSmemTmemPtr + 16;
+  static_assert(kSmemBytes <= 232448, "shared memory over budget");
+  static_assert(8 * 4096 <= kStagesQ * kTileBytes, "epilogue scratch does not fit the Q stages");
+};
+
 template <uint32_t DPAD, bool kBF16, bool kConvertDO>
 __global__ void __launch_bounds__(kThreads, 1)
     attention_backward_key_value_tcgen05(const __grid_constant__ CUtensorMap mapQ,
                                          const __grid_constant__ CUtensorMap mapdO,
                                          const __grid_constant__ CUtensorMap mapK,
                                          const __grid_constant__ CUtensorMap mapV, const BackwardArgs a) {
-  using Cfg = Config<DPAD>;
+  using Cfg = KeyValueConfig<DPAD>;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
 
@@ -511,17 +542,19 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kSmemBar);
   uint64_t *kv_full = bars;           // K and V tiles landed
-  uint64_t *q_full = bars + 1;        // [2] Q(r) and dO(r) landed
-  uint64_t *q_empty = bars + 3;       // [2]
-  uint64_t *vec_full = bars + 5;      // [2] L(r), D(r) vectors in shared memory (32 arrivals)
-  uint64_t *vec_empty = bars + 7;     // [2] (256 arrivals)
-  uint64_t *st_full = bars + 9;       // S^T(r) in TMEM
-  uint64_t *p_full = bars + 10;       // P^T(r) written (256 arrivals)
-  uint64_t *acc_final = bars + 11;
-  uint64_t *do_ready = bars + 12;     // [2] kConvertDO: staged dO(r) rewritten as FP16 (warps 10 and 11: 64 arrivals)
-  uint64_t *dpt_full = bars + 14;     // dP^T(r) in TMEM
-  uint64_t *rd_free = bars + 15;      // dP^T(r) is in registers: its region may take S^T(r+1) (256 arrivals)
-  uint64_t *ds_full = bars + 16;      // dS^T(r) written (256 arrivals)
+  uint64_t *q_full = bars + 1;        // [3] Q(r) landed
+  uint64_t *q_empty = bars + 4;       // [3]
+  uint64_t *do_full = bars + 7;       // [2] dO(r) landed
+  uint64_t *do_empty = bars + 9;      // [2]
+  uint64_t *vec_full = bars + 11;     // [2] L(r), D(r) vectors in shared memory (32 arrivals)
+  uint64_t *vec_empty = bars + 13;    // [2] (256 arrivals)
+  uint64_t *st_full = bars + 15;      // S^T(r) in TMEM
+  uint64_t *p_full = bars + 16;       // P^T(r) written (256 arrivals)
+  uint64_t *acc_final = bars + 17;
+  uint64_t *do_ready = bars + 18;     // [2] kConvertDO: staged dO(r) rewritten as FP16 (warps 10 and 11: 64 arrivals)
+  uint64_t *dpt_full = bars + 20;     // dP^T(r) in TMEM
+  uint64_t *rd_free = bars + 21;      // dP^T(r) is in registers: its region may take S^T(r+1) (256 arrivals)
+  uint64_t *ds_full = bars + 22;      // dS^T(r) written (256 arrivals)
   static_assert(!(kBF16 && kConvertDO), "dO is only converted when Q, K, V are FP16");
   float *vecL = reinterpret_cast<float *>(smem + Cfg::kSmemVec);  // [stage][128]
   float *vecD = vecL + 2 * kTile;
@@ -529,9 +562,13 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   if (threadIdx.x == 0) {
     mbar_init(kv_full, 1);
-    for (uint32_t s = 0; s < 2; ++s) {
+    for (uint32_t s = 0; s < Cfg::kStagesQ; ++s) {
       mbar_init(&q_full[s], 1);
       mbar_init(&q_empty[s], 1);
+    }
+    for (uint32_t s = 0; s < 2; ++s) {
+      mbar_init(&do_full[s], 1);
+      mbar_init(&do_empty[s], 1);
       mbar_init(&vec_full[s], 32);
       mbar_init(&vec_empty[s], kElemThreads);
       mbar_init(&do_ready[s], 64);
@@ -585,8 +622,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         uint32_t pp[16];
 #pragma unroll
         for (uint32_t k = 0; k < 16; ++k) {
-          p[c + 2 * k] = ex2_approx(fmaf(p[c + 2 * k], a.scale_log2, -Lq[c + 2 * k]));
-          p[c + 2 * k + 1] = ex2_approx(fmaf(p[c + 2 * k + 1], a.scale_log2, -Lq[c + 2 * k + 1]));
+          exp2_pair<kPolyPairs<DPAD>>(k, p[c + 2 * k], p[c + 2 * k + 1], a.scale_log2, Lq[c + 2 * k], Lq[c + 2 * k + 1]);
           pp[k] = kBF16 ? pack_bf16x2(p[c + 2 * k], p[c + 2 * k + 1]) : pack_f16x2(p[c + 2 * k], p[c + 2 * k + 1]);
         }
         tmem_st16(tLane + rs + h * (kHalf / 2) + (c >> 1), pp);  // P^T of queries [64h + c, +32) -> columns [32h + c/2, +16)
@@ -625,8 +661,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     mbar_wait(acc_final, 0);
     tc_fence_after();
     {
-      static_assert(8 * 4096 <= Cfg::kStages * Cfg::kTileBytes, "epilogue scratch does not fit the Q stages");
-      float4 *scratch = reinterpret_cast<float4 *>(smem + Cfg::kSmemStage0) + warp * 256;  // Q stages are dead now
+      float4 *scratch = reinterpret_cast<float4 *>(smem + Cfg::kSmemQ) + warp * 256;  // the Q stages are dead now
       const uint32_t warp_row0 = c0 + quarter * 32;
       const size_t base = (static_cast<size_t>(head) * a.C + warp_row0) * a.D;
       store_accumulator_coalesced(tLane + kTmemdV, h * (DPAD / 2), DPAD / 2, scratch, a.dV + base, warp_row0, a.C, a.D, lane);
@@ -635,10 +670,10 @@ __global__ void __launch_bounds__(kThreads, 1)
   } else {
     setmaxnreg_dec<kOtherRegs>();
     // kConvertDO: warps 10 and 11 each rewrite one half of the staged BF16 dO tile as FP16 once the TMA has landed it
-    // (the tile cannot be reloaded before the MMAs that wait on do_ready have retired: q_empty)
+    // (the tile cannot be reloaded before the MMAs that wait on do_ready have retired: do_empty)
     auto convert_dO = [&](uint32_t stage, uint32_t phase, uint32_t half) {
-      mbar_wait(&q_full[stage], phase);
-      uint4 *tile = reinterpret_cast<uint4 *>(smem + Cfg::kSmemStage1 + stage * Cfg::kTileBytes + half * (Cfg::kTileBytes / 2));
+      mbar_wait(&do_full[stage], phase);
+      uint4 *tile = reinterpret_cast<uint4 *>(smem + Cfg::kSmemdO + stage * Cfg::kTileBytes + half * (Cfg::kTileBytes / 2));
 #pragma unroll 8
       for (uint32_t i = 0; i < Cfg::kTileBytes / 2 / 512; ++i) tile[i * 32 + lane] = bf16x8_to_f16x8(tile[i * 32 + lane]);
       fence_proxy_async_smem();
@@ -650,22 +685,28 @@ __global__ void __launch_bounds__(kThreads, 1)
         mbar_arrive_expect_tx(kv_full, 2 * Cfg::kTileBytes);
 #pragma unroll
         for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds) {
-          tma_load_3d(smem + Cfg::kSmemResident0 + ds * kSubTileBytes, &mapK, kv_full, ds * 64, c0, head);
-          tma_load_3d(smem + Cfg::kSmemResident1 + ds * kSubTileBytes, &mapV, kv_full, ds * 64, c0, head);
+          tma_load_3d(smem + Cfg::kSmemK + ds * kSubTileBytes, &mapK, kv_full, ds * 64, c0, head);
+          tma_load_3d(smem + Cfg::kSmemV + ds * kSubTileBytes, &mapV, kv_full, ds * 64, c0, head);
         }
       }
       for (uint32_t r = 0; r < num_blocks; ++r) {
-        const uint32_t stage = r & 1, phase = (r >> 1) & 1;
-        mbar_wait(&q_empty[stage], phase ^ 1);
+        const uint32_t qs = r % Cfg::kStagesQ, qphase = (r / Cfg::kStagesQ) & 1;
+        const uint32_t os = r & 1, ophase = (r >> 1) & 1;
+        mbar_wait(&q_empty[qs], qphase ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&q_full[stage], 2 * Cfg::kTileBytes);
+          mbar_arrive_expect_tx(&q_full[qs], Cfg::kTileBytes);
 #pragma unroll
-          for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds) {
-            tma_load_3d(smem + Cfg::kSmemStage0 + stage * Cfg::kTileBytes + ds * kSubTileBytes, &mapQ, &q_full[stage],
-                        ds * 64, r * kTile, head);
-            tma_load_3d(smem + Cfg::kSmemStage1 + stage * Cfg::kTileBytes + ds * kSubTileBytes, &mapdO, &q_full[stage],
-                        ds * 64, r * kTile, head);
-          }
+          for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
+            tma_load_3d(smem + Cfg::kSmemQ + qs * Cfg::kTileBytes + ds * kSubTileBytes, &mapQ, &q_full[qs], ds * 64,
+                        r * kTile, head);
+        }
+        mbar_wait(&do_empty[os], ophase ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&do_full[os], Cfg::kTileBytes);
+#pragma unroll
+          for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
+            tma_load_3d(smem + Cfg::kSmemdO + os * Cfg::kTileBytes + ds * kSubTileBytes, &mapdO, &do_full[os], ds * 64,
+                        r * kTile, head);
         }
       }
     } else if (warp == 10) {
@@ -692,12 +733,12 @@ __global__ void __launch_bounds__(kThreads, 1)
       constexpr uint32_t kFormat = kBF16 ? 1u : 0u;
       constexpr uint32_t idescNT = make_idesc_f16(kTile, kTile, kFormat, 0, 0);
       constexpr uint32_t idescAcc = make_idesc_f16(kTile, DPAD, kFormat, 0, 1);
-      const uint64_t descK = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemResident0), 16, 1024);
-      const uint64_t descV = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemResident1), 16, 1024);
-      const uint64_t descQ = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemStage0), 16, 1024);
-      const uint64_t descdO = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemStage1), 16, 1024);
-      const uint64_t descQmn = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemStage0), kSubTileBytes, 1024);
-      const uint64_t descdOmn = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemStage1), kSubTileBytes, 1024);
+      const uint64_t descK = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemK), 16, 1024);
+      const uint64_t descV = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemV), 16, 1024);
+      const uint64_t descQ = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemQ), 16, 1024);
+      const uint64_t descdO = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemdO), 16, 1024);
+      const uint64_t descQmn = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemQ), kSubTileBytes, 1024);
+      const uint64_t descdOmn = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemdO), kSubTileBytes, 1024);
 
       auto issue_nt = [&](uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc) {
 #pragma unroll
@@ -722,10 +763,9 @@ __global__ void __launch_bounds__(kThreads, 1)
         umma_commit(st_full);
       }
       __syncwarp();
-      if constexpr (kConvertDO) {
-        mbar_wait(&do_ready[0], 0);
-        tc_fence_after();
-      }
+      mbar_wait(&do_full[0], 0);
+      if constexpr (kConvertDO) mbar_wait(&do_ready[0], 0);
+      tc_fence_after();
       if (elect_one()) {
         issue_nt(tmem_base + kTmemY, descV, descdO);  // dP^T = V dO^T
         umma_commit(dpt_full);
@@ -733,45 +773,46 @@ __global__ void __launch_bounds__(kThreads, 1)
       __syncwarp();
 
       for (uint32_t r = 0; r < num_blocks; ++r) {
-        const uint32_t stage = r & 1;
-        const uint32_t soff = (stage * Cfg::kTileBytes) >> 4;
-        const uint32_t nstage = (r + 1) & 1, nphase = ((r + 1) >> 1) & 1;
-        const uint32_t nsoff = (nstage * Cfg::kTileBytes) >> 4;
+        const uint32_t qs = r % Cfg::kStagesQ, os = r & 1;
+        const uint32_t nqs = (r + 1) % Cfg::kStagesQ, nqphase = ((r + 1) / Cfg::kStagesQ) & 1;
+        const uint32_t nos = (r + 1) & 1, nophase = ((r + 1) >> 1) & 1;
         const uint32_t rs = tmem_base + ((r & 1) ? kTmemY : kTmemX), rd = tmem_base + ((r & 1) ? kTmemX : kTmemY);
         const bool has_next = r + 1 < num_blocks;
-        // (a) dV += P^T(r) dO(r)
+        // (a) dV += P^T(r) dO(r); dO(r) is done with after this
         mbar_wait(p_full, r & 1);
         tc_fence_after();
-        if (elect_one()) issue_acc(tmem_base + kTmemdV, rs, descdOmn + soff, r > 0 ? 1u : 0u);
+        if (elect_one()) {
+          issue_acc(tmem_base + kTmemdV, rs, descdOmn + ((os * Cfg::kTileBytes) >> 4), r > 0 ? 1u : 0u);
+          umma_commit(&do_empty[os]);
+        }
         __syncwarp();
         // (b) S^T(r+1) = K Q(r+1)^T into the region dP^T(r) has just been read out of
         if (has_next) {
           mbar_wait(rd_free, r & 1);
-          mbar_wait(&q_full[nstage], nphase);
+          mbar_wait(&q_full[nqs], nqphase);
           tc_fence_after();
           if (elect_one()) {
-            issue_nt(rd, descK, descQ + nsoff);
+            issue_nt(rd, descK, descQ + ((nqs * Cfg::kTileBytes) >> 4));
             umma_commit(st_full);
           }
           __syncwarp();
         }
-        // (c) dK += dS^T(r) Q(r); Q(r) / dO(r) are done with after this
+        // (c) dK += dS^T(r) Q(r); Q(r) is done with after this
         mbar_wait(ds_full, r & 1);
         tc_fence_after();
         if (elect_one()) {
-          issue_acc(tmem_base + kTmemdK, rs + kHalf, descQmn + soff, r > 0 ? 1u : 0u);
-          umma_commit(&q_empty[stage]);
+          issue_acc(tmem_base + kTmemdK, rs + kHalf, descQmn + ((qs * Cfg::kTileBytes) >> 4), r > 0 ? 1u : 0u);
+          umma_commit(&q_empty[qs]);
           if (!has_next) umma_commit(acc_final);
         }
         __syncwarp();
         // (d) dP^T(r+1) = V dO(r+1)^T into the region P^T(r) / dS^T(r) occupied (in-order pipe: after dV(r), dK(r))
         if (has_next) {
-          if constexpr (kConvertDO) {
-            mbar_wait(&do_ready[nstage], nphase);
-            tc_fence_after();
-          }
+          mbar_wait(&do_full[nos], nophase);
+          if constexpr (kConvertDO) mbar_wait(&do_ready[nos], nophase);
+          tc_fence_after();
           if (elect_one()) {
-            issue_nt(rs, descV, descdO + nsoff);
+            issue_nt(rs, descV, descdO + ((nos * Cfg::kTileBytes) >> 4));
             umma_commit(dpt_full);
           }
           __syncwarp();
@@ -790,7 +831,6 @@ __global__ void __launch_bounds__(kThreads, 1)
 
 template <uint32_t DPAD, bool kBF16, bool kConvertDO = false>
 cudaError_t launch(const AttentionParams &p, cudaStream_t stream, bool key_value) {
-  using Cfg = Config<DPAD>;
   auto kernel_q = attention_backward_query_tcgen05<DPAD, kBF16, kConvertDO>;
   auto kernel_kv = attention_backward_key_value_tcgen05<DPAD, kBF16, kConvertDO>;
   static std::once_flag once;
@@ -798,7 +838,7 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, bool key_value
   std::call_once(once, [&] {
     attr_status = cudaFuncSetAttribute(kernel_q, cudaFuncAttributeMaxDynamicSharedMemorySize, QueryConfig<DPAD>::kSmemBytes);
     if (attr_status == cudaSuccess)
-      attr_status = cudaFuncSetAttribute(kernel_kv, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+      attr_status = cudaFuncSetAttribute(kernel_kv, cudaFuncAttributeMaxDynamicSharedMemorySize, KeyValueConfig<DPAD>::kSmemBytes);
   });
   if (attr_status != cudaSuccess) return attr_status;
 
@@ -829,7 +869,7 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, bool key_value
     kernel_q<<<grid, kThreads, QueryConfig<DPAD>::kSmemBytes, stream>>>(mapQ, mapdO, mapK, mapV, a);
   } else {
     dim3 grid((p.C + kTile - 1) / kTile, p.batch);
-    kernel_kv<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mapQ, mapdO, mapK, mapV, a);
+    kernel_kv<<<grid, kThreads, KeyValueConfig<DPAD>::kSmemBytes, stream>>>(mapQ, mapdO, mapK, mapV, a);
   }
   return cudaGetLastError();
 }
@@ -877,7 +917,7 @@ void tcgen05_backward_geometry(int type, uint32_t D, uint32_t *threads, uint32_t
   if (type == 1)  // MFA_BACKWARD_QUERY
     *smem_bytes = D <= 64 ? bwd::QueryConfig<64>::kSmemBytes : bwd::QueryConfig<128>::kSmemBytes;
   else
-    *smem_bytes = D <= 64 ? bwd::Config<64>::kSmemBytes : bwd::Config<128>::kSmemBytes;
+    *smem_bytes = D <= 64 ? bwd::KeyValueConfig<64>::kSmemBytes : bwd::KeyValueConfig<128>::kSmemBytes;
   *par = bwd::kTile;
   *trav = bwd::kTile;
   *head = D <= 64 ? 64 : 128;

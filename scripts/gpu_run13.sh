@@ -9,7 +9,7 @@ N, D, prec, H = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3], int(sys.argv[4]
 p = {"bf16": mfa.GEMMOperandPrecision.BF16, "fp16": mfa.GEMMOperandPrecision.FP16, "ref": None}[prec]
 print(run(N, D, p, H, steps=1))
 PY
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention_backward -s 3 -c 2 -f -o gpurun_out/r1_bwd_d128 python /tmp/prof_bwd.py 4096 128 bf16 32 > gpurun_out/ncu_bwd_d128.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention_backward -s 3 -c 2 -f -o gpurun_out/r1_bwd_d64 python /tmp/prof_bwd.py 2048 64 ref 128 > gpurun_out/ncu_bwd_d64.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention_backward -s 3 -c 2 -f -o gpurun_out/r1_bwd2_d128 python /tmp/prof_bwd.py 4096 128 bf16 32 > gpurun_out/ncu_bwd_d128.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention_backward -s 3 -c 2 -f -o gpurun_out/r1_bwd2_d64 python /tmp/prof_bwd.py 2048 64 ref 128 > gpurun_out/ncu_bwd_d64.log 2>&1
 tail -n 3 gpurun_out/ncu_bwd_d128.log gpurun_out/ncu_bwd_d64.log
 ls -la gpurun_out/*.ncu-rep
