@@ -52,10 +52,15 @@ constexpr uint32_t kThreads = 384;
 // must not exceed the launch allocation or the second setmaxnreg.inc never returns.
 constexpr uint32_t kLaunchRegs = 168, kSoftmaxRegs = 208, kOtherRegs = 88;
 static_assert(kSoftmaxRegs * 256 + kOtherRegs * 128 <= kLaunchRegs * kThreads, "setmaxnreg over-subscribed");
-#ifndef MFA_POLY_PAIRS
-#define MFA_POLY_PAIRS 1  // swept on B200: 0 and 1 tie (1.205 PF), 2 loses 4 %, 3 loses 12 %
+// Of every 4 element pairs, how many take exp2 on the FMA pipe (exp2_poly2) instead of the MUFU pipe.  Swept on B200
+// (TFLOP/s at N = 4096, 64 heads):  D=128: 0 -> 1258, 1 -> 1241, 2 -> 1183, 3 -> 1094;  D=64: 0 -> 729, 1 -> 765,
+// 2 -> 737, 3 -> 626.  At D = 64 the tensor pipe needs half as long per block, the MUFU pipe (16 ex2 / clk / SM) just
+// as long, so taking a quarter of the exponentials off it pays; at D = 128 it only costs issue slots.
+#ifdef MFA_POLY_PAIRS
+template <uint32_t DPAD> constexpr uint32_t kPolyPairsFor = MFA_POLY_PAIRS;
+#else
+template <uint32_t DPAD> constexpr uint32_t kPolyPairsFor = DPAD <= 64 ? 1 : 0;
 #endif
-constexpr uint32_t kPolyPairs = MFA_POLY_PAIRS;  // of every 4 pairs, how many take exp2 on the FMA pipe (0 = all MUFU)
 constexpr float kLazySumLimit = 256.0f;  // a half-row of P summing to <= 2^8 proves every element is <= 2^8
 
 template <uint32_t DPAD>
@@ -111,6 +116,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   // into the next item while the softmax warps drain the current one; TMEM alloc, barrier init and descriptor
   // prefetch are paid once per SM instead of once per tile.
   using Cfg = Config<DPAD>;
+  constexpr uint32_t kPolyPairs = kPolyPairsFor<DPAD>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
