@@ -250,7 +250,8 @@ MFA_API int mfa_debug_forward_trace(const mfa_attention_kernel_t *kernel, const 
   AttentionParams p;
   int status = build_params(kernel, constants, buffers, p);
   if (status != MFA_SUCCESS) return status;
-  cudaError_t e = launch_tcgen05_forward_trace(p, static_cast<cudaStream_t>(cuda_stream), trace);
+  cudaError_t e = p.D > 128 ? launch_tcgen05_forward_d256_trace(p, static_cast<cudaStream_t>(cuda_stream), trace)
+                            : launch_tcgen05_forward_trace(p, static_cast<cudaStream_t>(cuda_stream), trace);
   if (e != cudaSuccess) return fail(MFA_ERROR_CUDA, std::string("trace launch failed: ") + cudaGetErrorString(e));
   return MFA_SUCCESS;
 }

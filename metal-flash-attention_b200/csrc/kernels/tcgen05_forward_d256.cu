@@ -8,10 +8,12 @@
 //     (Q 64 KB + 2 x 32 KB K + 2 x 32 KB V);
 //   * S is double-buffered in TMEM (2 x 64 columns), so S(i+1) = Q K^T runs while the softmax warps work on S(i);
 //     P (16-bit) overwrites S in place and feeds O += P V straight from TMEM.
-// Warp roles (384 threads): warps 0-3 softmax (thread = query row = TMEM lane), warp 8 MMA issuer, warp 9 TMA
-// producer, the rest idle.  The tensor pipe dominates at this head dimension (16 + 4 MMAs of N = 64 / 256 per 64 keys
-// against 64 exp2 per thread), so one softmax warpgroup is enough.  Softmax conventions are those of
-// tcgen05_forward.cu (log2 domain, lazy rescale, L = m + log2 l).
+// Warp roles (384 threads): warps 0-7 softmax -- two warpgroups that split every 64-key block's columns in half
+// (thread = query row x 32 columns; the two warps of a row quarter agree on rescales through a 64-thread named
+// barrier), warp 8 MMA issuer, warp 9 TMA producer, the rest idle.  With one softmax warpgroup (one warp per SM
+// sub-partition, which cannot issue ex2 faster than one per ~16 cycles) the softmax pass, not the tensor pipe, set the
+// pace: 956 TFLOP/s at N = 8192; see DESIGN.md for the measured effect of the split.  Softmax conventions are those of
+// tcgen05_forward.cu (log2 domain, lazy rescale on a half-row-sum check, L = m + log2 l).
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -41,7 +43,26 @@ constexpr uint32_t kThreads = 384;
 // must not exceed the launch allocation or the second setmaxnreg.inc never returns.
 constexpr uint32_t kLaunchRegs = 168, kSoftmaxRegs = 208, kOtherRegs = 88;
 static_assert(kSoftmaxRegs * 256 + kOtherRegs * 128 <= kLaunchRegs * kThreads, "setmaxnreg over-subscribed");
-constexpr float kRescaleThreshold = 8.0f;  // log2 units
+constexpr float kLazySumLimit = 256.0f;  // a half-row of P summing to <= 2^8 proves every element is <= 2^8
+
+// named barrier over `count` threads with an OR reduction of `flag` (all participating warps get the result)
+__device__ __forceinline__ bool bar_red_or(uint32_t id, uint32_t count, bool flag) {
+  uint32_t out;
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "setp.ne.u32 q, %3, 0;\n"
+      "barrier.cta.red.or.pred p, %1, %2, q;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(out)
+      : "r"(id), "r"(count), "r"(static_cast<uint32_t>(flag))
+      : "memory");
+  return out != 0;
+}
+__device__ __forceinline__ void bar_sync(uint32_t id, uint32_t count) {
+  asm volatile("barrier.cta.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
 
 template <uint32_t DPAD>
 struct Config {
@@ -52,7 +73,9 @@ struct Config {
   static constexpr uint32_t kSmemQ = 0;
   static constexpr uint32_t kSmemK = kSmemQ + kTilesPerCta * kQTileBytes;
   static constexpr uint32_t kSmemV = kSmemK + kStages * kKVTileBytes;
-  static constexpr uint32_t kSmemBar = kSmemV + kStages * kKVTileBytes;
+  static constexpr uint32_t kSmemXch = kSmemV + kStages * kKVTileBytes;  // float [2][128]: row max / row sum exchange
+  static constexpr uint32_t kSmemBar = kSmemXch + 2 * kTileM * 4;
+  static_assert(8 * 4096 <= 2 * kStages * kKVTileBytes, "epilogue scratch does not fit the K / V stages");
   static constexpr uint32_t kNumBars = 1 + 4 * kStages + kTilesPerCta * (2 * kSBuffers + 2);
   static constexpr uint32_t kSmemTmemPtr = kSmemBar + kNumBars * 8;
   static constexpr uint32_t kSmemBytes = kSmemTmemPtr + 16 + 1024;  // + slack for manual 1024 B alignment
@@ -112,7 +135,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     for (uint32_t t = 0; t < kTilesPerCta; ++t) {
       for (uint32_t bf = 0; bf < kSBuffers; ++bf) {
         mbar_init(&s_full[t * kSBuffers + bf], 1);
-        mbar_init(&p_full[t * kSBuffers + bf], kTileM);
+        mbar_init(&p_full[t * kSBuffers + bf], 2 * kTileM);
       }
       mbar_init(&o_full[t], 1);
       mbar_init(&o_final[t], 1);
@@ -133,122 +156,168 @@ __global__ void __launch_bounds__(kThreads, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // =====================================================================================
-    // softmax warps: thread <-> query row <-> TMEM lane
+    // softmax warps: thread <-> (query row, half of the block's 64 key columns).  Warpgroup h = warp / 4 owns columns
+    // [32 h, 32 h + 32); warps w and w + 4 share the 32 rows of TMEM lane quarter w and take their joint decisions
+    // (lazy rescale) through a 64-thread named barrier with an OR reduction.  Two warps per SM sub-partition instead
+    // of one: a single warp cannot issue MUFU ex2 faster than about one per 16 cycles, half of what the pipe takes.
     // =====================================================================================
     setmaxnreg_inc<kSoftmaxRegs>();
-    const uint32_t t = 0;  // single tile
-    const uint32_t row_in_tile = (warp & 3) * 32 + lane;
-    const uint32_t lane_addr = ((warp & 3) * 32) << 16;  // this warp's TMEM lane quarter
-    const uint32_t tTile = tmem_base + lane_addr + t * Cfg::kTmemTileStride;
+    constexpr uint32_t kCols = kBlockN / 2;  // columns per thread and block
+    const uint32_t h = warp >> 2, quarter = warp & 3;
+    const uint32_t row_in_tile = quarter * 32 + lane;
+    const uint32_t tTile = tmem_base + ((quarter * 32) << 16);
     const uint32_t tO = tTile + Cfg::kTmemO;
+    const uint32_t pair_bar = 2 + quarter;  // named barrier of the two warps that share these rows
     const uint32_t trace_role = warp == 0 ? 0 : (warp == 4 ? 1 : 3);
+    float *xch = reinterpret_cast<float *>(smem + Cfg::kSmemXch);  // [2][128] row-max / row-sum exchange
 
-    float m = -FLT_MAX;  // running max, log2 domain   (AttentionKernel+Caching.swift:310)
-    float l = 0.f;       // running sum
+    float m = -FLT_MAX;  // running max, log2 domain   (AttentionKernel+Caching.swift:310); identical in both threads of a row
+    float l = 0.f;       // running sum over this thread's columns
     const uint32_t tail_cols = C - (num_blocks - 1) * kBlockN;  // valid columns in the last block
 
     for (uint32_t i = 0; i < num_blocks; ++i) {
       const uint32_t bf = i & 1, ph = (i >> 1) & 1;
       const uint32_t tS = tTile + bf * kBlockN;
-      mbar_wait(&s_full[t * kSBuffers + bf], ph);
+      mbar_wait(&s_full[bf], ph);
       tc_fence_after();
       MFA_TRACE(trace_role, i, 0);
 
-      float s[kBlockN];
-#pragma unroll
-      for (uint32_t c = 0; c < kBlockN; c += 32) tmem_ld32(tS + c, *reinterpret_cast<uint32_t(*)[32]>(&s[c]));
+      float s[kCols];
+      tmem_ld32(tS + h * kCols, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
       tc_wait_ld();
       MFA_TRACE(trace_role, i, 1);
 
       // edge mask (maskAttentionMatrixEdge, AttentionKernel+Softmax.swift:228-260)
       if (i == num_blocks - 1 && tail_cols < kBlockN) {
 #pragma unroll
-        for (uint32_t c = 0; c < kBlockN; ++c)
-          if (c >= tail_cols) s[c] = -INFINITY;
+        for (uint32_t c = 0; c < kCols; ++c)
+          if (h * kCols + c >= tail_cols) s[c] = -INFINITY;
       }
 
-      // online max (onlineReduceMaximum, :267-287): the whole row is in this thread's registers
-      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+      // Lazy running max, as in tcgen05_forward.cu: P is computed against the current (possibly stale) m straight away;
+      // only if some half-row of P sums to more than 2^8 -- or m was never set -- do the two warps of these rows fall
+      // back to the exact path (joint row max, wait for every issued O += P V, rescale O and l, recompute).
+      uint32_t packed[kCols / 2];
+      float half_sum;
+      if (i == 0) {
+        half_sum = INFINITY;
+      } else {
+        float2 sum2 = make_float2(0.f, 0.f);
+        const float2 scale2 = make_float2(scale_log2, scale_log2), negm2 = make_float2(-m, -m);
 #pragma unroll
-      for (uint32_t c = 4; c < kBlockN; c += 4) {
-        mx0 = fmaxf(mx0, s[c]);
-        mx1 = fmaxf(mx1, s[c + 1]);
-        mx2 = fmaxf(mx2, s[c + 2]);
-        mx3 = fmaxf(mx3, s[c + 3]);
+        for (uint32_t k = 0; k < kCols / 2; ++k) {
+          const float2 x = ffma2(make_float2(s[2 * k], s[2 * k + 1]), scale2, negm2);
+          float2 pr;
+          pr.x = ex2_approx(x.x);
+          pr.y = ex2_approx(x.y);
+          sum2 = fadd2(sum2, pr);
+          packed[k] = kBF16 ? pack_bf16x2(pr.x, pr.y) : pack_f16x2(pr.x, pr.y);
+        }
+        half_sum = sum2.x + sum2.y;
       }
-      const float m_cand = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2);
-
-      // lazy correction (onlineCorrectO, :290-301): refresh m only when it grew by > 2^8
-      if (__any_sync(0xffffffffu, m_cand - m > kRescaleThreshold)) {
+      // (also orders both warps' S loads before either overwrites the buffer with P: warpgroup 1's P columns
+      // [16, 32) lie inside warpgroup 0's S columns [0, 32))
+      if (bar_red_or(pair_bar, 64, !(half_sum <= kLazySumLimit))) {  // also catches inf / NaN
+        // ---- exact path (rare) ----
+        float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+#pragma unroll
+        for (uint32_t c = 4; c < kCols; c += 4) {
+          mx0 = fmaxf(mx0, s[c]);
+          mx1 = fmaxf(mx1, s[c + 1]);
+          mx2 = fmaxf(mx2, s[c + 2]);
+          mx3 = fmaxf(mx3, s[c + 3]);
+        }
+        const float m_loc = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+        xch[h * kTileM + row_in_tile] = m_loc;
+        bar_sync(pair_bar, 64);
+        const float m_new = fmaxf(m, fmaxf(m_loc, xch[(1 - h) * kTileM + row_in_tile]));
         if (i > 0) {
-          const float correction = ex2_approx(m - m_cand);
-          mbar_wait(&o_full[t], (i - 1) & 1);  // O += P V of the previous block has landed
+          mbar_wait(o_full, (i - 1) & 1);  // O += P V of the previous block has landed (the current one is not issued yet)
           tc_fence_after();
+          const float correction = ex2_approx(m - m_new);
 #pragma unroll
-          for (uint32_t c = 0; c < DPAD; c += 32) {
+          for (uint32_t c = 0; c < DPAD / 2; c += 32) {  // each warpgroup rescales its half of the O columns
             uint32_t o[32];
-            tmem_ld32(tO + c, o);
+            tmem_ld32(tO + h * (DPAD / 2) + c, o);
             tc_wait_ld();
 #pragma unroll
             for (uint32_t k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * correction);
-            tmem_st32(tO + c, o);
+            tmem_st32(tO + h * (DPAD / 2) + c, o);
           }
           l *= correction;
         }
-        m = m_cand;
-      }
-      MFA_TRACE(trace_role, i, 2);
-
-      // P = exp2(S * log2e/sqrt(D) - m), rounded to the MMA input type, written over S
-      // (softmax, :409-416; onlineReduceSum, :304-324)
-      float sum0 = 0.f, sum1 = 0.f;
+        m = m_new;
+        float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-      for (uint32_t c = 0; c < kBlockN; c += 32) {
-        uint32_t packed[16];
-#pragma unroll
-        for (uint32_t k = 0; k < 16; ++k) {
-          const float p0 = ex2_approx(fmaf(s[c + 2 * k], scale_log2, -m));
-          const float p1 = ex2_approx(fmaf(s[c + 2 * k + 1], scale_log2, -m));
+        for (uint32_t k = 0; k < kCols / 2; ++k) {
+          const float p0 = ex2_approx(fmaf(s[2 * k], scale_log2, -m));
+          const float p1 = ex2_approx(fmaf(s[2 * k + 1], scale_log2, -m));
           sum0 += p0;
           sum1 += p1;
           packed[k] = kBF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
         }
-        tmem_st16(tS + (c >> 1), packed);
+        half_sum = sum0 + sum1;
+        bar_sync(pair_bar, 64);  // the exchange slots may be rewritten in a later block only after both have read them
       }
-      l += sum0 + sum1;
+      l += half_sum;
+      MFA_TRACE(trace_role, i, 2);
+      // P (16-bit) over S: keys [32 h, 32 h + 32) -> columns [16 h, 16 h + 16)
+      tmem_st16(tS + h * (kCols / 2), packed);
       MFA_TRACE(trace_role, i, 3);
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(&p_full[t * kSBuffers + bf]);
+      mbar_arrive(&p_full[bf]);
       MFA_TRACE(trace_role, i, 4);
     }
 
     // ---------------- epilogue: O / l -> global (FP32), L = m + log2(l) ----------------
     // (o_full may be up to two phases behind here, which a parity wait cannot tell apart; o_final is one-shot)
-    mbar_wait(&o_final[t], 0);
+    xch[h * kTileM + row_in_tile] = l;
+    bar_sync(pair_bar, 64);
+    l += xch[(1 - h) * kTileM + row_in_tile];
+    mbar_wait(o_final, 0);
     tc_fence_after();
-    const uint32_t row = q_row0 + t * kTileM + row_in_tile;
+    const uint32_t row = q_row0 + row_in_tile;
     const float inv_l = 1.0f / l;
-    float *o_row = O + (static_cast<size_t>(head) * R + row) * D;
+    {
+      // Warpgroup h stores columns [h DPAD/2, (h+1) DPAD/2).  TMEM hands every thread one row; each warp transposes
+      // 32 x 32 chunks through a private XOR-swizzled scratch tile (overlaying the K / V stages, dead after the last MMA)
+      // so that every global store instruction writes four full 128 B lines (see tcgen05_forward.cu).
+      float4 *scratch = reinterpret_cast<float4 *>(smem + Cfg::kSmemK) + warp * 256;
+      const uint32_t warp_row0 = q_row0 + quarter * 32;
+      float *o_base = O + (static_cast<size_t>(head) * R + warp_row0) * D;
+      const uint32_t sub_row = lane >> 3, quad = lane & 7;
+#pragma unroll 1
+      for (uint32_t cc = 0; cc < DPAD / 2; cc += 32) {
+        const uint32_t c = h * (DPAD / 2) + cc;
+        uint32_t o[32];
+        tmem_ld32(tO + c, o);
+        tc_wait_ld();
 #pragma unroll
-    for (uint32_t c = 0; c < DPAD; c += 32) {
-      uint32_t o[32];
-      tmem_ld32(tO + c, o);
-      tc_wait_ld();
-      if (row < R) {
+        for (uint32_t j = 0; j < 8; ++j)
+          scratch[lane * 8 + (j ^ (lane & 7))] =
+              make_float4(__uint_as_float(o[4 * j]) * inv_l, __uint_as_float(o[4 * j + 1]) * inv_l,
+                          __uint_as_float(o[4 * j + 2]) * inv_l, __uint_as_float(o[4 * j + 3]) * inv_l);
+        __syncwarp();
+        float4 v[8];
 #pragma unroll
-        for (uint32_t k = 0; k < 32; k += 4) {
-          if (c + k < D) {  // D % 8 == 0, so a float4 is either fully inside or fully outside
-            float4 v = make_float4(__uint_as_float(o[k]) * inv_l, __uint_as_float(o[k + 1]) * inv_l,
-                                   __uint_as_float(o[k + 2]) * inv_l, __uint_as_float(o[k + 3]) * inv_l);
-            *reinterpret_cast<float4 *>(o_row + c + k) = v;
+        for (uint32_t k = 0; k < 8; ++k) {
+          const uint32_t r = 4 * k + sub_row;
+          v[k] = scratch[r * 8 + (quad ^ (r & 7))];
+        }
+        if (c + 4 * quad < D) {  // D % 8 == 0: a float4 is either fully inside or fully outside
+#pragma unroll
+          for (uint32_t k = 0; k < 8; ++k) {
+            const uint32_t r = 4 * k + sub_row;
+            if (warp_row0 + r < R) *reinterpret_cast<float4 *>(o_base + static_cast<size_t>(r) * D + c + 4 * quad) = v[k];
           }
         }
+        __syncwarp();
       }
     }
-    if (row < R && L != nullptr) {
+    if (h == 0 && row < R && L != nullptr) {
       const float lse2 = m + log2f(l);  // AttentionKernel+Caching.swift:373-377
       const size_t idx = static_cast<size_t>(head) * R + row;
       if (l_is_fp16)
@@ -256,7 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       else
         reinterpret_cast<float *>(L)[idx] = lse2;
     }
-  } else if (warp >= 8) {
+  } else {
     setmaxnreg_dec<kOtherRegs>();
     // Both producer warps run their control flow warp-wide and hand exactly one elected lane to the
     // TMA / tcgen05 instructions: operands stay in uniform registers and the issue loops are branch-free.
@@ -275,7 +344,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       for (uint32_t i = 0; i < num_blocks; ++i) {
         const uint32_t stage = i % Cfg::kStages, phase = (i / Cfg::kStages) & 1;
+        MFA_TRACE(4, i, 0);
         mbar_wait(&k_empty[stage], phase ^ 1);
+        MFA_TRACE(4, i, 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&k_full[stage], Cfg::kKVTileBytes);
 #pragma unroll
@@ -283,7 +354,18 @@ __global__ void __launch_bounds__(kThreads, 1)
             tma_load_3d(smem + Cfg::kSmemK + stage * Cfg::kKVTileBytes + ds * kKVSubTileBytes, &mapK, &k_full[stage],
                         ds * 64, i * kBlockN, head);
         }
+      }
+    } else if (warp == 10) {
+      // ===================================================================================
+      // TMA producer for the V ring.  A separate warp: with one in-order producer the load of K(i+2) -- whose stage
+      // S(i) freed long ago -- queued behind the wait for V(i+1)'s stage (freed only by O += P V (i-1)), and the MMA
+      // warp, which issues S(i+2) right behind O += P V (i), stalled on it every block (trace: 1877 cycles per block
+      // against 1536 on the tensor pipe).
+      // ===================================================================================
+      for (uint32_t i = 0; i < num_blocks; ++i) {
+        const uint32_t stage = i % Cfg::kStages, phase = (i / Cfg::kStages) & 1;
         mbar_wait(&v_empty[stage], phase ^ 1);
+        MFA_TRACE(4, i, 2);
         if (elect_one()) {
           mbar_arrive_expect_tx(&v_full[stage], Cfg::kKVTileBytes);
 #pragma unroll
@@ -352,33 +434,30 @@ __global__ void __launch_bounds__(kThreads, 1)
         const uint32_t nstage = ni % Cfg::kStages, nphase = (ni / Cfg::kStages) & 1;
         const bool has_next = ni < num_blocks;
         mbar_wait(&v_full[stage], phase);
-        if (has_next) mbar_wait(&k_full[nstage], nphase);
         MFA_TRACE(2, i, 0);
-#pragma unroll
-        for (uint32_t t = 0; t < kTilesPerCta; ++t) {
-          mbar_wait(&p_full[t * kSBuffers + bf], ph);
+        mbar_wait(&p_full[bf], ph);
+        tc_fence_after();
+        MFA_TRACE(2, i, 1);
+        if (elect_one()) {
+          issue_PV(0, bf, stage, i > 0 ? 1u : 0u);
+          umma_commit(o_full);
+          if (i == num_blocks - 1) umma_commit(o_final);
+          umma_commit(&v_empty[stage]);
+        }
+        __syncwarp();
+        if (has_next) {
+          mbar_wait(&k_full[nstage], nphase);
           tc_fence_after();
-          MFA_TRACE(2, i, 1 + 2 * t);
           if (elect_one()) {
-            issue_PV(t, bf, stage, i > 0 ? 1u : 0u);
-            umma_commit(&o_full[t]);
-            if (i == num_blocks - 1) umma_commit(&o_final[t]);
-            if (t == kTilesPerCta - 1) umma_commit(&v_empty[stage]);
-            if (has_next) {
-              issue_S(t, bf, nstage);  // overwrites P(i) only after PV(i): the tensor pipe runs in order
-              umma_commit(&s_full[t * kSBuffers + bf]);
-              if (t == kTilesPerCta - 1) umma_commit(&k_empty[nstage]);
-            }
+            issue_S(0, bf, nstage);  // overwrites P(i) only after PV(i): the tensor pipe runs in order
+            umma_commit(&s_full[bf]);
+            umma_commit(&k_empty[nstage]);
           }
           __syncwarp();
-          MFA_TRACE(2, i, 2 + 2 * t);
         }
+        MFA_TRACE(2, i, 2);
       }
     }
-  }
-
-  else {
-    setmaxnreg_dec<kOtherRegs>();  // warps 4-7: idle warpgroup, donates its registers
   }
 
   // ---------------- teardown ----------------
@@ -414,6 +493,12 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, long long *tra
 }
 
 }  // namespace fwd256
+
+// Debug entry (not in include/mfa_b200.h): the D <= 256 bf16 kernel with pipeline timestamps of CTA (0,0)
+// (5 roles x 128 iterations x 8 slots of clock64()).  Used by scripts/trace_forward_d256.py.
+cudaError_t launch_tcgen05_forward_d256_trace(const AttentionParams &p, cudaStream_t stream, long long *trace) {
+  return fwd256::launch<256, true, true>(p, stream, trace);
+}
 
 cudaError_t launch_tcgen05_forward_d256(const AttentionParams &p, cudaStream_t stream) {
   return p.prec[sQ] == BF16 ? fwd256::launch<256, true>(p, stream) : fwd256::launch<256, false>(p, stream);

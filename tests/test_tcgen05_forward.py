@@ -169,6 +169,30 @@ def test_adversarial_growing_max_forces_rescale():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("C", [512, 417, 33])
+def test_adversarial_growing_max_large_head(C):
+    """Same adversarial construction on the 128 < D <= 256 kernel, whose rows are split over two warps that take the
+    rescale decision jointly (named barrier with OR reduction) and rescale half of the O columns each; the ragged
+    column counts put the masked tail into one warp's half only."""
+    import mfa_b200 as mfa
+    import oracle
+    from tests.attention_harness import run_attention, check
+
+    R, D = 200, 256
+    net = oracle.Network(R, C, D, seed=13, threads=8)
+    ramp = np.linspace(0.0, 4.0, C, dtype=np.float32)[:, None]
+    net.K = net.K + ramp * np.sign(net.Q.mean(axis=0, keepdims=True) + 1e-3)
+    net.Q = np.abs(net.Q) * np.sign(net.Q.mean(axis=0, keepdims=True) + 1e-3)
+    net.K[C // 2 + 5] = net.Q[7] * 1.5     # a late jump for row 7
+    net.round_inputs(oracle.BF16)
+    desc = _descriptor(R, C, D, True)
+    out = run_attention(desc, net, types=[mfa.AttentionKernelType.forward])
+    O, L = net.inferenceAttention(with_L=True)
+    check_O(O, out["O"], net.V, True)
+    check(L, out["L"], 2e-3, "L")
+
+
+@pytest.mark.gpu
 def test_batched_heads_are_independent_problems():
     """batch extension: problem b of the batch equals the single-head run on the same tensors; and the
     softmax identity O == 1 when V == 1 holds at the full N=4096 (size-independent property)."""
