@@ -94,7 +94,7 @@ int register_precision(const mfa_attention_descriptor_t &d, int operand) {
 static const char *kForwardTcgen05 =
     "| 64  | 256 | 128 | 64  | Q, O |\n"
     "| 128 | 256 | 128 | 128 | Q, O |\n"
-    "| 256 | 128 | 64  | 256 | Q, O |\n"
+    "| 256 | 128 | 128 | 256 | Q, O |\n"
     "\n";
 static const char *kBackwardQueryTcgen05 =
     "| 64  | 128 | 128 | 64  | Q, dO, dQ |\n"

@@ -3,17 +3,23 @@
 //
 // At D = 256 one query tile's O accumulator alone takes 256 of the 512 TMEM columns and a 128-key K or V tile takes
 // 64 KB of shared memory, so the residency choices change relative to tcgen05_forward.cu:
-//   * one 128-row tcgen05 M-tile per CTA (not two), O resident in TMEM columns [128, 384);
-//   * keys are walked in blocks of 64 so that K and V can still be double-buffered next to the resident Q tile
-//     (Q 64 KB + 2 x 32 KB K + 2 x 32 KB V);
-//   * S is double-buffered in TMEM (2 x 64 columns), so S(i+1) = Q K^T runs while the softmax warps work on S(i);
-//     P (16-bit) overwrites S in place and feeds O += P V straight from TMEM.
-// Warp roles (384 threads): warps 0-7 softmax -- two warpgroups that split every 64-key block's columns in half
-// (thread = query row x 32 columns; the two warps of a row quarter agree on rescales through a 64-thread named
-// barrier), warp 8 MMA issuer, warp 9 TMA producer, the rest idle.  With one softmax warpgroup (one warp per SM
-// sub-partition, which cannot issue ex2 faster than one per ~16 cycles) the softmax pass, not the tensor pipe, set the
-// pace: 956 TFLOP/s at N = 8192; see DESIGN.md for the measured effect of the split.  Softmax conventions are those of
-// tcgen05_forward.cu (log2 domain, lazy rescale on a half-row-sum check, L = m + log2 l).
+//   * one 128-row tcgen05 M-tile per CTA (not two), O resident in TMEM columns [256, 512);
+//   * keys are walked in blocks of 128 (S = Q K^T as M128 x N128 MMAs: an N = 64 MMA costs the tensor pipe as many
+//     cycles as an N = 128 one -- measured, 64 cycles each -- so 64-key blocks ran S at half rate);
+//   * K and V are SINGLE-buffered (Q 64 KB + K 64 KB + V 64 KB) but recycled at sub-tile granularity: S walks K's four
+//     64-column sub-tiles in order and releases each as soon as its four k-steps have retired, O += P V releases V in
+//     two 64-key halves; because S and P V alternate on the in-order tensor pipe, every reload has at least one whole
+//     GEMM (~1000 cycles) to land before it is needed;
+//   * S is double-buffered in TMEM (2 x 128 columns), so S(i+1) runs while the softmax warps work on S(i); P (16-bit)
+//     overwrites S in place and feeds O += P V straight from TMEM.
+// Warp roles (384 threads): warps 0-7 softmax -- two warpgroups that split every block's 128 key columns in half
+// (thread = query row x 64 columns; the two warps of a row quarter agree on rescales through a 64-thread named
+// barrier with an OR reduction) -- warp 8 MMA issuer, warp 9 TMA producer for Q and K, warp 10 for V.  One softmax
+// warp per SM sub-partition cannot issue ex2 faster than about one per 16 cycles (half the pipe's rate), hence two.
+// Softmax conventions are those of tcgen05_forward.cu (log2 domain, lazy rescale on a half-row-sum check,
+// L = m + log2 l).  History of this kernel (N = 8192, D = 256, 16 heads, TFLOP/s): 64-key blocks, one softmax
+// warpgroup, one TMA producer 956; two warpgroups 970; separate K / V producers and P V decoupled from the next S
+// 1155-1257; 128-key blocks: see DESIGN.md.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -31,12 +37,11 @@ namespace fwd256 {
 
 using namespace ptx;
 
-constexpr uint32_t kTileM = 128;       // rows per tcgen05 M-tile
-constexpr uint32_t kTilesPerCta = 1;   // one M-tile per CTA
-constexpr uint32_t kBlockN = 64;       // keys per traversal block
-constexpr uint32_t kSBuffers = 2;      // S/P buffers per tile
-constexpr uint32_t kQSubTileBytes = kTileM * 128;    // [128 rows][64 x 16-bit]: one 128B-swizzled TMA box
-constexpr uint32_t kKVSubTileBytes = kBlockN * 128;  // [64 keys][64 x 16-bit]
+constexpr uint32_t kTileM = 128;       // rows per tcgen05 M-tile (one per CTA)
+constexpr uint32_t kBlockN = 128;      // keys per traversal block
+constexpr uint32_t kSBuffers = 2;      // S/P buffers
+constexpr uint32_t kSubTileBytes = 128 * 128;  // [128 rows][64 x 16-bit]: one 128B-swizzled sub-tile
+constexpr uint32_t kVHalfBytes = 64 * 128;     // [64 keys][64 x 16-bit]: half a V sub-tile (one TMA box)
 constexpr uint32_t kThreads = 384;
 // setmaxnreg budget: the CTA is launched with floor(65536 / 384 / 8) * 8 = 168 registers per thread; the two
 // softmax warpgroups grow to kSoftmaxRegs after the producer warpgroup has shrunk to kOtherRegs.  The sum
@@ -66,27 +71,26 @@ __device__ __forceinline__ void bar_sync(uint32_t id, uint32_t count) {
 
 template <uint32_t DPAD>
 struct Config {
-  static constexpr uint32_t kSubTiles = DPAD / 64;                      // 64-element sub-tiles along D
-  static constexpr uint32_t kQTileBytes = kSubTiles * kQSubTileBytes;   // 128 x DPAD
-  static constexpr uint32_t kKVTileBytes = kSubTiles * kKVSubTileBytes; // 64 x DPAD
-  static constexpr uint32_t kStages = 2;
+  static constexpr uint32_t kSubTiles = DPAD / 64;                  // 64-element sub-tiles along D
+  static constexpr uint32_t kTileBytes = kSubTiles * kSubTileBytes;  // one 128 x DPAD operand tile
   static constexpr uint32_t kSmemQ = 0;
-  static constexpr uint32_t kSmemK = kSmemQ + kTilesPerCta * kQTileBytes;
-  static constexpr uint32_t kSmemV = kSmemK + kStages * kKVTileBytes;
-  static constexpr uint32_t kSmemXch = kSmemV + kStages * kKVTileBytes;  // float [2][128]: row max / row sum exchange
+  static constexpr uint32_t kSmemK = kSmemQ + kTileBytes;
+  static constexpr uint32_t kSmemV = kSmemK + kTileBytes;
+  static constexpr uint32_t kSmemXch = kSmemV + kTileBytes;  // float [2][128]: row max / row sum exchange
   static constexpr uint32_t kSmemBar = kSmemXch + 2 * kTileM * 4;
-  static_assert(8 * 4096 <= 2 * kStages * kKVTileBytes, "epilogue scratch does not fit the K / V stages");
-  static constexpr uint32_t kNumBars = 1 + 4 * kStages + kTilesPerCta * (2 * kSBuffers + 2);
+  // q_full, k_full[sub], k_empty[sub], v_full[2], v_empty[2], s_full[2], p_full[2], o_full, o_final
+  static constexpr uint32_t kNumBars = 1 + 2 * kSubTiles + 4 + 2 * kSBuffers + 2;
   static constexpr uint32_t kSmemTmemPtr = kSmemBar + kNumBars * 8;
   static constexpr uint32_t kSmemBytes = kSmemTmemPtr + 16 + 1024;  // + slack for manual 1024 B alignment
-  static constexpr uint32_t kTmemTileStride = 512;
+  static_assert(kSmemBytes <= 232448, "shared memory over budget");
+  static_assert(8 * 4096 <= kTileBytes, "epilogue scratch does not fit the K tile");
   static constexpr uint32_t kTmemO = kSBuffers * kBlockN;  // O follows the two S buffers
   static constexpr uint32_t kTmemCols = 512;
-  static_assert(kTmemO + DPAD <= kTmemTileStride, "tile does not fit its TMEM slice");
+  static_assert(kTmemO + DPAD <= kTmemCols, "tile does not fit TMEM");
 };
 
 // kTrace: debug instantiation that records clock64() at the pipeline hand-off points of CTA (0,0)
-// (scripts/trace_forward.py); the production instantiation compiles all of it away.
+// (scripts/trace_forward_d256.py); the production instantiation compiles all of it away.
 constexpr uint32_t kTraceSlots = 8;    // per (role, iteration)
 constexpr uint32_t kTraceIters = 128;  // iterations recorded per role
 #define MFA_TRACE(role, iter, slot)                                                                   \
@@ -108,38 +112,38 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t head = blockIdx.y;
-  const uint32_t q_row0 = blockIdx.x * (kTileM * kTilesPerCta);
+  const uint32_t q_row0 = blockIdx.x * kTileM;
   const uint32_t num_blocks = (C + kBlockN - 1) / kBlockN;
 
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kSmemBar);
   uint64_t *q_full = bars;
-  uint64_t *k_full = q_full + 1;
-  uint64_t *k_empty = k_full + Cfg::kStages;
-  uint64_t *v_full = k_empty + Cfg::kStages;
-  uint64_t *v_empty = v_full + Cfg::kStages;
-  uint64_t *s_full = v_empty + Cfg::kStages;            // [tile][buffer]
-  uint64_t *p_full = s_full + kTilesPerCta * kSBuffers;  // [tile][buffer]
-  uint64_t *o_full = p_full + kTilesPerCta * kSBuffers;  // [tile]  one phase per key block
-  uint64_t *o_final = o_full + kTilesPerCta;             // [tile]  completes once, after the last O += P V
+  uint64_t *k_full = q_full + 1;                 // [sub-tile]  one phase per key block
+  uint64_t *k_empty = k_full + Cfg::kSubTiles;   // [sub-tile]
+  uint64_t *v_full = k_empty + Cfg::kSubTiles;   // [key half]
+  uint64_t *v_empty = v_full + 2;                // [key half]
+  uint64_t *s_full = v_empty + 2;                // [buffer]
+  uint64_t *p_full = s_full + kSBuffers;         // [buffer] (256 arrivals)
+  uint64_t *o_full = p_full + kSBuffers;         // one phase per key block
+  uint64_t *o_final = o_full + 1;                // completes once, after the last O += P V
   uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem + Cfg::kSmemTmemPtr);
 
   // ---------------- one-time setup ----------------
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
-    for (uint32_t s = 0; s < Cfg::kStages; ++s) {
+    for (uint32_t s = 0; s < Cfg::kSubTiles; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
+    }
+    for (uint32_t s = 0; s < 2; ++s) {
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
     }
-    for (uint32_t t = 0; t < kTilesPerCta; ++t) {
-      for (uint32_t bf = 0; bf < kSBuffers; ++bf) {
-        mbar_init(&s_full[t * kSBuffers + bf], 1);
-        mbar_init(&p_full[t * kSBuffers + bf], 2 * kTileM);
-      }
-      mbar_init(&o_full[t], 1);
-      mbar_init(&o_final[t], 1);
+    for (uint32_t bf = 0; bf < kSBuffers; ++bf) {
+      mbar_init(&s_full[bf], 1);
+      mbar_init(&p_full[bf], 2 * kTileM);
     }
+    mbar_init(o_full, 1);
+    mbar_init(o_final, 1);
     fence_barrier_init();
   }
   if (warp == 8) {
@@ -158,10 +162,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   if (warp < 8) {
     // =====================================================================================
-    // softmax warps: thread <-> (query row, half of the block's 64 key columns).  Warpgroup h = warp / 4 owns columns
-    // [32 h, 32 h + 32); warps w and w + 4 share the 32 rows of TMEM lane quarter w and take their joint decisions
-    // (lazy rescale) through a 64-thread named barrier with an OR reduction.  Two warps per SM sub-partition instead
-    // of one: a single warp cannot issue MUFU ex2 faster than about one per 16 cycles, half of what the pipe takes.
+    // softmax warps: thread <-> (query row, half of the block's 128 key columns).  Warpgroup h = warp / 4 owns columns
+    // [64 h, 64 h + 64); warps w and w + 4 share the 32 rows of TMEM lane quarter w and take their joint decisions
+    // (lazy rescale) through a 64-thread named barrier with an OR reduction.
     // =====================================================================================
     setmaxnreg_inc<kSoftmaxRegs>();
     constexpr uint32_t kCols = kBlockN / 2;  // columns per thread and block
@@ -173,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     const uint32_t trace_role = warp == 0 ? 0 : (warp == 4 ? 1 : 3);
     float *xch = reinterpret_cast<float *>(smem + Cfg::kSmemXch);  // [2][128] row-max / row-sum exchange
 
-    float m = -FLT_MAX;  // running max, log2 domain   (AttentionKernel+Caching.swift:310); identical in both threads of a row
+    float m = -FLT_MAX;  // running max, log2 domain (AttentionKernel+Caching.swift:310); identical in both threads of a row
     float l = 0.f;       // running sum over this thread's columns
     const uint32_t tail_cols = C - (num_blocks - 1) * kBlockN;  // valid columns in the last block
 
@@ -185,7 +188,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       MFA_TRACE(trace_role, i, 0);
 
       float s[kCols];
-      tmem_ld32(tS + h * kCols, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+#pragma unroll
+      for (uint32_t c = 0; c < kCols; c += 32) tmem_ld32(tS + h * kCols + c, *reinterpret_cast<uint32_t(*)[32]>(&s[c]));
       tc_wait_ld();
       MFA_TRACE(trace_role, i, 1);
 
@@ -218,7 +222,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         half_sum = sum2.x + sum2.y;
       }
       // (also orders both warps' S loads before either overwrites the buffer with P: warpgroup 1's P columns
-      // [16, 32) lie inside warpgroup 0's S columns [0, 32))
+      // [32, 64) lie inside warpgroup 0's S columns [0, 64))
       if (bar_red_or(pair_bar, 64, !(half_sum <= kLazySumLimit))) {  // also catches inf / NaN
         // ---- exact path (rare) ----
         float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
@@ -263,8 +267,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       l += half_sum;
       MFA_TRACE(trace_role, i, 2);
-      // P (16-bit) over S: keys [32 h, 32 h + 32) -> columns [16 h, 16 h + 16)
-      tmem_st16(tS + h * (kCols / 2), packed);
+      // P (16-bit) over S: keys [64 h, 64 h + 64) -> columns [32 h, 32 h + 32)
+      tmem_st32(tS + h * (kCols / 2), packed);
       MFA_TRACE(trace_role, i, 3);
       tc_wait_st();
       tc_fence_before();
@@ -283,7 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     const float inv_l = 1.0f / l;
     {
       // Warpgroup h stores columns [h DPAD/2, (h+1) DPAD/2).  TMEM hands every thread one row; each warp transposes
-      // 32 x 32 chunks through a private XOR-swizzled scratch tile (overlaying the K / V stages, dead after the last MMA)
+      // 32 x 32 chunks through a private XOR-swizzled scratch tile (overlaying the K tile, dead after the last MMA)
       // so that every global store instruction writes four full 128 B lines (see tcgen05_forward.cu).
       float4 *scratch = reinterpret_cast<float4 *>(smem + Cfg::kSmemK) + warp * 256;
       const uint32_t warp_row0 = q_row0 + quarter * 32;
@@ -327,51 +331,47 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else {
     setmaxnreg_dec<kOtherRegs>();
-    // Both producer warps run their control flow warp-wide and hand exactly one elected lane to the
+    // The producer warps run their control flow warp-wide and hand exactly one elected lane to the
     // TMA / tcgen05 instructions: operands stay in uniform registers and the issue loops are branch-free.
     if (warp == 9) {
       // ===================================================================================
-      // TMA producer
+      // TMA producer: Q once, then K -- one sub-tile ([128 keys][64 columns of D]) at a time, each reloaded as soon
+      // as the S MMAs that read it have retired
       // ===================================================================================
       if (elect_one()) {
-        mbar_arrive_expect_tx(q_full, kTilesPerCta * Cfg::kQTileBytes);
+        mbar_arrive_expect_tx(q_full, Cfg::kTileBytes);
 #pragma unroll
-        for (uint32_t t = 0; t < kTilesPerCta; ++t)
-#pragma unroll
-          for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
-            tma_load_3d(smem + Cfg::kSmemQ + t * Cfg::kQTileBytes + ds * kQSubTileBytes, &mapQ, q_full, ds * 64,
-                        q_row0 + t * kTileM, head);
+        for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
+          tma_load_3d(smem + Cfg::kSmemQ + ds * kSubTileBytes, &mapQ, q_full, ds * 64, q_row0, head);
       }
       for (uint32_t i = 0; i < num_blocks; ++i) {
-        const uint32_t stage = i % Cfg::kStages, phase = (i / Cfg::kStages) & 1;
         MFA_TRACE(4, i, 0);
-        mbar_wait(&k_empty[stage], phase ^ 1);
-        MFA_TRACE(4, i, 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&k_full[stage], Cfg::kKVTileBytes);
 #pragma unroll
-          for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
-            tma_load_3d(smem + Cfg::kSmemK + stage * Cfg::kKVTileBytes + ds * kKVSubTileBytes, &mapK, &k_full[stage],
-                        ds * 64, i * kBlockN, head);
+        for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds) {
+          mbar_wait(&k_empty[ds], (i & 1) ^ 1);
+          if (ds == 0) MFA_TRACE(4, i, 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&k_full[ds], kSubTileBytes);
+            tma_load_3d(smem + Cfg::kSmemK + ds * kSubTileBytes, &mapK, &k_full[ds], ds * 64, i * kBlockN, head);
+          }
         }
       }
     } else if (warp == 10) {
       // ===================================================================================
-      // TMA producer for the V ring.  A separate warp: with one in-order producer the load of K(i+2) -- whose stage
-      // S(i) freed long ago -- queued behind the wait for V(i+1)'s stage (freed only by O += P V (i-1)), and the MMA
-      // warp, which issues S(i+2) right behind O += P V (i), stalled on it every block (trace: 1877 cycles per block
-      // against 1536 on the tensor pipe).
+      // TMA producer for V, one 64-key half at a time (a separate warp: K reloads must not queue behind V's)
       // ===================================================================================
       for (uint32_t i = 0; i < num_blocks; ++i) {
-        const uint32_t stage = i % Cfg::kStages, phase = (i / Cfg::kStages) & 1;
-        mbar_wait(&v_empty[stage], phase ^ 1);
-        MFA_TRACE(4, i, 2);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&v_full[stage], Cfg::kKVTileBytes);
 #pragma unroll
-          for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
-            tma_load_3d(smem + Cfg::kSmemV + stage * Cfg::kKVTileBytes + ds * kKVSubTileBytes, &mapV, &v_full[stage],
-                        ds * 64, i * kBlockN, head);
+        for (uint32_t half = 0; half < 2; ++half) {
+          mbar_wait(&v_empty[half], (i & 1) ^ 1);
+          if (half == 0) MFA_TRACE(4, i, 2);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&v_full[half], Cfg::kSubTiles * kVHalfBytes);
+#pragma unroll
+            for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
+              tma_load_3d(smem + Cfg::kSmemV + ds * kSubTileBytes + half * kVHalfBytes, &mapV, &v_full[half], ds * 64,
+                          i * kBlockN + half * 64, head);
+          }
         }
       }
     } else if (warp == 8) {
@@ -379,82 +379,73 @@ __global__ void __launch_bounds__(kThreads, 1)
       // MMA issuer
       // ===================================================================================
       constexpr uint32_t kFormat = kBF16 ? 1u : 0u;
-      // S[128 x 64] = Q[128 x D] . K[64 x D]^T : A and B both K-major
+      // S[128 x 128] = Q[128 x D] . K[128 x D]^T : A and B both K-major
       constexpr uint32_t idescS = make_idesc_f16(kTileM, kBlockN, kFormat, 0, 0);
-      // O[128 x DPAD] += P[128 x 64] . V[64 x DPAD] : A from TMEM, B (= V, [key][d]) is MN-major
+      // O[128 x DPAD] += P[128 x 128] . V[128 x DPAD] : A from TMEM, B (= V, [key][d]) is MN-major
       constexpr uint32_t idescO = make_idesc_f16(kTileM, DPAD, kFormat, 0, 1);
       // Descriptors differ only in the 14-bit start-address field; build each once and add (bytes >> 4).
       const uint64_t descQ = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemQ), 16, 1024);
       const uint64_t descK = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemK), 16, 1024);
-      const uint64_t descV = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemV), kKVSubTileBytes, 1024);
+      const uint64_t descV = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemV), kSubTileBytes, 1024);
 
-      // every tcgen05.mma / commit below is issued by the one elected lane
-      auto issue_S = [&](uint32_t t, uint32_t bf, uint32_t stage) {
-        const uint32_t d_tmem = tmem_base + t * Cfg::kTmemTileStride + bf * kBlockN;
-        const uint64_t a0 = descQ + ((t * Cfg::kQTileBytes) >> 4);
-        const uint64_t b0 = descK + ((stage * Cfg::kKVTileBytes) >> 4);
+      // S(block) into buffer bf: per 64-column sub-tile of D, wait for K's sub-tile, four k-steps, release it
+      auto issue_S = [&](uint32_t block, uint32_t bf) {
+        const uint32_t d_tmem = tmem_base + bf * kBlockN;
 #pragma unroll
-        for (uint32_t k = 0; k < DPAD / 16; ++k) {
-          // 16 elements = 32 B inside the 128 B swizzle row; 4 k-steps per 64-element sub-tile
-          const uint32_t a_off = ((k >> 2) * kQSubTileBytes + (k & 3) * 32) >> 4;
-          const uint32_t b_off = ((k >> 2) * kKVSubTileBytes + (k & 3) * 32) >> 4;
-          umma_ss(d_tmem, a0 + a_off, b0 + b_off, idescS, k > 0);
-        }
-      };
-      auto issue_PV = [&](uint32_t t, uint32_t bf, uint32_t stage, uint32_t accumulate) {
-        const uint32_t d_tmem = tmem_base + t * Cfg::kTmemTileStride + Cfg::kTmemO;
-        const uint32_t a_tmem = tmem_base + t * Cfg::kTmemTileStride + bf * kBlockN;
-        const uint64_t b0 = descV + ((stage * Cfg::kKVTileBytes) >> 4);
+        for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds) {
+          mbar_wait(&k_full[ds], block & 1);
+          tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-        for (uint32_t k = 0; k < kBlockN / 16; ++k)
-          // 16 keys = two 8-row groups of 1024 B; 64-wide column blocks are kKVSubTileBytes apart (LBO)
-          umma_ts(d_tmem, a_tmem + k * 8, b0 + ((k * 2048) >> 4), idescO, k > 0 ? 1u : accumulate);
-      };
-
-      // prologue: S(0) and S(1) for both tiles
-      mbar_wait(q_full, 0);
-      for (uint32_t i = 0; i < kSBuffers && i < num_blocks; ++i) {
-        mbar_wait(&k_full[i], 0);
-        tc_fence_after();
-        if (elect_one()) {
-#pragma unroll
-          for (uint32_t t = 0; t < kTilesPerCta; ++t) {
-            issue_S(t, i, i);
-            umma_commit(&s_full[t * kSBuffers + i]);
+            for (uint32_t kk = 0; kk < 4; ++kk) {
+              // 16 elements = 32 B inside the 128 B swizzle row; 4 k-steps per 64-element sub-tile
+              const uint32_t off = (ds * kSubTileBytes + kk * 32) >> 4;
+              umma_ss(d_tmem, descQ + off, descK + off, idescS, (ds | kk) != 0);
+            }
+            umma_commit(&k_empty[ds]);
+            if (ds == Cfg::kSubTiles - 1) umma_commit(&s_full[bf]);
           }
-          umma_commit(&k_empty[i]);
+          __syncwarp();
         }
-        __syncwarp();
-      }
+      };
+      // O += P(block) V(block): two 64-key halves, each released as soon as its four k-steps have retired
+      auto issue_PV = [&](uint32_t block, uint32_t bf) {
+        const uint32_t d_tmem = tmem_base + Cfg::kTmemO;
+        const uint32_t a_tmem = tmem_base + bf * kBlockN;
+#pragma unroll
+        for (uint32_t half = 0; half < 2; ++half) {
+          mbar_wait(&v_full[half], block & 1);
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (uint32_t kk = 0; kk < 4; ++kk) {
+              const uint32_t k = half * 4 + kk;
+              // 16 keys = two 8-row groups of 1024 B; 64-wide column blocks are kSubTileBytes apart (LBO)
+              umma_ts(d_tmem, a_tmem + k * 8, descV + ((k * 2048) >> 4), idescO, (block | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&v_empty[half]);
+            if (half == 1) {
+              umma_commit(o_full);
+              if (block == num_blocks - 1) umma_commit(o_final);
+            }
+          }
+          __syncwarp();
+        }
+      };
+
+      // prologue: S(0) and S(1)
+      mbar_wait(q_full, 0);
+      for (uint32_t i = 0; i < kSBuffers && i < num_blocks; ++i) issue_S(i, i);
 
       for (uint32_t i = 0; i < num_blocks; ++i) {
         const uint32_t bf = i & 1, ph = (i >> 1) & 1;
-        const uint32_t stage = i % Cfg::kStages, phase = (i / Cfg::kStages) & 1;
-        const uint32_t ni = i + kSBuffers;  // the S block that reuses this buffer
-        const uint32_t nstage = ni % Cfg::kStages, nphase = (ni / Cfg::kStages) & 1;
-        const bool has_next = ni < num_blocks;
-        mbar_wait(&v_full[stage], phase);
         MFA_TRACE(2, i, 0);
         mbar_wait(&p_full[bf], ph);
         tc_fence_after();
         MFA_TRACE(2, i, 1);
-        if (elect_one()) {
-          issue_PV(0, bf, stage, i > 0 ? 1u : 0u);
-          umma_commit(o_full);
-          if (i == num_blocks - 1) umma_commit(o_final);
-          umma_commit(&v_empty[stage]);
-        }
-        __syncwarp();
-        if (has_next) {
-          mbar_wait(&k_full[nstage], nphase);
-          tc_fence_after();
-          if (elect_one()) {
-            issue_S(0, bf, nstage);  // overwrites P(i) only after PV(i): the tensor pipe runs in order
-            umma_commit(&s_full[bf]);
-            umma_commit(&k_empty[nstage]);
-          }
-          __syncwarp();
-        }
+        issue_PV(i, bf);
+        // S(i+2) overwrites P(i) only after O += P V (i): the tensor pipe runs in order
+        if (i + kSBuffers < num_blocks) issue_S(i + kSBuffers, bf);
         MFA_TRACE(2, i, 2);
       }
     }
@@ -484,9 +475,9 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, long long *tra
   cudaError_t e;
   if ((e = make_tensor_map_16bit(&mapQ, p.buf[sQ], p.R, p.D, p.batch, kTileM)) != cudaSuccess) return e;
   if ((e = make_tensor_map_16bit(&mapK, p.buf[sK], p.C, p.D, p.batch, kBlockN)) != cudaSuccess) return e;
-  if ((e = make_tensor_map_16bit(&mapV, p.buf[sV], p.C, p.D, p.batch, kBlockN)) != cudaSuccess) return e;
+  if ((e = make_tensor_map_16bit(&mapV, p.buf[sV], p.C, p.D, p.batch, 64)) != cudaSuccess) return e;
 
-  dim3 grid((p.R + kTileM * kTilesPerCta - 1) / (kTileM * kTilesPerCta), p.batch);
+  dim3 grid((p.R + kTileM - 1) / kTileM, p.batch);
   kernel<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mapQ, mapK, mapV, static_cast<float *>(p.buf[sO]), p.buf[sL],
                                                       p.R, p.C, p.D, p.scale_log2, p.prec[sL] == FP16 ? 1 : 0, trace);
   return cudaGetLastError();

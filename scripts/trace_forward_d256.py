@@ -37,7 +37,7 @@ for _ in range(3):
     assert st == 0, lib.mfa_last_error()
     torch.cuda.synchronize()
 t = trace.cpu().numpy().reshape(5, 128, 8)
-nb = min(N // 64, 128)
+nb = min(N // 128, 128)
 t0 = t[2, 0, 0]
 print("softmax slots: 0 S ready, 1 S in regs, 2 P computed (after joint decision), 3 P store issued, 4 arrived; "
       "mma: 0 V/K ready, 1 P ready, 2 PV + next S issued; tma: 0 loop top, 1 k_empty passed, 2 v_empty passed")
