@@ -308,7 +308,7 @@ using namespace mfa;
 extern "C" {
 
 const char *mfa_last_error(void) { return g_last_error.c_str(); }
-const char *mfa_version(void) { return "mfa_b200 0.1 (sm_100a; tcgen05+TMA+TMEM forward, SIMT FP32 family)"; }
+const char *mfa_version(void) { return "mfa_b200 0.2 (sm_100a; tcgen05+TMA+TMEM forward / dQ / dK-dV, SIMT FP32 family)"; }
 
 int mfa_precision_size(mfa_precision_t precision) { return precision == MFA_FP32 ? 4 : 2; }
 const char *mfa_precision_name(mfa_precision_t precision) {

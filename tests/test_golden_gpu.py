@@ -1,0 +1,52 @@
+"""The CUDA kernels against the committed golden fixtures (tests/golden/*.npz: inputs and the oracle's outputs frozen
+by tests/golden/make_golden.py), through the C ABI -- these vectors do not depend on rebuilding the oracle on the GPU
+box.  FP32 fixtures: the reference's FP32 bar, 2e-5 absolute on O, L, D, dV, dK, dQ (SquareAttentionTest.swift:547-554).
+16-bit fixtures (inputs already rounded to the memory format): the tensor-core family, relative RMS error <= 2e-3 (BF16)
+/ 1e-3 (FP16) on O and <= 4e-3 / 1.5e-3 on the gradients, L within 1e-3."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+FIXTURES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+class _Inputs:
+    def __init__(self, g):
+        self.Q, self.K, self.V, self.dO = (np.asarray(g[k], np.float32) for k in ("Q", "K", "V", "dO"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p)[:-4] for p in FIXTURES])
+def test_kernels_reproduce_golden_fixture(path):
+    import mfa_b200 as mfa
+    import oracle
+    from tests.attention_harness import run_attention, check
+
+    g = np.load(path)
+    R, C, D, _, rounding = (int(v) for v in g["meta"])
+    desc = mfa.AttentionDescriptor()
+    desc.matrixDimensions = (R, C, D)
+    desc.transposeState = (False, False, False, False)
+    if rounding >= 0:
+        desc.lowPrecisionInputs = True
+        desc.inputPrecisionOverride = (mfa.GEMMOperandPrecision.BF16 if rounding == oracle.BF16
+                                       else mfa.GEMMOperandPrecision.FP16)
+        for t in mfa.AttentionKernelType:
+            assert desc.kernelDescriptor(t).backend == mfa.Backend.tcgen05
+    out = run_attention(desc, _Inputs(g))
+    if rounding < 0:
+        for name in ("O", "L", "D", "dV", "dK", "dQ"):
+            check(g[name], out[name], 2e-5, name)
+        return
+    bf16 = rounding == oracle.BF16
+
+    def rel_rms(a, b):
+        return float(np.sqrt(np.mean((a - b) ** 2)) / max(np.sqrt(np.mean(b ** 2)), 1e-30))
+
+    assert rel_rms(out["O"], g["O"]) <= (2e-3 if bf16 else 1e-3)
+    check(g["L"], out["L"], 1e-3, "L")
+    check(g["D"], out["D"], 2e-2, "D")
+    for name in ("dV", "dK", "dQ"):
+        assert rel_rms(out[name], g[name]) <= (4e-3 if bf16 else 1.5e-3), name
