@@ -162,16 +162,13 @@ static int parse_table(const char *file, std::vector<ParameterRow> &rows) {
     if (line.empty()) continue;  // Swift's split(separator:) omits empty subsequences
     std::vector<std::string> segments;
     size_t p = 0;
-    bool lineEndsWithBar = false;
     while (p <= line.size()) {
       size_t bar = line.find('|', p);
       if (bar == std::string::npos) bar = line.size();
       std::string seg = line.substr(p, bar - p);
       if (!seg.empty()) segments.push_back(strip_spaces(seg));
-      lineEndsWithBar = (bar < line.size());
       p = bar + 1;
     }
-    (void)lineEndsWithBar;
     if (segments.size() != 5)
       return fail(MFA_ERROR_INVALID_ARGUMENT, "Number of segments was invalid: " + std::to_string(segments.size()));
     ParameterRow row;
