@@ -236,7 +236,8 @@ MFA_API int mfa_attention_kernel_encode(const mfa_attention_kernel_t *kernel,
                                         const mfa_function_constants_t *constants,
                                         void *const buffers[MFA_BUFFER_COUNT], void *cuda_stream);
 
-/** Number of CUDA kernels one encode() launches (1; +1 when a split-KV combine is needed). */
+/** Number of CUDA kernels one encode() launches (1; +1 when a small grid is split along the traversal axis and a
+ *  merge kernel follows: split-KV combine for the forward, a plain sum of partial accumulators for dQ and dK/dV). */
 MFA_API int mfa_attention_kernel_launch_count(const mfa_attention_kernel_t *kernel,
                                               const mfa_function_constants_t *constants, uint32_t *out);
 

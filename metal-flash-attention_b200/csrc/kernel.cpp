@@ -210,6 +210,8 @@ int mfa_attention_kernel_launch_count(const mfa_attention_kernel_t *kernel, cons
   if (kernel->backend == MFA_BACKEND_TCGEN05 && kernel->type == MFA_FORWARD)
     *out = tcgen05_forward_launch_count(c->row, c->column, kernel->descriptor.head_dimension,
                                         c->batch_count ? c->batch_count : 1);
+  if (kernel->backend == MFA_BACKEND_TCGEN05 && kernel->type != MFA_FORWARD)
+    *out = tcgen05_backward_launch_count(kernel->type, c->row, c->column, c->batch_count ? c->batch_count : 1);
   return MFA_SUCCESS;
 }
 

@@ -131,6 +131,30 @@ __device__ __forceinline__ void store_accumulator_coalesced(uint32_t t_acc, uint
   }
 }
 
+static uint32_t backward_sm_count() {
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess)
+      sm_count = 148;
+  }
+  return static_cast<uint32_t>(sm_count);
+}
+// keep freed scratch cached in the device's default memory pool instead of returning it to the OS at every
+// synchronisation (the default release threshold is 0)
+static void backward_keep_pool_cached() {
+  static std::once_flag pool_once;
+  std::call_once(pool_once, [] {
+    int device = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&device) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t threshold = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+  });
+}
+
 struct BackwardArgs {
   const void *dO;   // [batch][R][D] 16-bit (element type of Q/K/V, or BF16 beside FP16 Q/K/V: kConvertDO)
   const float *O;   // [batch][R][D] FP32
@@ -140,6 +164,10 @@ struct BackwardArgs {
   uint32_t R, C, D;
   float scale, scale_log2;
   int l_prec, d_prec;
+  // traversal split (small grids): blockIdx.z = split s handles traversal blocks [s * blocks_per_split, ...) and writes
+  // its partial accumulators to slice s of the outputs (which then point at scratch; split_stride floats apart)
+  uint32_t blocks_per_split;
+  size_t split_stride;
 };
 
 // ================================================================================================
@@ -182,7 +210,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t head = blockIdx.y;
   const uint32_t r0 = blockIdx.x * kTile;
-  const uint32_t num_blocks = (a.C + kTile - 1) / kTile;
+  const uint32_t total_blocks = (a.C + kTile - 1) / kTile;
+  const uint32_t blk0 = blockIdx.z * a.blocks_per_split;  // first key block of this split (host: never empty)
+  const uint32_t num_blocks = min(a.blocks_per_split, total_blocks - blk0);
   constexpr uint32_t kTmemS = 0, kTmemdP = 128, kTmemdQ = 384, kTmemCols = 512;
 
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kSmemBar);
@@ -227,6 +257,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // traversal split: let the sum kernel (launched with programmatic stream serialisation) be set up now; its
+  // griddepcontrol.wait still holds it until this grid has completed and flushed
+  if (gridDim.z > 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp < 8) {
     // ---------------- elementwise warpgroups ----------------
@@ -294,7 +327,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     const size_t stat_idx = static_cast<size_t>(head) * a.R + row_c;
     const float Lrow = load_stat(a.L, stat_idx, a.l_prec);
-    if (h == 0 && row < a.R) store_stat(a.Dterm, stat_idx, a.d_prec, Dterm);
+    if (h == 0 && row < a.R && blockIdx.z == 0) store_stat(a.Dterm, stat_idx, a.d_prec, Dterm);
 
     for (uint32_t j = 0; j < num_blocks; ++j) {
       const uint32_t bf = j & 1;
@@ -310,8 +343,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       tc_fence_before();
       mbar_arrive(s_free);  // S(j+1) may overwrite the S buffer now
 
-      const uint32_t col0 = j * kTile + h * kHalf;
-      if (j + 1 == num_blocks && col0 + kHalf > a.C) {  // padded key columns (maskAttentionMatrixEdge): P = 0 there
+      const uint32_t col0 = (blk0 + j) * kTile + h * kHalf;
+      if (blk0 + j + 1 == total_blocks && col0 + kHalf > a.C) {  // padded key columns (maskAttentionMatrixEdge): P = 0 there
 #pragma unroll
         for (uint32_t c = 0; c < kHalf; ++c)
           if (col0 + c >= a.C) p[c] = -INFINITY;
@@ -350,7 +383,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       float4 *scratch = reinterpret_cast<float4 *>(smem + Cfg::kSmemK) + warp * 256;  // the K stages are dead now
       const uint32_t warp_row0 = r0 + quarter * 32;
       store_accumulator_coalesced(tLane + kTmemdQ, h * (DPAD / 2), DPAD / 2, scratch,
-                                  a.dQ + (static_cast<size_t>(head) * a.R + warp_row0) * a.D, warp_row0, a.R, a.D, lane);
+                                  a.dQ + blockIdx.z * a.split_stride + (static_cast<size_t>(head) * a.R + warp_row0) * a.D,
+                                  warp_row0, a.R, a.D, lane);
     }
   } else {
     setmaxnreg_dec<kOtherRegs>();
@@ -372,7 +406,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
           for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
             tma_load_3d(smem + Cfg::kSmemK + stage * Cfg::kTileBytes + ds * kSubTileBytes, &mapK, &k_full[stage],
-                        ds * 64, j * kTile, head);
+                        ds * 64, (blk0 + j) * kTile, head);
         }
       }
     } else if (warp == 10) {
@@ -385,7 +419,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
           for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
             tma_load_3d(smem + Cfg::kSmemV + stage * Cfg::kTileBytes + ds * kSubTileBytes, &mapV, &v_full[stage],
-                        ds * 64, j * kTile, head);
+                        ds * 64, (blk0 + j) * kTile, head);
         }
       }
     } else if (warp == 8) {
@@ -537,7 +571,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t head = blockIdx.y;
   const uint32_t c0 = blockIdx.x * kTile;
-  const uint32_t num_blocks = (a.R + kTile - 1) / kTile;
+  const uint32_t total_blocks = (a.R + kTile - 1) / kTile;
+  const uint32_t blk0 = blockIdx.z * a.blocks_per_split;  // first query block of this split (host: never empty)
+  const uint32_t num_blocks = min(a.blocks_per_split, total_blocks - blk0);
   constexpr uint32_t kTmemX = 0, kTmemY = 128, kTmemdV = 256, kTmemdK = 256 + DPAD, kTmemCols = 512;
 
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kSmemBar);
@@ -589,6 +625,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (gridDim.z > 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp < 8) {
     // ---------------- elementwise warpgroups: thread = key row, columns = queries ----------------
@@ -611,8 +648,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       // both warpgroups hold S^T(r) in registers before either overwrites the region with P^T / dS^T (warpgroup 1's
       // P^T columns [32,64) lie inside warpgroup 0's S^T columns [0,64))
       asm volatile("bar.sync 1, %0;" ::"n"(kElemThreads) : "memory");
-      const uint32_t q0 = r * kTile + h * kHalf;
-      if (r + 1 == num_blocks && q0 + kHalf > a.R) {  // padded query rows: P^T = 0 there
+      const uint32_t q0 = (blk0 + r) * kTile + h * kHalf;
+      if (blk0 + r + 1 == total_blocks && q0 + kHalf > a.R) {  // padded query rows: P^T = 0 there
 #pragma unroll
         for (uint32_t c = 0; c < kHalf; ++c)
           if (q0 + c >= a.R) p[c] = -INFINITY;
@@ -663,7 +700,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     {
       float4 *scratch = reinterpret_cast<float4 *>(smem + Cfg::kSmemQ) + warp * 256;  // the Q stages are dead now
       const uint32_t warp_row0 = c0 + quarter * 32;
-      const size_t base = (static_cast<size_t>(head) * a.C + warp_row0) * a.D;
+      const size_t base = blockIdx.z * a.split_stride + (static_cast<size_t>(head) * a.C + warp_row0) * a.D;
       store_accumulator_coalesced(tLane + kTmemdV, h * (DPAD / 2), DPAD / 2, scratch, a.dV + base, warp_row0, a.C, a.D, lane);
       store_accumulator_coalesced(tLane + kTmemdK, h * (DPAD / 2), DPAD / 2, scratch, a.dK + base, warp_row0, a.C, a.D, lane);
     }
@@ -698,7 +735,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
           for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
             tma_load_3d(smem + Cfg::kSmemQ + qs * Cfg::kTileBytes + ds * kSubTileBytes, &mapQ, &q_full[qs], ds * 64,
-                        r * kTile, head);
+                        (blk0 + r) * kTile, head);
         }
         mbar_wait(&do_empty[os], ophase ^ 1);
         if (elect_one()) {
@@ -706,7 +743,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
           for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
             tma_load_3d(smem + Cfg::kSmemdO + os * Cfg::kTileBytes + ds * kSubTileBytes, &mapdO, &do_full[os], ds * 64,
-                        r * kTile, head);
+                        (blk0 + r) * kTile, head);
         }
       }
     } else if (warp == 10) {
@@ -717,7 +754,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         mbar_wait(&vec_empty[stage], phase ^ 1);
 #pragma unroll
         for (uint32_t i = 0; i < kTile / 32; ++i) {
-          const uint32_t q = r * kTile + i * 32 + lane;
+          const uint32_t q = (blk0 + r) * kTile + i * 32 + lane;
           const size_t idx = static_cast<size_t>(head) * a.R + min(q, a.R - 1);
           vecL[stage * kTile + i * 32 + lane] = load_stat(a.L, idx, a.l_prec);
           vecD[stage * kTile + i * 32 + lane] = load_stat(a.Dterm, idx, a.d_prec);
@@ -829,6 +866,44 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
 }
 
+// Sums the partial accumulators of a traversal split: out[t][i] = sum_s part[s][t][i] (t = tensor: dQ, or dV and dK).
+// The backward pass needs no softmax re-normalisation across splits (L and D are inputs), so unlike the forward's
+// split-KV merge this is a plain, deterministic sum -- still no atomics (README.md:11).  Every load of a thread is
+// issued before the first add; launched with programmatic stream serialisation.
+template <uint32_t kMaxSplits>
+__global__ void __launch_bounds__(256)
+    sum_splits(const float4 *__restrict__ part, float4 *__restrict__ out0, float4 *__restrict__ out1, size_t tensor_quads,
+               size_t split_stride_quads, uint32_t num_splits) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= tensor_quads) return;
+  const float4 *src = part + blockIdx.y * tensor_quads + i;
+  float4 v[kMaxSplits];
+#pragma unroll
+  for (uint32_t s = 0; s < kMaxSplits; ++s)
+    v[s] = s < num_splits ? __ldcg(src + s * split_stride_quads) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 acc = v[0];
+#pragma unroll
+  for (uint32_t s = 1; s < kMaxSplits; ++s) {
+    acc.x += v[s].x;
+    acc.y += v[s].y;
+    acc.z += v[s].z;
+    acc.w += v[s].w;
+  }
+  (blockIdx.y == 0 ? out0 : out1)[i] = acc;
+}
+
+// How many ranges to cut the traversal axis into: only when the SMs would otherwise idle (a single head at N = 4096 is
+// 32 CTAs for 148 SMs), at least two blocks per range, at most 8 ranges.
+static uint32_t choose_blocks_per_split(uint32_t ctas, uint32_t total_blocks, uint32_t sm_count) {
+  if (ctas * 2 > sm_count || total_blocks < 4) return total_blocks;
+  uint32_t splits = sm_count / ctas;
+  if (splits > 8) splits = 8;
+  uint32_t per = (total_blocks + splits - 1) / splits;
+  if (per < 2) per = 2;
+  return per;
+}
+
 template <uint32_t DPAD, bool kBF16, bool kConvertDO = false>
 cudaError_t launch(const AttentionParams &p, cudaStream_t stream, bool key_value) {
   auto kernel_q = attention_backward_query_tcgen05<DPAD, kBF16, kConvertDO>;
@@ -864,14 +939,60 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, bool key_value
   a.scale_log2 = p.scale_log2;
   a.l_prec = p.prec[sL];
   a.d_prec = p.prec[sD];
-  if (!key_value) {
-    dim3 grid((p.R + kTile - 1) / kTile, p.batch);
-    kernel_q<<<grid, kThreads, QueryConfig<DPAD>::kSmemBytes, stream>>>(mapQ, mapdO, mapK, mapV, a);
-  } else {
-    dim3 grid((p.C + kTile - 1) / kTile, p.batch);
-    kernel_kv<<<grid, kThreads, KeyValueConfig<DPAD>::kSmemBytes, stream>>>(mapQ, mapdO, mapK, mapV, a);
+
+  // parallelised dimension -> CTAs; traversed dimension -> blocks, possibly split over blockIdx.z
+  const uint32_t par = key_value ? p.C : p.R, trav = key_value ? p.R : p.C;
+  const uint32_t tiles = (par + kTile - 1) / kTile, total_blocks = (trav + kTile - 1) / kTile;
+  const uint32_t per = choose_blocks_per_split(tiles * p.batch, total_blocks, backward_sm_count());
+  const uint32_t splits = (total_blocks + per - 1) / per;
+  a.blocks_per_split = per;
+  a.split_stride = 0;
+  dim3 grid(tiles, p.batch, splits);
+  const size_t smem = key_value ? KeyValueConfig<DPAD>::kSmemBytes : QueryConfig<DPAD>::kSmemBytes;
+  if (splits == 1) {
+    if (!key_value)
+      kernel_q<<<grid, kThreads, smem, stream>>>(mapQ, mapdO, mapK, mapV, a);
+    else
+      kernel_kv<<<grid, kThreads, smem, stream>>>(mapQ, mapdO, mapK, mapV, a);
+    return cudaGetLastError();
   }
-  return cudaGetLastError();
+
+  // partial accumulators in stream-ordered scratch: [split][tensor][batch][rows][D] FP32, tensor = dQ | (dV, dK)
+  const size_t tensor_elems = static_cast<size_t>(p.batch) * par * p.D;
+  const uint32_t tensors = key_value ? 2 : 1;
+  backward_keep_pool_cached();
+  float *scratch = nullptr;
+  if ((e = cudaMallocAsync(reinterpret_cast<void **>(&scratch), splits * tensors * tensor_elems * sizeof(float), stream)) !=
+      cudaSuccess)
+    return e;
+  a.split_stride = tensors * tensor_elems;
+  a.dQ = scratch;
+  a.dV = scratch;
+  a.dK = scratch + tensor_elems;
+  if (!key_value)
+    kernel_q<<<grid, kThreads, smem, stream>>>(mapQ, mapdO, mapK, mapV, a);
+  else
+    kernel_kv<<<grid, kThreads, smem, stream>>>(mapQ, mapdO, mapK, mapV, a);
+  e = cudaGetLastError();
+  if (e == cudaSuccess) {
+    const size_t quads = tensor_elems / 4;  // D % 8 == 0
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t config = {};
+    config.gridDim = dim3(static_cast<uint32_t>((quads + 255) / 256), tensors, 1);
+    config.blockDim = dim3(256, 1, 1);
+    config.stream = stream;
+    config.attrs = &attr;
+    config.numAttrs = 1;
+    float4 *out0 = reinterpret_cast<float4 *>(key_value ? p.buf[sdV] : p.buf[sdQ]);
+    float4 *out1 = reinterpret_cast<float4 *>(key_value ? p.buf[sdK] : p.buf[sdQ]);
+    e = cudaLaunchKernelEx(&config, sum_splits<8>, reinterpret_cast<const float4 *>(scratch), out0, out1, quads,
+                           a.split_stride / 4, splits);
+    if (e == cudaSuccess) e = cudaGetLastError();
+  }
+  cudaError_t free_status = cudaFreeAsync(scratch, stream);
+  return e != cudaSuccess ? e : free_status;
 }
 
 }  // namespace bwd
@@ -909,6 +1030,14 @@ cudaError_t launch_tcgen05_backward_query(const AttentionParams &p, cudaStream_t
 }
 cudaError_t launch_tcgen05_backward_key_value(const AttentionParams &p, cudaStream_t stream) {
   return launch_backward(p, stream, true);
+}
+
+// 1 launch, or 2 (kernel + sum_splits) when the traversal split engages for this problem size
+uint32_t tcgen05_backward_launch_count(int type, uint32_t R, uint32_t C, uint32_t batch) {
+  const bool key_value = type == 2;  // MFA_BACKWARD_KEY_VALUE
+  const uint32_t par = key_value ? C : R, trav = key_value ? R : C;
+  const uint32_t tiles = (par + bwd::kTile - 1) / bwd::kTile, total_blocks = (trav + bwd::kTile - 1) / bwd::kTile;
+  return bwd::choose_blocks_per_split(tiles * batch, total_blocks, bwd::backward_sm_count()) < total_blocks ? 2 : 1;
 }
 
 void tcgen05_backward_geometry(int type, uint32_t D, uint32_t *threads, uint32_t *smem_bytes, uint32_t *par,

@@ -69,6 +69,26 @@ def test_backward_fp16_matches_oracle(R, C, D):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("R,C,D,bf16,referencePolicy", [(700, 900, 128, True, False), (900, 700, 64, False, True),
+                                                        (2048, 2048, 128, True, False), (1000, 520, 72, False, False)])
+def test_backward_traversal_split_small_grids(R, C, D, bf16, referencePolicy):
+    """Few CTAs for 148 SMs: the traversal axis (keys for dQ, queries for dK/dV) is cut into ranges handled by separate
+    CTAs whose partial accumulators a sum kernel adds up; ragged last ranges, ragged last blocks."""
+    import mfa_b200 as mfa
+    desc = mfa.AttentionDescriptor()
+    desc.lowPrecisionInputs = True
+    if not referencePolicy:
+        desc.inputPrecisionOverride = mfa.GEMMOperandPrecision.BF16 if bf16 else mfa.GEMMOperandPrecision.FP16
+    desc.matrixDimensions = (R, C, D)
+    desc.transposeState = (False, False, False, False)
+    constants = mfa.FunctionConstantValues()
+    desc.setFunctionConstants(constants)
+    for t in (mfa.AttentionKernelType.backwardQuery, mfa.AttentionKernelType.backwardKeyValue):
+        assert mfa.AttentionKernel(desc.kernelDescriptor(t)).launchCount(constants) == 2, t
+    _run(R, C, D, bf16, seed=R + C + D, referencePolicy=referencePolicy)
+
+
+@pytest.mark.gpu
 def test_backward_low_precision_intermediates_bf16():
     """L stored FP16, D stored BF16 (AttentionDescriptor+Precisions.swift:81-87) and read back by dK/dV."""
     _run(256, 384, 64, True, seed=4, lowMid=True)
