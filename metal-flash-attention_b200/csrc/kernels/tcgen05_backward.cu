@@ -55,7 +55,7 @@ template <uint32_t kPoly>
 __device__ __forceinline__ void exp2_pair(uint32_t pair, float &p0, float &p1, float scale, float l0, float l1) {
   const float2 x = ffma2(make_float2(p0, p1), make_float2(scale, scale), make_float2(-l0, -l1));
   if (kPoly > 0 && (pair & 3) < kPoly) {
-    const float2 r = exp2_poly2(x);
+    const float2 r = exp2_poly2<false>(x);  // x = s - L <= ~0: no upper clamp needed
     p0 = r.x;
     p1 = r.y;
   } else {
@@ -574,7 +574,14 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t total_blocks = (a.R + kTile - 1) / kTile;
   const uint32_t blk0 = blockIdx.z * a.blocks_per_split;  // first query block of this split (host: never empty)
   const uint32_t num_blocks = min(a.blocks_per_split, total_blocks - blk0);
-  constexpr uint32_t kTmemX = 0, kTmemY = 128, kTmemdV = 256, kTmemdK = 256 + DPAD, kTmemCols = 512;
+  // At D <= 64 the accumulators leave room for a THIRD 128-column region: dP^T then has a region of its own (Z) and
+  // S^T / P^T / dS^T alternate between X and Y, so S^T(r+2) is issued a whole pass ahead and dP^T(r+1) in the middle of
+  // pass r -- the elementwise warps never wait for the tensor pipe in steady state (they waited 24 % of the time at
+  // D = 64 with two regions).  At D = 128 TMEM is full (128 + 128 + 128 + 128) and the two-region scheme above applies.
+  constexpr bool kThird = DPAD <= 64;
+  constexpr uint32_t kTmemX = 0, kTmemY = 128, kTmemZ = 256;
+  constexpr uint32_t kTmemdV = kThird ? 384 : 256, kTmemdK = kTmemdV + DPAD, kTmemCols = 512;
+  static_assert(kTmemdK + DPAD <= kTmemCols, "accumulators do not fit TMEM");
 
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kSmemBar);
   uint64_t *kv_full = bars;           // K and V tiles landed
@@ -584,7 +591,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t *do_empty = bars + 9;      // [2]
   uint64_t *vec_full = bars + 11;     // [2] L(r), D(r) vectors in shared memory (32 arrivals)
   uint64_t *vec_empty = bars + 13;    // [2] (256 arrivals)
-  uint64_t *st_full = bars + 15;      // S^T(r) in TMEM
+  uint64_t *st_full = bars + 15;      // S^T(r) in TMEM (two regions: kThird uses st_full and st_full2 = bars + 23 alternately)
+  uint64_t *st_full2 = bars + 23;
   uint64_t *p_full = bars + 16;       // P^T(r) written (256 arrivals)
   uint64_t *acc_final = bars + 17;
   uint64_t *do_ready = bars + 18;     // [2] kConvertDO: staged dO(r) rewritten as FP16 (warps 10 and 11: 64 arrivals)
@@ -610,6 +618,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&do_ready[s], 64);
     }
     mbar_init(st_full, 1);
+    mbar_init(st_full2, 1);
     mbar_init(p_full, kElemThreads);
     mbar_init(acc_final, 1);
     mbar_init(dpt_full, 1);
@@ -635,10 +644,13 @@ __global__ void __launch_bounds__(kThreads, 1)
 
     for (uint32_t r = 0; r < num_blocks; ++r) {
       const uint32_t stage = r & 1;
-      const uint32_t rs = (r & 1) ? kTmemY : kTmemX, rd = (r & 1) ? kTmemX : kTmemY;
+      const uint32_t rs = (r & 1) ? kTmemY : kTmemX, rd = kThird ? kTmemZ : ((r & 1) ? kTmemX : kTmemY);
       const float *Lq = vecL + stage * kTile + h * kHalf, *Dq = vecD + stage * kTile + h * kHalf;
       // ---- first half: P^T = exp2(S^T * log2e/sqrt(D) - L[q])   (+Softmax.swift:419-427) ----
-      mbar_wait(st_full, r & 1);
+      if (kThird)
+        mbar_wait((r & 1) ? st_full2 : st_full, (r >> 1) & 1);  // one barrier per S^T region: two S^T can be outstanding
+      else
+        mbar_wait(st_full, r & 1);
       mbar_wait(&vec_full[stage], (r >> 1) & 1);
       tc_fence_after();
       float p[kHalf];
@@ -791,7 +803,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           umma_ts(d_tmem, a_base + k * 8, b_desc + ((k * 2048) >> 4), idescAcc, k > 0 ? 1u : accumulate);
       };
 
-      // prologue: S^T(0) -> X, dP^T(0) -> Y
+      // prologue: S^T(0) -> X, dP^T(0) -> Y (Z with three regions)
       mbar_wait(kv_full, 0);
       mbar_wait(&q_full[0], 0);
       tc_fence_after();
@@ -804,55 +816,113 @@ __global__ void __launch_bounds__(kThreads, 1)
       if constexpr (kConvertDO) mbar_wait(&do_ready[0], 0);
       tc_fence_after();
       if (elect_one()) {
-        issue_nt(tmem_base + kTmemY, descV, descdO);  // dP^T = V dO^T
+        issue_nt(tmem_base + (kThird ? kTmemZ : kTmemY), descV, descdO);  // dP^T = V dO^T
         umma_commit(dpt_full);
       }
       __syncwarp();
 
-      for (uint32_t r = 0; r < num_blocks; ++r) {
-        const uint32_t qs = r % Cfg::kStagesQ, os = r & 1;
-        const uint32_t nqs = (r + 1) % Cfg::kStagesQ, nqphase = ((r + 1) / Cfg::kStagesQ) & 1;
-        const uint32_t nos = (r + 1) & 1, nophase = ((r + 1) >> 1) & 1;
-        const uint32_t rs = tmem_base + ((r & 1) ? kTmemY : kTmemX), rd = tmem_base + ((r & 1) ? kTmemX : kTmemY);
-        const bool has_next = r + 1 < num_blocks;
-        // (a) dV += P^T(r) dO(r); dO(r) is done with after this
-        mbar_wait(p_full, r & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          issue_acc(tmem_base + kTmemdV, rs, descdOmn + ((os * Cfg::kTileBytes) >> 4), r > 0 ? 1u : 0u);
-          umma_commit(&do_empty[os]);
-        }
-        __syncwarp();
-        // (b) S^T(r+1) = K Q(r+1)^T into the region dP^T(r) has just been read out of
-        if (has_next) {
-          mbar_wait(rd_free, r & 1);
-          mbar_wait(&q_full[nqs], nqphase);
+      if constexpr (kThird) {
+        // three regions: S^T(1) straight away, then per block  dV(r) -> dP^T(r+1) -> dK(r) -> S^T(r+2)
+        if (num_blocks > 1) {
+          mbar_wait(&q_full[1 % Cfg::kStagesQ], 0);
           tc_fence_after();
           if (elect_one()) {
-            issue_nt(rd, descK, descQ + ((nqs * Cfg::kTileBytes) >> 4));
-            umma_commit(st_full);
+            issue_nt(tmem_base + kTmemY, descK, descQ + (((1 % Cfg::kStagesQ) * Cfg::kTileBytes) >> 4));
+            umma_commit(st_full2);
           }
           __syncwarp();
         }
-        // (c) dK += dS^T(r) Q(r); Q(r) is done with after this
-        mbar_wait(ds_full, r & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          issue_acc(tmem_base + kTmemdK, rs + kHalf, descQmn + ((qs * Cfg::kTileBytes) >> 4), r > 0 ? 1u : 0u);
-          umma_commit(&q_empty[qs]);
-          if (!has_next) umma_commit(acc_final);
-        }
-        __syncwarp();
-        // (d) dP^T(r+1) = V dO(r+1)^T into the region P^T(r) / dS^T(r) occupied (in-order pipe: after dV(r), dK(r))
-        if (has_next) {
-          mbar_wait(&do_full[nos], nophase);
-          if constexpr (kConvertDO) mbar_wait(&do_ready[nos], nophase);
+        for (uint32_t r = 0; r < num_blocks; ++r) {
+          const uint32_t qs = r % Cfg::kStagesQ, os = r & 1;
+          const uint32_t nos = (r + 1) & 1, nophase = ((r + 1) >> 1) & 1;
+          const uint32_t nqs = (r + 2) % Cfg::kStagesQ, nqphase = ((r + 2) / Cfg::kStagesQ) & 1;
+          const uint32_t rs = tmem_base + ((r & 1) ? kTmemY : kTmemX);
+          // (a) dV += P^T(r) dO(r); dO(r) is done with after this
+          mbar_wait(p_full, r & 1);
           tc_fence_after();
           if (elect_one()) {
-            issue_nt(rs, descV, descdO + ((nos * Cfg::kTileBytes) >> 4));
-            umma_commit(dpt_full);
+            issue_acc(tmem_base + kTmemdV, rs, descdOmn + ((os * Cfg::kTileBytes) >> 4), r > 0 ? 1u : 0u);
+            umma_commit(&do_empty[os]);
           }
           __syncwarp();
+          // (b) dP^T(r+1) = V dO(r+1)^T into Z as soon as dP^T(r) has been read out of it
+          if (r + 1 < num_blocks) {
+            mbar_wait(rd_free, r & 1);
+            mbar_wait(&do_full[nos], nophase);
+            if constexpr (kConvertDO) mbar_wait(&do_ready[nos], nophase);
+            tc_fence_after();
+            if (elect_one()) {
+              issue_nt(tmem_base + kTmemZ, descV, descdO + ((nos * Cfg::kTileBytes) >> 4));
+              umma_commit(dpt_full);
+            }
+            __syncwarp();
+          }
+          // (c) dK += dS^T(r) Q(r); Q(r) is done with after this
+          mbar_wait(ds_full, r & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_acc(tmem_base + kTmemdK, rs + kHalf, descQmn + ((qs * Cfg::kTileBytes) >> 4), r > 0 ? 1u : 0u);
+            umma_commit(&q_empty[qs]);
+            if (r + 1 == num_blocks) umma_commit(acc_final);
+          }
+          __syncwarp();
+          // (d) S^T(r+2) = K Q(r+2)^T into the region P^T(r) / dS^T(r) occupied (in-order pipe: after dV(r), dK(r))
+          if (r + 2 < num_blocks) {
+            mbar_wait(&q_full[nqs], nqphase);
+            tc_fence_after();
+            if (elect_one()) {
+              issue_nt(rs, descK, descQ + ((nqs * Cfg::kTileBytes) >> 4));
+              umma_commit((r & 1) ? st_full2 : st_full);
+            }
+            __syncwarp();
+          }
+        }
+      } else {
+        for (uint32_t r = 0; r < num_blocks; ++r) {
+          const uint32_t qs = r % Cfg::kStagesQ, os = r & 1;
+          const uint32_t nqs = (r + 1) % Cfg::kStagesQ, nqphase = ((r + 1) / Cfg::kStagesQ) & 1;
+          const uint32_t nos = (r + 1) & 1, nophase = ((r + 1) >> 1) & 1;
+          const uint32_t rs = tmem_base + ((r & 1) ? kTmemY : kTmemX), rd = tmem_base + ((r & 1) ? kTmemX : kTmemY);
+          const bool has_next = r + 1 < num_blocks;
+          // (a) dV += P^T(r) dO(r); dO(r) is done with after this
+          mbar_wait(p_full, r & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_acc(tmem_base + kTmemdV, rs, descdOmn + ((os * Cfg::kTileBytes) >> 4), r > 0 ? 1u : 0u);
+            umma_commit(&do_empty[os]);
+          }
+          __syncwarp();
+          // (b) S^T(r+1) = K Q(r+1)^T into the region dP^T(r) has just been read out of
+          if (has_next) {
+            mbar_wait(rd_free, r & 1);
+            mbar_wait(&q_full[nqs], nqphase);
+            tc_fence_after();
+            if (elect_one()) {
+              issue_nt(rd, descK, descQ + ((nqs * Cfg::kTileBytes) >> 4));
+              umma_commit(st_full);
+            }
+            __syncwarp();
+          }
+          // (c) dK += dS^T(r) Q(r); Q(r) is done with after this
+          mbar_wait(ds_full, r & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_acc(tmem_base + kTmemdK, rs + kHalf, descQmn + ((qs * Cfg::kTileBytes) >> 4), r > 0 ? 1u : 0u);
+            umma_commit(&q_empty[qs]);
+            if (!has_next) umma_commit(acc_final);
+          }
+          __syncwarp();
+          // (d) dP^T(r+1) = V dO(r+1)^T into the region P^T(r) / dS^T(r) occupied (in-order pipe: after dV(r), dK(r))
+          if (has_next) {
+            mbar_wait(&do_full[nos], nophase);
+            if constexpr (kConvertDO) mbar_wait(&do_ready[nos], nophase);
+            tc_fence_after();
+            if (elect_one()) {
+              issue_nt(rs, descV, descdO + ((nos * Cfg::kTileBytes) >> 4));
+              umma_commit(dpt_full);
+            }
+            __syncwarp();
+          }
         }
       }
     }
