@@ -431,6 +431,11 @@ int mfa_attention_run_host(const mfa_attention_descriptor_t *descriptor, uint32_
 
   const uint32_t per_chunk = chunk_heads(batch, traffic_per_head);
   cudaStream_t upload = s.stream[0], compute = s.stream[1], download = s.stream[2];
+  // every exit drains the three streams: the call is synchronous and the scratch is reused by the next one
+  auto drained = [&](int result) {
+    for (int i = 0; i < kHostStreams; ++i) cudaStreamSynchronize(s.stream[i]);
+    return result;
+  };
   uint32_t chunk_index = 0;
   for (uint32_t h0 = 0; h0 < batch; h0 += per_chunk, ++chunk_index) {
     const uint32_t heads = batch - h0 < per_chunk ? batch - h0 : per_chunk;
@@ -441,26 +446,26 @@ int mfa_attention_run_host(const mfa_attention_descriptor_t *descriptor, uint32_
       if (inputs & (1u << op)) {
         const char *src = static_cast<const char *>(host_buffers[op]) + head_bytes[op] * h0;
         if ((e = cudaMemcpyAsync(chunk_dev[op], src, head_bytes[op] * heads, cudaMemcpyHostToDevice, upload)) != cudaSuccess)
-          return fail(MFA_ERROR_CUDA, std::string("H2D copy: ") + cudaGetErrorString(e));
+          return drained(fail(MFA_ERROR_CUDA, std::string("H2D copy: ") + cudaGetErrorString(e)));
       }
     }
     if ((e = cudaEventRecord(s.uploaded[chunk_index], upload)) != cudaSuccess ||
         (e = cudaStreamWaitEvent(compute, s.uploaded[chunk_index], 0)) != cudaSuccess)
-      return fail(MFA_ERROR_CUDA, std::string("event: ") + cudaGetErrorString(e));
+      return drained(fail(MFA_ERROR_CUDA, std::string("event: ") + cudaGetErrorString(e)));
     mfa_function_constants_t chunk_constants = constants;
     chunk_constants.batch_count = heads;
     for (int type = MFA_FORWARD; type <= MFA_BACKWARD_KEY_VALUE; ++type)
       if (kernels[type] &&
           (status = mfa_attention_kernel_encode(kernels[type], &chunk_constants, chunk_dev, compute)) != MFA_SUCCESS)
-        return status;
+        return drained(status);
     if ((e = cudaEventRecord(s.computed[chunk_index], compute)) != cudaSuccess ||
         (e = cudaStreamWaitEvent(download, s.computed[chunk_index], 0)) != cudaSuccess)
-      return fail(MFA_ERROR_CUDA, std::string("event: ") + cudaGetErrorString(e));
+      return drained(fail(MFA_ERROR_CUDA, std::string("event: ") + cudaGetErrorString(e)));
     for (int op = 0; op < MFA_BUFFER_COUNT; ++op) {
       if (!(outputs & (1u << op)) || !host_buffers[op]) continue;
       char *dst = static_cast<char *>(host_buffers[op]) + head_bytes[op] * h0;
       if ((e = cudaMemcpyAsync(dst, chunk_dev[op], head_bytes[op] * heads, cudaMemcpyDeviceToHost, download)) != cudaSuccess)
-        return fail(MFA_ERROR_CUDA, std::string("D2H copy: ") + cudaGetErrorString(e));
+        return drained(fail(MFA_ERROR_CUDA, std::string("D2H copy: ") + cudaGetErrorString(e)));
     }
   }
   // (the device scratch is reused by the next call on this thread: every stream must have drained before returning,

@@ -9,10 +9,14 @@
 //       ->  dV += P^T dO,  dK += dS^T Q
 //
 // Shared structure (384 threads): warps 0-3 / 4-7 are two elementwise warpgroups (thread = TMEM lane = one row of
-// the 128 x 128 block; warpgroup h owns columns [64 h, 64 h + 64)); warp 8 issues every tcgen05.mma; warp 9 is the
-// TMA producer; warps 10-11 idle or load the L / D vectors.  No row reductions are needed in the backward pass
-// (L and D are inputs), so the two warpgroups never exchange anything.  All four "accumulate" GEMMs take their A
-// operand (P, dS, P^T, dS^T: 16-bit) straight from TMEM, written in place over the FP32 S / dP they came from.
+// the 128 x 128 block; warpgroup h owns columns [64 h, 64 h + 64)); warp 8 issues every tcgen05.mma; warps 9-10 are
+// TMA producers (dQ: K ring / V ring; dK-dV: Q and dO rings / the L, D vector loader); warps 10-11 also rewrite BF16 dO
+// tiles as FP16 when the reference's mixed policy is in use.  No row reductions are needed in the backward pass (L and
+// D are inputs).  All four "accumulate" GEMMs take their A operand (P, dS, P^T, dS^T: 16-bit) straight from TMEM,
+// written over the FP32 S / dP they came from.  Each elementwise pass is split in two -- the exponentials need only S,
+// the dS half needs dP -- and the tensor-pipe issue order and operand rings are arranged so that what the next pass
+// starts with is issued a pass ahead (kernel headers below; measurements in DESIGN.md 4.1c).  Small grids are split
+// along the traversal axis (blockIdx.z) and merged by sum_splits.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
