@@ -140,7 +140,9 @@ MFA_API int mfa_attention_descriptor_register_precision(const mfa_attention_desc
 /* ------------------------------------------------------------------------------------------ */
 typedef enum mfa_backend {
   MFA_BACKEND_SIMT_FP32 = 0, /* CUDA-core FP32 FMA kernels: any R, C, D <= 512, any transposes/precisions */
-  MFA_BACKEND_TCGEN05 = 1    /* TMA + tcgen05.mma + TMEM kernels: 16-bit inputs, row-major, D % 8 == 0 */
+  MFA_BACKEND_TCGEN05 = 1    /* TMA + tcgen05.mma + TMEM kernels: 16-bit inputs, D % 8 == 0; forward D <= 256 (transposed
+                                operands too, where the transposed row pitch is a multiple of 16 bytes), backward D <= 128
+                                row-major */
 } mfa_backend_t;
 
 typedef struct mfa_attention_kernel_descriptor {

@@ -96,6 +96,11 @@ static const char *kForwardTcgen05 =
     "| 128 | 256 | 128 | 128 | Q, O |\n"
     "| 256 | 128 | 128 | 256 | Q, O |\n"
     "\n";
+// forward with transposed operands: the layout-generic kernel (one 128-row tile per CTA, 128-key blocks)
+static const char *kForwardTcgen05Transposed =
+    "| 128 | 128 | 128 | 128 | Q, O |\n"
+    "| 256 | 128 | 128 | 256 | Q, O |\n"
+    "\n";
 static const char *kBackwardQueryTcgen05 =
     "| 64  | 128 | 128 | 64  | Q, dO, dQ |\n"
     "| 128 | 128 | 128 | 128 | Q, dO, dQ |\n"
@@ -117,9 +122,18 @@ static const char *kBackwardKeyValueSimt =
 
 // Which kernel family can serve this descriptor.  The tcgen05 family needs 16-bit row-major operands
 // whose row pitch is a multiple of 16 bytes (TMA global-stride rule), i.e. D % 8 == 0.
+static bool any_transpose(const mfa_attention_descriptor_t &d) {
+  return d.transpose_Q || d.transpose_K || d.transpose_V || d.transpose_O;
+}
+
 int select_backend(const mfa_attention_descriptor_t &d, int type) {
   if (!d.low_precision_inputs) return MFA_BACKEND_SIMT_FP32;
-  if (d.transpose_Q || d.transpose_K || d.transpose_V || d.transpose_O) return MFA_BACKEND_SIMT_FP32;
+  if (any_transpose(d)) {
+    // transposed operands: tensor-core forward only, and only where TMA can address the transposed view (row pitch =
+    // sequence length, a multiple of 8 elements); the backward kernels take row-major operands
+    if (type != MFA_FORWARD || !tcgen05_forward_transposes_ok(d.row, d.column, d.transpose_Q, d.transpose_K, d.transpose_V))
+      return MFA_BACKEND_SIMT_FP32;
+  }
   if (d.head % 8 != 0 || d.head == 0) return MFA_BACKEND_SIMT_FP32;
   const uint32_t maxHead = (type == MFA_FORWARD) ? tcgen05_forward_max_head() : tcgen05_backward_max_head();
   if (d.head > maxHead) return MFA_BACKEND_SIMT_FP32;
@@ -131,7 +145,7 @@ int select_backend(const mfa_attention_descriptor_t &d, int type) {
 const char *parameter_file(const mfa_attention_descriptor_t &d, int type) {
   const bool tc = select_backend(d, type) == MFA_BACKEND_TCGEN05;
   switch (type) {
-    case MFA_FORWARD: return tc ? kForwardTcgen05 : kForwardSimt;
+    case MFA_FORWARD: return tc ? (any_transpose(d) ? kForwardTcgen05Transposed : kForwardTcgen05) : kForwardSimt;
     case MFA_BACKWARD_QUERY: return tc ? kBackwardQueryTcgen05 : kBackwardQuerySimt;
     default: return tc ? kBackwardKeyValueTcgen05 : kBackwardKeyValueSimt;
   }

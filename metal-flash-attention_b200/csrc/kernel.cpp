@@ -124,8 +124,10 @@ int mfa_attention_kernel_create(const mfa_attention_kernel_descriptor_t *kd, mfa
     bool ok = (pq == MFA_FP16 || pq == MFA_BF16) && kd->memory_precisions[MFA_K] == pq &&
               kd->memory_precisions[MFA_V] == pq && D % 8 == 0 &&
               D <= (k->type == MFA_FORWARD ? tcgen05_forward_max_head() : tcgen05_backward_max_head());
+    bool transposed = false;
     for (int i = 0; i < n; ++i)
-      if ((kd->transpose_state_mask >> ops[i]) & 1) ok = false;
+      if ((kd->transpose_state_mask >> ops[i]) & 1) transposed = true;
+    if (transposed && k->type != MFA_FORWARD) ok = false;  // only the forward has a layout-generic tensor-core kernel
     // dO: same element type, or BF16 beside FP16 Q/K/V (the reference's policy; converted on chip)
     if (k->type != MFA_FORWARD && kd->memory_precisions[MFA_dO] != pq &&
         !(pq == MFA_FP16 && kd->memory_precisions[MFA_dO] == MFA_BF16))
@@ -133,10 +135,12 @@ int mfa_attention_kernel_create(const mfa_attention_kernel_descriptor_t *kd, mfa
     if (!ok) {
       delete k;
       return fail(MFA_ERROR_UNSUPPORTED,
-                  "MFA_BACKEND_TCGEN05 needs FP16/BF16 row-major Q,K,V (dO of the same type, or BF16 with FP16 Q,K,V), head % 8 == 0 "
+                  "MFA_BACKEND_TCGEN05 needs FP16/BF16 Q,K,V (row-major for the backward kernels; dO of the same type, or BF16 with FP16 Q,K,V), head % 8 == 0 "
                   "and head <= the compiled maximum; use MFA_BACKEND_SIMT_FP32 for this descriptor.");
     }
-    if (k->type == MFA_FORWARD)
+    if (k->type == MFA_FORWARD && transposed)
+      tcgen05_forward_generic_geometry(D, &k->threads, &k->smem_bytes, &k->par, &k->trav, &k->head);
+    else if (k->type == MFA_FORWARD)
       tcgen05_forward_geometry(D, &k->threads, &k->smem_bytes, &k->par, &k->trav, &k->head);
     else
       tcgen05_backward_geometry(k->type, D, &k->threads, &k->smem_bytes, &k->par, &k->trav, &k->head);
@@ -207,7 +211,9 @@ int mfa_attention_kernel_launch_count(const mfa_attention_kernel_t *kernel, cons
                                       uint32_t *out) {
   if (!kernel || !c || !out) return fail(MFA_ERROR_INVALID_ARGUMENT, "NULL argument.");
   *out = 1;
-  if (kernel->backend == MFA_BACKEND_TCGEN05 && kernel->type == MFA_FORWARD)
+  const uint16_t forward_operands = (1u << MFA_Q) | (1u << MFA_K) | (1u << MFA_V) | (1u << MFA_O);
+  if (kernel->backend == MFA_BACKEND_TCGEN05 && kernel->type == MFA_FORWARD &&
+      !(kernel->descriptor.transpose_state_mask & forward_operands))  // (the layout-generic kernel never splits)
     *out = tcgen05_forward_launch_count(c->row, c->column, kernel->descriptor.head_dimension,
                                         c->batch_count ? c->batch_count : 1);
   if (kernel->backend == MFA_BACKEND_TCGEN05 && kernel->type != MFA_FORWARD)
@@ -285,7 +291,9 @@ bool same_descriptor(const mfa_attention_descriptor_t &a, const mfa_attention_de
          a.has_matrix_dimensions == b.has_matrix_dimensions && a.has_transpose_state == b.has_transpose_state &&
          a.head == b.head && a.transpose_Q == b.transpose_Q && a.transpose_K == b.transpose_K &&
          a.transpose_V == b.transpose_V && a.transpose_O == b.transpose_O &&
-         a.input_precision_override == b.input_precision_override;
+         a.input_precision_override == b.input_precision_override &&
+         // with transposed operands the kernel family depends on R % 8 / C % 8 (TMA row pitch)
+         select_backend(a, MFA_FORWARD) == select_backend(b, MFA_FORWARD);
 }
 }  // namespace
 

@@ -40,6 +40,10 @@ void tcgen05_forward_geometry(uint32_t D, uint32_t *threads, uint32_t *smem_byte
                               uint32_t *head);
 uint32_t tcgen05_forward_launch_count(uint32_t R, uint32_t C, uint32_t D, uint32_t batch);
 cudaError_t launch_tcgen05_forward_d256(const AttentionParams &p, cudaStream_t stream);  // 128 < D <= 256
+cudaError_t launch_tcgen05_forward_generic(const AttentionParams &p, cudaStream_t stream);  // transposed operands, D <= 256
+bool tcgen05_forward_transposes_ok(uint32_t R, uint32_t C, bool tQ, bool tK, bool tV);
+void tcgen05_forward_generic_geometry(uint32_t D, uint32_t *threads, uint32_t *smem_bytes, uint32_t *par, uint32_t *trav,
+                                      uint32_t *head);
 void tcgen05_forward_d256_geometry(uint32_t *threads, uint32_t *smem_bytes, uint32_t *par, uint32_t *trav);
 bool tcgen05_backward_supported(const AttentionParams &p);
 cudaError_t launch_tcgen05_backward_query(const AttentionParams &p, cudaStream_t stream);

@@ -858,10 +858,16 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, long long *tra
 
 uint32_t tcgen05_forward_max_head() { return 256; }
 
+// Transposed operands are served by the layout-generic kernel (tcgen05_forward_d256.cu) when TMA can address them: a
+// transposed operand's row pitch is its sequence length, which must then be a multiple of 8 elements (16 bytes).
+bool tcgen05_forward_transposes_ok(uint32_t R, uint32_t C, bool tQ, bool tK, bool tV) {
+  return (!tQ || R % 8 == 0) && (!tK || C % 8 == 0) && (!tV || C % 8 == 0);
+}
+
 bool tcgen05_forward_supported(const AttentionParams &p) {
   return (p.prec[sQ] == FP16 || p.prec[sQ] == BF16) && p.prec[sK] == p.prec[sQ] && p.prec[sV] == p.prec[sQ] &&
-         p.prec[sO] == FP32 && p.D % 8 == 0 && p.D <= tcgen05_forward_max_head() && !p.transposed[sQ] &&
-         !p.transposed[sK] && !p.transposed[sV] && !p.transposed[sO];
+         p.prec[sO] == FP32 && p.D % 8 == 0 && p.D <= tcgen05_forward_max_head() &&
+         tcgen05_forward_transposes_ok(p.R, p.C, p.transposed[sQ], p.transposed[sK], p.transposed[sV]);
 }
 
 cudaError_t launch_tcgen05_forward(const AttentionParams &p, cudaStream_t stream) {
@@ -869,6 +875,8 @@ cudaError_t launch_tcgen05_forward(const AttentionParams &p, cudaStream_t stream
     set_launch_detail("descriptor is outside the tcgen05 forward kernel's domain");
     return cudaErrorInvalidValue;
   }
+  if (p.transposed[sQ] || p.transposed[sK] || p.transposed[sV] || p.transposed[sO])
+    return launch_tcgen05_forward_generic(p, stream);  // tcgen05_forward_d256.cu
   const bool bf16 = p.prec[sQ] == BF16;
   if (p.D > 128) return launch_tcgen05_forward_d256(p, stream);  // tcgen05_forward_d256.cu
   if (p.D <= 64) return bf16 ? fwd::launch<64, true>(p, stream) : fwd::launch<64, false>(p, stream);

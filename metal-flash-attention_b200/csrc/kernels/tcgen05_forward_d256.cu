@@ -100,13 +100,20 @@ constexpr uint32_t kTraceIters = 128;  // iterations recorded per role
       trace[((role) * kTraceIters + (iter)) * kTraceSlots + (slot)] = clock64();                      \
   } while (0)
 
-template <uint32_t DPAD, bool kBF16, bool kTrace = false>
+// kGeneric: the layout-generic instantiation, which also serves TRANSPOSED operands (stored [D][seq], leading dimension
+// = sequence length: AttentionKernel.swift:189-195) for any D <= 256.  `tmask` bit 0/1/2/3 = Q/K/V/O transposed.  A
+// transposed operand is fetched through a tensor map of the transposed view (inner dimension = sequence) and consumed
+// through the other UMMA major-ness: Q^T and K^T tiles are MN-major operands of S = Q K^T, V^T is a K-major operand of
+// O += P V; a transposed O is stored straight from registers (a warp's 32 rows are contiguous in memory then).
+template <uint32_t DPAD, bool kBF16, bool kTrace = false, bool kGeneric = false>
 __global__ void __launch_bounds__(kThreads, 1)
     attention_forward_d256_tcgen05(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                               const __grid_constant__ CUtensorMap mapV, float *__restrict__ O, void *__restrict__ L,
-                              uint32_t R, uint32_t C, uint32_t D, float scale_log2, int l_is_fp16,
+                              uint32_t R, uint32_t C, uint32_t D, float scale_log2, int l_is_fp16, uint32_t tmask,
                               long long *__restrict__ trace) {
   using Cfg = Config<DPAD>;
+  const bool transQ = kGeneric && (tmask & 1u), transK = kGeneric && (tmask & 2u), transV = kGeneric && (tmask & 4u),
+             transO = kGeneric && (tmask & 8u);
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -285,7 +292,22 @@ __global__ void __launch_bounds__(kThreads, 1)
     tc_fence_after();
     const uint32_t row = q_row0 + row_in_tile;
     const float inv_l = 1.0f / l;
-    {
+    if (transO) {
+      // O stored [D][R]: for a fixed column the warp's 32 rows are 32 consecutive floats -- one 128 B line per store
+      float *o_col = O + static_cast<size_t>(head) * D * R + row;
+#pragma unroll 1
+      for (uint32_t cc = 0; cc < DPAD / 2; cc += 32) {
+        const uint32_t c = h * (DPAD / 2) + cc;
+        uint32_t o[32];
+        tmem_ld32(tO + c, o);
+        tc_wait_ld();
+        if (row < R) {
+#pragma unroll
+          for (uint32_t k = 0; k < 32; ++k)
+            if (c + k < D) o_col[static_cast<size_t>(c + k) * R] = __uint_as_float(o[k]) * inv_l;
+        }
+      }
+    } else {
       // Warpgroup h stores columns [h DPAD/2, (h+1) DPAD/2).  TMEM hands every thread one row; each warp transposes
       // 32 x 32 chunks through a private XOR-swizzled scratch tile (overlaying the K tile, dead after the last MMA)
       // so that every global store instruction writes four full 128 B lines (see tcgen05_forward.cu).
@@ -340,9 +362,14 @@ __global__ void __launch_bounds__(kThreads, 1)
       // ===================================================================================
       if (elect_one()) {
         mbar_arrive_expect_tx(q_full, Cfg::kTileBytes);
+        if (transQ) {  // two boxes of [DPAD rows of D][64 query rows]: the 64-row halves of the M tile
+          tma_load_3d(smem + Cfg::kSmemQ, &mapQ, q_full, q_row0, 0, head);
+          tma_load_3d(smem + Cfg::kSmemQ + DPAD * 128, &mapQ, q_full, q_row0 + 64, 0, head);
+        } else {
 #pragma unroll
-        for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
-          tma_load_3d(smem + Cfg::kSmemQ + ds * kSubTileBytes, &mapQ, q_full, ds * 64, q_row0, head);
+          for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
+            tma_load_3d(smem + Cfg::kSmemQ + ds * kSubTileBytes, &mapQ, q_full, ds * 64, q_row0, head);
+        }
       }
       for (uint32_t i = 0; i < num_blocks; ++i) {
         MFA_TRACE(4, i, 0);
@@ -352,7 +379,13 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (ds == 0) MFA_TRACE(4, i, 1);
           if (elect_one()) {
             mbar_arrive_expect_tx(&k_full[ds], kSubTileBytes);
-            tma_load_3d(smem + Cfg::kSmemK + ds * kSubTileBytes, &mapK, &k_full[ds], ds * 64, i * kBlockN, head);
+            if (transK) {  // two boxes of [64 rows of D][64 keys]: the key halves of this 64-column group of D
+              tma_load_3d(smem + Cfg::kSmemK + ds * kSubTileBytes, &mapK, &k_full[ds], i * kBlockN, ds * 64, head);
+              tma_load_3d(smem + Cfg::kSmemK + ds * kSubTileBytes + kVHalfBytes, &mapK, &k_full[ds], i * kBlockN + 64,
+                          ds * 64, head);
+            } else {
+              tma_load_3d(smem + Cfg::kSmemK + ds * kSubTileBytes, &mapK, &k_full[ds], ds * 64, i * kBlockN, head);
+            }
           }
         }
       }
@@ -367,10 +400,14 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (half == 0) MFA_TRACE(4, i, 2);
           if (elect_one()) {
             mbar_arrive_expect_tx(&v_full[half], Cfg::kSubTiles * kVHalfBytes);
+            if (transV) {  // one box of [DPAD rows of D][64 keys] per key half
+              tma_load_3d(smem + Cfg::kSmemV + half * (DPAD * 128), &mapV, &v_full[half], i * kBlockN + half * 64, 0, head);
+            } else {
 #pragma unroll
-            for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
-              tma_load_3d(smem + Cfg::kSmemV + ds * kSubTileBytes + half * kVHalfBytes, &mapV, &v_full[half], ds * 64,
-                          i * kBlockN + half * 64, head);
+              for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
+                tma_load_3d(smem + Cfg::kSmemV + ds * kSubTileBytes + half * kVHalfBytes, &mapV, &v_full[half], ds * 64,
+                            i * kBlockN + half * 64, head);
+            }
           }
         }
       }
@@ -380,13 +417,16 @@ __global__ void __launch_bounds__(kThreads, 1)
       // ===================================================================================
       constexpr uint32_t kFormat = kBF16 ? 1u : 0u;
       // S[128 x 128] = Q[128 x D] . K[128 x D]^T : A and B both K-major
-      constexpr uint32_t idescS = make_idesc_f16(kTileM, kBlockN, kFormat, 0, 0);
-      // O[128 x DPAD] += P[128 x 128] . V[128 x DPAD] : A from TMEM, B (= V, [key][d]) is MN-major
-      constexpr uint32_t idescO = make_idesc_f16(kTileM, DPAD, kFormat, 0, 1);
+      // (a transposed Q or K tile is an MN-major operand: rows = D, 64 sequence elements per 128 B swizzle row)
+      const uint32_t idescS = make_idesc_f16(kTileM, kBlockN, kFormat, transQ ? 1u : 0u, transK ? 1u : 0u);
+      // O[128 x DPAD] += P[128 x 128] . V[128 x DPAD] : A from TMEM, B (= V, [key][d]) is MN-major; a transposed V
+      // ([d][key]) is K-major
+      const uint32_t idescO = make_idesc_f16(kTileM, DPAD, kFormat, 0, transV ? 0u : 1u);
       // Descriptors differ only in the 14-bit start-address field; build each once and add (bytes >> 4).
-      const uint64_t descQ = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemQ), 16, 1024);
-      const uint64_t descK = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemK), 16, 1024);
-      const uint64_t descV = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemV), kSubTileBytes, 1024);
+      // MN-major: LBO = distance between the 64-element blocks along M / N, SBO = 1024 between 8-row groups along K.
+      const uint64_t descQ = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemQ), transQ ? DPAD * 128 : 16, 1024);
+      const uint64_t descK = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemK), transK ? kVHalfBytes : 16, 1024);
+      const uint64_t descV = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemV), transV ? 16 : kSubTileBytes, 1024);
 
       // S(block) into buffer bf: per 64-column sub-tile of D, wait for K's sub-tile, four k-steps, release it
       auto issue_S = [&](uint32_t block, uint32_t bf) {
@@ -398,9 +438,12 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (elect_one()) {
 #pragma unroll
             for (uint32_t kk = 0; kk < 4; ++kk) {
-              // 16 elements = 32 B inside the 128 B swizzle row; 4 k-steps per 64-element sub-tile
-              const uint32_t off = (ds * kSubTileBytes + kk * 32) >> 4;
-              umma_ss(d_tmem, descQ + off, descK + off, idescS, (ds | kk) != 0);
+              // K-major: 16 elements = 32 B inside the 128 B swizzle row, 4 k-steps per 64-element sub-tile;
+              // MN-major: 16 rows of D = 2048 B
+              const uint32_t k_major_off = ds * kSubTileBytes + kk * 32;
+              const uint32_t a_off = transQ ? (ds * 4 + kk) * 2048 : k_major_off;
+              const uint32_t b_off = transK ? ds * kSubTileBytes + kk * 2048 : k_major_off;
+              umma_ss(d_tmem, descQ + (a_off >> 4), descK + (b_off >> 4), idescS, (ds | kk) != 0);
             }
             umma_commit(&k_empty[ds]);
             if (ds == Cfg::kSubTiles - 1) umma_commit(&s_full[bf]);
@@ -420,8 +463,10 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
             for (uint32_t kk = 0; kk < 4; ++kk) {
               const uint32_t k = half * 4 + kk;
-              // 16 keys = two 8-row groups of 1024 B; 64-wide column blocks are kSubTileBytes apart (LBO)
-              umma_ts(d_tmem, a_tmem + k * 8, descV + ((k * 2048) >> 4), idescO, (block | k) != 0 ? 1u : 0u);
+              // MN-major V: 16 keys = two 8-row groups of 1024 B, 64-wide column blocks kSubTileBytes apart (LBO);
+              // K-major V^T: 16 keys = 32 B inside the swizzle row of this key half
+              const uint32_t b_off = transV ? half * (DPAD * 128) + kk * 32 : k * 2048;
+              umma_ts(d_tmem, a_tmem + k * 8, descV + (b_off >> 4), idescO, (block | k) != 0 ? 1u : 0u);
             }
             umma_commit(&v_empty[half]);
             if (half == 1) {
@@ -460,10 +505,10 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
 }
 
-template <uint32_t DPAD, bool kBF16, bool kTrace = false>
+template <uint32_t DPAD, bool kBF16, bool kTrace = false, bool kGeneric = false>
 cudaError_t launch(const AttentionParams &p, cudaStream_t stream, long long *trace = nullptr) {
   using Cfg = Config<DPAD>;
-  auto kernel = attention_forward_d256_tcgen05<DPAD, kBF16, kTrace>;
+  auto kernel = attention_forward_d256_tcgen05<DPAD, kBF16, kTrace, kGeneric>;
   static std::once_flag once;
   static cudaError_t attr_status = cudaSuccess;
   std::call_once(once, [&] {
@@ -473,13 +518,22 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, long long *tra
 
   CUtensorMap mapQ, mapK, mapV;
   cudaError_t e;
-  if ((e = make_tensor_map_16bit(&mapQ, p.buf[sQ], p.R, p.D, p.batch, kTileM)) != cudaSuccess) return e;
-  if ((e = make_tensor_map_16bit(&mapK, p.buf[sK], p.C, p.D, p.batch, kBlockN)) != cudaSuccess) return e;
-  if ((e = make_tensor_map_16bit(&mapV, p.buf[sV], p.C, p.D, p.batch, 64)) != cudaSuccess) return e;
+  const bool tQ = kGeneric && p.transposed[sQ], tK = kGeneric && p.transposed[sK], tV = kGeneric && p.transposed[sV];
+  e = tQ ? make_tensor_map_16bit_transposed(&mapQ, p.buf[sQ], p.R, p.D, p.batch, DPAD)
+         : make_tensor_map_16bit(&mapQ, p.buf[sQ], p.R, p.D, p.batch, kTileM);
+  if (e != cudaSuccess) return e;
+  e = tK ? make_tensor_map_16bit_transposed(&mapK, p.buf[sK], p.C, p.D, p.batch, 64)
+         : make_tensor_map_16bit(&mapK, p.buf[sK], p.C, p.D, p.batch, kBlockN);
+  if (e != cudaSuccess) return e;
+  e = tV ? make_tensor_map_16bit_transposed(&mapV, p.buf[sV], p.C, p.D, p.batch, DPAD)
+         : make_tensor_map_16bit(&mapV, p.buf[sV], p.C, p.D, p.batch, 64);
+  if (e != cudaSuccess) return e;
+  const uint32_t tmask = (tQ ? 1u : 0u) | (tK ? 2u : 0u) | (tV ? 4u : 0u) | ((kGeneric && p.transposed[sO]) ? 8u : 0u);
 
   dim3 grid((p.R + kTileM - 1) / kTileM, p.batch);
   kernel<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mapQ, mapK, mapV, static_cast<float *>(p.buf[sO]), p.buf[sL],
-                                                      p.R, p.C, p.D, p.scale_log2, p.prec[sL] == FP16 ? 1 : 0, trace);
+                                                      p.R, p.C, p.D, p.scale_log2, p.prec[sL] == FP16 ? 1 : 0, tmask,
+                                                      trace);
   return cudaGetLastError();
 }
 
@@ -489,6 +543,24 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, long long *tra
 // (5 roles x 128 iterations x 8 slots of clock64()).  Used by scripts/trace_forward_d256.py.
 cudaError_t launch_tcgen05_forward_d256_trace(const AttentionParams &p, cudaStream_t stream, long long *trace) {
   return fwd256::launch<256, true, true>(p, stream, trace);
+}
+
+// Forward with transposed operands (any D <= 256, D % 8 == 0): the layout-generic instantiations.
+cudaError_t launch_tcgen05_forward_generic(const AttentionParams &p, cudaStream_t stream) {
+  const bool bf16 = p.prec[sQ] == BF16;
+  if (p.D <= 128)
+    return bf16 ? fwd256::launch<128, true, false, true>(p, stream) : fwd256::launch<128, false, false, true>(p, stream);
+  return bf16 ? fwd256::launch<256, true, false, true>(p, stream) : fwd256::launch<256, false, false, true>(p, stream);
+}
+
+void tcgen05_forward_generic_geometry(uint32_t D, uint32_t *threads, uint32_t *smem_bytes, uint32_t *par, uint32_t *trav,
+                                      uint32_t *head) {
+  *threads = fwd256::kThreads;
+  *smem_bytes = D <= 128 ? fwd256::Config<128>::kSmemBytes : fwd256::Config<256>::kSmemBytes;
+  *par = fwd256::kTileM;
+  *trav = fwd256::kBlockN;
+  const uint32_t padded = (D + 7) / 8 * 8, block = D <= 128 ? 128u : 256u;
+  *head = block < padded ? block : padded;
 }
 
 cudaError_t launch_tcgen05_forward_d256(const AttentionParams &p, cudaStream_t stream) {

@@ -107,8 +107,22 @@ def test_heuristic_selects_tensor_core_family_only_where_it_applies():
     assert make(4096, 4096, 64, lowIn=True).kernelDescriptor(KT.forward).backend == mfa.Backend.tcgen05
     assert make(4096, 4096, 128).kernelDescriptor(KT.forward).backend == mfa.Backend.simtFP32       # FP32 inputs
     assert make(64, 64, 77, lowIn=True).kernelDescriptor(KT.forward).backend == mfa.Backend.simtFP32  # D % 8 != 0
-    assert make(64, 64, 64, lowIn=True, transposes=(False, True, False, False)).kernelDescriptor(
-        KT.forward).backend == mfa.Backend.simtFP32                                                # transposed K
+    # transposed operands: the layout-generic tensor-core forward where TMA can address the transposed view (row pitch =
+    # sequence length, a multiple of 8 elements); the backward kernels take row-major operands only
+    tK = make(64, 64, 64, lowIn=True, transposes=(False, True, False, False))
+    assert tK.kernelDescriptor(KT.forward).backend == mfa.Backend.tcgen05
+    assert tK.kernelDescriptor(KT.forward).blockDimensions == (128, 128, 64)
+    assert tK.kernelDescriptor(KT.backwardQuery).backend == mfa.Backend.simtFP32
+    assert make(64, 77, 64, lowIn=True, transposes=(False, True, False, False)).kernelDescriptor(
+        KT.forward).backend == mfa.Backend.simtFP32                                                # C % 8 != 0
+    assert make(77, 64, 64, lowIn=True, transposes=(False, True, False, True)).kernelDescriptor(
+        KT.forward).backend == mfa.Backend.tcgen05                                                 # only K's pitch matters
+    assert make(77, 64, 64, lowIn=True, transposes=(True, False, False, False)).kernelDescriptor(
+        KT.forward).backend == mfa.Backend.simtFP32                                                # R % 8 != 0
+    # the kernel cache must not hand the tcgen05 kernel of an aligned shape to an unaligned one
+    a = mfa.AttentionKernel.cached(make(64, 64, 64, lowIn=True, transposes=(True, False, False, False)), KT.forward)
+    b = mfa.AttentionKernel.cached(make(77, 64, 64, lowIn=True, transposes=(True, False, False, False)), KT.forward)
+    assert a._handle.value != b._handle.value and "tcgen05" in a.sourceName() and "simt" in b.sourceName()
     kd = make(4096, 4096, 128, lowIn=True, bf16=True).kernelDescriptor(KT.forward)
     assert kd.preferAsyncLoad and kd.preferAsyncCache           # "async" == TMA on B200
     assert kd.cacheState == {Op.Q: True, Op.O: True}             # Q resident in SMEM, O resident in TMEM

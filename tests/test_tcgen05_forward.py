@@ -193,6 +193,33 @@ def test_adversarial_growing_max_large_head(C):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("R,C,D", [(256, 384, 128), (200, 136, 64), (264, 520, 256), (8, 8, 8), (136, 1000, 192),
+                                   (1024, 1024, 128)])
+@pytest.mark.parametrize("mask", range(1, 16))
+def test_forward_transposed_operands(R, C, D, mask):
+    """Every combination of transposed Q, K, V, O (stored [D][seq], AttentionKernel.swift:189-195;
+    RectangularAttentionTest.swift:88-138) on the layout-generic tensor-core kernel: transposed Q / K tiles are MN-major
+    MMA operands, a transposed V is K-major, a transposed O is stored straight from registers."""
+    import mfa_b200 as mfa
+    import oracle
+    from tests.attention_harness import run_attention, check
+
+    if (R, C, D) == (1024, 1024, 128) and mask not in (5, 10, 15):
+        pytest.skip("large shape: three masks only")
+    bf16 = mask % 2 == 1
+    desc = _descriptor(R, C, D, bf16)
+    desc.transposeState = tuple(bool(mask & (1 << i)) for i in range(4))
+    kd = desc.kernelDescriptor(mfa.AttentionKernelType.forward)
+    assert kd.backend == mfa.Backend.tcgen05 and kd.blockDimensions[:2] == (128, 128)
+    net = oracle.Network(R, C, D, seed=mask + R, threads=8)
+    net.round_inputs(oracle.BF16 if bf16 else oracle.FP16)
+    out = run_attention(desc, net, types=[mfa.AttentionKernelType.forward])
+    O, L = net.inferenceAttention(with_L=True)
+    check_O(O, out["O"], net.V, bf16)
+    check(L, out["L"], 1e-3, "L")
+
+
+@pytest.mark.gpu
 def test_batched_heads_are_independent_problems():
     """batch extension: problem b of the batch equals the single-head run on the same tensors; and the
     softmax identity O == 1 when V == 1 holds at the full N=4096 (size-independent property)."""
