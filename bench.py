@@ -50,7 +50,7 @@ def measured_peaks():
 class ClockSampler:
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, device_index, period_s=0.002):
+    def __init__(self, device_index, period_s=0.0005):
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self._thread = None
@@ -97,6 +97,12 @@ class ClockSampler:
         self._stop.set()
         if self._thread:
             self._thread.join()
+            # one more reading right at the end of the timed region (the kernels have only just drained): short runs
+            # otherwise end up with a single sample
+            try:
+                self.samples.append(self._nvml.nvmlDeviceGetClockInfo(self._handle, self._nvml.NVML_CLOCK_SM))
+            except Exception:
+                pass
 
     def summary(self):
         if not self._nvml:
