@@ -15,7 +15,15 @@ TFLOP/s counts the two GEMMs only, 4*N^2*D per head.
 Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.  Inputs
 for one step (Q,K,V = 192 MiB at H=64) exceed the 126 MB L2 and two buffer sets alternate between steps.
 `e2e` goes through the C ABI's host-buffer entry point (mfa_attention_run_host: pinned host Q,K,V -> device,
-kernel, O and L -> host) inside the timed region.
+kernel, O and L -> host) inside the timed region; the host buffers come from mfa_host_alloc (page-locked, on the
+GPU's NUMA node) and every rank pins itself to its GPU's socket first.
+
+Further legs on the same JSON line (none of them replaces `value`):
+  sustained  the same step looped for >= 2 s: the power-capped regime, fraction against bf16_tflops_sustained
+  config5    BASELINE.json configs[4] as written: 64 x 32 = 2048 independent (N=4096, D=128) problems block-partitioned
+             over the ranks; data starts on rank 0 (NCCL send/recv scatter), O and L end on rank 0 (gather); kernel
+             time and the scatter / gather times are reported separately
+  single_head one problem per call (split-KV across the SMs, merged inside the kernel)
 """
 import argparse
 import json
@@ -36,6 +44,7 @@ UNIT = "GINSTRS"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
 # (profiles/), for the default H; None until a capture exists.
 NCU_TRAFFIC_BYTES_PER_LAUNCH = 299422976  # profiles/r1_fwd_ncu_summary.csv: 201.59 MB read + 97.84 MB written
+NCU_TRAFFIC_SOURCE = "profiles/r1_fwd_ncu_summary.csv (ncu --set full, one 64-head launch; not re-measured in this run)"
 
 
 def measured_peaks():
@@ -112,6 +121,122 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+def host_tensor(mfa, shape, dtype, device):
+    """A torch view of a page-locked buffer from mfa_host_alloc (NUMA-local to `device`); returns (tensor, address)."""
+    import ctypes
+    import torch
+    nbytes = 1
+    for n in shape:
+        nbytes *= int(n)
+    nbytes *= torch.empty((), dtype=dtype).element_size()
+    addr = mfa.hostAlloc(nbytes, device)
+    raw = (ctypes.c_uint8 * nbytes).from_address(addr)
+    return torch.frombuffer(raw, dtype=torch.uint8).view(dtype).reshape(tuple(shape)), addr
+
+
+def run_config5(args, mfa, torch, dist, rank, world, stream, heads_per_launch):
+    """BASELINE.json configs[4]: `total` independent (N=4096, D=128) problems, contiguous block partition over the
+    ranks (sharding.head_partition).  All inputs start on rank 0 and reach the shards through NCCL send/recv, every
+    rank runs the same single-GPU kernel over its shard in launches of `heads_per_launch`, O and L are gathered back to
+    rank 0.  Scatter, kernels and gather are timed separately with CUDA events (max over ranks)."""
+    from mfa_b200.sharding import head_partition, scatter_heads, gather_heads
+    Op = mfa.AttentionOperand
+    total = args.config5_heads
+    start_head, count = head_partition(total, world, rank)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    full = {}
+    if rank == 0:
+        gen = torch.Generator(device="cuda").manual_seed(77)
+        for op in (Op.Q, Op.K, Op.V):
+            full[op] = torch.empty(total, N_SEQ, D_HEAD, device="cuda", dtype=torch.bfloat16)
+            for h0 in range(0, total, 64):   # generated in slices: the FP32 staging of randn stays small
+                n = min(64, total - h0)
+                full[op][h0:h0 + n] = torch.randn(n, N_SEQ, D_HEAD, device="cuda", generator=gen).to(torch.bfloat16)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync()
+        a.record(stream)
+        out = fn()
+        b.record(stream)
+        sync()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return out, ms
+
+    if world > 1:   # open the NCCL point-to-point connections outside the timed region
+        warm = torch.zeros(world, 1024, device="cuda") if rank == 0 else None
+        scatter_heads(warm, world, (1024,), torch.float32, dev)
+
+    if world > 1:
+        shards, scatter_ms = timed(lambda: {op: scatter_heads(full.get(op), total, (N_SEQ, D_HEAD), torch.bfloat16, dev)
+                                            for op in (Op.Q, Op.K, Op.V)})
+    else:   # one rank owns everything: nothing to scatter
+        shards, scatter_ms = {op: full[op] for op in (Op.Q, Op.K, Op.V)}, 0.0
+    scatter_bytes = 3 * (total - head_partition(total, world, 0)[1]) * N_SEQ * D_HEAD * 2
+
+    o = torch.empty(count, N_SEQ, D_HEAD, device="cuda", dtype=torch.float32)
+    lse = torch.empty(count, N_SEQ, device="cuda", dtype=torch.float32)
+    desc = mfa.AttentionDescriptor()
+    desc.lowPrecisionInputs = True
+    desc.inputPrecisionOverride = mfa.GEMMOperandPrecision.BF16
+    desc.matrixDimensions = (N_SEQ, N_SEQ, D_HEAD)
+    desc.transposeState = (False, False, False, False)
+    launches = []
+    for h0 in range(0, count, heads_per_launch):
+        n = min(heads_per_launch, count - h0)
+        desc.batchCount = n
+        c = mfa.FunctionConstantValues()
+        desc.setFunctionConstants(c)
+        ptrs = {Op.Q: shards[Op.Q][h0:].data_ptr(), Op.K: shards[Op.K][h0:].data_ptr(),
+                Op.V: shards[Op.V][h0:].data_ptr(), Op.O: o[h0:].data_ptr(), Op.L: lse[h0:].data_ptr()}
+        launches.append((c, ptrs))
+    kernel = mfa.AttentionKernel.cached(desc, mfa.AttentionKernelType.forward)
+
+    def compute():
+        for c, ptrs in launches:
+            kernel.encode(c, ptrs, stream.cuda_stream)
+
+    compute()   # warm (first touch of O / L)
+    _, kernel_ms = timed(compute)
+    if world > 1:
+        (full_o, full_l), gather_ms = timed(lambda: (gather_heads(o, total), gather_heads(lse, total)))
+    else:
+        (full_o, full_l), gather_ms = (o, lse), 0.0
+    gather_bytes = (total - head_partition(total, world, 0)[1]) * (N_SEQ * D_HEAD + N_SEQ) * 4
+    ok = None
+    if rank == 0:
+        # the gathered result is the per-shard result: spot-check a head that travelled (the last one) through the
+        # softmax identity rowsum(P) = 1  <=>  O with V := 1 ... not available here, so check finiteness and L's range
+        last = full_o[total - 1]
+        ok = bool(torch.isfinite(last).all().item()) and bool(torch.isfinite(full_l[total - 1]).all().item())
+    work = FMA_PER_HEAD * total
+    return {
+        "workload": f"{total} independent (N=4096, D=128) bf16 problems = batch 64 x heads 32, block-partitioned over "
+                    f"{world} GPU(s): {count} on this rank, launches of {heads_per_launch}",
+        "kernel_ms": kernel_ms, "kernel_ginstrs": work / kernel_ms / 1e6,
+        "kernel_tflops": FLOP_PER_HEAD * total / kernel_ms / 1e9,
+        "scatter_ms": scatter_ms, "gather_ms": gather_ms,
+        "scatter_bytes": scatter_bytes, "gather_bytes": gather_bytes,
+        "scatter_gbs": (scatter_bytes / scatter_ms / 1e6) if world > 1 and scatter_ms > 0 else None,
+        "gather_gbs": (gather_bytes / gather_ms / 1e6) if world > 1 and gather_ms > 0 else None,
+        "with_scatter_gather_ms": scatter_ms + kernel_ms + gather_ms,
+        "with_scatter_gather_ginstrs": work / (scatter_ms + kernel_ms + gather_ms) / 1e6,
+        "comm": {"backend": dist.get_backend() if world > 1 else None, "nranks": world,
+                 "p2p_messages": 5 * (world - 1),
+                 "pattern": "rank 0 -> ranks: ncclSend/ncclRecv of Q, K, V shards; ranks -> rank 0: O, L shards"},
+        "gathered_result_finite": ok,
+    }
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path.  The reference (Swift) cannot be
     built here, so this is the C port of its `Network` oracle (oracle/network_oracle.c), row-parallel over all
@@ -155,6 +280,10 @@ def main():
     ap.add_argument("--heads", type=int, default=64, help="independent single-head problems per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-config5", action="store_true")
+    ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--sustained-seconds", type=float, default=2.0)
+    ap.add_argument("--config5-heads", type=int, default=2048, help="batch 64 x heads 32 of BASELINE.json configs[4]")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -173,6 +302,9 @@ def main():
 
     assert torch.cuda.is_available(), "bench.py (our arm) needs a B200"
     torch.cuda.set_device(local_rank)
+    # this rank's host threads (and everything it allocates from here on: pinned staging buffers, NCCL proxies) stay on
+    # the socket its GPU hangs off -- the H2D / D2H copies of the e2e leg never cross the inter-socket link
+    numa_node = mfa.bindThreadToDevice(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     H = args.heads
@@ -242,12 +374,12 @@ def main():
     # ---- `e2e`: host buffers through mfa_attention_run_host ------------------------------------
     e2e = None
     if not args.no_e2e:
-        host = {}
+        host, host_addr = {}, {}
         for op, t in sets[0].items():
-            host[op] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            host[op], host_addr[op] = host_tensor(mfa, t.shape, t.dtype, torch.cuda.current_device())
             if op in (Op.Q, Op.K, Op.V):
-                host[op].copy_(t)
-        host_ptrs = {op: t.data_ptr() for op, t in host.items()}
+                host[op].copy_(t.cpu())
+        host_ptrs = dict(host_addr)
         fwd = [mfa.AttentionKernelType.forward]
         e2e_steps = max(3, min(args.steps, 10))
         for _ in range(2):
@@ -266,7 +398,9 @@ def main():
         e2e = {"value": FMA_PER_HEAD * total_heads * e2e_steps / dt / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                "ms_per_step": dt / e2e_steps * 1e3,
-               "api": "mfa_attention_run_host (pinned host Q,K,V -> device, kernel, O,L -> host)"}
+               "api": "mfa_attention_run_host (pinned host Q,K,V -> device, kernel, O,L -> host)",
+               "host_buffers": "mfa_host_alloc: cudaHostAlloc(portable) first-touched on the GPU's NUMA node",
+               "numa_node": numa_node}
         # spot-check that the e2e path produced the same O as the device path.  The host path works through the batch in
         # chunks of a few heads, for which the library may split the key axis across SMs and merge; each split rounds
         # P to BF16 against its own running maximum, so the two paths agree to the kernel's accuracy (relative RMS
@@ -277,6 +411,9 @@ def main():
             got, want = host[Op.O][sl].float(), sets[0][Op.O][sl].cpu().float()
             rel = float((got - want).norm() / want.norm())
             assert rel < 4e-3, f"e2e != device path (relative RMS {rel:.2e})"
+        del host
+        for addr in host_addr.values():
+            mfa.hostFree(addr)
 
     # ---- literal single-head latency (BASELINE.json configs[1] as written): one (N=4096, D=128) problem per launch;
     #      too few tiles to fill 148 SMs, so the library splits the key axis across SMs and merges (split-KV) --------
@@ -306,6 +443,33 @@ def main():
                        "launches_per_call": k1.launchCount(c1),
                        "note": "one head per call, 50 back-to-back calls, inputs L2-resident (5 MB problem)"}
 
+    # ---- sustained regime: the same step looped for >= 2 s (power-capped clocks), every rank in lock step ----------
+    sustained = None
+    if not args.no_sustained:
+        reps = max(1, int(args.sustained_seconds * 1e3 / ms_per_step))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sus_sampler = ClockSampler(int(ids[local_rank]) if local_rank < len(ids) else local_rank, period_s=0.01)
+        with sus_sampler:
+            barrier()
+            a.record(stream)
+            for i in range(reps):
+                step(i)
+            b.record(stream)
+            barrier()
+        sus_ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([sus_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sus_ms = float(t.item())
+        sustained = {"seconds": sus_ms / 1e3, "steps": reps, "ms_per_step": sus_ms / reps,
+                     "tflops_per_gpu": FLOP_PER_HEAD * H * reps / sus_ms / 1e9,
+                     "ginstrs": FMA_PER_HEAD * total_heads * reps / sus_ms / 1e6, "clocks": sus_sampler.summary()}
+
+    # ---- BASELINE.json configs[4] as written: 2048 problems over the ranks, NCCL scatter / gather timed apart --------
+    config5 = None
+    if not args.no_config5:
+        config5 = run_config5(args, mfa, torch, dist, rank, world, stream, H)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -319,10 +483,14 @@ def main():
         "frac": per_gpu_tflops / peak_burst, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
         "peak_kind": f"{peak_kind} cuBLAS bf16 burst (MEASURED_PEAKS.json)" if peak_kind == "measured"
                      else "fallback 1590 TF/s (B200_PROFILING.md)",
-        "frac_of_sustained_peak": per_gpu_tflops / peak_sustained,
         "kernel": kernel.sourceName(), "flops_per_launch": FLOP_PER_HEAD * H,
-        "kernel_ms": ms_per_step,
+        "kernel_ms": ms_per_step, "algorithmic_bytes_per_launch": H * (3 * N_SEQ * D_HEAD * 2 + N_SEQ * D_HEAD * 4 + N_SEQ * 4),
+        "traffic_source": NCU_TRAFFIC_SOURCE,
     }
+    if sustained is not None:
+        # like for like: seconds of back-to-back launches against the seconds-long cuBLAS figure
+        sustained["peak"] = peak_sustained
+        sustained["frac_of_sustained_peak"] = sustained["tflops_per_gpu"] / peak_sustained
 
     # ---- CPU baseline: the oracle port, single thread "as written", on a bounded sample ----------
     cpu_baseline = None
@@ -347,6 +515,7 @@ def main():
                    "l2": "inputs per step (192 MiB at H=64) exceed the 126 MB L2; two buffer sets alternate"},
         "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": args.steps * launches_per_step,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "single_head": single_head,
+        "sustained": sustained, "config5": config5, "numa_node": numa_node,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -174,6 +174,13 @@ typedef struct mfa_attention_kernel_descriptor {
 /** AttentionKernelDescriptor.init(): everything nil / empty. */
 MFA_API void mfa_attention_kernel_descriptor_init(mfa_attention_kernel_descriptor_t *kernel_descriptor);
 
+/** Element access to memory_precisions / register_precisions for host languages that import C arrays awkwardly (Swift
+ *  sees them as 14-tuples): returns the precision raw value or -1 when unset; set with value < 0 to clear. */
+MFA_API int mfa_attention_kernel_descriptor_get_precision(const mfa_attention_kernel_descriptor_t *kernel_descriptor,
+                                                          mfa_operand_t operand, int register_file);
+MFA_API void mfa_attention_kernel_descriptor_set_precision(mfa_attention_kernel_descriptor_t *kernel_descriptor,
+                                                           mfa_operand_t operand, int register_file, int value);
+
 /** descriptor.kernelDescriptor(type:)  (AttentionDescriptor.swift:33-130): looks up the B200
  *  parameter table for (type, precision class), picks the first row with head <= max head
  *  (AttentionDescriptor+Parameters.swift:41-66), clamps the head block to pad8(D) (:41-54),
@@ -267,12 +274,29 @@ MFA_API int mfa_attention_kernel_cache_size(void);
  *  memoryPrecisions[operand]).  Inputs (Q,K,V, and dO for backward) are copied to the device,
  *  the kernels in `run_mask` are encoded in the reference's order fwd -> dQ -> dK/dV, and every
  *  output they produce whose host pointer is non-NULL is copied back.  Device scratch is owned
- *  by the library (grown on demand, per calling thread).  `device` = CUDA device ordinal.
+ *  by the library (grown on demand, one set per calling thread and device).  `device` = CUDA device
+ *  ordinal; the caller's current device is restored before the call returns.
  *  With batch_count > 1 the independent problems are processed in chunks that rotate over three
  *  streams, so uploads, kernels and downloads of neighbouring chunks overlap (pass page-locked host
  *  memory to get the overlap; pageable memory still works, serialised by the driver). */
 MFA_API int mfa_attention_run_host(const mfa_attention_descriptor_t *descriptor, uint32_t run_mask,
                                    void *const host_buffers[MFA_BUFFER_COUNT], int device);
+
+/* Host-memory placement for the host-buffer path (B200 extension; the reference's buffers are Metal shared-storage
+ * buffers, MTLContext+Buffers.swift:5-45, with no placement to speak of on a unified-memory SoC). */
+/** Page-locked host buffer for mfa_attention_run_host, allocated (first-touched) on the NUMA node `device` hangs
+ *  off and portable across CUDA contexts.  The calling thread's CPU affinity is unchanged on return. */
+MFA_API int mfa_host_alloc(size_t bytes, int device, void **out);
+MFA_API int mfa_host_free(void *ptr);
+/** Restricts the calling thread to the CPUs of `device`'s NUMA node (within the affinity it already has), so that
+ *  memory it allocates afterwards and the copies it issues stay on the GPU's socket.  `*numa_node` (optional) receives
+ *  the node, or -1 when the platform reports none (then nothing is changed). */
+MFA_API int mfa_host_bind_thread_to_device(int device, int *numa_node);
+
+/** Frees what the library holds on `device`: the calling thread's run_host scratch (operand buffers, streams, events)
+ *  and every split-grid workspace of the device.  Synchronises the device first.  Optional -- everything is reused
+ *  across calls and reclaimed at process exit; long-lived hosts that are done with a device call this. */
+MFA_API int mfa_release_device_resources(int device);
 
 /** Element count of operand's buffer for one problem (R*D, C*D, R ...) times batch_count. */
 MFA_API int mfa_attention_descriptor_operand_elements(const mfa_attention_descriptor_t *descriptor,

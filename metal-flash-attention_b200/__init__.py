@@ -128,6 +128,15 @@ def _load():
     lib.mfa_attention_kernel_cache_size.restype = c.c_int
     lib.mfa_attention_run_host.argtypes = [c.POINTER(_CDescriptor), c.c_uint32,
                                            c.POINTER(c.c_void_p * MFA_BUFFER_COUNT), c.c_int]
+    try:
+        lib.mfa_host_alloc.argtypes = [c.c_size_t, c.c_int, c.POINTER(c.c_void_p)]
+        lib.mfa_host_free.argtypes = [c.c_void_p]
+        lib.mfa_host_bind_thread_to_device.argtypes = [c.c_int, c.POINTER(c.c_int)]
+        lib.mfa_release_device_resources.argtypes = [c.c_int]
+    except AttributeError:
+        # only an older tuning build selected through MFA_B200_LIBRARY can lack these (A/B timing against it still works)
+        if not os.environ.get("MFA_B200_LIBRARY"):
+            raise
     return lib
 
 
@@ -137,6 +146,30 @@ _lib = _load()
 def _check(status: int):
     if status != 0:
         raise MFAError(status, _lib.mfa_last_error().decode())
+
+
+def hostAlloc(nbytes: int, device: int = 0) -> int:
+    """mfa_host_alloc: page-locked host buffer on the NUMA node of `device` (for runHost); returns the address."""
+    out = ctypes.c_void_p()
+    _check(_lib.mfa_host_alloc(int(nbytes), int(device), ctypes.byref(out)))
+    return out.value
+
+
+def hostFree(address: int) -> None:
+    _check(_lib.mfa_host_free(ctypes.c_void_p(address)))
+
+
+def bindThreadToDevice(device: int = 0) -> int:
+    """mfa_host_bind_thread_to_device: pin the calling thread to the CPUs of the GPU's NUMA node; returns the node
+    (-1: the platform reports none, nothing changed)."""
+    node = ctypes.c_int(-1)
+    _check(_lib.mfa_host_bind_thread_to_device(int(device), ctypes.byref(node)))
+    return node.value
+
+
+def releaseDeviceResources(device: int = 0) -> None:
+    """mfa_release_device_resources: free the library's scratch and workspaces on `device`."""
+    _check(_lib.mfa_release_device_resources(int(device)))
 
 
 def library_path() -> str:
@@ -473,5 +506,5 @@ class AttentionKernel:
 __all__ = [
     "AttentionDescriptor", "AttentionKernelDescriptor", "AttentionKernel", "AttentionKernelType",
     "AttentionOperand", "GEMMOperandPrecision", "FunctionConstantValues", "Backend", "MFAError",
-    "library_path", "version",
+    "library_path", "version", "hostAlloc", "hostFree", "bindThreadToDevice", "releaseDeviceResources",
 ]

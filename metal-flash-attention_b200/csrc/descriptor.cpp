@@ -48,9 +48,14 @@ int memory_precision(const mfa_attention_descriptor_t &d, int operand) {
 }
 
 // registerPrecisions (AttentionDescriptor+Precisions.swift:149-215).  B200 has native BF16
-// conversion, so the `hasNativeBF16Casting` (Apple9) branch applies.
-int register_precision(const mfa_attention_descriptor_t &d, int operand) {
+// conversion, so the `hasNativeBF16Casting` (Apple9) branch applies.  `type` selects the kernel whose registers are
+// described: the precision of P and dS depends on the kernel family that serves (descriptor, type) -- on the tcgen05
+// family they are operands of a tensor-core MMA and therefore ALWAYS carried in the 16-bit input element type, whatever
+// lowPrecisionIntermediates says (the reference keeps them in FP32 registers when that flag is off, :203-205; this is a
+// documented deviation, DESIGN.md section 3, and the descriptor reports what the kernel really does).
+int register_precision_for(const mfa_attention_descriptor_t &d, int operand, int type) {
   const bool bf16Inputs = d.input_precision_override == MFA_BF16;
+  const bool tensorCore = select_backend(d, type) == MFA_BACKEND_TCGEN05;
   switch (operand) {
     case MFA_Q: case MFA_K: case MFA_V:
       return d.low_precision_inputs ? (bf16Inputs ? MFA_BF16 : MFA_FP16) : MFA_FP32;  // :158-168
@@ -65,19 +70,27 @@ int register_precision(const mfa_attention_descriptor_t &d, int operand) {
       // accumulate S in FP32 in TMEM, which is the more accurate of the two; report FP32.
       return MFA_FP32;
     case MFA_P:
-      // :198  P is a 16-bit MMA operand under lowPrecisionIntermediates; on the tcgen05 path P is
-      // always rounded to the input element type (it is the A operand of O += P V).
-      if (d.low_precision_intermediates) return bf16Inputs ? MFA_BF16 : MFA_FP16;
+      // :198  P is a 16-bit value under lowPrecisionIntermediates; on the tcgen05 family it is always rounded to the
+      // input element type (it is the A operand of O += P V, dV += P^T dO)
+      if (tensorCore || d.low_precision_intermediates) return bf16Inputs ? MFA_BF16 : MFA_FP16;
       return MFA_FP32;
     case MFA_dP:
       return MFA_FP32;  // :199
     case MFA_dS:
-      return d.low_precision_intermediates ? MFA_BF16 : MFA_FP32;  // :200
+      // :200  BF16 under lowPrecisionIntermediates (Apple9); on the tcgen05 family the A operand of dQ += dS K,
+      // dK += dS^T Q, in the input element type
+      if (tensorCore) return bf16Inputs ? MFA_BF16 : MFA_FP16;
+      return d.low_precision_intermediates ? MFA_BF16 : MFA_FP32;
     case MFA_O: case MFA_dV: case MFA_dK: case MFA_dQ:
       return MFA_FP32;  // :209-212  all outputs accumulate in FP32
     default:
       return -1;
   }
+}
+
+// descriptor-level view (no kernel type in the reference's API): P as the forward kernel holds it, dS as backwardQuery
+int register_precision(const mfa_attention_descriptor_t &d, int operand) {
+  return register_precision_for(d, operand, operand == MFA_dS ? MFA_BACKWARD_QUERY : MFA_FORWARD);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -286,7 +299,7 @@ int kernel_descriptor(const mfa_attention_descriptor_t &d, int type, mfa_attenti
 
   for (int operand = 0; operand < MFA_OPERAND_COUNT; ++operand) {
     int mem = memory_precision(d, operand);
-    int reg = register_precision(d, operand);
+    int reg = register_precision_for(d, operand, type);
     out.memory_precisions[operand] = mem < 0 ? 0xFF : static_cast<uint8_t>(mem);
     out.register_precisions[operand] = reg < 0 ? 0xFF : static_cast<uint8_t>(reg);
   }
@@ -373,6 +386,20 @@ void mfa_attention_kernel_descriptor_init(mfa_attention_kernel_descriptor_t *kd)
   kd->prefer_async_cache = 0xFF;
   kd->prefer_async_load = 0xFF;
   kd->type = 0xFF;
+}
+
+int mfa_attention_kernel_descriptor_get_precision(const mfa_attention_kernel_descriptor_t *kd, mfa_operand_t operand,
+                                                  int register_file) {
+  if (!kd || operand < 0 || operand >= MFA_OPERAND_COUNT) return -1;
+  const uint8_t v = register_file ? kd->register_precisions[operand] : kd->memory_precisions[operand];
+  return v == 0xFF ? -1 : static_cast<int>(v);
+}
+
+void mfa_attention_kernel_descriptor_set_precision(mfa_attention_kernel_descriptor_t *kd, mfa_operand_t operand,
+                                                   int register_file, int value) {
+  if (!kd || operand < 0 || operand >= MFA_OPERAND_COUNT) return;
+  const uint8_t v = (value < 0 || value > MFA_BF16) ? 0xFF : static_cast<uint8_t>(value);
+  (register_file ? kd->register_precisions : kd->memory_precisions)[operand] = v;
 }
 
 int mfa_attention_descriptor_kernel_descriptor(const mfa_attention_descriptor_t *descriptor, mfa_kernel_type_t type,

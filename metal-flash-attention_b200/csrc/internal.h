@@ -12,6 +12,7 @@ int fail(int status, const std::string &message);
 
 int memory_precision(const mfa_attention_descriptor_t &d, int operand);
 int register_precision(const mfa_attention_descriptor_t &d, int operand);
+int register_precision_for(const mfa_attention_descriptor_t &d, int operand, int type);
 int select_backend(const mfa_attention_descriptor_t &d, int type);
 const char *parameter_file(const mfa_attention_descriptor_t &d, int type);
 int kernel_descriptor(const mfa_attention_descriptor_t &d, int type, mfa_attention_kernel_descriptor_t &out);

@@ -6,11 +6,13 @@
 
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
 
 #include "internal.h"
+#include "kernels/device_state.h"
 
 struct mfa_attention_kernel {
   mfa_attention_kernel_descriptor_t descriptor;
@@ -42,18 +44,28 @@ static const int *operands_of(int type, int *count) {
   }
 }
 
+// sm_100 check of the current device, cached per device ordinal (encode() of a microsecond-scale kernel must not pay
+// two runtime queries per call)
 static int check_device() {
-  int device = 0;
-  cudaError_t e = cudaGetDevice(&device);
-  if (e != cudaSuccess)
-    return fail(MFA_ERROR_NO_DEVICE, std::string("No CUDA device: ") + cudaGetErrorString(e) +
-                                         " (this library has no CPU fallback).");
+  const int device = current_device();
+  if (device < 0)
+    return fail(MFA_ERROR_NO_DEVICE, "No CUDA device (cudaGetDevice failed; this library has no CPU fallback).");
+  static std::mutex mutex;
+  static int8_t verdict[kMaxDevices] = {};  // 0 unknown, 1 sm_100, -1 other
+  if (device < kMaxDevices) {
+    std::lock_guard<std::mutex> lock(mutex);
+    if (verdict[device] == 1) return MFA_SUCCESS;
+  }
   int major = 0;
-  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+  cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
   if (e != cudaSuccess) return fail(MFA_ERROR_NO_DEVICE, std::string("cudaDeviceGetAttribute: ") + cudaGetErrorString(e));
   if (major != 10)
     return fail(MFA_ERROR_NO_DEVICE, "Device is not sm_100 (compute capability " + std::to_string(major) +
                                          ".x); these kernels are built for sm_100a only.");
+  if (device < kMaxDevices) {
+    std::lock_guard<std::mutex> lock(mutex);
+    verdict[device] = 1;
+  }
   return MFA_SUCCESS;
 }
 
@@ -231,23 +243,40 @@ int mfa_attention_kernel_encode(const mfa_attention_kernel_t *kernel, const mfa_
   if (status != MFA_SUCCESS) return status;
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
 
-  cudaError_t e = cudaSuccess;
-  if (kernel->backend == MFA_BACKEND_TCGEN05) {
-    switch (kernel->type) {
-      case MFA_FORWARD: e = launch_tcgen05_forward(p, stream); break;
-      case MFA_BACKWARD_QUERY: e = launch_tcgen05_backward_query(p, stream); break;
-      default: e = launch_tcgen05_backward_key_value(p, stream); break;
-    }
-  } else {
-    switch (kernel->type) {
-      case MFA_FORWARD: e = launch_simt_forward(p, stream); break;
-      case MFA_BACKWARD_QUERY: e = launch_simt_backward_query(p, stream); break;
-      default: e = launch_simt_backward_key_value(p, stream); break;
-    }
+  // Several kernels carry the batch in gridDim.y (limit 65535; the SIMT dK/dV kernel multiplies it by up to four head
+  // slices): larger batches go out as several launches over slices of the batch -- the problems are independent and
+  // stored back to back, so a slice is just a pointer offset.
+  constexpr uint32_t kMaxBatchPerLaunch = 16384;
+  const uint32_t batch = p.batch;
+  size_t head_bytes[kSlots];
+  for (int slot = 0; slot < kSlots; ++slot) {
+    const size_t seq = (slot == sK || slot == sV || slot == sdK || slot == sdV) ? p.C : p.R;
+    const size_t elements = (slot == sL || slot == sD) ? seq : seq * p.D;
+    head_bytes[slot] = elements * (p.prec[slot] == FP32 ? 4 : 2);
   }
-  if (e != cudaSuccess)
-    return fail(MFA_ERROR_CUDA, std::string("launch of ") + kernel->source_name + " failed: " + cudaGetErrorString(e) +
-                                    " " + last_launch_detail());
+  for (uint32_t h0 = 0; h0 < batch; h0 += kMaxBatchPerLaunch) {
+    AttentionParams q = p;
+    q.batch = batch - h0 < kMaxBatchPerLaunch ? batch - h0 : kMaxBatchPerLaunch;
+    for (int slot = 0; slot < kSlots; ++slot)
+      if (q.buf[slot]) q.buf[slot] = static_cast<char *>(q.buf[slot]) + head_bytes[slot] * h0;
+    cudaError_t e = cudaSuccess;
+    if (kernel->backend == MFA_BACKEND_TCGEN05) {
+      switch (kernel->type) {
+        case MFA_FORWARD: e = launch_tcgen05_forward(q, stream); break;
+        case MFA_BACKWARD_QUERY: e = launch_tcgen05_backward_query(q, stream); break;
+        default: e = launch_tcgen05_backward_key_value(q, stream); break;
+      }
+    } else {
+      switch (kernel->type) {
+        case MFA_FORWARD: e = launch_simt_forward(q, stream); break;
+        case MFA_BACKWARD_QUERY: e = launch_simt_backward_query(q, stream); break;
+        default: e = launch_simt_backward_key_value(q, stream); break;
+      }
+    }
+    if (e != cudaSuccess)
+      return fail(MFA_ERROR_CUDA, std::string("launch of ") + kernel->source_name + " failed: " + cudaGetErrorString(e) +
+                                      " " + last_launch_detail());
+  }
   return MFA_SUCCESS;
 }
 
@@ -265,8 +294,7 @@ MFA_API int mfa_debug_forward_trace(const mfa_attention_kernel_t *kernel, const 
 }
 
 // Debug-only export: 0 forces split-KV onto its scratch + combine fallback (tests cover both forms).
-MFA_API void mfa_debug_set_forward_cluster(int enabled) { tcgen05_forward_set_cluster(enabled); }
-MFA_API int mfa_debug_forward_max_clusters(uint32_t splits) { return tcgen05_forward_max_clusters(splits); }
+MFA_API void mfa_debug_set_forward_fused(int enabled) { tcgen05_forward_set_fused(enabled); }
 
 // ------------------------------------------------------------------------------------------------
 // Kernel cache keyed by descriptor -- the useful half of the reference's pipeline cache
@@ -336,14 +364,47 @@ constexpr uint32_t kMaxChunks = 32;
 struct Scratch {
   void *ptr[MFA_BUFFER_COUNT] = {};
   size_t bytes[MFA_BUFFER_COUNT] = {};
-  int device = -1;
+  bool ready = false;  // streams and events exist
   cudaStream_t stream[kHostStreams] = {};
   cudaEvent_t uploaded[kMaxChunks] = {}, computed[kMaxChunks] = {};
-  ~Scratch() {
-    // Process teardown: the CUDA context may already be gone; leaking here is deliberate.
+};
+// One scratch set per (calling thread, device): a thread that alternates between devices keeps both sets, nothing
+// leaks on a device switch, and a set is only marked ready once every stream and event exists.  Released by
+// mfa_release_device_resources() (thread exit does not free device memory: the context may already be gone).
+thread_local std::map<int, Scratch> g_scratch;
+
+// RAII: mfa_attention_run_host selects `device` for the duration of the call and restores the caller's device
+struct DeviceGuard {
+  int previous = -1;
+  bool active = false;
+  cudaError_t enter(int device) {
+    if (cudaGetDevice(&previous) != cudaSuccess) {
+      cudaGetLastError();
+      previous = -1;
+    }
+    cudaError_t e = cudaSetDevice(device);
+    active = e == cudaSuccess && previous >= 0 && previous != device;
+    return e;
+  }
+  ~DeviceGuard() {
+    if (active) cudaSetDevice(previous);
   }
 };
-thread_local Scratch g_scratch;
+
+void destroy_scratch(Scratch &s) {
+  for (int i = 0; i < MFA_BUFFER_COUNT; ++i) {
+    if (s.ptr[i]) cudaFree(s.ptr[i]);
+    s.ptr[i] = nullptr;
+    s.bytes[i] = 0;
+  }
+  for (int i = 0; i < kHostStreams; ++i)
+    if (s.stream[i]) cudaStreamDestroy(s.stream[i]);
+  for (uint32_t i = 0; i < kMaxChunks; ++i) {
+    if (s.uploaded[i]) cudaEventDestroy(s.uploaded[i]);
+    if (s.computed[i]) cudaEventDestroy(s.computed[i]);
+  }
+  s = Scratch();
+}
 
 // heads per chunk: about sixteen chunks (fill + drain = two chunk times), but no chunk smaller than ~4 MB of traffic
 // (copy launch overheads), at most kMaxChunks chunks, and no chunking at all for a single problem
@@ -362,24 +423,24 @@ int mfa_attention_run_host(const mfa_attention_descriptor_t *descriptor, uint32_
                            void *const host_buffers[MFA_BUFFER_COUNT], int device) {
   if (!descriptor || !host_buffers) return fail(MFA_ERROR_INVALID_ARGUMENT, "NULL argument.");
   if (!(run_mask & 7u)) return fail(MFA_ERROR_INVALID_ARGUMENT, "run_mask selects no kernel.");
-  cudaError_t e = cudaSetDevice(device);
+  DeviceGuard guard;  // the caller's current device is restored on every exit
+  cudaError_t e = guard.enter(device);
   if (e != cudaSuccess)
     return fail(MFA_ERROR_NO_DEVICE, std::string("cudaSetDevice: ") + cudaGetErrorString(e) +
                                          " (this library has no CPU fallback).");
-  Scratch &s = g_scratch;
-  if (s.device != device) {
-    for (int i = 0; i < MFA_BUFFER_COUNT; ++i) {
-      s.ptr[i] = nullptr;
-      s.bytes[i] = 0;
+  Scratch &s = g_scratch[device];
+  if (!s.ready) {
+    for (int i = 0; i < kHostStreams && e == cudaSuccess; ++i)
+      e = cudaStreamCreateWithFlags(&s.stream[i], cudaStreamNonBlocking);
+    for (uint32_t i = 0; i < kMaxChunks && e == cudaSuccess; ++i) {
+      e = cudaEventCreateWithFlags(&s.uploaded[i], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.computed[i], cudaEventDisableTiming);
     }
-    s.device = device;
-    for (int i = 0; i < kHostStreams; ++i)
-      if ((e = cudaStreamCreateWithFlags(&s.stream[i], cudaStreamNonBlocking)) != cudaSuccess)
-        return fail(MFA_ERROR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
-    for (uint32_t i = 0; i < kMaxChunks; ++i)
-      if ((e = cudaEventCreateWithFlags(&s.uploaded[i], cudaEventDisableTiming)) != cudaSuccess ||
-          (e = cudaEventCreateWithFlags(&s.computed[i], cudaEventDisableTiming)) != cudaSuccess)
-        return fail(MFA_ERROR_CUDA, std::string("cudaEventCreate: ") + cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+      destroy_scratch(s);  // never leave a half-initialised set behind
+      return fail(MFA_ERROR_CUDA, std::string("stream / event creation: ") + cudaGetErrorString(e));
+    }
+    s.ready = true;
   }
 
   // which operands each kernel reads / writes (AttentionKernelType.swift:10-22)
@@ -481,6 +542,21 @@ int mfa_attention_run_host(const mfa_attention_descriptor_t *descriptor, uint32_
   for (int i = 0; i < kHostStreams; ++i)
     if ((e = cudaStreamSynchronize(s.stream[i])) != cudaSuccess)
       return fail(MFA_ERROR_CUDA, std::string("kernel execution failed: ") + cudaGetErrorString(e));
+  return MFA_SUCCESS;
+}
+
+int mfa_release_device_resources(int device) {
+  DeviceGuard guard;
+  cudaError_t e = guard.enter(device);
+  if (e != cudaSuccess) return fail(MFA_ERROR_NO_DEVICE, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+  if ((e = cudaDeviceSynchronize()) != cudaSuccess)
+    return fail(MFA_ERROR_CUDA, std::string("cudaDeviceSynchronize: ") + cudaGetErrorString(e));
+  auto it = g_scratch.find(device);
+  if (it != g_scratch.end()) {
+    destroy_scratch(it->second);
+    g_scratch.erase(it);
+  }
+  release_workspaces(device);
   return MFA_SUCCESS;
 }
 

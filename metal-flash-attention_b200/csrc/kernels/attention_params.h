@@ -52,8 +52,7 @@ uint32_t tcgen05_backward_launch_count(int type, uint32_t R, uint32_t C, uint32_
 void tcgen05_backward_geometry(int type, uint32_t D, uint32_t *threads, uint32_t *smem_bytes, uint32_t *par,
                                uint32_t *trav, uint32_t *head);
 
-int tcgen05_forward_max_clusters(uint32_t splits);  // debug: co-resident clusters of `splits` CTAs (D=128 kernel)
-void tcgen05_forward_set_cluster(int enabled);  // debug: 0 = split-KV through scratch + combine kernel
+void tcgen05_forward_set_fused(int enabled);  // debug: 0 = split-KV through scratch + combine kernel (two launches)
 cudaError_t launch_tcgen05_forward_trace(const AttentionParams &p, cudaStream_t stream, long long *trace);  // debug
 cudaError_t launch_tcgen05_forward_d256_trace(const AttentionParams &p, cudaStream_t stream, long long *trace);  // debug
 const char *last_launch_detail();  // thread-local detail string for MFA_ERROR_CUDA messages

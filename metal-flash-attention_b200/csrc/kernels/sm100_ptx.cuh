@@ -195,6 +195,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 #undef MFA_R4
+// 64 consecutive columns in one instruction (the wait is the caller's: several loads may be put in flight first)
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&r)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "
@@ -215,6 +224,18 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 
+// ---------------------------------------------------------------- shared memory, explicit state space ----
+// Pointers derived from the manually aligned dynamic shared-memory base are generic to the compiler (LD.E / ST.E in
+// SASS); the staging tiles of the epilogues go through these instead so that they compile to LDS / STS.
+__device__ __forceinline__ void sts_f32x4(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 // ---------------------------------------------------------------- math helpers ----------------
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -230,12 +251,29 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
         "l"(*reinterpret_cast<const uint64_t *>(&c)));
   return *reinterpret_cast<float2 *>(&d);
 }
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<const uint64_t *>(&a)), "l"(*reinterpret_cast<const uint64_t *>(&b)));
+  return *reinterpret_cast<float2 *>(&d);
+}
 __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
   uint64_t d;
   asm("add.rn.f32x2 %0, %1, %2;"
       : "=l"(d)
       : "l"(*reinterpret_cast<const uint64_t *>(&a)), "l"(*reinterpret_cast<const uint64_t *>(&b)));
   return *reinterpret_cast<float2 *>(&d);
+}
+__device__ __forceinline__ float max_nan(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ float min_nan(float a, float b) {
+  float r;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
 }
 // exp2 of two values on the FMA / ALU pipes (no MUFU): Cody-Waite split x = n + f, n = round(x), f in [-0.5, 0.5],
 // 2^f by a degree-3 minimax polynomial (max relative error 7.6e-5, below the 16-bit rounding P gets anyway), then
@@ -247,11 +285,13 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
   const float kMagic = 12582912.0f;  // 1.5 * 2^23: adding it leaves round(x) in the low mantissa bits
   // clamp to the finite exponent range: -inf / very negative inputs give ~0, and an input far above the running max
   // (stale or unset m) gives a huge finite value, which is what the caller's overflow check looks for
-  x.x = fmaxf(x.x, -126.0f);
-  x.y = fmaxf(x.y, -126.0f);
+  // (max.NaN / min.NaN: a NaN score stays NaN -- it reaches the sum, the caller's overflow check and the output, as
+  // it does through ex2.approx -- where fmaxf would quietly turn it into 2^-126)
+  x.x = max_nan(x.x, -126.0f);
+  x.y = max_nan(x.y, -126.0f);
   if (kClampUpper) {
-    x.x = fminf(x.x, 127.0f);
-    x.y = fminf(x.y, 127.0f);
+    x.x = min_nan(x.x, 127.0f);
+    x.y = min_nan(x.y, 127.0f);
   }
   const float2 t = fadd2(x, make_float2(kMagic, kMagic));
   const float2 n = fadd2(t, make_float2(-kMagic, -kMagic));
@@ -275,6 +315,74 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
+}
+
+// the two 16-bit halves of a packed register, widened back to FP32 (exact)
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t w) {
+  float2 r;
+  asm("{\n"
+      ".reg .b16 lo, hi;\n"
+      "mov.b32 {lo, hi}, %2;\n"
+      "cvt.f32.f16 %0, lo;\n"
+      "cvt.f32.f16 %1, hi;\n"
+      "}\n"
+      : "=f"(r.x), "=f"(r.y)
+      : "r"(w));
+  return r;
+}
+
+// ---------------------------------------------------------------- online-softmax inner loop ---
+// l accumulates the P values the tensor core will actually multiply (rounded to the 16-bit MMA input type), as the
+// reference does (AttentionKernel+Softmax.swift:304-324 sums P after the cast to its register type): rows of P / l then
+// sum to one exactly, whatever the rounding did.
+#ifndef MFA_SUM_ROUNDED_P
+#define MFA_SUM_ROUNDED_P 0
+#endif
+constexpr bool kSumRoundedP = MFA_SUM_ROUNDED_P != 0;
+// Pairs by which "sum and pack" trails "exp2" in softmax_exp_half.  A warp issues in order: with the consumer of an
+// ex2 right behind it (what a plain loop compiles to) every pair exposes the MUFU latency -- measured 26 cycles per
+// pair against the pipe's 16 (two ex2 at 4 lanes / clk / sub-partition).
+#ifndef MFA_EXP_SKEW
+#define MFA_EXP_SKEW 4
+#endif
+
+// One half-row (64 scores, FP32 bits in v) -> P = exp2(s * scale_log2 - m) rounded to 16 bits in `packed`; returns the
+// half-row sum.  v is consumed in place.  kPolyPairs of every 4 element pairs take exp2 on the FMA pipe (exp2_poly2)
+// instead of the MUFU pipe.
+template <bool kBF16, uint32_t kPolyPairs>
+__device__ __forceinline__ float softmax_exp_half(uint32_t (&v)[64], uint32_t (&packed)[32], float scale_log2, float m) {
+  constexpr uint32_t kSkew = MFA_EXP_SKEW;
+  const float2 scale2 = make_float2(scale_log2, scale_log2), negm2 = make_float2(-m, -m);
+  float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (uint32_t i = 0; i < 32 + kSkew; ++i) {
+    if (i < 32) {
+      float2 x = ffma2(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), scale2, negm2);
+      if (kPolyPairs > 0 && (i & 3) < kPolyPairs) {
+        x = exp2_poly2(x);
+      } else {
+        x.x = ex2_approx(x.x);
+        x.y = ex2_approx(x.y);
+      }
+      v[2 * i] = __float_as_uint(x.x);
+      v[2 * i + 1] = __float_as_uint(x.y);
+    }
+    if (i >= kSkew) {
+      const uint32_t k = i - kSkew;
+      float2 e = make_float2(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]));
+      packed[k] = kBF16 ? pack_bf16x2(e.x, e.y) : pack_f16x2(e.x, e.y);
+      if (kSumRoundedP) e = kBF16 ? unpack_bf16x2(packed[k]) : unpack_f16x2(packed[k]);
+      if (k & 1)
+        acc1 = fadd2(acc1, e);
+      else
+        acc0 = fadd2(acc0, e);
+    }
+  }
+  const float2 acc = fadd2(acc0, acc1);
+  return acc.x + acc.y;
 }
 
 // ---------------------------------------------------------------- thread-block clusters ------

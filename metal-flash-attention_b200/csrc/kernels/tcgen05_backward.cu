@@ -23,9 +23,8 @@
 #include <float.h>
 #include <stdint.h>
 
-#include <mutex>
-
 #include "attention_params.h"
+#include "device_state.h"
 #include "sm100_ptx.cuh"
 #include "tma_host.h"
 
@@ -133,30 +132,6 @@ __device__ __forceinline__ void store_accumulator_coalesced(uint32_t t_acc, uint
     }
     __syncwarp();
   }
-}
-
-static uint32_t backward_sm_count() {
-  static int sm_count = 0;
-  if (sm_count == 0) {
-    int device = 0;
-    if (cudaGetDevice(&device) != cudaSuccess ||
-        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess)
-      sm_count = 148;
-  }
-  return static_cast<uint32_t>(sm_count);
-}
-// keep freed scratch cached in the device's default memory pool instead of returning it to the OS at every
-// synchronisation (the default release threshold is 0)
-static void backward_keep_pool_cached() {
-  static std::once_flag pool_once;
-  std::call_once(pool_once, [] {
-    int device = 0;
-    cudaMemPool_t pool;
-    if (cudaGetDevice(&device) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-      uint64_t threshold = UINT64_MAX;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
-    }
-  });
 }
 
 struct BackwardArgs {
@@ -364,14 +339,17 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
       for (uint32_t c = 0; c < kHalf; c += 32) tmem_ld32(tdP + c, *reinterpret_cast<uint32_t(*)[32]>(&dp[c]));
       tc_wait_ld();
+      const float2 scale2 = make_float2(a.scale, a.scale), negD2 = make_float2(-Dterm, -Dterm);
 #pragma unroll
       for (uint32_t c = 0; c < kHalf; c += 32) {
         uint32_t packed[16];
 #pragma unroll
         for (uint32_t k = 0; k < 16; ++k) {
-          const float ds0 = p[c + 2 * k] * fmaf(__uint_as_float(dp[c + 2 * k]), a.scale, -Dterm);
-          const float ds1 = p[c + 2 * k + 1] * fmaf(__uint_as_float(dp[c + 2 * k + 1]), a.scale, -Dterm);
-          packed[k] = kBF16 ? pack_bf16x2(ds0, ds1) : pack_f16x2(ds0, ds1);
+          // packed FP32x2 arithmetic: the elementwise pass is bound by instruction issue (one 32-wide FP32
+          // instruction per two cycles and sub-partition), so two elements per FFMA2 / FMUL2 halve its cost
+          const float2 t = ffma2(make_float2(__uint_as_float(dp[c + 2 * k]), __uint_as_float(dp[c + 2 * k + 1])), scale2, negD2);
+          const float2 ds = fmul2(make_float2(p[c + 2 * k], p[c + 2 * k + 1]), t);
+          packed[k] = kBF16 ? pack_bf16x2(ds.x, ds.y) : pack_f16x2(ds.x, ds.y);
         }
         tmem_st16(tdP + (c >> 1), packed);  // dS of keys [64h + c, +32) -> columns [64h + c/2, +16) of the dP buffer
       }
@@ -693,14 +671,18 @@ __global__ void __launch_bounds__(kThreads, 1)
       tc_wait_ld();
       tc_fence_before();
       mbar_arrive(rd_free);  // S^T(r+1) may overwrite the dP^T region now
+      const float2 scale2 = make_float2(a.scale, a.scale);
 #pragma unroll
       for (uint32_t c = 0; c < kHalf; c += 32) {
         uint32_t dd[16];
 #pragma unroll
         for (uint32_t k = 0; k < 16; ++k) {
-          const float ds0 = p[c + 2 * k] * fmaf(__uint_as_float(dp[c + 2 * k]), a.scale, -Dq[c + 2 * k]);
-          const float ds1 = p[c + 2 * k + 1] * fmaf(__uint_as_float(dp[c + 2 * k + 1]), a.scale, -Dq[c + 2 * k + 1]);
-          dd[k] = kBF16 ? pack_bf16x2(ds0, ds1) : pack_f16x2(ds0, ds1);
+          // (the vector loader stores -D, so the pair of D terms is one 64-bit shared-memory load and the
+          // subtraction folds into the packed FMA; see backwardQuery for why packed arithmetic)
+          const float2 negD2 = *reinterpret_cast<const float2 *>(&Dq[c + 2 * k]);
+          const float2 t = ffma2(make_float2(__uint_as_float(dp[c + 2 * k]), __uint_as_float(dp[c + 2 * k + 1])), scale2, negD2);
+          const float2 ds = fmul2(make_float2(p[c + 2 * k], p[c + 2 * k + 1]), t);
+          dd[k] = kBF16 ? pack_bf16x2(ds.x, ds.y) : pack_f16x2(ds.x, ds.y);
         }
         tmem_st16(tLane + rs + kHalf + h * (kHalf / 2) + (c >> 1), dd);  // dS^T -> columns [64 + 32h + c/2, +16)
       }
@@ -773,7 +755,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           const uint32_t q = (blk0 + r) * kTile + i * 32 + lane;
           const size_t idx = static_cast<size_t>(head) * a.R + min(q, a.R - 1);
           vecL[stage * kTile + i * 32 + lane] = load_stat(a.L, idx, a.l_prec);
-          vecD[stage * kTile + i * 32 + lane] = load_stat(a.Dterm, idx, a.d_prec);
+          vecD[stage * kTile + i * 32 + lane] = -load_stat(a.Dterm, idx, a.d_prec);  // negated: see the dS^T pass
         }
         mbar_arrive(&vec_full[stage]);  // release semantics order the shared-memory writes above
         if constexpr (kConvertDO) convert_dO(stage, phase, 0);
@@ -982,17 +964,15 @@ template <uint32_t DPAD, bool kBF16, bool kConvertDO = false>
 cudaError_t launch(const AttentionParams &p, cudaStream_t stream, bool key_value) {
   auto kernel_q = attention_backward_query_tcgen05<DPAD, kBF16, kConvertDO>;
   auto kernel_kv = attention_backward_key_value_tcgen05<DPAD, kBF16, kConvertDO>;
-  static std::once_flag once;
-  static cudaError_t attr_status = cudaSuccess;
-  std::call_once(once, [&] {
-    attr_status = cudaFuncSetAttribute(kernel_q, cudaFuncAttributeMaxDynamicSharedMemorySize, QueryConfig<DPAD>::kSmemBytes);
-    if (attr_status == cudaSuccess)
-      attr_status = cudaFuncSetAttribute(kernel_kv, cudaFuncAttributeMaxDynamicSharedMemorySize, KeyValueConfig<DPAD>::kSmemBytes);
-  });
-  if (attr_status != cudaSuccess) return attr_status;
+  const int device = current_device();
+  cudaError_t e;
+  if (!key_value)
+    e = ensure_max_dynamic_smem(reinterpret_cast<const void *>(kernel_q), QueryConfig<DPAD>::kSmemBytes, device);
+  else
+    e = ensure_max_dynamic_smem(reinterpret_cast<const void *>(kernel_kv), KeyValueConfig<DPAD>::kSmemBytes, device);
+  if (e != cudaSuccess) return e;
 
   CUtensorMap mapQ, mapdO, mapK, mapV;
-  cudaError_t e;
   if ((e = make_tensor_map_16bit(&mapQ, p.buf[sQ], p.R, p.D, p.batch, kTile)) != cudaSuccess) return e;
   if ((e = make_tensor_map_16bit(&mapdO, p.buf[sdO], p.R, p.D, p.batch, kTile)) != cudaSuccess) return e;
   if ((e = make_tensor_map_16bit(&mapK, p.buf[sK], p.C, p.D, p.batch, kTile)) != cudaSuccess) return e;
@@ -1017,7 +997,7 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, bool key_value
   // parallelised dimension -> CTAs; traversed dimension -> blocks, possibly split over blockIdx.z
   const uint32_t par = key_value ? p.C : p.R, trav = key_value ? p.R : p.C;
   const uint32_t tiles = (par + kTile - 1) / kTile, total_blocks = (trav + kTile - 1) / kTile;
-  const uint32_t per = choose_blocks_per_split(tiles * p.batch, total_blocks, backward_sm_count());
+  const uint32_t per = choose_blocks_per_split(tiles * p.batch, total_blocks, device_sm_count(device));
   const uint32_t splits = (total_blocks + per - 1) / per;
   a.blocks_per_split = per;
   a.split_stride = 0;
@@ -1031,14 +1011,13 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, bool key_value
     return cudaGetLastError();
   }
 
-  // partial accumulators in stream-ordered scratch: [split][tensor][batch][rows][D] FP32, tensor = dQ | (dV, dK)
+  // partial accumulators in the library's per-(device, stream) workspace: [split][tensor][batch][rows][D] FP32,
+  // tensor = dQ | (dV, dK)
   const size_t tensor_elems = static_cast<size_t>(p.batch) * par * p.D;
   const uint32_t tensors = key_value ? 2 : 1;
-  backward_keep_pool_cached();
-  float *scratch = nullptr;
-  if ((e = cudaMallocAsync(reinterpret_cast<void **>(&scratch), splits * tensors * tensor_elems * sizeof(float), stream)) !=
-      cudaSuccess)
-    return e;
+  void *ws = nullptr;
+  if ((e = workspace_for(device, stream, splits * tensors * tensor_elems * sizeof(float), &ws)) != cudaSuccess) return e;
+  float *scratch = reinterpret_cast<float *>(static_cast<char *>(ws) + kWorkspaceCounterBytes);
   a.split_stride = tensors * tensor_elems;
   a.dQ = scratch;
   a.dV = scratch;
@@ -1065,8 +1044,7 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, bool key_value
                            a.split_stride / 4, splits);
     if (e == cudaSuccess) e = cudaGetLastError();
   }
-  cudaError_t free_status = cudaFreeAsync(scratch, stream);
-  return e != cudaSuccess ? e : free_status;
+  return e;
 }
 
 }  // namespace bwd
@@ -1111,7 +1089,7 @@ uint32_t tcgen05_backward_launch_count(int type, uint32_t R, uint32_t C, uint32_
   const bool key_value = type == 2;  // MFA_BACKWARD_KEY_VALUE
   const uint32_t par = key_value ? C : R, trav = key_value ? R : C;
   const uint32_t tiles = (par + bwd::kTile - 1) / bwd::kTile, total_blocks = (trav + bwd::kTile - 1) / bwd::kTile;
-  return bwd::choose_blocks_per_split(tiles * batch, total_blocks, bwd::backward_sm_count()) < total_blocks ? 2 : 1;
+  return bwd::choose_blocks_per_split(tiles * batch, total_blocks, device_sm_count(current_device())) < total_blocks ? 2 : 1;
 }
 
 void tcgen05_backward_geometry(int type, uint32_t D, uint32_t *threads, uint32_t *smem_bytes, uint32_t *par,

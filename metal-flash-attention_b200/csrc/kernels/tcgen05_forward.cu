@@ -24,19 +24,26 @@
 #include <float.h>
 #include <stdint.h>
 
-#include <mutex>
-
 #include "attention_params.h"
+#include "device_state.h"
 #include "sm100_ptx.cuh"
 #include "tma_host.h"
 
 namespace mfa {
-// Split-KV has two forms.  Measured on B200 (single head, N = 4096, D = 128, CUDA-graph replay): scratch + combine
-// kernel 18.5 us, cluster + distributed-shared-memory reduce 37 us -- only 15 clusters of 8 CTAs are co-resident (16
-// needed, so it falls back to clusters of 4 = 64 CTAs) and the DSMEM pull of the partials runs at ~6 B/clk/SM.  The
-// cluster form therefore stays off unless mfa_debug_set_forward_cluster(1) asks for it (tests cover both).
-static int g_forward_cluster_enabled = 0;
-void tcgen05_forward_set_cluster(int enabled) { g_forward_cluster_enabled = enabled; }
+// Split-KV has two forms (tests cover both; mfa_debug_set_forward_fused() selects):
+//   scratch -- TWO launches (default): normalised partials in the library's workspace + the combine_splits kernel,
+//              launched with programmatic stream serialisation so that it is resident when the attention kernel drains;
+//   fused   -- ONE launch: every split CTA leaves its raw partial (unnormalised O, m, l) in the workspace, announces it
+//              on a per-tile-pair arrival counter, waits for its siblings and then merges and stores a 1 / num_splits
+//              slice of the pair's rows (all CTAs are co-resident: cooperative launch, one item each).
+// Measured on B200, one N = 4096, D = 128 bf16 head (profiles/r2_single_head_latency.jsonl), eager / CUDA graph:
+// scratch 20.5 / 18.3 us, fused 22.6 / 20.5 us -- the merge is the same L2 traffic either way, and the second launch
+// (hidden behind the first by programmatic stream serialisation) costs less than the cooperative launch plus the
+// arrive-and-spin round trip, so the one-launch form is not the default.  A third form that reduced through
+// distributed shared memory inside a thread-block cluster was measured at 37 us in round 1 (only 15 clusters of 8 CTAs
+// are co-resident, DSMEM pulls at ~6 B/clk/SM) and removed.
+static int g_forward_fused_enabled = 0;
+void tcgen05_forward_set_fused(int enabled) { g_forward_fused_enabled = enabled; }
 
 namespace fwd {
 
@@ -61,7 +68,11 @@ template <uint32_t DPAD> constexpr uint32_t kPolyPairsFor = MFA_POLY_PAIRS;
 #else
 template <uint32_t DPAD> constexpr uint32_t kPolyPairsFor = DPAD <= 64 ? 1 : 0;
 #endif
-constexpr float kLazySumLimit = 256.0f;  // a half-row of P summing to <= 2^8 proves every element is <= 2^8
+constexpr float kLazySumLimit = 256.0f;
+#ifndef MFA_FWD_WARP_ARRIVE
+#define MFA_FWD_WARP_ARRIVE 0
+#endif
+constexpr bool kWarpArrive = MFA_FWD_WARP_ARRIVE != 0;  // P hand-off: one mbarrier arrival per softmax warp, not per thread  // a half-row of P summing to <= 2^8 proves every element is <= 2^8
 
 template <uint32_t DPAD>
 struct Config {
@@ -72,12 +83,6 @@ struct Config {
   static constexpr uint32_t kSmemK = kSmemQ + kTilesPerCta * kTileBytes;
   static constexpr uint32_t kSmemV = kSmemK + kStages * kTileBytes;
   static constexpr uint32_t kSmemScratch = kSmemV + kStages * kTileBytes;  // epilogue transpose: 8 warps x 32 x 32 floats
-  // cluster split-KV epilogue: the raw O partial of the tile pair ([256][DPAD] FP32, 16 B slots XOR-swizzled in
-  // groups of 8) overlays the K / V stages, which are dead once the last MMA has completed; (m, l) per row
-  // goes to the head of the transpose scratch
-  static constexpr uint32_t kSmemPart = kSmemK;
-  static constexpr uint32_t kSmemML = kSmemScratch;
-  static_assert(kTilesPerCta * kTileM * DPAD * 4 <= 2 * kStages * kTileBytes, "O partial does not fit the K/V stages");
   static constexpr uint32_t kSmemBar = kSmemScratch + 8 * 32 * 32 * 4;
   static constexpr uint32_t kNumBars = 2 + 4 * kStages + 6 * kTilesPerCta;
   static constexpr uint32_t kSmemTmemPtr = kSmemBar + kNumBars * 8;
@@ -104,13 +109,14 @@ constexpr uint32_t kTraceSlots = 8;  // per (role, iteration)
 // item-level probes: roles 4 (tile 0 softmax), 5 (tile 1 softmax), 6 (MMA), indexed by the CTA's item counter
 #define MFA_TRACE_ITEM(role, it, slot) MFA_TRACE(role, it, slot)
 
-template <uint32_t DPAD, bool kBF16, bool kTrace = false, bool kCluster = false>
+template <uint32_t DPAD, bool kBF16, bool kTrace = false, bool kFused = false>
 __global__ void __launch_bounds__(kThreads, 1)
     attention_forward_tcgen05(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                               const __grid_constant__ CUtensorMap mapV, float *__restrict__ O, void *__restrict__ L,
                               uint32_t R, uint32_t C, uint32_t D, float scale_log2, int l_is_fp16,
                               uint32_t num_items, uint32_t pairs_per_head, uint32_t num_splits, uint32_t batch,
-                              long long *__restrict__ trace) {
+                              float *__restrict__ part_O, float2 *__restrict__ part_ml,
+                              uint32_t *__restrict__ counters, long long *__restrict__ trace) {
   // Persistent CTAs: one per SM, each walking the work items (head, 256-row tile pair) blockIdx.x,
   // blockIdx.x + gridDim.x, ...  Barrier phases are carried across items, so the producers (TMA, MMA) run ahead
   // into the next item while the softmax warps drain the current one; TMEM alloc, barrier init and descriptor
@@ -123,9 +129,10 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Split-KV: when there are fewer (head, tile pair) items than SMs, the key axis of every item is cut into
   // num_splits equal ranges that become separate work items.
-  //  kCluster: the num_splits CTAs of an item form one thread-block cluster (rank = split); each leaves its raw O
-  //    partial and (m, l) in its own shared memory and, after a cluster barrier, reduces and stores a 1/num_splits
-  //    slice of the rows by reading all partials through distributed shared memory -- one launch, no HBM scratch.
+  //  kFused: every CTA has exactly one item (cooperative launch: all are co-resident).  It leaves its raw partial --
+  //    unnormalised O, running max m and sum l -- in the workspace ([pair][split][256 rows]), bumps the pair's
+  //    arrival counter, waits until all num_splits siblings have arrived and then merges and stores the rows
+  //    [split * 256 / num_splits, ...) of the pair: one launch, and the merge is spread over all split CTAs.
   //  otherwise (fallback): each item writes a normalised partial O and its L as if it were a whole problem (O and L
   //    then point at scratch laid out [split][head][row]) and the combine_splits kernel merges them.
   const uint32_t total_blocks = (C + kBlockN - 1) / kBlockN;
@@ -158,8 +165,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     for (uint32_t t = 0; t < kTilesPerCta; ++t) {
       mbar_init(&b.s_full[t], 1);
-      mbar_init(&b.p_full[2 * t], kTileM);
-      mbar_init(&b.p_full[2 * t + 1], kTileM);
+      mbar_init(&b.p_full[2 * t], kWarpArrive ? kTileM / 32 : kTileM);
+      mbar_init(&b.p_full[2 * t + 1], kWarpArrive ? kTileM / 32 : kTileM);
       mbar_init(&b.o_full[t], 1);
       mbar_init(&b.o_free[t], kTileM);
       mbar_init(&b.pv_half[t], 1);
@@ -181,7 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t tmem_base = *tmem_ptr_smem;
   // scratch split-KV: let the combine kernel (launched with programmatic stream serialisation) be set up now; its
   // griddepcontrol.wait still holds it until this grid has completed and flushed
-  if (!kCluster && num_splits > 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (!kFused && num_splits > 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp < 8) {
     // =====================================================================================
@@ -199,7 +206,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     for (uint32_t item = blockIdx.x, it = 0; item < num_items; item += gridDim.x, ++it) {
     const uint32_t split = item % num_splits;
     // output slot; the scratch fallback lays partials out as [split][head]
-    const uint32_t head = (item / num_splits) / pairs_per_head + (kCluster ? 0u : split * batch);
+    const uint32_t head = (item / num_splits) / pairs_per_head + (kFused ? 0u : split * batch);
     const uint32_t q_row0 = ((item / num_splits) % pairs_per_head) * (kTileM * kTilesPerCta);
     const uint32_t key_block0 = split * num_blocks;
     const uint32_t g0 = it * num_blocks;  // key blocks this CTA has processed before this item (barrier phases)
@@ -254,8 +261,9 @@ __global__ void __launch_bounds__(kThreads, 1)
               pr.x = ex2_approx(x.x);
               pr.y = ex2_approx(x.y);
             }
-            sum2 = fadd2(sum2, pr);
             packed[i] = kBF16 ? pack_bf16x2(pr.x, pr.y) : pack_f16x2(pr.x, pr.y);
+            if (kSumRoundedP) pr = kBF16 ? unpack_bf16x2(packed[i]) : unpack_f16x2(packed[i]);
+            sum2 = fadd2(sum2, pr);
           }
           half_sum = sum2.x + sum2.y;
         }
@@ -296,9 +304,15 @@ __global__ void __launch_bounds__(kThreads, 1)
           for (uint32_t i = 0; i < 32; ++i) {
             const float p0 = ex2_approx(fmaf(s[c0 + 2 * i], scale_log2, -m));
             const float p1 = ex2_approx(fmaf(s[c0 + 2 * i + 1], scale_log2, -m));
-            sum0 += p0;
-            sum1 += p1;
             packed[i] = kBF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
+            if (kSumRoundedP) {
+              const float2 q = kBF16 ? unpack_bf16x2(packed[i]) : unpack_f16x2(packed[i]);
+              sum0 += q.x;
+              sum1 += q.y;
+            } else {
+              sum0 += p0;
+              sum1 += p1;
+            }
           }
           half_sum = sum0 + sum1;
         }
@@ -309,117 +323,39 @@ __global__ void __launch_bounds__(kThreads, 1)
         tc_fence_before();
         // the first 64 columns of P are released on their own so that the MMA warp starts O += P V on them while
         // the MUFU pipe works through the other half
-        mbar_arrive(&b.p_full[2 * t + half]);
+        if (kWarpArrive) {
+          // one arrival per warp: tcgen05.wait::st is warp-collective, so once the warp has passed it (and
+          // synchronised) every lane's stores are complete; 4 arrivals instead of 128 reach the MMA warp sooner
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&b.p_full[2 * t + half]);
+        } else {
+          mbar_arrive(&b.p_full[2 * t + half]);
+        }
         MFA_TRACE(warp == 0 ? 0 : (warp == 4 ? 1 : 5), j, 2 + half);
       }
       MFA_TRACE(warp == 0 ? 0 : (warp == 4 ? 1 : 5), j, 4);
     }
 
-    if constexpr (kCluster) {
-      // ---------------- cluster epilogue: reduce the splits through distributed shared memory ----------------
-      MFA_TRACE_ITEM(warp == 0 ? 4 : (warp == 4 ? 5 : 7), it, 1);
-      mbar_wait(&b.o_full[t], (g0 + num_blocks - 1) & 1);
-      // the partial overlays the K / V stages: every MMA of the CTA must be done, and tile 1's last O += P V is the
-      // last one issued (its predecessors complete in order, so this parity cannot alias an older phase)
-      mbar_wait(&b.o_full[kTilesPerCta - 1], (g0 + num_blocks - 1) & 1);
-      tc_fence_after();
-      MFA_TRACE_ITEM(warp == 0 ? 4 : (warp == 4 ? 5 : 7), it, 2);
-      constexpr uint32_t kQuadsPerRow = DPAD / 4;
-      constexpr uint32_t kPairRows = kTileM * kTilesPerCta;
-      float4 *part = reinterpret_cast<float4 *>(smem + Cfg::kSmemPart);
-      float2 *ml = reinterpret_cast<float2 *>(smem + Cfg::kSmemML);
-      {
-        const uint32_t rt = t * kTileM + row_in_tile;  // row inside the tile pair
-#pragma unroll
-        for (uint32_t c = 0; c < DPAD; c += 32) {
-          uint32_t o[32];
-          tmem_ld32(tO + c, o);
-          tc_wait_ld();
-#pragma unroll
-          for (uint32_t q = 0; q < 8; ++q)
-            part[rt * kQuadsPerRow + ((c / 4 + q) ^ (rt & 7))] =
-                make_float4(__uint_as_float(o[4 * q]), __uint_as_float(o[4 * q + 1]), __uint_as_float(o[4 * q + 2]),
-                            __uint_as_float(o[4 * q + 3]));
-        }
-        ml[rt] = make_float2(m, l);
-      }
-      cluster_arrive_release();
-      cluster_wait_acquire();
-      MFA_TRACE_ITEM(warp == 0 ? 4 : (warp == 4 ? 5 : 7), it, 4);
-      // rank `split` owns rows [split * rows_per_rank, (split + 1) * rows_per_rank) of the pair: thread <-> (row, 16 B
-      // column slot), 32 (DPAD 128) or 16 (DPAD 64) consecutive threads per row, so global stores are full lines
-      const uint32_t rows_per_rank = (kPairRows + num_splits - 1) / num_splits;
-      const uint32_t quad = threadIdx.x % kQuadsPerRow;
-      const uint32_t part_addr = smem_u32(part), ml_addr = smem_u32(ml);
-      uint32_t part_rank[8], ml_rank[8];
-#pragma unroll
-      for (uint32_t s = 0; s < 8; ++s) {
-        // start with the own partial, then walk the ring: spreads the remote reads over the cluster
-        const uint32_t src = s < num_splits ? (split + s) % num_splits : split;
-        part_rank[s] = map_shared_rank(part_addr, src);
-        ml_rank[s] = map_shared_rank(ml_addr, src);
-      }
-      for (uint32_t r = threadIdx.x / kQuadsPerRow; r < rows_per_rank; r += (kThreads - 128) / kQuadsPerRow) {
-        const uint32_t rt = split * rows_per_rank + r;
-        if (rt >= kPairRows) break;
-        float2 mls[8];
-        float4 v[8];
-#pragma unroll
-        for (uint32_t s = 0; s < 8; ++s)
-          if (s < num_splits) {
-            mls[s] = ld_dsmem_f32x2(ml_rank[s] + rt * 8);
-            v[s] = ld_dsmem_f32x4(part_rank[s] + (rt * kQuadsPerRow + (quad ^ (rt & 7))) * 16);
-          }
-        float m_all = -FLT_MAX;
-#pragma unroll
-        for (uint32_t s = 0; s < 8; ++s)
-          if (s < num_splits) m_all = fmaxf(m_all, mls[s].x);
-        float denom = 0.f;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (uint32_t s = 0; s < 8; ++s)
-          if (s < num_splits) {
-            const float w = exp2f(mls[s].x - m_all);
-            denom = fmaf(w, mls[s].y, denom);
-            acc.x = fmaf(w, v[s].x, acc.x);
-            acc.y = fmaf(w, v[s].y, acc.y);
-            acc.z = fmaf(w, v[s].z, acc.z);
-            acc.w = fmaf(w, v[s].w, acc.w);
-          }
-        const float inv = 1.0f / denom;
-        const uint32_t row = q_row0 + rt;
-        if (row < R) {
-          if (4 * quad < D)
-            *reinterpret_cast<float4 *>(O + (static_cast<size_t>(head) * R + row) * D + 4 * quad) =
-                make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
-          if (quad == 0 && L != nullptr) {
-            const float lse2 = m_all + log2f(denom);  // AttentionKernel+Caching.swift:373-377
-            const size_t idx = static_cast<size_t>(head) * R + row;
-            if (l_is_fp16)
-              reinterpret_cast<__half *>(L)[idx] = __float2half_rn(lse2);
-            else
-              reinterpret_cast<float *>(L)[idx] = lse2;
-          }
-        }
-      }
-      MFA_TRACE_ITEM(warp == 0 ? 4 : (warp == 4 ? 5 : 7), it, 5);
-      // no CTA may exit (or reuse its shared memory) while a peer is still reading its partial
-      cluster_arrive_release();
-      cluster_wait_acquire();
-    } else {
+    {
       // ---------------- epilogue: O / l -> global (FP32), L = m + log2(l) ----------------
+      // (fused split-KV: the RAW accumulator -> this split's slot of the workspace instead, then the merge below)
       MFA_TRACE_ITEM(warp == 0 ? 4 : (warp == 4 ? 5 : 7), it, 1);
       mbar_wait(&b.o_full[t], (g0 + num_blocks - 1) & 1);
       tc_fence_after();
       MFA_TRACE_ITEM(warp == 0 ? 4 : (warp == 4 ? 5 : 7), it, 2);
       const uint32_t row = q_row0 + t * kTileM + row_in_tile;
-      const float inv_l = 1.0f / l;
+      const uint32_t pair_item = item / num_splits;  // (head, tile pair)
+      const float out_scale = kFused ? 1.0f : 1.0f / l;
       // TMEM hands every thread one row; storing rows straight from registers would touch 32 different cache
       // lines per warp store.  Each warp therefore transposes 32 x 32 chunks through a private XOR-swizzled scratch
       // tile in shared memory (128-bit accesses, conflict-free both ways) and writes four full 128 B lines per store.
-      float4 *scratch = reinterpret_cast<float4 *>(smem + Cfg::kSmemScratch) + warp * (32 * 8);
+      const uint32_t scratch = smem_u32(smem + Cfg::kSmemScratch) + warp * (32 * 8 * 16);  // this warp's 4 KB tile
       const uint32_t warp_row0 = q_row0 + t * kTileM + (warp & 3) * 32;
-      float *o_base = O + (static_cast<size_t>(head) * R + warp_row0) * D;
+      // rows the stores may touch: the problem's R rows, or all 256 slots of the pair in the workspace
+      const uint32_t row_limit = kFused ? q_row0 + kTileM * kTilesPerCta : R;
+      float *o_base = kFused ? part_O + ((static_cast<size_t>(pair_item) * num_splits + split) * (kTileM * kTilesPerCta) +
+                                         (t * kTileM + (warp & 3) * 32)) * D
+                             : O + (static_cast<size_t>(head) * R + warp_row0) * D;
       const uint32_t sub_row = lane >> 3, quad = lane & 7;  // transposed view: 4 rows x 8 float4 per warp access
   #pragma unroll
       for (uint32_t c = 0; c < DPAD; c += 32) {
@@ -428,9 +364,9 @@ __global__ void __launch_bounds__(kThreads, 1)
         tc_wait_ld();
   #pragma unroll
         for (uint32_t j = 0; j < 8; ++j)
-          scratch[lane * 8 + (j ^ (lane & 7))] =
-              make_float4(__uint_as_float(o[4 * j]) * inv_l, __uint_as_float(o[4 * j + 1]) * inv_l,
-                          __uint_as_float(o[4 * j + 2]) * inv_l, __uint_as_float(o[4 * j + 3]) * inv_l);
+          sts_f32x4(scratch + (lane * 8 + (j ^ (lane & 7))) * 16,
+                    make_float4(__uint_as_float(o[4 * j]) * out_scale, __uint_as_float(o[4 * j + 1]) * out_scale,
+                                __uint_as_float(o[4 * j + 2]) * out_scale, __uint_as_float(o[4 * j + 3]) * out_scale));
         __syncwarp();
         // read the whole transposed chunk into distinct registers BEFORE the first store: a store keeps its source
         // registers busy until the data has left the SM, so reusing a handful of registers would serialise the
@@ -439,24 +375,106 @@ __global__ void __launch_bounds__(kThreads, 1)
   #pragma unroll
         for (uint32_t i = 0; i < 8; ++i) {
           const uint32_t r = 4 * i + sub_row;
-          v[i] = scratch[r * 8 + (quad ^ (r & 7))];
+          v[i] = lds_f32x4(scratch + (r * 8 + (quad ^ (r & 7))) * 16);
         }
         if (c + 4 * quad < D) {  // D % 8 == 0: a float4 is either fully inside or fully outside
   #pragma unroll
           for (uint32_t i = 0; i < 8; ++i) {
             const uint32_t r = 4 * i + sub_row;
-            if (warp_row0 + r < R) *reinterpret_cast<float4 *>(o_base + static_cast<size_t>(r) * D + c + 4 * quad) = v[i];
+            if (warp_row0 + r < row_limit) *reinterpret_cast<float4 *>(o_base + static_cast<size_t>(r) * D + c + 4 * quad) = v[i];
           }
         }
         __syncwarp();
       }
-      if (row < R && L != nullptr) {
-        const float lse2 = m + log2f(l);  // AttentionKernel+Caching.swift:373-377
-        const size_t idx = static_cast<size_t>(head) * R + row;
-        if (l_is_fp16)
-          reinterpret_cast<__half *>(L)[idx] = __float2half_rn(lse2);
-        else
-          reinterpret_cast<float *>(L)[idx] = lse2;
+      if constexpr (!kFused) {
+        if (row < R && L != nullptr) {
+          const float lse2 = m + log2f(l);  // AttentionKernel+Caching.swift:373-377
+          const size_t idx = static_cast<size_t>(head) * R + row;
+          if (l_is_fp16)
+            reinterpret_cast<__half *>(L)[idx] = __float2half_rn(lse2);
+          else
+            reinterpret_cast<float *>(L)[idx] = lse2;
+        }
+      } else {
+        // ---------------- fused split-KV: publish the partial, wait for the siblings, merge a slice of the rows ------
+        constexpr uint32_t kPairRows = kTileM * kTilesPerCta;
+        const size_t slot0 = static_cast<size_t>(pair_item) * num_splits * kPairRows;  // first row slot of this pair
+        part_ml[slot0 + static_cast<size_t>(split) * kPairRows + t * kTileM + row_in_tile] = make_float2(m, l);
+        __threadfence();  // the partial is visible device-wide before the arrival is
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight softmax warps
+        uint32_t *arrived = counters + 2 * pair_item, *merged = arrived + 1;
+        if (threadIdx.x == 0) {
+          atomicAdd(arrived, 1u);
+          // bounded spin (a protocol bug must trap, not hang): the siblings are co-resident, so this is short
+          const long long start = clock64();
+          uint32_t seen;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrived) : "memory");
+            if (seen < num_splits && clock64() - start > MFA_MBAR_TIMEOUT_CYCLES) {
+              printf("mfa_b200: split-KV arrival timeout block %d (%u of %u)\n", blockIdx.x, seen, num_splits);
+              __trap();
+            }
+          } while (seen < num_splits);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        MFA_TRACE_ITEM(warp == 0 ? 4 : (warp == 4 ? 5 : 7), it, 4);
+        // rows [split * rows_per_rank, ...) of the pair: thread <-> (row, 16 B column slot), DPAD / 4 consecutive threads
+        // per row, so the global stores are full lines; every load of a thread is issued before the first use
+        constexpr uint32_t kQuadsPerRow = DPAD / 4;
+        const uint32_t rows_per_rank = (kPairRows + num_splits - 1) / num_splits;
+        const uint32_t mq = threadIdx.x % kQuadsPerRow;
+        for (uint32_t r = threadIdx.x / kQuadsPerRow; r < rows_per_rank; r += 256 / kQuadsPerRow) {
+          const uint32_t rt = split * rows_per_rank + r;
+          if (rt >= kPairRows) break;
+          float2 mls[16];
+          float4 vs[16];
+#pragma unroll
+          for (uint32_t sp = 0; sp < 16; ++sp) {
+            mls[sp] = make_float2(-FLT_MAX, 0.f);
+            vs[sp] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (sp < num_splits) {
+              const size_t slot = slot0 + static_cast<size_t>(sp) * kPairRows + rt;
+              mls[sp] = __ldcg(part_ml + slot);
+              if (4 * mq < D) vs[sp] = __ldcg(reinterpret_cast<const float4 *>(part_O + slot * D) + mq);
+            }
+          }
+          float m_all = -FLT_MAX;
+#pragma unroll
+          for (uint32_t sp = 0; sp < 16; ++sp) m_all = fmaxf(m_all, mls[sp].x);
+          float denom = 0.f;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (uint32_t sp = 0; sp < 16; ++sp) {
+            const float w = exp2f(mls[sp].x - m_all);  // unused slots: l = 0 and O = 0, so their weight is irrelevant
+            denom = fmaf(w, mls[sp].y, denom);
+            acc.x = fmaf(w, vs[sp].x, acc.x);
+            acc.y = fmaf(w, vs[sp].y, acc.y);
+            acc.z = fmaf(w, vs[sp].z, acc.z);
+            acc.w = fmaf(w, vs[sp].w, acc.w);
+          }
+          const float inv = 1.0f / denom;
+          const uint32_t out_row = q_row0 + rt;
+          if (out_row < R) {
+            if (4 * mq < D)
+              *reinterpret_cast<float4 *>(O + (static_cast<size_t>(head) * R + out_row) * D + 4 * mq) =
+                  make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+            if (mq == 0 && L != nullptr) {
+              const float lse2 = m_all + log2f(denom);  // AttentionKernel+Caching.swift:373-377
+              const size_t idx = static_cast<size_t>(head) * R + out_row;
+              if (l_is_fp16)
+                reinterpret_cast<__half *>(L)[idx] = __float2half_rn(lse2);
+              else
+                reinterpret_cast<float *>(L)[idx] = lse2;
+            }
+          }
+        }
+        // the last CTA to finish reading returns both counters to zero for the next launch on this stream
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 0 && atomicAdd(merged, 1u) == num_splits - 1) {
+          *arrived = 0;
+          *merged = 0;
+        }
+        MFA_TRACE_ITEM(warp == 0 ? 4 : (warp == 4 ? 5 : 7), it, 5);
       }
     }
     // O of this tile is out of TMEM: the next item's first O = P V (accumulate off) may overwrite it
@@ -614,15 +632,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       MFA_TRACE_ITEM(6, it, 2);
       }  // work items
     }
-    if constexpr (kCluster) {
-      // the producer warpgroup takes part in the two cluster barriers of the softmax warps' epilogue
-      cluster_arrive_release();
-      cluster_wait_acquire();
-      cluster_arrive_release();
-      cluster_wait_acquire();
-    }
   }
-
 
   // ---------------- teardown ----------------
   tc_fence_before();
@@ -695,163 +705,93 @@ static uint32_t choose_splits(uint32_t items, uint32_t total_blocks, uint32_t sm
   return best;
 }
 
-constexpr uint32_t kMaxClusterSplits = 8;  // portable cluster size
-
-template <typename Kernel>
-static cudaLaunchConfig_t cluster_config(Kernel, uint32_t grid, uint32_t smem_bytes, cudaStream_t stream,
-                                         cudaLaunchAttribute *attr, uint32_t splits) {
-  cudaLaunchConfig_t config = {};
-  config.gridDim = dim3(grid, 1, 1);
-  config.blockDim = dim3(kThreads, 1, 1);
-  config.dynamicSmemBytes = smem_bytes;
-  config.stream = stream;
-  attr->id = cudaLaunchAttributeClusterDimension;
-  attr->val.clusterDim.x = splits;
-  attr->val.clusterDim.y = 1;
-  attr->val.clusterDim.z = 1;
-  config.attrs = attr;
-  config.numAttrs = 1;
-  return config;
-}
-
-// max_clusters[s]: how many clusters of s CTAs (each CTA owns a whole SM) the device can hold at once
-template <uint32_t DPAD, bool kBF16>
-static const int *cluster_occupancy() {
-  using Cfg = Config<DPAD>;
-  auto kernel = attention_forward_tcgen05<DPAD, kBF16, false, true>;
-  static std::once_flag once;
-  static int max_clusters[kMaxClusterSplits + 1] = {};
-  std::call_once(once, [&] {
-    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) {
-      cudaGetLastError();
-      return;
-    }
-    for (uint32_t s = 2; s <= kMaxClusterSplits; ++s) {
-      cudaLaunchAttribute attr;
-      cudaLaunchConfig_t config = cluster_config(kernel, s, Cfg::kSmemBytes, nullptr, &attr, s);
-      int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, kernel, &config) == cudaSuccess)
-        max_clusters[s] = n;
-      else
-        cudaGetLastError();
-    }
-  });
-  return max_clusters;
-}
-
-// Largest split count (<= 8) whose clusters can all be co-resident: `items` clusters of `splits` CTAs have to fit the
-// GPCs at once or the launch runs in waves.  0 = use the scratch fallback.
-template <uint32_t DPAD, bool kBF16>
-static uint32_t choose_cluster_splits(uint32_t items, uint32_t total_blocks, uint32_t sm_count) {
-  const int *max_clusters = cluster_occupancy<DPAD, kBF16>();
-  if (items * 2 > sm_count) return 0;
-  const uint32_t target = sm_count / items;
-  for (uint32_t s = target < kMaxClusterSplits ? target : kMaxClusterSplits; s >= 2; --s)
-    if (total_blocks % s == 0 && total_blocks / s >= 4 && static_cast<uint32_t>(max_clusters[s]) >= items) return s;
-  return 0;
-}
-
 template <uint32_t DPAD, bool kBF16, bool kTrace = false>
 cudaError_t launch(const AttentionParams &p, cudaStream_t stream, long long *trace = nullptr) {
   using Cfg = Config<DPAD>;
-  auto kernel = attention_forward_tcgen05<DPAD, kBF16, kTrace>;
-  static std::once_flag once;
-  static cudaError_t attr_status = cudaSuccess;
-  std::call_once(once, [&] {
-    attr_status = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-  });
-  if (attr_status != cudaSuccess) return attr_status;
+  auto kernel = attention_forward_tcgen05<DPAD, kBF16, kTrace, false>;
+  const int device = current_device();
+  cudaError_t e;
+  if ((e = ensure_max_dynamic_smem(reinterpret_cast<const void *>(kernel), Cfg::kSmemBytes, device)) != cudaSuccess) return e;
 
   CUtensorMap mapQ, mapK, mapV;
-  cudaError_t e;
   if ((e = make_tensor_map_16bit(&mapQ, p.buf[sQ], p.R, p.D, p.batch, kTileM)) != cudaSuccess) return e;
   if ((e = make_tensor_map_16bit(&mapK, p.buf[sK], p.C, p.D, p.batch, kBlockN)) != cudaSuccess) return e;
   if ((e = make_tensor_map_16bit(&mapV, p.buf[sV], p.C, p.D, p.batch, kBlockN)) != cudaSuccess) return e;
 
   const uint32_t pairs_per_head = (p.R + kTileM * kTilesPerCta - 1) / (kTileM * kTilesPerCta);
   const uint32_t num_items = pairs_per_head * p.batch;
-  static int sm_count = 0;
-  if (sm_count == 0) {
-    int device = 0;
-    if ((e = cudaGetDevice(&device)) != cudaSuccess) return e;
-    if ((e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return e;
-  }
+  const uint32_t sm_count = device_sm_count(device);
   const uint32_t total_blocks = (p.C + kBlockN - 1) / kBlockN;
   const int l_is_fp16 = p.prec[sL] == FP16 ? 1 : 0;
 
-  // split-KV, preferred form: one cluster per item, reduced through distributed shared memory inside the kernel
-  {
-    const uint32_t cluster_splits =
-        g_forward_cluster_enabled ? choose_cluster_splits<DPAD, kBF16>(num_items, total_blocks, static_cast<uint32_t>(sm_count)) : 0;
-    if (cluster_splits > 1) {
-      auto cluster_kernel = attention_forward_tcgen05<DPAD, kBF16, kTrace, true>;
-      if (kTrace) {
-        static std::once_flag trace_once;
-        std::call_once(trace_once, [&] {
-          cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-        });
-      }
-      cudaLaunchAttribute attr;
-      cudaLaunchConfig_t config =
-          cluster_config(cluster_kernel, num_items * cluster_splits, Cfg::kSmemBytes, stream, &attr, cluster_splits);
-      e = cudaLaunchKernelEx(&config, cluster_kernel, mapQ, mapK, mapV, static_cast<float *>(p.buf[sO]), p.buf[sL], p.R,
-                             p.C, p.D, p.scale_log2, l_is_fp16, num_items * cluster_splits, pairs_per_head,
-                             cluster_splits, p.batch, trace);
-      if (e == cudaSuccess) return cudaGetLastError();
-      cudaGetLastError();  // cluster launch refused (e.g. partitioned GPU): fall through to the scratch path
-    }
-  }
-
-  const uint32_t splits = choose_splits(num_items, total_blocks, static_cast<uint32_t>(sm_count));
+  const uint32_t splits = choose_splits(num_items, total_blocks, sm_count);
   if (splits == 1) {
-    const uint32_t grid = num_items < static_cast<uint32_t>(sm_count) ? num_items : static_cast<uint32_t>(sm_count);
+    const uint32_t grid = num_items < sm_count ? num_items : sm_count;
     kernel<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mapQ, mapK, mapV, static_cast<float *>(p.buf[sO]), p.buf[sL],
                                                         p.R, p.C, p.D, p.scale_log2, l_is_fp16, num_items,
-                                                        pairs_per_head, 1u, p.batch, trace);
+                                                        pairs_per_head, 1u, p.batch, nullptr, nullptr, nullptr, trace);
     return cudaGetLastError();
   }
-  // split-KV fallback: partial O / L in stream-ordered scratch, then the combine kernel
-  const uint64_t rows_total = static_cast<uint64_t>(p.batch) * p.R;
-  const size_t o_bytes = static_cast<size_t>(splits) * rows_total * p.D * sizeof(float);
-  const size_t l_bytes = static_cast<size_t>(splits) * rows_total * sizeof(float);
-  // keep freed scratch cached in the device's default memory pool instead of returning it to the OS at every
-  // synchronisation (the default release threshold is 0)
-  static std::once_flag pool_once;
-  std::call_once(pool_once, [] {
-    int device = 0;
-    cudaMemPool_t pool;
-    if (cudaGetDevice(&device) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-      uint64_t threshold = UINT64_MAX;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
-    }
-  });
-  float *scratch = nullptr;
-  if ((e = cudaMallocAsync(reinterpret_cast<void **>(&scratch), o_bytes + l_bytes, stream)) != cudaSuccess) return e;
-  float *L_part = scratch + static_cast<size_t>(splits) * rows_total * p.D;
-  const uint32_t split_items = num_items * splits;
-  const uint32_t grid = split_items < static_cast<uint32_t>(sm_count) ? split_items : static_cast<uint32_t>(sm_count);
-  kernel<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mapQ, mapK, mapV, scratch, L_part, p.R, p.C, p.D, p.scale_log2,
-                                                      0, split_items, pairs_per_head, splits, p.batch, trace);
-  e = cudaGetLastError();
-  if (e == cudaSuccess) {
-    const uint64_t threads = rows_total * (p.D / 4);
+
+  // ---- split-KV: partials live in the library's per-(device, stream) workspace -----------------------------------
+  const uint32_t split_items = num_items * splits;  // <= sm_count by construction of choose_splits
+  constexpr uint32_t kPairRows = kTileM * kTilesPerCta;
+  if (g_forward_fused_enabled && split_items <= sm_count && 2 * num_items * sizeof(uint32_t) <= kWorkspaceCounterBytes) {
+    // fused form: one cooperative launch (every CTA resident, one item each); [counters | O partials | (m, l)]
+    auto fused = attention_forward_tcgen05<DPAD, kBF16, kTrace, true>;
+    if ((e = ensure_max_dynamic_smem(reinterpret_cast<const void *>(fused), Cfg::kSmemBytes, device)) != cudaSuccess) return e;
+    const size_t slots = static_cast<size_t>(split_items) * kPairRows;
+    const size_t o_bytes = slots * p.D * sizeof(float), ml_bytes = slots * sizeof(float2);
+    void *ws = nullptr;
+    if ((e = workspace_for(device, stream, o_bytes + ml_bytes, &ws)) != cudaSuccess) return e;
+    uint32_t *counters = static_cast<uint32_t *>(ws);
+    float *part_O = reinterpret_cast<float *>(static_cast<char *>(ws) + kWorkspaceCounterBytes);
+    float2 *part_ml = reinterpret_cast<float2 *>(reinterpret_cast<char *>(part_O) + o_bytes);
     cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr.val.programmaticStreamSerializationAllowed = 1;
+    attr.id = cudaLaunchAttributeCooperative;
+    attr.val.cooperative = 1;
     cudaLaunchConfig_t config = {};
-    config.gridDim = dim3(static_cast<uint32_t>((threads + 127) / 128), 1, 1);
-    config.blockDim = dim3(128, 1, 1);
+    config.gridDim = dim3(split_items, 1, 1);
+    config.blockDim = dim3(kThreads, 1, 1);
+    config.dynamicSmemBytes = Cfg::kSmemBytes;
     config.stream = stream;
     config.attrs = &attr;
     config.numAttrs = 1;
-    auto combine = splits <= 4 ? combine_splits<4> : (splits <= 8 ? combine_splits<8> : combine_splits<16>);
-    e = cudaLaunchKernelEx(&config, combine, static_cast<const float *>(scratch), static_cast<const float *>(L_part),
-                           static_cast<float *>(p.buf[sO]), p.buf[sL], static_cast<uint32_t>(rows_total), p.D, splits,
-                           l_is_fp16);
-    if (e == cudaSuccess) e = cudaGetLastError();
+    e = cudaLaunchKernelEx(&config, fused, mapQ, mapK, mapV, static_cast<float *>(p.buf[sO]), p.buf[sL], p.R, p.C, p.D,
+                           p.scale_log2, l_is_fp16, split_items, pairs_per_head, splits, p.batch, part_O, part_ml,
+                           counters, trace);
+    if (e == cudaSuccess) return cudaGetLastError();
+    cudaGetLastError();  // cooperative launch refused (e.g. a partitioned GPU): fall through to the two-launch form
   }
-  cudaError_t free_status = cudaFreeAsync(scratch, stream);
-  return e != cudaSuccess ? e : free_status;
+
+  // scratch form: normalised partial O / L per split ([split][head][row]), then the combine kernel
+  const uint64_t rows_total = static_cast<uint64_t>(p.batch) * p.R;
+  const size_t o_bytes = static_cast<size_t>(splits) * rows_total * p.D * sizeof(float);
+  const size_t l_bytes = static_cast<size_t>(splits) * rows_total * sizeof(float);
+  void *ws = nullptr;
+  if ((e = workspace_for(device, stream, o_bytes + l_bytes, &ws)) != cudaSuccess) return e;
+  float *scratch = reinterpret_cast<float *>(static_cast<char *>(ws) + kWorkspaceCounterBytes);
+  float *L_part = scratch + static_cast<size_t>(splits) * rows_total * p.D;
+  const uint32_t grid = split_items < sm_count ? split_items : sm_count;
+  kernel<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mapQ, mapK, mapV, scratch, L_part, p.R, p.C, p.D, p.scale_log2,
+                                                      0, split_items, pairs_per_head, splits, p.batch, nullptr, nullptr,
+                                                      nullptr, trace);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  const uint64_t threads = rows_total * (p.D / 4);
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t config = {};
+  config.gridDim = dim3(static_cast<uint32_t>((threads + 127) / 128), 1, 1);
+  config.blockDim = dim3(128, 1, 1);
+  config.stream = stream;
+  config.attrs = &attr;
+  config.numAttrs = 1;
+  auto combine = splits <= 4 ? combine_splits<4> : (splits <= 8 ? combine_splits<8> : combine_splits<16>);
+  e = cudaLaunchKernelEx(&config, combine, static_cast<const float *>(scratch), static_cast<const float *>(L_part),
+                         static_cast<float *>(p.buf[sO]), p.buf[sL], static_cast<uint32_t>(rows_total), p.D, splits,
+                         l_is_fp16);
+  return e == cudaSuccess ? cudaGetLastError() : e;
 }
 
 }  // namespace fwd
@@ -883,10 +823,6 @@ cudaError_t launch_tcgen05_forward(const AttentionParams &p, cudaStream_t stream
   return bf16 ? fwd::launch<128, true>(p, stream) : fwd::launch<128, false>(p, stream);
 }
 
-int tcgen05_forward_max_clusters(uint32_t splits) {
-  return splits <= fwd::kMaxClusterSplits ? fwd::cluster_occupancy<128, true>()[splits] : 0;
-}
-
 // Debug entry (not in include/mfa_b200.h): the D=128 bf16 forward with pipeline timestamps of CTA (0,0)
 // written to `trace` (3 roles x 64 iterations x 8 slots of clock64()).  Used by scripts/trace_forward.py.
 cudaError_t launch_tcgen05_forward_trace(const AttentionParams &p, cudaStream_t stream, long long *trace) {
@@ -896,17 +832,11 @@ cudaError_t launch_tcgen05_forward_trace(const AttentionParams &p, cudaStream_t 
 // 1 launch, or 2 (attention + combine) when the scratch form of split-KV engages for this problem size
 uint32_t tcgen05_forward_launch_count(uint32_t R, uint32_t C, uint32_t D, uint32_t batch) {
   if (D > 128) return 1;
-  int device = 0, sm_count = 148;
-  if (cudaGetDevice(&device) == cudaSuccess)
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
+  const uint32_t sm_count = device_sm_count(current_device());
   const uint32_t pairs = (R + fwd::kTileM * fwd::kTilesPerCta - 1) / (fwd::kTileM * fwd::kTilesPerCta);
   const uint32_t blocks = (C + fwd::kBlockN - 1) / fwd::kBlockN;
-  if (g_forward_cluster_enabled) {
-    const uint32_t cs = D <= 64 ? fwd::choose_cluster_splits<64, true>(pairs * batch, blocks, static_cast<uint32_t>(sm_count))
-                                : fwd::choose_cluster_splits<128, true>(pairs * batch, blocks, static_cast<uint32_t>(sm_count));
-    if (cs > 1) return 1;  // cluster split-KV reduces inside the attention kernel
-  }
-  return fwd::choose_splits(pairs * batch, blocks, static_cast<uint32_t>(sm_count)) > 1 ? 2 : 1;
+  if (fwd::choose_splits(pairs * batch, blocks, sm_count) == 1) return 1;
+  return g_forward_fused_enabled ? 1 : 2;  // fused split-KV merges inside the attention kernel
 }
 
 void tcgen05_forward_geometry(uint32_t D, uint32_t *threads, uint32_t *smem_bytes, uint32_t *par, uint32_t *trav,

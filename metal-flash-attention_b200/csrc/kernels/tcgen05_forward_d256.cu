@@ -26,9 +26,8 @@
 #include <float.h>
 #include <stdint.h>
 
-#include <mutex>
-
 #include "attention_params.h"
+#include "device_state.h"
 #include "sm100_ptx.cuh"
 #include "tma_host.h"
 
@@ -509,15 +508,11 @@ template <uint32_t DPAD, bool kBF16, bool kTrace = false, bool kGeneric = false>
 cudaError_t launch(const AttentionParams &p, cudaStream_t stream, long long *trace = nullptr) {
   using Cfg = Config<DPAD>;
   auto kernel = attention_forward_d256_tcgen05<DPAD, kBF16, kTrace, kGeneric>;
-  static std::once_flag once;
-  static cudaError_t attr_status = cudaSuccess;
-  std::call_once(once, [&] {
-    attr_status = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-  });
-  if (attr_status != cudaSuccess) return attr_status;
+  cudaError_t e;
+  if ((e = ensure_max_dynamic_smem(reinterpret_cast<const void *>(kernel), Cfg::kSmemBytes, current_device())) != cudaSuccess)
+    return e;
 
   CUtensorMap mapQ, mapK, mapV;
-  cudaError_t e;
   const bool tQ = kGeneric && p.transposed[sQ], tK = kGeneric && p.transposed[sK], tV = kGeneric && p.transposed[sV];
   e = tQ ? make_tensor_map_16bit_transposed(&mapQ, p.buf[sQ], p.R, p.D, p.batch, DPAD)
          : make_tensor_map_16bit(&mapQ, p.buf[sQ], p.R, p.D, p.batch, kTileM);

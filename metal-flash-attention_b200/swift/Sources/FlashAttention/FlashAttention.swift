@@ -92,22 +92,195 @@ public struct AttentionDescriptor {
     return output
   }
 
+  /// AttentionDescriptor+Precisions.swift:149-215.  P and dS read as the 16-bit input type whenever the tensor-core
+  /// family serves the descriptor (they are MMA operands there) -- see `registerPrecisions` of the kernel descriptor
+  /// for the per-kernel view.
+  public var registerPrecisions: [AttentionOperand: GEMMOperandPrecision] {
+    var descriptor = c
+    var output: [AttentionOperand: GEMMOperandPrecision] = [:]
+    for raw in UInt32(0)..<UInt32(MFA_OPERAND_COUNT) {
+      var precision = mfa_precision_t(0)
+      check(mfa_attention_descriptor_register_precision(&descriptor, mfa_operand_t(raw), &precision))
+      output[AttentionOperand(rawValue: raw)!] = GEMMOperandPrecision(rawValue: UInt16(precision.rawValue))!
+    }
+    return output
+  }
+
   /// AttentionDescriptor.swift:139-148 (R at index 0, C at index 1).
   public func setFunctionConstants(_ constants: inout mfa_function_constants_t) {
     var descriptor = c
     check(mfa_attention_descriptor_set_function_constants(&descriptor, &constants))
   }
+
+  /// The B200 parameter table this descriptor reads for `type` (AttentionDescriptor+Parameters.swift:106-285 format).
+  public func parameterFile(type: AttentionKernelType) -> String {
+    var descriptor = c
+    return String(cString: mfa_attention_descriptor_parameter_file(&descriptor, mfa_kernel_type_t(type.rawValue)))
+  }
+
+  /// Elements of `operand`'s buffer (all `batchCount` problems).
+  public func operandElements(_ operand: AttentionOperand) -> Int {
+    var descriptor = c
+    var count = 0
+    check(mfa_attention_descriptor_operand_elements(&descriptor, mfa_operand_t(operand.rawValue), &count))
+    return count
+  }
+
+  /// End-to-end call on HOST pointers (mfa_attention_run_host): H2D -> the selected kernels in the reference's order
+  /// forward -> backwardQuery -> backwardKeyValue (SquareAttentionTest.swift:355-368) -> D2H, synchronous.
+  public func runHost(types: [AttentionKernelType],
+                      hostBuffers: [AttentionOperand: UnsafeMutableRawPointer],
+                      device: Int32 = 0) {
+    var descriptor = c
+    var mask: UInt32 = 0
+    for type in types { mask |= 1 << type.rawValue }
+    var table = [UnsafeMutableRawPointer?](repeating: nil, count: Int(MFA_BUFFER_COUNT))
+    for (operand, pointer) in hostBuffers {
+      guard let binding = operand.bufferBinding else { fatalError("Operand \(operand) has no buffer binding.") }
+      table[Int(binding)] = pointer
+    }
+    check(mfa_attention_run_host(&descriptor, mask, &table, device))
+  }
 }
 
-/// AttentionKernelDescriptor.swift:7-48 -- a plain, editable value (here: the C struct).
+/// Page-locked host buffers on the GPU's NUMA node for `AttentionDescriptor.runHost` (B200 extension).
+public enum HostMemory {
+  public static func allocate(byteCount: Int, device: Int32 = 0) -> UnsafeMutableRawPointer {
+    var pointer: UnsafeMutableRawPointer?
+    check(mfa_host_alloc(byteCount, device, &pointer))
+    return pointer!
+  }
+  public static func free(_ pointer: UnsafeMutableRawPointer) { check(mfa_host_free(pointer)) }
+  /// Pins the calling thread to the CPUs of the GPU's NUMA node; returns the node (-1: none reported).
+  @discardableResult public static func bindThread(toDevice device: Int32) -> Int32 {
+    var node: Int32 = -1
+    check(mfa_host_bind_thread_to_device(device, &node))
+    return node
+  }
+  /// Frees the library's scratch and workspaces on `device`.
+  public static func releaseResources(device: Int32) { check(mfa_release_device_resources(device)) }
+}
+
+/// Which kernel family serves a descriptor (B200 extension; the reference has one family).
+public enum AttentionBackend: UInt8 {
+  case simtFP32 = 0
+  case tcgen05 = 1
+}
+
+/// AttentionKernelDescriptor.swift:7-48 -- a plain, editable value.  Every field of the reference's struct is here,
+/// readable and settable with the same types (optionals start as nil, dictionaries empty); storage is the C struct.
 public struct AttentionKernelDescriptor {
   public var c = mfa_attention_kernel_descriptor_t()
   public init() { mfa_attention_kernel_descriptor_init(&c) }
+
+  /// :8  blockDimensions
   public var blockDimensions: (parallelization: UInt16, traversal: UInt16, head: UInt16)? {
-    c.has_block_dimensions == 0 ? nil : (c.block_parallelization, c.block_traversal, c.block_head)
+    get { c.has_block_dimensions == 0 ? nil : (c.block_parallelization, c.block_traversal, c.block_head) }
+    set {
+      c.has_block_dimensions = newValue == nil ? 0 : 1
+      c.block_parallelization = newValue?.parallelization ?? 0
+      c.block_traversal = newValue?.traversal ?? 0
+      c.block_head = newValue?.head ?? 0
+    }
   }
-  public var headDimension: UInt16? { c.has_head_dimension == 0 ? nil : c.head_dimension }
-  public var type: AttentionKernelType? { c.type == 0xFF ? nil : AttentionKernelType(rawValue: UInt32(c.type)) }
+
+  /// :11  cacheState -- whether each operand stays resident on chip for the whole traversal
+  public var cacheState: [AttentionOperand: Bool] {
+    get {
+      var output: [AttentionOperand: Bool] = [:]
+      for raw in UInt32(0)..<UInt32(MFA_OPERAND_COUNT) where (c.cache_state_valid_mask >> UInt16(raw)) & 1 == 1 {
+        output[AttentionOperand(rawValue: raw)!] = (c.cache_state_mask >> UInt16(raw)) & 1 == 1
+      }
+      return output
+    }
+    set {
+      c.cache_state_valid_mask = 0
+      c.cache_state_mask = 0
+      for (operand, cached) in newValue {
+        c.cache_state_valid_mask |= 1 << UInt16(operand.rawValue)
+        if cached { c.cache_state_mask |= 1 << UInt16(operand.rawValue) }
+      }
+    }
+  }
+
+  /// :14  headDimension
+  public var headDimension: UInt16? {
+    get { c.has_head_dimension == 0 ? nil : c.head_dimension }
+    set {
+      c.has_head_dimension = newValue == nil ? 0 : 1
+      c.head_dimension = newValue ?? 0
+    }
+  }
+
+  private static func precisions(_ tuple: inout mfa_attention_kernel_descriptor_t,
+                                 register: Bool) -> [AttentionOperand: GEMMOperandPrecision] {
+    var output: [AttentionOperand: GEMMOperandPrecision] = [:]
+    for raw in UInt32(0)..<UInt32(MFA_OPERAND_COUNT) {
+      let value = mfa_attention_kernel_descriptor_get_precision(&tuple, mfa_operand_t(raw), register ? 1 : 0)
+      if value >= 0 { output[AttentionOperand(rawValue: raw)!] = GEMMOperandPrecision(rawValue: UInt16(value))! }
+    }
+    return output
+  }
+  private static func setPrecisions(_ tuple: inout mfa_attention_kernel_descriptor_t, register: Bool,
+                                    _ values: [AttentionOperand: GEMMOperandPrecision]) {
+    for raw in UInt32(0)..<UInt32(MFA_OPERAND_COUNT) {
+      let value = values[AttentionOperand(rawValue: raw)!].map { Int32($0.rawValue) } ?? -1
+      mfa_attention_kernel_descriptor_set_precision(&tuple, mfa_operand_t(raw), register ? 1 : 0, value)
+    }
+  }
+
+  /// :17  memoryPrecisions
+  public var memoryPrecisions: [AttentionOperand: GEMMOperandPrecision] {
+    get { var copy = c; return Self.precisions(&copy, register: false) }
+    set { Self.setPrecisions(&c, register: false, newValue) }
+  }
+  /// :19  registerPrecisions
+  public var registerPrecisions: [AttentionOperand: GEMMOperandPrecision] {
+    get { var copy = c; return Self.precisions(&copy, register: true) }
+    set { Self.setPrecisions(&c, register: true, newValue) }
+  }
+
+  /// :22  preferAsyncCache ("async" == TMA bulk-tensor copies on B200)
+  public var preferAsyncCache: Bool? {
+    get { c.prefer_async_cache == 0xFF ? nil : c.prefer_async_cache != 0 }
+    set { c.prefer_async_cache = newValue.map { $0 ? 1 : 0 } ?? 0xFF }
+  }
+  /// :25  preferAsyncLoad
+  public var preferAsyncLoad: Bool? {
+    get { c.prefer_async_load == 0xFF ? nil : c.prefer_async_load != 0 }
+    set { c.prefer_async_load = newValue.map { $0 ? 1 : 0 } ?? 0xFF }
+  }
+
+  /// :42  transposeState -- per operand; derivatives follow their forward operand (AttentionDescriptor.swift:96-111)
+  public var transposeState: [AttentionOperand: Bool] {
+    get {
+      var output: [AttentionOperand: Bool] = [:]
+      for raw in UInt32(0)..<UInt32(MFA_OPERAND_COUNT) where (c.transpose_state_valid_mask >> UInt16(raw)) & 1 == 1 {
+        output[AttentionOperand(rawValue: raw)!] = (c.transpose_state_mask >> UInt16(raw)) & 1 == 1
+      }
+      return output
+    }
+    set {
+      c.transpose_state_valid_mask = 0
+      c.transpose_state_mask = 0
+      for (operand, transposed) in newValue {
+        c.transpose_state_valid_mask |= 1 << UInt16(operand.rawValue)
+        if transposed { c.transpose_state_mask |= 1 << UInt16(operand.rawValue) }
+      }
+    }
+  }
+
+  /// :45  type
+  public var type: AttentionKernelType? {
+    get { c.type == 0xFF ? nil : AttentionKernelType(rawValue: UInt32(c.type)) }
+    set { c.type = newValue.map { UInt8($0.rawValue) } ?? 0xFF }
+  }
+
+  /// B200 extension: the kernel family `AttentionDescriptor.kernelDescriptor(type:)` selected.
+  public var backend: AttentionBackend {
+    get { AttentionBackend(rawValue: c.backend) ?? .simtFP32 }
+    set { c.backend = newValue.rawValue }
+  }
 }
 
 /// AttentionKernel.swift:11-50, 268-363
@@ -150,6 +323,24 @@ public final class AttentionKernel {
     check(mfa_attention_kernel_threadgroup_memory_allocation(handle, &out))
     return out
   }
+
+  /// Thread blocks along the parallelization dimension (R for forward / backwardQuery, C for backwardKeyValue) times
+  /// the batch: what the reference's caller computes for dispatchThreadgroups (SquareAttentionTest.swift:328-339).
+  public func gridSize(constants: mfa_function_constants_t) -> UInt32 {
+    var constants = constants
+    var out: UInt32 = 0
+    check(mfa_attention_kernel_grid_size(handle, &constants, &out))
+    return out
+  }
+  /// CUDA kernels one `encode` launches (2 only when a small grid is split and a merge kernel follows).
+  public func launchCount(constants: mfa_function_constants_t) -> UInt32 {
+    var constants = constants
+    var out: UInt32 = 0
+    check(mfa_attention_kernel_launch_count(handle, &constants, &out))
+    return out
+  }
+  /// Stands in for `createSource()` (AttentionKernel+Source.swift:11-55): the name of the ahead-of-time compiled kernel.
+  public var sourceName: String { String(cString: mfa_attention_kernel_source_name(handle)) }
 
   /// What the reference's callers do by hand around `createSource()` (SquareAttentionTest.swift:240-372):
   /// `buffers[binding]` are DEVICE pointers at AttentionOperand.bufferBinding; `stream` is a cudaStream_t.

@@ -10,6 +10,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import mfa_b200 as mfa
+from bench import ClockSampler   # NVML clock / throttle-reason sampler shared with bench.py
 
 KT, Op, P = mfa.AttentionKernelType, mfa.AttentionOperand, mfa.GEMMOperandPrecision
 
@@ -44,15 +45,17 @@ def run(N, D, precision, H, steps=20):
             k.encode(c, ptrs, stream)
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(steps):
-            k.encode(c, ptrs, stream)
-        b.record()
-        torch.cuda.synchronize()
+        with ClockSampler(torch.cuda.current_device()) as sampler:
+            a.record()
+            for _ in range(steps):
+                k.encode(c, ptrs, stream)
+            b.record()
+            torch.cuda.synchronize()
         ms = a.elapsed_time(b) / steps
         fma, gemm = work[t]
         out[t.name] = {"ms": round(ms, 4), "ginstrs": round(fma * N * N * H / ms / 1e6, 1),
-                       "tflops": round(gemm * N * N * D * H / ms / 1e9, 1), "kernel": k.sourceName()}
+                       "tflops": round(gemm * N * N * D * H / ms / 1e9, 1), "kernel": k.sourceName(),
+                       "clocks": sampler.summary()}
     return out
 
 

@@ -11,6 +11,8 @@ RectangularAttentionTest.swift:39-473), against the C ABI instead of Metal.
   * results are decoded, un-transposed and converted back to the oracle's units:
     L / log2(e), D * sqrt(D) (Square:405-413).
 """
+import os
+
 import numpy as np
 import torch
 
@@ -132,10 +134,30 @@ def oracle_outputs(network, backward=True):
     return out
 
 
+# Measured errors of every check() in the session; tests/conftest.py writes them to gpurun_out/parity_tests.jsonl so
+# that the achieved accuracy (not just pass / fail) of each GPU test is on record.
+RECORDS = []
+
+
+def record(name, expected, actual, tolerance=None):
+    e, a = np.asarray(expected, np.float64), np.asarray(actual, np.float64)
+    if e.size == 0:
+        return
+    err = np.abs(e - a)
+    rms = float(np.sqrt(np.mean(e * e)))
+    floor = max(1e-3 * rms, 1e-30)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        RECORDS.append({"test": os.environ.get("PYTEST_CURRENT_TEST", "").split(" (")[0], "output": name, "shape": list(e.shape), "tolerance": tolerance,
+                        "max_abs": float(np.nanmax(err)),
+                        "max_rel": float(np.nanmax(err / np.maximum(np.abs(e), floor))),
+                        "rel_rms": float(np.sqrt(np.nanmean(err * err)) / max(rms, 1e-30))})
+
+
 def check(expected, actual, tolerance, name=""):
     """check() of SquareAttentionTest.swift:513-536, but asserting (the reference only prints)."""
     expected, actual = np.asarray(expected), np.asarray(actual)
     assert expected.shape == actual.shape, (name, expected.shape, actual.shape)
+    record(name, expected, actual, tolerance)
     err = np.abs(expected - actual)
     bad = (err > tolerance) | np.isnan(err)
     # NaN/Inf-vs-NaN/Inf pairs are skipped by the reference (Square:521-524)

@@ -67,11 +67,30 @@ def test_memory_precisions_follow_reference_policy():
 
 
 def test_register_precisions():
-    r = make(lowIn=True, lowMid=True).registerPrecisions
+    # a descriptor the FP32 CUDA-core family serves (head % 8 != 0): the reference's policy verbatim
+    r = make(head=35, lowIn=True, lowMid=True).registerPrecisions
     assert r[Op.O] == r[Op.dV] == r[Op.dK] == r[Op.dQ] == P.FP32            # :209-212
     assert r[Op.dS] == P.BF16 and r[Op.dP] == P.FP32 and r[Op.P] == P.FP16  # :198-200 (native BF16 branch)
+    r = make(head=35, lowIn=True, lowMid=False).registerPrecisions
+    assert r[Op.P] == P.FP32 and r[Op.dS] == P.FP32                         # :203-205
     r = make().registerPrecisions
     assert all(v == P.FP32 for v in r.values())
+
+
+def test_register_precisions_report_what_the_tensor_core_kernels_do():
+    """On the tcgen05 family P and dS are MMA operands: always the 16-bit input element type, whatever
+    lowPrecisionIntermediates says (documented deviation from AttentionDescriptor+Precisions.swift:203-205) -- the
+    descriptor must not advertise FP32 registers the kernel does not have."""
+    for lowMid in (False, True):
+        d = make(head=64, lowIn=True, lowMid=lowMid)
+        assert d.kernelDescriptor(KT.forward).backend == mfa.Backend.tcgen05
+        r = d.registerPrecisions
+        assert r[Op.P] == P.FP16 and r[Op.dS] == P.FP16 and r[Op.dP] == P.FP32 and r[Op.S] == P.FP32
+        for t in KT:
+            kd = d.kernelDescriptor(t).registerPrecisions
+            assert kd[Op.P] == P.FP16 and kd[Op.dS] == P.FP16
+        rb = make(head=64, lowIn=True, lowMid=lowMid, bf16=True).registerPrecisions
+        assert rb[Op.P] == P.BF16 and rb[Op.dS] == P.BF16
 
 
 def test_incomplete_descriptor_is_an_error_not_a_crash():

@@ -90,3 +90,122 @@ def test_run_host_forward_only_leaves_other_outputs_untouched():
     assert np.isfinite(out["O"]).all() and np.isnan(out["dQ"]).all() and np.isnan(out["dK"]).all()
     O = nets[7].inferenceAttention()
     assert np.abs(out["O"][7] - O).max() <= 5e-3
+
+
+@pytest.mark.gpu
+def test_run_host_with_numa_local_buffers_and_release():
+    """mfa_host_alloc buffers (page-locked, first-touched on the GPU's NUMA node) through run_host; the caller's CPU
+    affinity and current device are unchanged afterwards; mfa_release_device_resources frees the scratch and the next call
+    simply allocates again."""
+    import ctypes
+    import os
+    import torch
+    import mfa_b200 as mfa
+    import oracle
+    Op = mfa.AttentionOperand
+    B, R, C, D = 6, 256, 384, 128
+    desc = mfa.AttentionDescriptor()
+    desc.lowPrecisionInputs = True
+    desc.inputPrecisionOverride = mfa.GEMMOperandPrecision.BF16
+    desc.matrixDimensions = (R, C, D)
+    desc.transposeState = (False, False, False, False)
+    desc.batchCount = B
+    nets = [oracle.Network(R, C, D, seed=40 + b, threads=8).round_inputs(oracle.BF16) for b in range(B)]
+    affinity = os.sched_getaffinity(0)
+    device = torch.cuda.current_device()
+    sizes = {Op.Q: B * R * D * 2, Op.K: B * C * D * 2, Op.V: B * C * D * 2, Op.O: B * R * D * 4, Op.L: B * R * 4}
+    addr = {op: mfa.hostAlloc(n, device) for op, n in sizes.items()}
+    try:
+        assert os.sched_getaffinity(0) == affinity, "mfa_host_alloc must not leave the thread re-bound"
+        for op, name in ((Op.Q, "Q"), (Op.K, "K"), (Op.V, "V")):
+            raw = oracle.encode(np.stack([getattr(n, name) for n in nets]).astype(np.float32), oracle.BF16)
+            ctypes.memmove(addr[op], raw.ctypes.data, raw.nbytes)
+        for round_ in range(2):
+            ctypes.memset(addr[Op.O], 0xFF, sizes[Op.O])
+            desc.runHost([mfa.AttentionKernelType.forward], addr, device=device)
+            assert torch.cuda.current_device() == device
+            O = np.ctypeslib.as_array((ctypes.c_float * (B * R * D)).from_address(addr[Op.O])).reshape(B, R, D)
+            for b in (0, B - 1):
+                assert np.abs(O[b] - nets[b].inferenceAttention()).max() <= 5e-3
+            mfa.releaseDeviceResources(device)   # second round: everything is allocated afresh
+    finally:
+        for a in addr.values():
+            mfa.hostFree(a)
+    node = mfa.bindThreadToDevice(device)
+    try:
+        assert node >= -1 and len(os.sched_getaffinity(0)) >= 1
+    finally:
+        os.sched_setaffinity(0, affinity)
+
+
+@pytest.mark.gpu
+def test_one_process_drives_two_gpus():
+    """The API lets one process use several devices (run_host takes the device; encode runs on the current one): kernel
+    attributes, SM counts, scratch and workspaces are all per device.  Skipped on a single-GPU box."""
+    import torch
+    import mfa_b200 as mfa
+    import oracle
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process")
+    KT = mfa.AttentionKernelType
+    for R, C, D, batch in ((256, 256, 128, 3), (4096, 4096, 128, 1)):   # plain and split-KV (fused, cooperative) grids
+        desc = mfa.AttentionDescriptor()
+        desc.lowPrecisionInputs = True
+        desc.inputPrecisionOverride = mfa.GEMMOperandPrecision.BF16
+        desc.matrixDimensions = (R, C, D)
+        desc.transposeState = (False, False, False, False)
+        desc.batchCount = batch
+        nets = [oracle.Network(R, C, D, seed=70 + b, threads=16).round_inputs(oracle.BF16) for b in range(batch)]
+        types = list(KT) if R <= 256 else [KT.forward]
+        for device in (0, 1, 0):
+            torch.cuda.set_device(0)
+            prev = torch.cuda.current_device()
+            Op = mfa.AttentionOperand
+            prec = desc.memoryPrecisions
+            host = {}
+            for op, name in ((Op.Q, "Q"), (Op.K, "K"), (Op.V, "V"), (Op.dO, "dO")):
+                raw = oracle.encode(np.stack([getattr(n, name) for n in nets]).astype(np.float32), int(prec[op]))
+                host[op] = torch.from_numpy(raw.view(np.int16)).pin_memory()
+            for op, shape in {Op.O: (batch, R, D), Op.L: (batch, R), Op.D: (batch, R), Op.dQ: (batch, R, D),
+                              Op.dK: (batch, C, D), Op.dV: (batch, C, D)}.items():
+                host[op] = torch.full(shape, float("nan"), dtype=torch.float32).pin_memory()
+            desc.runHost(types, {op: t.data_ptr() for op, t in host.items()}, device=device)
+            assert torch.cuda.current_device() == prev, "run_host must restore the caller's device"
+            O = nets[batch - 1].inferenceAttention()
+            assert np.abs(host[Op.O][batch - 1].numpy() - O).max() <= 5e-3, (device, R)
+            if len(types) == 3:
+                dQ = nets[0].derivativeQ()
+                assert np.abs(host[Op.dQ][0].numpy() - dQ).max() <= 5e-2, device
+
+
+@pytest.mark.gpu
+def test_batches_beyond_the_grid_limit_are_sliced():
+    """batch_count > 16384 problems per encode(): kernels that carry the batch in gridDim.y (limit 65535) are launched
+    over slices of the batch; every slice must land at the right offset."""
+    import torch
+    import mfa_b200 as mfa
+    import oracle
+    from tests.attention_harness import run_attention
+    batch, R, C, D = 16384 + 37, 16, 24, 16
+    desc = mfa.AttentionDescriptor()
+    desc.lowPrecisionInputs = True
+    desc.inputPrecisionOverride = mfa.GEMMOperandPrecision.FP16
+    desc.matrixDimensions = (R, C, D)
+    desc.transposeState = (False, False, False, False)
+    desc.batchCount = batch
+    base = oracle.Network(R, C, D, seed=5).round_inputs(oracle.FP16)
+    rng = np.random.default_rng(0)
+    scale = (1.0 + 0.25 * rng.standard_normal(batch)).astype(np.float16).astype(np.float32)[:, None, None]
+    Op = mfa.AttentionOperand
+    inputs = {Op.Q: np.broadcast_to(base.Q, (batch, R, D)).copy(), Op.K: np.broadcast_to(base.K, (batch, C, D)).copy(),
+              Op.V: oracle.roundtrip(base.V[None] * scale, oracle.FP16), Op.dO: np.broadcast_to(base.dO, (batch, R, D)).copy()}
+    out = run_attention(desc, None, inputs=inputs)
+    O = base.inferenceAttention()
+    # same Q and K everywhere, V scaled per problem: O[b] = scale'[b] * O (V was re-rounded, so compare against the
+    # rounded per-problem V through linearity in V for a few problems on both sides of the slice boundary)
+    for b in (0, 1, 16383, 16384, 16385, batch - 1):
+        net = oracle.Network(R, C, D, seed=5).round_inputs(oracle.FP16)
+        net.V = inputs[Op.V][b]
+        assert np.abs(out["O"][b] - net.inferenceAttention()).max() <= 5e-3, b
+        assert np.abs(out["dQ"][b] - net.derivativeQ()).max() <= 5e-2, b
+    assert np.isfinite(out["dV"]).all() and np.isfinite(out["dK"]).all()

@@ -68,48 +68,49 @@ def test_forward_matches_oracle(R, C, D, bf16):
 SPLIT_KV_CASES = [(4096, 4096, 128, True),   # 16 items x 8 splits: the headline single head
                   (256, 2048, 64, False),    # 1 item x 4 splits
                   (300, 2000, 128, True),    # ragged rows and a ragged last key block
-                  (512, 1536, 96, True),     # 12 key blocks -> 3 splits: cluster of 3, uneven row slices
+                  (512, 1536, 96, True),     # 12 key blocks -> 3 splits: uneven row slices in the fused merge
                   (1, 4096, 128, False),     # a single query row
                   (2048, 2048, 64, True)]    # BASELINE configs[2] shape
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("cluster", [True, False], ids=["cluster-dsmem", "scratch-combine"])
+@pytest.mark.parametrize("fused", [True, False], ids=["fused-one-launch", "scratch-combine"])
 @pytest.mark.parametrize("R,C,D,bf16", SPLIT_KV_CASES)
-def test_split_kv_small_grids(R, C, D, bf16, cluster):
-    """Few (head, tile pair) items: the key axis is split across SMs.  Preferred form: the splits of an item are one
-    thread-block cluster and reduce through distributed shared memory inside the attention kernel (1 launch);
-    fallback: partials in scratch + the combine kernel (2 launches).  Both must match the oracle."""
+def test_split_kv_small_grids(R, C, D, bf16, fused):
+    """Few (head, tile pair) items: the key axis is split across SMs.  Default form: normalised partials in the library's
+    workspace + the combine kernel (2 launches); one-launch form: every split CTA publishes its raw partial, waits on the
+    tile pair's arrival counter and merges a slice of the rows inside the attention kernel.  Both must match the oracle, also
+    when run back to back (the fused form must leave its counters at zero)."""
     import mfa_b200 as mfa
     desc = _descriptor(R, C, D, bf16)
     kernel = mfa.AttentionKernel(desc.kernelDescriptor(mfa.AttentionKernelType.forward))
     constants = mfa.FunctionConstantValues()
     desc.setFunctionConstants(constants)
-    mfa._lib.mfa_debug_set_forward_cluster(1 if cluster else 0)
+    mfa._lib.mfa_debug_set_forward_fused(1 if fused else 0)
     try:
-        assert kernel.launchCount(constants) == (1 if cluster else 2), "split-KV should engage for this grid"
+        assert kernel.launchCount(constants) == (1 if fused else 2), "split-KV should engage for this grid"
         _run_and_check(R, C, D, bf16, seed=R + C + D)
+        _run_and_check(R, C, D, bf16, seed=R + C + D + 1)
     finally:
-        mfa._lib.mfa_debug_set_forward_cluster(0)   # library default: the scratch form (faster on B200, see kernel source)
+        mfa._lib.mfa_debug_set_forward_fused(0)   # library default: scratch + combine (measured faster)
 
 
 @pytest.mark.gpu
-def test_split_kv_cluster_batched_heads_and_fp16_L():
-    """Cluster split-KV with several heads in one launch (item -> (head, pair) -> cluster) and FP16 L storage."""
+@pytest.mark.parametrize("fused", [True, False], ids=["fused-one-launch", "scratch-combine"])
+def test_split_kv_batched_heads_and_fp16_L(fused):
+    """Split-KV with several heads in one launch (item -> (head, tile, split)) and FP16 L storage."""
     import mfa_b200 as mfa
-    import oracle
-    from tests.attention_harness import run_attention, check
     H, N, D = 3, 1024, 128
     desc = _descriptor(N, N, D, True, lowMid=True, batch=H)
     kernel = mfa.AttentionKernel(desc.kernelDescriptor(mfa.AttentionKernelType.forward))
     constants = mfa.FunctionConstantValues()
     desc.setFunctionConstants(constants)
-    mfa._lib.mfa_debug_set_forward_cluster(1)
+    mfa._lib.mfa_debug_set_forward_fused(1 if fused else 0)
     try:
-        assert kernel.launchCount(constants) == 1
+        assert kernel.launchCount(constants) == (1 if fused else 2)
         _check_batched_cluster(desc, H, N, D)
     finally:
-        mfa._lib.mfa_debug_set_forward_cluster(0)
+        mfa._lib.mfa_debug_set_forward_fused(0)
 
 
 def _check_batched_cluster(desc, H, N, D):
