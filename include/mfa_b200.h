@@ -169,6 +169,14 @@ typedef struct mfa_attention_kernel_descriptor {
   uint8_t type;
   /* ---- B200 extension: which sm_100a kernel family the heuristic picked ---- */
   uint8_t backend; /* mfa_backend_t */
+  /* ---- B200 extension: the tuning columns of the parameter-table row (tcgen05 family).  Like blockDimensions they
+     are plain data the caller may edit before AttentionKernel(descriptor:); kernel creation accepts every value that has
+     a compiled instantiation (exp2_fma_quarters <= mfa_max_exp2_fma_quarters(type)) and rejects the rest. ---- */
+  uint8_t exp2_fma_quarters; /* of every 4 element pairs of P, how many take exp2 on the FMA pipe (Cody-Waite +
+                                polynomial) instead of the MUFU pipe: selects the kernel instantiation */
+  uint8_t split_min_blocks;  /* small grids: a traversal range handed to one CTA has at least this many 128-key (or
+                                128-query) blocks; 0 = never split */
+  uint8_t split_max;         /* small grids: at most this many ranges per tile (forward <= 16, backward <= 8) */
 } mfa_attention_kernel_descriptor_t;
 
 /** AttentionKernelDescriptor.init(): everything nil / empty. */
@@ -190,12 +198,24 @@ MFA_API int mfa_attention_descriptor_kernel_descriptor(const mfa_attention_descr
                                                        mfa_kernel_type_t type,
                                                        mfa_attention_kernel_descriptor_t *out);
 
-/** The parameter table text ("| maxD | par | trav | head | cached |" rows) that
- *  kernelDescriptor(type:) would parse for this descriptor -- the analogue of
- *  AttentionDescriptor.parameterFile(type:) (AttentionDescriptor+Parameters.swift:13-39).
- *  The returned pointer is static storage. */
+/** The parameter table text that kernelDescriptor(type:) would parse for this descriptor -- the analogue of
+ *  AttentionDescriptor.parameterFile(type:) (AttentionDescriptor+Parameters.swift:13-39).  Rows are the reference's
+ *  "| maxD | par | trav | head | cached |" with, for the tcgen05 family, three B200 tuning columns appended:
+ *  "| exp2 on the FMA pipe (quarters) | min blocks per split | max splits |".  The returned pointer stays valid until
+ *  the table is replaced. */
 MFA_API const char *mfa_attention_descriptor_parameter_file(const mfa_attention_descriptor_t *descriptor,
                                                             mfa_kernel_type_t type);
+
+/** The tables are DATA: this replaces the tcgen05-family table of `type` (`transposed_forward` != 0: the table of the
+ *  layout-generic forward kernel) with `text` in the format above; NULL restores the built-in table.  The text is
+ *  parsed and validated first (unknown operand names, malformed rows, tuning values without a compiled kernel are
+ *  rejected and the current table stays).  Kernels fetched from the descriptor-keyed cache afterwards follow the new
+ *  table.  At load time the library also reads the file named by the environment variable MFA_B200_PARAMETER_FILE
+ *  (sections "[forward]", "[forward.transposed]", "[backwardQuery]", "[backwardKeyValue]"; scripts/sweep.py writes
+ *  one from measurements on the current GPU).  Not thread-safe against concurrent kernelDescriptor() calls. */
+MFA_API int mfa_set_parameter_table(mfa_kernel_type_t type, int transposed_forward, const char *text);
+/** Largest exp2_fma_quarters with a compiled instantiation for `type`. */
+MFA_API int mfa_max_exp2_fma_quarters(mfa_kernel_type_t type);
 
 /** descriptor.setFunctionConstants(_:)  (AttentionDescriptor.swift:139-148): the two launch-time
  *  constants R (index 0) and C (index 1), plus the batch extension. */

@@ -82,6 +82,9 @@ class _CKernelDescriptor(ctypes.Structure):
         ("transpose_state_mask", ctypes.c_uint16),
         ("type", ctypes.c_uint8),
         ("backend", ctypes.c_uint8),
+        ("exp2_fma_quarters", ctypes.c_uint8),
+        ("split_min_blocks", ctypes.c_uint8),
+        ("split_max", ctypes.c_uint8),
     ]
 
 
@@ -129,6 +132,7 @@ def _load():
     lib.mfa_attention_run_host.argtypes = [c.POINTER(_CDescriptor), c.c_uint32,
                                            c.POINTER(c.c_void_p * MFA_BUFFER_COUNT), c.c_int]
     try:
+        lib.mfa_set_parameter_table.argtypes = [c.c_int, c.c_int, c.c_char_p]
         lib.mfa_host_alloc.argtypes = [c.c_size_t, c.c_int, c.POINTER(c.c_void_p)]
         lib.mfa_host_free.argtypes = [c.c_void_p]
         lib.mfa_host_bind_thread_to_device.argtypes = [c.c_int, c.POINTER(c.c_int)]
@@ -170,6 +174,16 @@ def bindThreadToDevice(device: int = 0) -> int:
 def releaseDeviceResources(device: int = 0) -> None:
     """mfa_release_device_resources: free the library's scratch and workspaces on `device`."""
     _check(_lib.mfa_release_device_resources(int(device)))
+
+
+def setParameterTable(type: "AttentionKernelType", text: Optional[str], transposedForward: bool = False) -> None:
+    """mfa_set_parameter_table: replace (text) or restore (None) the tcgen05-family parameter table of `type`."""
+    _check(_lib.mfa_set_parameter_table(int(type), int(bool(transposedForward)),
+                                        None if text is None else text.encode()))
+
+
+def maxExp2FmaQuarters(type: "AttentionKernelType") -> int:
+    return _lib.mfa_max_exp2_fma_quarters(int(type))
 
 
 def library_path() -> str:
@@ -423,6 +437,25 @@ class AttentionKernelDescriptor:
     def backend(self, value):
         self._c.backend = int(value)
 
+    # ---- B200 extension: the tuning columns of the parameter-table row (plain, editable data like blockDimensions)
+    @property
+    def exp2FmaQuarters(self) -> int:
+        """Of every 4 element pairs of P, how many take exp2 on the FMA pipe: selects the kernel instantiation."""
+        return self._c.exp2_fma_quarters
+
+    @exp2FmaQuarters.setter
+    def exp2FmaQuarters(self, value):
+        self._c.exp2_fma_quarters = int(value)
+
+    @property
+    def splitPolicy(self) -> Tuple[int, int]:
+        """(minimum blocks per traversal range, maximum ranges) for small grids; minimum 0 = never split."""
+        return (self._c.split_min_blocks, self._c.split_max)
+
+    @splitPolicy.setter
+    def splitPolicy(self, value):
+        self._c.split_min_blocks, self._c.split_max = (int(v) for v in value)
+
 
 # -------------------------------------------------------------------------------------------------
 # AttentionKernel
@@ -506,5 +539,5 @@ class AttentionKernel:
 __all__ = [
     "AttentionDescriptor", "AttentionKernelDescriptor", "AttentionKernel", "AttentionKernelType",
     "AttentionOperand", "GEMMOperandPrecision", "FunctionConstantValues", "Backend", "MFAError",
-    "library_path", "version", "hostAlloc", "hostFree", "bindThreadToDevice", "releaseDeviceResources",
+    "library_path", "version", "setParameterTable", "maxExp2FmaQuarters", "hostAlloc", "hostFree", "bindThreadToDevice", "releaseDeviceResources",
 ]

@@ -4,6 +4,7 @@
 //   .../AttentionDescriptor+Precisions.swift, +Parameters.swift, AttentionParameterRow.swift
 // The tables hold B200 tile shapes and on-chip residency instead of Apple register-cache choices.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -104,23 +105,27 @@ int register_precision(const mfa_attention_descriptor_t &d, int operand) {
 //     stay in SMEM/TMEM for the entire traversal.
 //   * SIMT family: 64 x 64 blocks, 32-wide head chunks, accumulators resident in registers.
 // ------------------------------------------------------------------------------------------------
+// tcgen05 rows carry three B200 tuning columns after the reference's five:
+//     | exp2 on the FMA pipe (quarters of the element pairs) | min blocks per split | max splits |
+// (measured values: scripts/sweep.py regenerates them on the current GPU and writes parameters/b200.txt, which these
+// strings reproduce; the raw timings are in profiles/r2_parameter_sweep.jsonl).
 static const char *kForwardTcgen05 =
-    "| 64  | 256 | 128 | 64  | Q, O |\n"
-    "| 128 | 256 | 128 | 128 | Q, O |\n"
-    "| 256 | 128 | 128 | 256 | Q, O |\n"
+    "| 64  | 256 | 128 | 64  | Q, O | 1 | 2 | 8 |\n"
+    "| 128 | 256 | 128 | 128 | Q, O | 0 | 4 | 8 |\n"
+    "| 256 | 128 | 128 | 256 | Q, O | 0 | 0 | 1 |\n"
     "\n";
 // forward with transposed operands: the layout-generic kernel (one 128-row tile per CTA, 128-key blocks)
 static const char *kForwardTcgen05Transposed =
-    "| 128 | 128 | 128 | 128 | Q, O |\n"
-    "| 256 | 128 | 128 | 256 | Q, O |\n"
+    "| 128 | 128 | 128 | 128 | Q, O | 0 | 0 | 1 |\n"
+    "| 256 | 128 | 128 | 256 | Q, O | 0 | 0 | 1 |\n"
     "\n";
 static const char *kBackwardQueryTcgen05 =
-    "| 64  | 128 | 128 | 64  | Q, dO, dQ |\n"
-    "| 128 | 128 | 128 | 128 | Q, dO, dQ |\n"
+    "| 64  | 128 | 128 | 64  | Q, dO, dQ | 1 | 2 | 8 |\n"
+    "| 128 | 128 | 128 | 128 | Q, dO, dQ | 0 | 2 | 8 |\n"
     "\n";
 static const char *kBackwardKeyValueTcgen05 =
-    "| 64  | 128 | 128 | 64  | K, V, dV, dK |\n"
-    "| 128 | 128 | 128 | 128 | K, V, dV, dK |\n"
+    "| 64  | 128 | 128 | 64  | K, V, dV, dK | 2 | 2 | 8 |\n"
+    "| 128 | 128 | 128 | 128 | K, V, dV, dK | 2 | 2 | 8 |\n"
     "\n";
 static const char *kForwardSimt =
     "| 512 | 64 | 64 | 32 | O |\n"
@@ -140,27 +145,53 @@ static bool any_transpose(const mfa_attention_descriptor_t &d) {
 }
 
 int select_backend(const mfa_attention_descriptor_t &d, int type) {
-  if (!d.low_precision_inputs) return MFA_BACKEND_SIMT_FP32;
+  if (!d.low_precision_inputs || d.head == 0) return MFA_BACKEND_SIMT_FP32;
+  const uint32_t padded = (static_cast<uint32_t>(d.head) + 7) / 8 * 8;
   if (any_transpose(d)) {
     // transposed operands: tensor-core forward only, and only where TMA can address the transposed view (row pitch =
     // sequence length, a multiple of 8 elements); the backward kernels take row-major operands
     if (type != MFA_FORWARD || !tcgen05_forward_transposes_ok(d.row, d.column, d.transpose_Q, d.transpose_K, d.transpose_V))
       return MFA_BACKEND_SIMT_FP32;
+    if (d.head % 8 != 0) return MFA_BACKEND_SIMT_FP32;  // (head-dimension padding is implemented for row-major operands)
   }
-  if (d.head % 8 != 0 || d.head == 0) return MFA_BACKEND_SIMT_FP32;
+  // D % 8 != 0 (row-major): the operands are staged with pad8(D) columns (kernels/pad_head.cu) and the tcgen05 kernels
+  // run at the padded head dimension -- the reference's zero-padded async copies (+OuterProduct.swift:237-254)
   const uint32_t maxHead = (type == MFA_FORWARD) ? tcgen05_forward_max_head() : tcgen05_backward_max_head();
-  if (d.head > maxHead) return MFA_BACKEND_SIMT_FP32;
+  if (padded > maxHead) return MFA_BACKEND_SIMT_FP32;
   // (the reference's own policy, FP16 Q/K/V + BF16 dO, is served too: tcgen05 kind::f16 cannot mix element types
   // inside one MMA, so the backward kernels rewrite the staged dO tile as FP16 in shared memory)
   return MFA_BACKEND_TCGEN05;
 }
 
+// The tcgen05 tables are data: mfa_set_parameter_table() / MFA_B200_PARAMETER_FILE replace them at run time.
+// slot 0 forward, 1 forward (transposed operands), 2 backwardQuery, 3 backwardKeyValue; empty = built-in
+static std::string g_table_override[4];
+static bool g_table_overridden[4] = {false, false, false, false};
+static unsigned g_table_generation = 0;
+unsigned parameter_table_generation() { return g_table_generation; }
+
+static const char *builtin_table(int slot) {
+  switch (slot) {
+    case 0: return kForwardTcgen05;
+    case 1: return kForwardTcgen05Transposed;
+    case 2: return kBackwardQueryTcgen05;
+    default: return kBackwardKeyValueTcgen05;
+  }
+}
+static int table_slot(int type, bool transposed_forward) {
+  return type == MFA_FORWARD ? (transposed_forward ? 1 : 0) : (type == MFA_BACKWARD_QUERY ? 2 : 3);
+}
+
 const char *parameter_file(const mfa_attention_descriptor_t &d, int type) {
   const bool tc = select_backend(d, type) == MFA_BACKEND_TCGEN05;
+  if (tc) {
+    const int slot = table_slot(type, type == MFA_FORWARD && any_transpose(d));
+    return g_table_overridden[slot] ? g_table_override[slot].c_str() : builtin_table(slot);
+  }
   switch (type) {
-    case MFA_FORWARD: return tc ? (any_transpose(d) ? kForwardTcgen05Transposed : kForwardTcgen05) : kForwardSimt;
-    case MFA_BACKWARD_QUERY: return tc ? kBackwardQueryTcgen05 : kBackwardQuerySimt;
-    default: return tc ? kBackwardKeyValueTcgen05 : kBackwardKeyValueSimt;
+    case MFA_FORWARD: return kForwardSimt;
+    case MFA_BACKWARD_QUERY: return kBackwardQuerySimt;
+    default: return kBackwardKeyValueSimt;
   }
 }
 
@@ -168,6 +199,8 @@ const char *parameter_file(const mfa_attention_descriptor_t &d, int type) {
 struct ParameterRow {
   unsigned maximumHeadDimension = 0;
   std::string parallelization, traversal, head, cachedOperands;
+  // B200 tuning columns (present in the tcgen05 tables; empty = defaults)
+  std::string exp2FmaQuarters, splitMinBlocks, splitMax;
 };
 
 static std::string strip_spaces(const std::string &s) {
@@ -196,7 +229,7 @@ static int parse_table(const char *file, std::vector<ParameterRow> &rows) {
       if (!seg.empty()) segments.push_back(strip_spaces(seg));
       p = bar + 1;
     }
-    if (segments.size() != 5)
+    if (segments.size() != 5 && segments.size() != 8)  // the reference's five columns, or five + three tuning columns
       return fail(MFA_ERROR_INVALID_ARGUMENT, "Number of segments was invalid: " + std::to_string(segments.size()));
     ParameterRow row;
     char *end = nullptr;
@@ -208,6 +241,11 @@ static int parse_table(const char *file, std::vector<ParameterRow> &rows) {
     row.traversal = segments[2];
     row.head = segments[3];
     row.cachedOperands = segments[4];
+    if (segments.size() == 8) {
+      row.exp2FmaQuarters = segments[5];
+      row.splitMinBlocks = segments[6];
+      row.splitMax = segments[7];
+    }
     rows.push_back(row);
   }
   return MFA_SUCCESS;
@@ -305,6 +343,19 @@ int kernel_descriptor(const mfa_attention_descriptor_t &d, int type, mfa_attenti
   }
 
   out.backend = static_cast<uint8_t>(select_backend(d, type));
+  // tuning columns (tcgen05 tables); rows without them (the FP32 family) leave the defaults: no FMA-pipe exp2, no splits
+  out.exp2_fma_quarters = 0;
+  out.split_min_blocks = 0;
+  out.split_max = 1;
+  if (!row->exp2FmaQuarters.empty()) {
+    uint16_t quarters = 0, minBlocks = 0, maxSplits = 0;
+    if (!parse_u16(row->exp2FmaQuarters, quarters) || !parse_u16(row->splitMinBlocks, minBlocks) ||
+        !parse_u16(row->splitMax, maxSplits) || quarters > 4 || minBlocks > 255 || maxSplits > 255)
+      return fail(MFA_ERROR_INVALID_ARGUMENT, "Could not decode tuning columns.");
+    out.exp2_fma_quarters = static_cast<uint8_t>(quarters);
+    out.split_min_blocks = static_cast<uint8_t>(minBlocks);
+    out.split_max = static_cast<uint8_t>(maxSplits < 1 ? 1 : maxSplits);
+  }
   // preferAsyncCache / preferAsyncLoad (:118-124): "async" == TMA bulk-tensor copies on B200.
   out.prefer_async_cache = out.backend == MFA_BACKEND_TCGEN05 ? 1 : 0;
   out.prefer_async_load = out.backend == MFA_BACKEND_TCGEN05 ? 1 : 0;
@@ -323,6 +374,45 @@ int kernel_descriptor(const mfa_attention_descriptor_t &d, int type, mfa_attenti
 }
 
 }  // namespace mfa
+
+// MFA_B200_PARAMETER_FILE: tables from a file, installed when the library is loaded.  Sections "[forward]",
+// "[forward.transposed]", "[backwardQuery]", "[backwardKeyValue]"; lines starting with '#' are comments.  A malformed
+// section is reported on stderr and skipped (the built-in table stays).
+namespace {
+struct ParameterFileLoader {
+  ParameterFileLoader() {
+    const char *path = getenv("MFA_B200_PARAMETER_FILE");
+    if (!path || !*path) return;
+    FILE *f = fopen(path, "r");
+    if (!f) {
+      fprintf(stderr, "mfa_b200: cannot open MFA_B200_PARAMETER_FILE=%s\n", path);
+      return;
+    }
+    static const char *names[4] = {"[forward]", "[forward.transposed]", "[backwardQuery]", "[backwardKeyValue]"};
+    static const int types[4] = {MFA_FORWARD, MFA_FORWARD, MFA_BACKWARD_QUERY, MFA_BACKWARD_KEY_VALUE};
+    std::string text[4];
+    int current = -1;
+    char line[1024];
+    while (fgets(line, sizeof(line), f)) {
+      std::string l(line);
+      while (!l.empty() && (l.back() == '\n' || l.back() == '\r' || l.back() == ' ')) l.pop_back();
+      if (l.empty() || l[0] == '#') continue;
+      if (l[0] == '[') {
+        current = -1;
+        for (int i = 0; i < 4; ++i)
+          if (l == names[i]) current = i;
+        continue;
+      }
+      if (current >= 0) text[current] += l + "\n";
+    }
+    fclose(f);
+    for (int i = 0; i < 4; ++i)
+      if (!text[i].empty() &&
+          mfa_set_parameter_table(static_cast<mfa_kernel_type_t>(types[i]), i == 1, text[i].c_str()) != MFA_SUCCESS)
+        fprintf(stderr, "mfa_b200: section %s of %s rejected: %s\n", names[i], path, mfa_last_error());
+  }
+} g_parameter_file_loader;
+}  // namespace
 
 // ------------------------------------------------------------------------------------------------
 // extern "C" surface
@@ -412,6 +502,52 @@ const char *mfa_attention_descriptor_parameter_file(const mfa_attention_descript
                                                     mfa_kernel_type_t type) {
   if (!descriptor) return "";
   return parameter_file(*descriptor, type);
+}
+
+int mfa_max_exp2_fma_quarters(mfa_kernel_type_t type) {
+  return type == MFA_FORWARD ? static_cast<int>(kMaxForwardExp2Quarters) : static_cast<int>(kMaxBackwardExp2Quarters);
+}
+
+int mfa_set_parameter_table(mfa_kernel_type_t type, int transposed_forward, const char *text) {
+  if (type < MFA_FORWARD || type > MFA_BACKWARD_KEY_VALUE) return fail(MFA_ERROR_INVALID_ARGUMENT, "Unrecognized kernel type.");
+  const int slot = table_slot(type, transposed_forward != 0);
+  if (!text) {
+    g_table_overridden[slot] = false;
+    g_table_override[slot].clear();
+    ++g_table_generation;
+    return MFA_SUCCESS;
+  }
+  // validate before installing: rows parse, operands are the expected ones, tuning values have a compiled kernel
+  std::vector<ParameterRow> rows;
+  int status = parse_table(text, rows);
+  if (status != MFA_SUCCESS) return status;
+  if (rows.empty()) return fail(MFA_ERROR_INVALID_ARGUMENT, "Parameter table has no rows.");
+  for (const ParameterRow &row : rows) {
+    uint16_t v = 0;
+    if (!parse_u16(row.parallelization, v) || !parse_u16(row.traversal, v) || !parse_u16(row.head, v))
+      return fail(MFA_ERROR_INVALID_ARGUMENT, "Could not decode block dimensions.");
+    std::vector<int> operands;
+    if ((status = parse_operands(row.cachedOperands, operands)) != MFA_SUCCESS) return status;
+    const uint16_t expected = type == MFA_FORWARD ? ((1u << MFA_Q) | (1u << MFA_O))
+                              : type == MFA_BACKWARD_QUERY ? ((1u << MFA_Q) | (1u << MFA_dO) | (1u << MFA_dQ))
+                                                           : ((1u << MFA_K) | (1u << MFA_V) | (1u << MFA_dV) | (1u << MFA_dK));
+    for (int operand : operands)  // createCacheState's check (AttentionDescriptor.swift:69-74), applied to every row
+      if (!(expected & (1u << operand)))
+        return fail(MFA_ERROR_UNEXPECTED_OPERAND, std::string("Unexpected operand: ") + kOperandNames[operand]);
+    if (row.exp2FmaQuarters.empty()) return fail(MFA_ERROR_INVALID_ARGUMENT, "A tcgen05 table row needs the three tuning columns.");
+    uint16_t quarters = 0, minBlocks = 0, maxSplits = 0;
+    if (!parse_u16(row.exp2FmaQuarters, quarters) || !parse_u16(row.splitMinBlocks, minBlocks) ||
+        !parse_u16(row.splitMax, maxSplits))
+      return fail(MFA_ERROR_INVALID_ARGUMENT, "Could not decode tuning columns.");
+    if (quarters > static_cast<uint16_t>(mfa_max_exp2_fma_quarters(type)))
+      return fail(MFA_ERROR_UNSUPPORTED, "exp2-on-FMA-pipe fraction " + std::to_string(quarters) +
+                                             "/4 has no compiled kernel (largest: " +
+                                             std::to_string(mfa_max_exp2_fma_quarters(type)) + "/4).");
+  }
+  g_table_override[slot] = text;
+  g_table_overridden[slot] = true;
+  ++g_table_generation;
+  return MFA_SUCCESS;
 }
 
 int mfa_attention_descriptor_set_function_constants(const mfa_attention_descriptor_t *descriptor,

@@ -85,6 +85,10 @@ static int build_params(const mfa_attention_kernel *k, const mfa_function_consta
   // dotProductScale (AttentionKernel+Softmax.swift:17-26)
   p.scale = 1.0f / std::sqrt(static_cast<float>(p.D));
   p.scale_log2 = 1.442695041f * p.scale;
+  // the tuning columns of the parameter-table row this kernel was created from
+  p.exp2_fma_quarters = k->descriptor.exp2_fma_quarters;
+  p.split_min_blocks = k->descriptor.split_min_blocks;
+  p.split_max = k->descriptor.split_max ? k->descriptor.split_max : 1;
   int n = 0;
   const int *ops = operands_of(k->type, &n);
   for (int i = 0; i < n; ++i)
@@ -133,13 +137,15 @@ int mfa_attention_kernel_create(const mfa_attention_kernel_descriptor_t *kd, mfa
     // The tcgen05 kernels only exist for 16-bit row-major operands; reject descriptors edited into
     // something they cannot serve instead of silently computing something else.
     const uint8_t pq = kd->memory_precisions[MFA_Q];
+    const uint32_t Dp = (D + 7) / 8 * 8;  // D % 8 != 0: operands are staged with pad8(D) columns (kernels/pad_head.cu)
     bool ok = (pq == MFA_FP16 || pq == MFA_BF16) && kd->memory_precisions[MFA_K] == pq &&
-              kd->memory_precisions[MFA_V] == pq && D % 8 == 0 &&
-              D <= (k->type == MFA_FORWARD ? tcgen05_forward_max_head() : tcgen05_backward_max_head());
+              kd->memory_precisions[MFA_V] == pq &&
+              Dp <= (k->type == MFA_FORWARD ? tcgen05_forward_max_head() : tcgen05_backward_max_head());
     bool transposed = false;
     for (int i = 0; i < n; ++i)
       if ((kd->transpose_state_mask >> ops[i]) & 1) transposed = true;
     if (transposed && k->type != MFA_FORWARD) ok = false;  // only the forward has a layout-generic tensor-core kernel
+    if (transposed && D % 8 != 0) ok = false;              // padding is implemented for row-major operands
     // dO: same element type, or BF16 beside FP16 Q/K/V (the reference's policy; converted on chip)
     if (k->type != MFA_FORWARD && kd->memory_precisions[MFA_dO] != pq &&
         !(pq == MFA_FP16 && kd->memory_precisions[MFA_dO] == MFA_BF16))
@@ -147,15 +153,24 @@ int mfa_attention_kernel_create(const mfa_attention_kernel_descriptor_t *kd, mfa
     if (!ok) {
       delete k;
       return fail(MFA_ERROR_UNSUPPORTED,
-                  "MFA_BACKEND_TCGEN05 needs FP16/BF16 Q,K,V (row-major for the backward kernels; dO of the same type, or BF16 with FP16 Q,K,V), head % 8 == 0 "
-                  "and head <= the compiled maximum; use MFA_BACKEND_SIMT_FP32 for this descriptor.");
+                  "MFA_BACKEND_TCGEN05 needs FP16/BF16 Q,K,V (row-major for the backward kernels and for head % 8 != 0; dO of the same "
+                  "type, or BF16 with FP16 Q,K,V) and pad8(head) <= the compiled maximum; use MFA_BACKEND_SIMT_FP32 for this "
+                  "descriptor.");
+    }
+    // tuning columns: every compiled exp2 variant is accepted, anything else is rejected with the list of what exists
+    const uint32_t max_quarters = k->type == MFA_FORWARD ? kMaxForwardExp2Quarters : kMaxBackwardExp2Quarters;
+    if (kd->exp2_fma_quarters > max_quarters) {
+      delete k;
+      return fail(MFA_ERROR_UNSUPPORTED, "exp2-on-FMA-pipe fraction " + std::to_string(kd->exp2_fma_quarters) +
+                                             "/4 has no compiled sm_100a kernel (available: 0.." +
+                                             std::to_string(max_quarters) + ").");
     }
     if (k->type == MFA_FORWARD && transposed)
       tcgen05_forward_generic_geometry(D, &k->threads, &k->smem_bytes, &k->par, &k->trav, &k->head);
     else if (k->type == MFA_FORWARD)
-      tcgen05_forward_geometry(D, &k->threads, &k->smem_bytes, &k->par, &k->trav, &k->head);
+      tcgen05_forward_geometry(Dp, &k->threads, &k->smem_bytes, &k->par, &k->trav, &k->head);
     else
-      tcgen05_backward_geometry(k->type, D, &k->threads, &k->smem_bytes, &k->par, &k->trav, &k->head);
+      tcgen05_backward_geometry(k->type, Dp, &k->threads, &k->smem_bytes, &k->par, &k->trav, &k->head);
   } else if (k->backend == MFA_BACKEND_SIMT_FP32) {
     if (D > 512) {
       delete k;
@@ -177,7 +192,11 @@ int mfa_attention_kernel_create(const mfa_attention_kernel_descriptor_t *kd, mfa
   }
   static const char *typeNames[] = {"forward", "backward_query", "backward_key_value"};
   k->source_name = std::string("attention_") + typeNames[k->type] +
-                   (k->backend == MFA_BACKEND_TCGEN05 ? "_tcgen05" : "_simt_fp32") + "<D=" + std::to_string(D) + ">";
+                   (k->backend == MFA_BACKEND_TCGEN05 ? "_tcgen05" : "_simt_fp32") + "<D=" + std::to_string(D) +
+                   (k->backend == MFA_BACKEND_TCGEN05 && D <= 128 && kd->exp2_fma_quarters
+                        ? ", exp2 on FMA pipe " + std::to_string(kd->exp2_fma_quarters) + "/4"
+                        : std::string()) +
+                   ">";
   *out = k;
   return MFA_SUCCESS;
 }
@@ -227,9 +246,14 @@ int mfa_attention_kernel_launch_count(const mfa_attention_kernel_t *kernel, cons
   if (kernel->backend == MFA_BACKEND_TCGEN05 && kernel->type == MFA_FORWARD &&
       !(kernel->descriptor.transpose_state_mask & forward_operands))  // (the layout-generic kernel never splits)
     *out = tcgen05_forward_launch_count(c->row, c->column, kernel->descriptor.head_dimension,
-                                        c->batch_count ? c->batch_count : 1);
+                                        c->batch_count ? c->batch_count : 1, kernel->descriptor.split_min_blocks,
+                                        kernel->descriptor.split_max);
   if (kernel->backend == MFA_BACKEND_TCGEN05 && kernel->type != MFA_FORWARD)
-    *out = tcgen05_backward_launch_count(kernel->type, c->row, c->column, c->batch_count ? c->batch_count : 1);
+    *out = tcgen05_backward_launch_count(kernel->type, c->row, c->column, c->batch_count ? c->batch_count : 1,
+                                         kernel->descriptor.split_min_blocks, kernel->descriptor.split_max);
+  // head % 8 != 0 on the tensor-core family: one padding copy per staged input, one un-padding copy per output
+  if (kernel->backend == MFA_BACKEND_TCGEN05 && kernel->descriptor.head_dimension % 8 != 0)
+    *out += kernel->type == MFA_FORWARD ? 4 : (kernel->type == MFA_BACKWARD_QUERY ? 6 : 6);
   return MFA_SUCCESS;
 }
 
@@ -254,12 +278,56 @@ int mfa_attention_kernel_encode(const mfa_attention_kernel_t *kernel, const mfa_
     const size_t elements = (slot == sL || slot == sD) ? seq : seq * p.D;
     head_bytes[slot] = elements * (p.prec[slot] == FP32 ? 4 : 2);
   }
+  // D % 8 != 0 on the tensor-core family: stage the operands with pad8(D) columns, run the kernels at the padded head
+  // dimension (the softmax scale stays 1 / sqrt(D) of the true D), copy the FP32 outputs back without the padding.
+  const bool padded = kernel->backend == MFA_BACKEND_TCGEN05 && p.D % 8 != 0;
+  const uint32_t Dp = (p.D + 7) / 8 * 8;
+  const int device = padded ? current_device() : 0;
   for (uint32_t h0 = 0; h0 < batch; h0 += kMaxBatchPerLaunch) {
     AttentionParams q = p;
     q.batch = batch - h0 < kMaxBatchPerLaunch ? batch - h0 : kMaxBatchPerLaunch;
     for (int slot = 0; slot < kSlots; ++slot)
       if (q.buf[slot]) q.buf[slot] = static_cast<char *>(q.buf[slot]) + head_bytes[slot] * h0;
     cudaError_t e = cudaSuccess;
+    void *user_out[kSlots] = {};  // padded path: where the un-padded outputs go
+    if (padded) {
+      // operands with a head dimension, by kernel type: inputs are staged, outputs are computed into staging
+      static const int fwd_in[] = {sQ, sK, sV}, fwd_out[] = {sO};
+      static const int dq_in[] = {sQ, sK, sV, sO, sdO}, dq_out[] = {sdQ};
+      static const int dkv_in[] = {sQ, sK, sV, sdO}, dkv_out[] = {sdV, sdK};
+      const int *ins = kernel->type == MFA_FORWARD ? fwd_in : (kernel->type == MFA_BACKWARD_QUERY ? dq_in : dkv_in);
+      const int nin = kernel->type == MFA_FORWARD ? 3 : (kernel->type == MFA_BACKWARD_QUERY ? 5 : 4);
+      const int *outs = kernel->type == MFA_FORWARD ? fwd_out : (kernel->type == MFA_BACKWARD_QUERY ? dq_out : dkv_out);
+      const int nout = kernel->type == MFA_BACKWARD_KEY_VALUE ? 2 : 1;
+      auto rows_of = [&](int slot) -> uint64_t {
+        return static_cast<uint64_t>(q.batch) * ((slot == sK || slot == sV || slot == sdK || slot == sdV) ? p.C : p.R);
+      };
+      auto bytes_of = [&](int slot) -> size_t {
+        return ((rows_of(slot) * Dp * (p.prec[slot] == FP32 ? 4 : 2)) + 255) & ~size_t(255);
+      };
+      size_t total = 0;
+      for (int i = 0; i < nin; ++i) total += bytes_of(ins[i]);
+      for (int i = 0; i < nout; ++i) total += bytes_of(outs[i]);
+      void *ws = nullptr;
+      if ((e = workspace_for(device, stream, total, &ws, /*slot=*/1)) != cudaSuccess)
+        return fail(MFA_ERROR_CUDA, std::string("padding workspace: ") + cudaGetErrorString(e) + " " + last_launch_detail());
+      char *cursor = static_cast<char *>(ws) + kWorkspaceCounterBytes;
+      for (int i = 0; i < nin && e == cudaSuccess; ++i) {
+        const int slot = ins[i];
+        e = launch_pad_columns(q.buf[slot], cursor, rows_of(slot), p.D, Dp, p.prec[slot] == FP32 ? 4 : 2, stream);
+        q.buf[slot] = cursor;
+        cursor += bytes_of(slot);
+      }
+      for (int i = 0; i < nout; ++i) {
+        const int slot = outs[i];
+        user_out[slot] = q.buf[slot];
+        q.buf[slot] = cursor;
+        cursor += bytes_of(slot);
+      }
+      q.D = Dp;  // (q.scale / q.scale_log2 keep the true head dimension)
+      if (e != cudaSuccess)
+        return fail(MFA_ERROR_CUDA, std::string("head-dimension padding failed: ") + cudaGetErrorString(e));
+    }
     if (kernel->backend == MFA_BACKEND_TCGEN05) {
       switch (kernel->type) {
         case MFA_FORWARD: e = launch_tcgen05_forward(q, stream); break;
@@ -276,6 +344,15 @@ int mfa_attention_kernel_encode(const mfa_attention_kernel_t *kernel, const mfa_
     if (e != cudaSuccess)
       return fail(MFA_ERROR_CUDA, std::string("launch of ") + kernel->source_name + " failed: " + cudaGetErrorString(e) +
                                       " " + last_launch_detail());
+    if (padded) {
+      for (int slot = 0; slot < kSlots && e == cudaSuccess; ++slot)
+        if (user_out[slot]) {
+          const uint64_t rows = static_cast<uint64_t>(q.batch) * ((slot == sdK || slot == sdV) ? p.C : p.R);
+          e = launch_unpad_columns(q.buf[slot], user_out[slot], rows, p.D, Dp, stream);
+        }
+      if (e != cudaSuccess)
+        return fail(MFA_ERROR_CUDA, std::string("head-dimension un-padding failed: ") + cudaGetErrorString(e));
+    }
   }
   return MFA_SUCCESS;
 }
@@ -307,6 +384,7 @@ namespace {
 struct CacheKey {
   mfa_attention_descriptor_t descriptor;
   int type;
+  unsigned table_generation;  // kernels created from an older parameter table are not handed out again
 };
 std::mutex g_cache_mutex;
 std::vector<std::pair<CacheKey, mfa_attention_kernel_t *>> g_kernel_cache;
@@ -330,7 +408,8 @@ int mfa_attention_kernel_cache_fetch(const mfa_attention_descriptor_t *descripto
   if (!descriptor || !out) return fail(MFA_ERROR_INVALID_ARGUMENT, "NULL argument.");
   std::lock_guard<std::mutex> lock(g_cache_mutex);
   for (const auto &entry : g_kernel_cache)
-    if (entry.first.type == static_cast<int>(type) && same_descriptor(entry.first.descriptor, *descriptor)) {
+    if (entry.first.type == static_cast<int>(type) && entry.first.table_generation == parameter_table_generation() &&
+        same_descriptor(entry.first.descriptor, *descriptor)) {
       *out = entry.second;
       return MFA_SUCCESS;
     }
@@ -339,7 +418,7 @@ int mfa_attention_kernel_cache_fetch(const mfa_attention_descriptor_t *descripto
   if (status != MFA_SUCCESS) return status;
   mfa_attention_kernel_t *kernel = nullptr;
   if ((status = mfa_attention_kernel_create(&kd, &kernel)) != MFA_SUCCESS) return status;
-  g_kernel_cache.push_back({CacheKey{*descriptor, static_cast<int>(type)}, kernel});
+  g_kernel_cache.push_back({CacheKey{*descriptor, static_cast<int>(type), parameter_table_generation()}, kernel});
   *out = kernel;
   return MFA_SUCCESS;
 }

@@ -55,12 +55,12 @@ struct Workspace {
   size_t bytes = 0;
 };
 std::mutex g_workspace_mutex;
-std::map<std::pair<int, cudaStream_t>, Workspace> g_workspaces;
+std::map<std::pair<std::pair<int, int>, cudaStream_t>, Workspace> g_workspaces;  // ((device, slot), stream)
 }  // namespace
 
-cudaError_t workspace_for(int device, cudaStream_t stream, size_t bytes, void **out) {
+cudaError_t workspace_for(int device, cudaStream_t stream, size_t bytes, void **out, int slot) {
   std::lock_guard<std::mutex> lock(g_workspace_mutex);
-  Workspace &w = g_workspaces[std::make_pair(device, stream)];
+  Workspace &w = g_workspaces[std::make_pair(std::make_pair(device, slot), stream)];
   const size_t need = bytes + kWorkspaceCounterBytes;
   if (w.bytes < need) {
     // growing means allocating: not possible while the stream is being captured into a graph (warm the kernel up once
@@ -95,7 +95,7 @@ cudaError_t workspace_for(int device, cudaStream_t stream, size_t bytes, void **
 void release_workspaces(int device) {
   std::lock_guard<std::mutex> lock(g_workspace_mutex);
   for (auto it = g_workspaces.begin(); it != g_workspaces.end();) {
-    if (it->first.first == device) {
+    if (it->first.first.first == device) {
       if (it->second.ptr) cudaFree(it->second.ptr);
       it = g_workspaces.erase(it);
     } else {

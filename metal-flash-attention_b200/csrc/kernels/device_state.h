@@ -26,7 +26,9 @@ cudaError_t ensure_max_dynamic_smem(const void *kernel, uint32_t bytes, int devi
 // needs more room.  The first `kWorkspaceCounterBytes` bytes of every workspace are arrival counters, zeroed at
 // allocation and returned to zero by the kernels that use them.
 constexpr size_t kWorkspaceCounterBytes = 4096;
-cudaError_t workspace_for(int device, cudaStream_t stream, size_t bytes, void **out);
+// `slot` separates independent users inside one encode(): 0 = split partials (forward / backward launchers), 1 = the
+// head-dimension padding staging of kernel.cpp, which is live across the launcher's own use of slot 0.
+cudaError_t workspace_for(int device, cudaStream_t stream, size_t bytes, void **out, int slot = 0);
 
 // Frees every workspace of `device` (the device must be idle); used by tests and by mfa_release_device_resources().
 void release_workspaces(int device);

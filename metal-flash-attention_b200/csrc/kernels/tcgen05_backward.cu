@@ -41,18 +41,13 @@ constexpr uint32_t kElemThreads = 256;
 constexpr uint32_t kLaunchRegs = 168, kElemRegs = 208, kOtherRegs = 88;
 static_assert(kElemRegs * 256 + kOtherRegs * 128 <= kLaunchRegs * kThreads, "setmaxnreg over-subscribed");
 
-// Of every 4 element pairs of P, how many take exp2 on the FMA pipe (exp2_poly2, sm100_ptx.cuh) instead of the MUFU
-// pipe.  At D = 64 a block's MMAs need 768 (dQ) / 1024 (dK/dV) tensor-pipe cycles but its 128 x 128 exponentials 1024
-// MUFU cycles (16 ex2 / clk / SM): the P half of the elementwise pass is MUFU-bound and the FMA pipe idles, so half of
-// the pairs go there.  At D = 128 the kernels are tensor-bound and the extra FMA-pipe instructions only cost issue
-// slots.  Swept on B200 (TFLOP/s, dQ | dK/dV): D=128: 0 -> 1353 | 1350, 1 -> 1288 | 1366, 2 -> 1261 | 1351,
-// 3 -> 1209 | 1301;  D=64: 0 -> 669 | 612, 1 -> 688 | 622, 2 -> 709 | 698, 3 -> 627 | 620.
-#ifdef MFA_BWD_POLY_PAIRS
-template <uint32_t DPAD> constexpr uint32_t kPolyPairs = MFA_BWD_POLY_PAIRS;
-#else
-template <uint32_t DPAD> constexpr uint32_t kPolyPairs = DPAD <= 64 ? 2 : 0;
-#endif
-
+// kPoly (template parameter of both kernels, from the parameter-table row): of every 4 element pairs of P, how many
+// take exp2 on the FMA pipe (exp2_poly2, sm100_ptx.cuh) instead of the MUFU pipe.  At D = 64 a block's MMAs need 768
+// (dQ) / 1024 (dK/dV) tensor-pipe cycles but its 128 x 128 exponentials 1024 MUFU cycles (16 ex2 / clk / SM): the P half
+// of the elementwise pass is MUFU-bound, so part of the pairs go to the FMA pipe.  At D = 128 the kernels are
+// tensor-bound and the extra FMA-pipe instructions only cost issue slots.  Swept on B200 (scripts/sweep.py; round-2
+// numbers with packed dS arithmetic, TFLOP/s, dQ | dK/dV, N = 4096):  D=128: 0 -> 1330 | 1280, 1 -> 1300 | 1290,
+// 3 -> 1270 | 1235;  D=64: 0 -> 924 | 873, 1 -> 962 | 911, 2 -> 946 | 948, 3 -> 862 | 846.
 // p0, p1 <- exp2(p * scale - l) for pair index `pair` (a compile-time constant once the caller's loop is unrolled)
 template <uint32_t kPoly>
 __device__ __forceinline__ void exp2_pair(uint32_t pair, float &p0, float &p1, float scale, float l0, float l1) {
@@ -147,6 +142,8 @@ struct BackwardArgs {
   // its partial accumulators to slice s of the outputs (which then point at scratch; split_stride floats apart)
   uint32_t blocks_per_split;
   size_t split_stride;
+  // work decomposition: item -> (split, head, tile)
+  uint32_t tiles, batch, num_splits, num_items;
 };
 
 // ================================================================================================
@@ -164,63 +161,82 @@ struct QueryConfig {
   static constexpr uint32_t kSubTiles = DPAD / 64;
   static constexpr uint32_t kTileBytes = kSubTiles * kSubTileBytes;  // one 128 x DPAD 16-bit tile
   static constexpr uint32_t kStagesK = 3, kStagesV = 2;
+  // D <= 64: persistent CTAs.  Q / dO are double-buffered in shared memory and the dQ accumulator in TMEM, so the next
+  // work item's tiles land -- and its first S / dP are computed -- while the elementwise warps finish and store the
+  // current one; the epilogue then needs a scratch tile of its own (the K ring is live).  D = 128 has no room for
+  // either (224 KB of operand tiles, 512 TMEM columns): one work item per CTA, scratch overlays the dead K ring.
+  static constexpr bool kPersistent = DPAD <= 64;
+  static constexpr uint32_t kBuffers = kPersistent ? 2 : 1;
   static constexpr uint32_t kSmemQ = 0;
-  static constexpr uint32_t kSmemdO = kTileBytes;
-  static constexpr uint32_t kSmemK = 2 * kTileBytes;
+  static constexpr uint32_t kSmemdO = kBuffers * kTileBytes;
+  static constexpr uint32_t kSmemK = 2 * kBuffers * kTileBytes;
   static constexpr uint32_t kSmemV = kSmemK + kStagesK * kTileBytes;
-  static constexpr uint32_t kSmemVec = kSmemV + kStagesV * kTileBytes;  // float D[128]: D terms, warp -> row owner
+  static constexpr uint32_t kSmemScratch = kPersistent ? kSmemV + kStagesV * kTileBytes : kSmemK;  // 8 warps x 4 KB
+  static constexpr uint32_t kSmemVec = kSmemV + kStagesV * kTileBytes + (kPersistent ? 8 * 4096 : 0);  // float D[128]
   static constexpr uint32_t kSmemBar = kSmemVec + kTile * 4;
-  static constexpr uint32_t kNumBars = 24;
+  static constexpr uint32_t kNumBars = 28;
   static constexpr uint32_t kSmemTmemPtr = kSmemBar + kNumBars * 8;
   static constexpr uint32_t kSmemBytes = kSmemTmemPtr + 16;
   static_assert(kSmemBytes <= 232448, "shared memory over budget");
   static_assert(8 * 4096 <= kStagesK * kTileBytes, "epilogue scratch does not fit the K stages");
+  static_assert(384 + kBuffers * DPAD <= 512, "dQ accumulators do not fit TMEM");
 };
 
-template <uint32_t DPAD, bool kBF16, bool kConvertDO>
+template <uint32_t DPAD, bool kBF16, bool kConvertDO, uint32_t kPoly>
 __global__ void __launch_bounds__(kThreads, 1)
     attention_backward_query_tcgen05(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapdO,
                                      const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV,
                                      const BackwardArgs a) {
   using Cfg = QueryConfig<DPAD>;
+  constexpr uint32_t kDB = Cfg::kBuffers;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t head = blockIdx.y;
-  const uint32_t r0 = blockIdx.x * kTile;
   const uint32_t total_blocks = (a.C + kTile - 1) / kTile;
-  const uint32_t blk0 = blockIdx.z * a.blocks_per_split;  // first key block of this split (host: never empty)
-  const uint32_t num_blocks = min(a.blocks_per_split, total_blocks - blk0);
   constexpr uint32_t kTmemS = 0, kTmemdP = 128, kTmemdQ = 384, kTmemCols = 512;
+  // work item -> (traversal split, head, 128-row tile of Q); items blockIdx.x, blockIdx.x + gridDim.x, ... (the
+  // non-persistent instantiation is launched with one CTA per item).  `g0` counts the key blocks this CTA has processed
+  // before the current item: every ring stage and barrier phase below is a function of the global block index g0 + j.
+  auto decode = [&](uint32_t item, uint32_t &r0, uint32_t &head, uint32_t &split, uint32_t &blk0, uint32_t &num_blocks) {
+    r0 = (item % a.tiles) * kTile;
+    head = (item / a.tiles) % a.batch;
+    split = item / (a.tiles * a.batch);
+    blk0 = split * a.blocks_per_split;  // first key block of this split (host: never empty)
+    num_blocks = min(a.blocks_per_split, total_blocks - blk0);
+  };
 
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kSmemBar);
-  uint64_t *q_full = bars;            // Q and dO tiles landed
-  uint64_t *k_full = bars + 1;        // [3]
-  uint64_t *k_empty = bars + 4;       // [3]
-  uint64_t *v_full = bars + 7;        // [2]
-  uint64_t *v_empty = bars + 9;       // [2]
-  uint64_t *s_full = bars + 11;       // S(j) in TMEM
-  uint64_t *s_free = bars + 12;       // S(j) is in registers (256 arrivals)
-  uint64_t *dp_full = bars + 13;      // [2] dP(j) in TMEM
-  uint64_t *ds_full = bars + 15;      // [2] dS(j) written over dP(j) (256 arrivals)
-  uint64_t *dq_final = bars + 17;     // every MMA has completed
-  uint64_t *do_ready = bars + 18;     // kConvertDO: the resident dO tile has been rewritten as FP16 (256 arrivals)
+  uint64_t *q_full = bars;            // [2] Q and dO tiles of the item landed
+  uint64_t *q_empty = bars + 2;       // [2] every MMA of the item has completed: the buffers may be reloaded
+  uint64_t *k_full = bars + 4;        // [3]
+  uint64_t *k_empty = bars + 7;       // [3]
+  uint64_t *v_full = bars + 10;       // [2]
+  uint64_t *v_empty = bars + 12;      // [2]
+  uint64_t *s_full = bars + 14;       // S(g) in TMEM
+  uint64_t *s_free = bars + 15;       // S(g) is in registers (256 arrivals)
+  uint64_t *dp_full = bars + 16;      // [2] dP(g) in TMEM
+  uint64_t *ds_full = bars + 18;      // [2] dS(g) written over dP(g) (256 arrivals)
+  uint64_t *dq_final = bars + 20;     // one phase per item: the item's last dQ += dS K has completed
+  uint64_t *do_ready = bars + 21;     // kConvertDO, one phase per item: the dO tile has been rewritten as FP16 (256)
+  uint64_t *dq_free = bars + 22;      // [2] the epilogue has read this dQ accumulator out of TMEM (256 arrivals)
   static_assert(!(kBF16 && kConvertDO), "dO is only converted when Q, K, V are FP16");
   constexpr bool kDOisBF16 = kBF16 || kConvertDO;  // element type of dO in global memory
   uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem + Cfg::kSmemTmemPtr);
 
   if (threadIdx.x == 0) {
-    mbar_init(q_full, 1);
-    for (uint32_t s = 0; s < Cfg::kStagesK; ++s) {
-      mbar_init(&k_full[s], 1);
-      mbar_init(&k_empty[s], 1);
-    }
     for (uint32_t s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 1);
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
       mbar_init(&dp_full[s], 1);
       mbar_init(&ds_full[s], kElemThreads);
+      mbar_init(&dq_free[s], kElemThreads);
+    }
+    for (uint32_t s = 0; s < Cfg::kStagesK; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
     }
     mbar_init(s_full, 1);
     mbar_init(s_free, kElemThreads);
@@ -238,171 +254,196 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t tmem_base = *tmem_ptr_smem;
   // traversal split: let the sum kernel (launched with programmatic stream serialisation) be set up now; its
   // griddepcontrol.wait still holds it until this grid has completed and flushed
-  if (gridDim.z > 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (a.num_splits > 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp < 8) {
     // ---------------- elementwise warpgroups ----------------
     setmaxnreg_inc<kElemRegs>();
     const uint32_t h = warp >> 2, quarter = warp & 3;
     const uint32_t row_in_tile = quarter * 32 + lane;
-    const uint32_t row = r0 + row_in_tile;
-    const uint32_t row_c = min(row, a.R - 1);  // clamped like clampedParallelizationThreadOffset (AttentionKernel.swift:224-226)
     const uint32_t tLane = tmem_base + ((quarter * 32) << 16);
 
-    if constexpr (kConvertDO) {
-      // BF16 dO tile (TMA) -> FP16 in place; elementwise, so the 128 B swizzle is irrelevant.  Generic-proxy writes
-      // must be fenced before the tensor core (async proxy) reads them.
-      mbar_wait(q_full, 0);
-      uint4 *tile = reinterpret_cast<uint4 *>(smem + Cfg::kSmemdO);
-#pragma unroll
-      for (uint32_t i = 0; i < Cfg::kTileBytes / (kElemThreads * 16); ++i)
-        tile[i * kElemThreads + threadIdx.x] = bf16x8_to_f16x8(tile[i * kElemThreads + threadIdx.x]);
-      fence_proxy_async_smem();
-      mbar_arrive(do_ready);
-    }
+    uint32_t g0 = 0;
+    for (uint32_t item = blockIdx.x, it = 0; item < a.num_items; item += gridDim.x, ++it) {
+      uint32_t r0, head, split, blk0, num_blocks;
+      decode(item, r0, head, split, blk0, num_blocks);
+      const uint32_t qb = it % kDB, q_phase = (it / kDB) & 1;
+      const uint32_t row = r0 + row_in_tile;
+      const uint32_t row_c = min(row, a.R - 1);  // clamped like clampedParallelizationThreadOffset (AttentionKernel.swift:224-226)
 
-    // computeD (AttentionKernel+Softmax.swift:32-221): D = (sum_d dO * O) / sqrt(D), kept in FP32 for this kernel and
-    // stored (possibly as BF16) for the dK/dV kernel.  A row per thread (what the MMA layout would suggest) makes every
-    // warp load touch 32 different cache lines -- the profile showed the elementwise warps spending 17 % of the kernel
-    // here -- so each warp instead takes 16 rows and spreads the columns over its lanes (one 512 B line of O per load),
-    // reduces with shuffles and hands the results to the row owners through shared memory.
-    float Dterm;
-    {
-      float *dvec = reinterpret_cast<float *>(smem + Cfg::kSmemVec);
-      constexpr uint32_t kRowsPerWarp = kTile / 8;
-      float4 o4[kRowsPerWarp];
-      uint2 g4[kRowsPerWarp];
-      const bool active = 4 * lane < a.D;
+      if constexpr (kConvertDO) {
+        // BF16 dO tile (TMA) -> FP16 in place; elementwise, so the 128 B swizzle is irrelevant.  Generic-proxy writes
+        // must be fenced before the tensor core (async proxy) reads them.
+        mbar_wait(&q_full[qb], q_phase);
+        uint4 *tile = reinterpret_cast<uint4 *>(smem + Cfg::kSmemdO + qb * Cfg::kTileBytes);
 #pragma unroll
-      for (uint32_t i = 0; i < kRowsPerWarp; ++i) {
-        const uint32_t rr = min(r0 + warp * kRowsPerWarp + i, a.R - 1);
-        const size_t base = (static_cast<size_t>(head) * a.R + rr) * a.D + 4 * lane;
-        o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        g4[i] = make_uint2(0u, 0u);
-        if (active) {
-          o4[i] = __ldg(reinterpret_cast<const float4 *>(a.O + base));
-          g4[i] = __ldg(reinterpret_cast<const uint2 *>(static_cast<const uint16_t *>(a.dO) + base));
-        }
+        for (uint32_t i = 0; i < Cfg::kTileBytes / (kElemThreads * 16); ++i)
+          tile[i * kElemThreads + threadIdx.x] = bf16x8_to_f16x8(tile[i * kElemThreads + threadIdx.x]);
+        fence_proxy_async_smem();
+        mbar_arrive(do_ready);
       }
-#pragma unroll
-      for (uint32_t i = 0; i < kRowsPerWarp; ++i) {
-        float v0, v1, v2, v3;
-        if (kDOisBF16) {
-          v0 = __uint_as_float(g4[i].x << 16);
-          v1 = __uint_as_float(g4[i].x & 0xFFFF0000u);
-          v2 = __uint_as_float(g4[i].y << 16);
-          v3 = __uint_as_float(g4[i].y & 0xFFFF0000u);
-        } else {
-          const __half2 lo = *reinterpret_cast<const __half2 *>(&g4[i].x), hi = *reinterpret_cast<const __half2 *>(&g4[i].y);
-          v0 = __low2float(lo); v1 = __high2float(lo); v2 = __low2float(hi); v3 = __high2float(hi);
-        }
-        float acc = fmaf(v0, o4[i].x, fmaf(v1, o4[i].y, fmaf(v2, o4[i].z, v3 * o4[i].w)));
-#pragma unroll
-        for (uint32_t off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-        if (lane == i) dvec[warp * kRowsPerWarp + i] = acc * a.scale;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(kElemThreads) : "memory");  // the eight elementwise warps only
-      Dterm = dvec[row_in_tile];
-    }
-    const size_t stat_idx = static_cast<size_t>(head) * a.R + row_c;
-    const float Lrow = load_stat(a.L, stat_idx, a.l_prec);
-    if (h == 0 && row < a.R && blockIdx.z == 0) store_stat(a.Dterm, stat_idx, a.d_prec, Dterm);
 
-    for (uint32_t j = 0; j < num_blocks; ++j) {
-      const uint32_t bf = j & 1;
-      const uint32_t tS = tLane + kTmemS + h * kHalf;
-      const uint32_t tdP = tLane + kTmemdP + bf * kTile + h * kHalf;
-      // ---- first half of the pass: P = exp2(S * log2e/sqrt(D) - L) needs only S ----
-      mbar_wait(s_full, j & 1);
+      // computeD (AttentionKernel+Softmax.swift:32-221): D = (sum_d dO * O) / sqrt(D), kept in FP32 for this kernel and
+      // stored (possibly as BF16) for the dK/dV kernel.  A row per thread (what the MMA layout would suggest) makes every
+      // warp load touch 32 different cache lines -- the profile showed the elementwise warps spending 17 % of the kernel
+      // here -- so each warp instead takes 16 rows and spreads the columns over its lanes (one 512 B line of O per load),
+      // reduces with shuffles and hands the results to the row owners through shared memory.
+      float Dterm;
+      {
+        float *dvec = reinterpret_cast<float *>(smem + Cfg::kSmemVec);
+        constexpr uint32_t kRowsPerWarp = kTile / 8;
+        float4 o4[kRowsPerWarp];
+        uint2 g4[kRowsPerWarp];
+        const bool active = 4 * lane < a.D;
+#pragma unroll
+        for (uint32_t i = 0; i < kRowsPerWarp; ++i) {
+          const uint32_t rr = min(r0 + warp * kRowsPerWarp + i, a.R - 1);
+          const size_t base = (static_cast<size_t>(head) * a.R + rr) * a.D + 4 * lane;
+          o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          g4[i] = make_uint2(0u, 0u);
+          if (active) {
+            o4[i] = __ldg(reinterpret_cast<const float4 *>(a.O + base));
+            g4[i] = __ldg(reinterpret_cast<const uint2 *>(static_cast<const uint16_t *>(a.dO) + base));
+          }
+        }
+#pragma unroll
+        for (uint32_t i = 0; i < kRowsPerWarp; ++i) {
+          float v0, v1, v2, v3;
+          if (kDOisBF16) {
+            v0 = __uint_as_float(g4[i].x << 16);
+            v1 = __uint_as_float(g4[i].x & 0xFFFF0000u);
+            v2 = __uint_as_float(g4[i].y << 16);
+            v3 = __uint_as_float(g4[i].y & 0xFFFF0000u);
+          } else {
+            const __half2 lo = *reinterpret_cast<const __half2 *>(&g4[i].x), hi = *reinterpret_cast<const __half2 *>(&g4[i].y);
+            v0 = __low2float(lo); v1 = __high2float(lo); v2 = __low2float(hi); v3 = __high2float(hi);
+          }
+          float acc = fmaf(v0, o4[i].x, fmaf(v1, o4[i].y, fmaf(v2, o4[i].z, v3 * o4[i].w)));
+#pragma unroll
+          for (uint32_t off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+          if (lane == i) dvec[warp * kRowsPerWarp + i] = acc * a.scale;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kElemThreads) : "memory");  // the eight elementwise warps only
+        Dterm = dvec[row_in_tile];
+      }
+      const size_t stat_idx = static_cast<size_t>(head) * a.R + row_c;
+      const float Lrow = load_stat(a.L, stat_idx, a.l_prec);
+      if (h == 0 && row < a.R && split == 0) store_stat(a.Dterm, stat_idx, a.d_prec, Dterm);
+
+      for (uint32_t j = 0; j < num_blocks; ++j) {
+        const uint32_t g = g0 + j, bf = g & 1;
+        const uint32_t tS = tLane + kTmemS + h * kHalf;
+        const uint32_t tdP = tLane + kTmemdP + bf * kTile + h * kHalf;
+        // ---- first half of the pass: P = exp2(S * log2e/sqrt(D) - L) needs only S ----
+        mbar_wait(s_full, g & 1);
+        tc_fence_after();
+        float p[kHalf];
+#pragma unroll
+        for (uint32_t c = 0; c < kHalf; c += 32) tmem_ld32(tS + c, *reinterpret_cast<uint32_t(*)[32]>(&p[c]));
+        tc_wait_ld();
+        tc_fence_before();
+        mbar_arrive(s_free);  // S(g+1) may overwrite the S buffer now
+
+        const uint32_t col0 = (blk0 + j) * kTile + h * kHalf;
+        if (blk0 + j + 1 == total_blocks && col0 + kHalf > a.C) {  // padded key columns (maskAttentionMatrixEdge): P = 0 there
+#pragma unroll
+          for (uint32_t c = 0; c < kHalf; ++c)
+            if (col0 + c >= a.C) p[c] = -INFINITY;
+        }
+        // P = exp2(S * log2e/sqrt(D) - L)   (+Softmax.swift:419-427)
+#pragma unroll
+        for (uint32_t i = 0; i < kHalf / 2; ++i) exp2_pair<kPoly>(i, p[2 * i], p[2 * i + 1], a.scale_log2, Lrow, Lrow);
+
+        // ---- second half: dS = P * (dP/sqrt(D) - D), written in place over dP as the 16-bit A operand of dQ += dS K ----
+        mbar_wait(&dp_full[bf], (g >> 1) & 1);
+        tc_fence_after();
+        uint32_t dp[kHalf];
+#pragma unroll
+        for (uint32_t c = 0; c < kHalf; c += 32) tmem_ld32(tdP + c, *reinterpret_cast<uint32_t(*)[32]>(&dp[c]));
+        tc_wait_ld();
+        const float2 scale2 = make_float2(a.scale, a.scale), negD2 = make_float2(-Dterm, -Dterm);
+#pragma unroll
+        for (uint32_t c = 0; c < kHalf; c += 32) {
+          uint32_t packed[16];
+#pragma unroll
+          for (uint32_t k = 0; k < 16; ++k) {
+            // packed FP32x2 arithmetic: the elementwise pass is bound by instruction issue (one 32-wide FP32
+            // instruction per two cycles and sub-partition), so two elements per FFMA2 / FMUL2 halve its cost
+            const float2 t = ffma2(make_float2(__uint_as_float(dp[c + 2 * k]), __uint_as_float(dp[c + 2 * k + 1])), scale2, negD2);
+            const float2 ds = fmul2(make_float2(p[c + 2 * k], p[c + 2 * k + 1]), t);
+            packed[k] = kBF16 ? pack_bf16x2(ds.x, ds.y) : pack_f16x2(ds.x, ds.y);
+          }
+          tmem_st16(tdP + (c >> 1), packed);  // dS of keys [64h + c, +32) -> columns [64h + c/2, +16) of the dP buffer
+        }
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(&ds_full[bf]);
+      }
+
+      // epilogue: dQ -> global (FP32); warpgroup h writes columns [h D/2, (h+1) D/2)
+      mbar_wait(dq_final, it & 1);
       tc_fence_after();
-      float p[kHalf];
-#pragma unroll
-      for (uint32_t c = 0; c < kHalf; c += 32) tmem_ld32(tS + c, *reinterpret_cast<uint32_t(*)[32]>(&p[c]));
-      tc_wait_ld();
-      tc_fence_before();
-      mbar_arrive(s_free);  // S(j+1) may overwrite the S buffer now
-
-      const uint32_t col0 = (blk0 + j) * kTile + h * kHalf;
-      if (blk0 + j + 1 == total_blocks && col0 + kHalf > a.C) {  // padded key columns (maskAttentionMatrixEdge): P = 0 there
-#pragma unroll
-        for (uint32_t c = 0; c < kHalf; ++c)
-          if (col0 + c >= a.C) p[c] = -INFINITY;
+      {
+        float4 *scratch = reinterpret_cast<float4 *>(smem + Cfg::kSmemScratch) + warp * 256;
+        const uint32_t warp_row0 = r0 + quarter * 32;
+        store_accumulator_coalesced(tLane + kTmemdQ + qb * DPAD, h * (DPAD / 2), DPAD / 2, scratch,
+                                    a.dQ + split * a.split_stride + (static_cast<size_t>(head) * a.R + warp_row0) * a.D,
+                                    warp_row0, a.R, a.D, lane);
       }
-      // P = exp2(S * log2e/sqrt(D) - L)   (+Softmax.swift:419-427)
-#pragma unroll
-      for (uint32_t i = 0; i < kHalf / 2; ++i) exp2_pair<kPolyPairs<DPAD>>(i, p[2 * i], p[2 * i + 1], a.scale_log2, Lrow, Lrow);
-
-      // ---- second half: dS = P * (dP/sqrt(D) - D), written in place over dP as the 16-bit A operand of dQ += dS K ----
-      mbar_wait(&dp_full[bf], (j >> 1) & 1);
-      tc_fence_after();
-      uint32_t dp[kHalf];
-#pragma unroll
-      for (uint32_t c = 0; c < kHalf; c += 32) tmem_ld32(tdP + c, *reinterpret_cast<uint32_t(*)[32]>(&dp[c]));
-      tc_wait_ld();
-      const float2 scale2 = make_float2(a.scale, a.scale), negD2 = make_float2(-Dterm, -Dterm);
-#pragma unroll
-      for (uint32_t c = 0; c < kHalf; c += 32) {
-        uint32_t packed[16];
-#pragma unroll
-        for (uint32_t k = 0; k < 16; ++k) {
-          // packed FP32x2 arithmetic: the elementwise pass is bound by instruction issue (one 32-wide FP32
-          // instruction per two cycles and sub-partition), so two elements per FFMA2 / FMUL2 halve its cost
-          const float2 t = ffma2(make_float2(__uint_as_float(dp[c + 2 * k]), __uint_as_float(dp[c + 2 * k + 1])), scale2, negD2);
-          const float2 ds = fmul2(make_float2(p[c + 2 * k], p[c + 2 * k + 1]), t);
-          packed[k] = kBF16 ? pack_bf16x2(ds.x, ds.y) : pack_f16x2(ds.x, ds.y);
-        }
-        tmem_st16(tdP + (c >> 1), packed);  // dS of keys [64h + c, +32) -> columns [64h + c/2, +16) of the dP buffer
-      }
-      tc_wait_st();
+      // this dQ accumulator is out of TMEM: a later item's first dQ = dS K (accumulate off) may overwrite it
       tc_fence_before();
-      mbar_arrive(&ds_full[bf]);
-    }
-
-    // epilogue: dQ -> global (FP32); warpgroup h writes columns [h D/2, (h+1) D/2)
-    mbar_wait(dq_final, 0);
-    tc_fence_after();
-    {
-      float4 *scratch = reinterpret_cast<float4 *>(smem + Cfg::kSmemK) + warp * 256;  // the K stages are dead now
-      const uint32_t warp_row0 = r0 + quarter * 32;
-      store_accumulator_coalesced(tLane + kTmemdQ, h * (DPAD / 2), DPAD / 2, scratch,
-                                  a.dQ + blockIdx.z * a.split_stride + (static_cast<size_t>(head) * a.R + warp_row0) * a.D,
-                                  warp_row0, a.R, a.D, lane);
-    }
+      mbar_arrive(&dq_free[qb]);
+      g0 += num_blocks;
+    }  // work items
   } else {
     setmaxnreg_dec<kOtherRegs>();
     if (warp == 9) {
-      // ---------------- TMA producer: Q, dO once, then the K ring ----------------
-      if (elect_one()) {
-        mbar_arrive_expect_tx(q_full, 2 * Cfg::kTileBytes);
-#pragma unroll
-        for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds) {
-          tma_load_3d(smem + Cfg::kSmemQ + ds * kSubTileBytes, &mapQ, q_full, ds * 64, r0, head);
-          tma_load_3d(smem + Cfg::kSmemdO + ds * kSubTileBytes, &mapdO, q_full, ds * 64, r0, head);
-        }
-      }
-      for (uint32_t j = 0; j < num_blocks; ++j) {
-        const uint32_t stage = j % Cfg::kStagesK, phase = (j / Cfg::kStagesK) & 1;
-        mbar_wait(&k_empty[stage], phase ^ 1);
+      // ---------------- TMA producer: Q, dO of every item, and the K ring ----------------
+      uint32_t g0 = 0;
+      for (uint32_t item = blockIdx.x, it = 0; item < a.num_items; item += gridDim.x, ++it) {
+        uint32_t r0, head, split, blk0, num_blocks;
+        decode(item, r0, head, split, blk0, num_blocks);
+        const uint32_t qb = it % kDB;
+        mbar_wait(&q_empty[qb], ((it / kDB) & 1) ^ 1);  // the item that used these buffers last is done with them
         if (elect_one()) {
-          mbar_arrive_expect_tx(&k_full[stage], Cfg::kTileBytes);
+          mbar_arrive_expect_tx(&q_full[qb], 2 * Cfg::kTileBytes);
 #pragma unroll
-          for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
-            tma_load_3d(smem + Cfg::kSmemK + stage * Cfg::kTileBytes + ds * kSubTileBytes, &mapK, &k_full[stage],
-                        ds * 64, (blk0 + j) * kTile, head);
+          for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds) {
+            tma_load_3d(smem + Cfg::kSmemQ + qb * Cfg::kTileBytes + ds * kSubTileBytes, &mapQ, &q_full[qb], ds * 64, r0, head);
+            tma_load_3d(smem + Cfg::kSmemdO + qb * Cfg::kTileBytes + ds * kSubTileBytes, &mapdO, &q_full[qb], ds * 64, r0, head);
+          }
         }
+        for (uint32_t j = 0; j < num_blocks; ++j) {
+          const uint32_t g = g0 + j, stage = g % Cfg::kStagesK, phase = (g / Cfg::kStagesK) & 1;
+          mbar_wait(&k_empty[stage], phase ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&k_full[stage], Cfg::kTileBytes);
+#pragma unroll
+            for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
+              tma_load_3d(smem + Cfg::kSmemK + stage * Cfg::kTileBytes + ds * kSubTileBytes, &mapK, &k_full[stage],
+                          ds * 64, (blk0 + j) * kTile, head);
+          }
+        }
+        g0 += num_blocks;
       }
     } else if (warp == 10) {
       // ---------------- TMA producer for the V ring ----------------
-      for (uint32_t j = 0; j < num_blocks; ++j) {
-        const uint32_t stage = j & 1, phase = (j >> 1) & 1;
-        mbar_wait(&v_empty[stage], phase ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&v_full[stage], Cfg::kTileBytes);
+      uint32_t g0 = 0;
+      for (uint32_t item = blockIdx.x; item < a.num_items; item += gridDim.x) {
+        uint32_t r0, head, split, blk0, num_blocks;
+        decode(item, r0, head, split, blk0, num_blocks);
+        for (uint32_t j = 0; j < num_blocks; ++j) {
+          const uint32_t g = g0 + j, stage = g & 1, phase = (g >> 1) & 1;
+          mbar_wait(&v_empty[stage], phase ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&v_full[stage], Cfg::kTileBytes);
 #pragma unroll
-          for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
-            tma_load_3d(smem + Cfg::kSmemV + stage * Cfg::kTileBytes + ds * kSubTileBytes, &mapV, &v_full[stage],
-                        ds * 64, (blk0 + j) * kTile, head);
+            for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
+              tma_load_3d(smem + Cfg::kSmemV + stage * Cfg::kTileBytes + ds * kSubTileBytes, &mapV, &v_full[stage],
+                          ds * 64, (blk0 + j) * kTile, head);
+          }
         }
+        g0 += num_blocks;
       }
     } else if (warp == 8) {
       // ---------------- MMA issuer ----------------
@@ -422,79 +463,100 @@ __global__ void __launch_bounds__(kThreads, 1)
           umma_ss(d_tmem, a_desc + off, b_desc + off, idescNT, k > 0);
         }
       };
-      auto issue_dQ = [&](uint32_t bf, uint32_t stage, uint32_t accumulate) {
+      auto issue_dQ = [&](uint32_t qb, uint32_t bf, uint32_t stage, uint32_t accumulate) {
         const uint64_t b0 = descKmn + ((stage * Cfg::kTileBytes) >> 4);
 #pragma unroll
         for (uint32_t k = 0; k < kTile / 16; ++k) {
           // dS of keys [64 hh, 64 hh + 64) sits in columns [64 hh, 64 hh + 32) of the dP buffer
           const uint32_t a_tmem = tmem_base + kTmemdP + bf * kTile + (k >> 2) * kHalf + (k & 3) * 8;
-          umma_ts(tmem_base + kTmemdQ, a_tmem, b0 + ((k * 2048) >> 4), idescAcc, k > 0 ? 1u : accumulate);
+          umma_ts(tmem_base + kTmemdQ + qb * DPAD, a_tmem, b0 + ((k * 2048) >> 4), idescAcc, k > 0 ? 1u : accumulate);
         }
       };
 
-      // prologue: S(0), dP(0)
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      if (elect_one()) {
-        issue_nt(tmem_base + kTmemS, descQ, descK);
-        umma_commit(s_full);
-      }
-      __syncwarp();
-      mbar_wait(&v_full[0], 0);
-      if constexpr (kConvertDO) mbar_wait(do_ready, 0);
-      tc_fence_after();
-      if (elect_one()) {
-        issue_nt(tmem_base + kTmemdP, descdO, descV);
-        umma_commit(&dp_full[0]);
-        umma_commit(&v_empty[0]);
-      }
-      __syncwarp();
+      uint32_t g0 = 0;
+      for (uint32_t item = blockIdx.x, it = 0; item < a.num_items; item += gridDim.x, ++it) {
+        uint32_t r0, head, split, blk0, num_blocks;
+        decode(item, r0, head, split, blk0, num_blocks);
+        const uint32_t qb = it % kDB, q_phase = (it / kDB) & 1;
+        const uint64_t descQb = descQ + ((qb * Cfg::kTileBytes) >> 4), descdOb = descdO + ((qb * Cfg::kTileBytes) >> 4);
 
-      for (uint32_t j = 0; j < num_blocks; ++j) {
-        // (a) dQ += dS(j-1) K(j-1): frees K's stage and the dP buffer that dP(j+1) is about to overwrite
-        if (j > 0) {
-          const uint32_t pj = j - 1, ks = pj % Cfg::kStagesK;
-          mbar_wait(&ds_full[pj & 1], (pj >> 1) & 1);
+        // prologue: S(g0), dP(g0).  For every item but the first they are issued while the elementwise warps are still
+        // storing the previous item's dQ: the S buffer only needs the previous item's last S to have been read out
+        // (s_free), the dP buffer's last reader dQ(g0 - 2) is ahead on the in-order tensor pipe.
+        {
+          const uint32_t ks = g0 % Cfg::kStagesK, vs = g0 & 1;
+          mbar_wait(&q_full[qb], q_phase);
+          if (it > 0) mbar_wait(s_free, (g0 - 1) & 1);
+          mbar_wait(&k_full[ks], (g0 / Cfg::kStagesK) & 1);
           tc_fence_after();
           if (elect_one()) {
-            issue_dQ(pj & 1, ks, pj > 0 ? 1u : 0u);
-            umma_commit(&k_empty[ks]);
-          }
-          __syncwarp();
-        }
-        if (j + 1 < num_blocks) {
-          const uint32_t nj = j + 1, ks = nj % Cfg::kStagesK, vs = nj & 1;
-          // (b) S(j+1) as soon as S(j) has been read out: first in line for the next elementwise pass
-          mbar_wait(s_free, j & 1);
-          mbar_wait(&k_full[ks], (nj / Cfg::kStagesK) & 1);
-          tc_fence_after();
-          if (elect_one()) {
-            issue_nt(tmem_base + kTmemS, descQ, descK + ((ks * Cfg::kTileBytes) >> 4));
+            issue_nt(tmem_base + kTmemS, descQb, descK + ((ks * Cfg::kTileBytes) >> 4));
             umma_commit(s_full);
           }
           __syncwarp();
-          // (c) dP(j+1) into the buffer dS(j-1) just left (in-order tensor pipe: after dQ(j-1))
-          mbar_wait(&v_full[vs], (nj >> 1) & 1);
+          mbar_wait(&v_full[vs], (g0 >> 1) & 1);
+          if constexpr (kConvertDO) mbar_wait(do_ready, it & 1);
           tc_fence_after();
           if (elect_one()) {
-            issue_nt(tmem_base + kTmemdP + vs * kTile, descdO, descV + ((vs * Cfg::kTileBytes) >> 4));
+            issue_nt(tmem_base + kTmemdP + vs * kTile, descdOb, descV + ((vs * Cfg::kTileBytes) >> 4));
             umma_commit(&dp_full[vs]);
             umma_commit(&v_empty[vs]);
           }
           __syncwarp();
         }
-      }
-      {
-        const uint32_t pj = num_blocks - 1, ks = pj % Cfg::kStagesK;
-        mbar_wait(&ds_full[pj & 1], (pj >> 1) & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          issue_dQ(pj & 1, ks, pj > 0 ? 1u : 0u);
-          umma_commit(dq_final);
+
+        for (uint32_t j = 0; j < num_blocks; ++j) {
+          const uint32_t g = g0 + j;
+          // (a) dQ += dS(g-1) K(g-1): frees K's stage and the dP buffer that dP(g+1) is about to overwrite
+          if (j > 0) {
+            const uint32_t pg = g - 1, ks = pg % Cfg::kStagesK;
+            mbar_wait(&ds_full[pg & 1], (pg >> 1) & 1);
+            // the item's first dQ MMA overwrites the accumulator: its previous user's epilogue must have read it out
+            if (j == 1) mbar_wait(&dq_free[qb], q_phase ^ 1);
+            tc_fence_after();
+            if (elect_one()) {
+              issue_dQ(qb, pg & 1, ks, j > 1 ? 1u : 0u);
+              umma_commit(&k_empty[ks]);
+            }
+            __syncwarp();
+          }
+          if (j + 1 < num_blocks) {
+            const uint32_t ng = g + 1, ks = ng % Cfg::kStagesK, vs = ng & 1;
+            // (b) S(g+1) as soon as S(g) has been read out: first in line for the next elementwise pass
+            mbar_wait(s_free, g & 1);
+            mbar_wait(&k_full[ks], (ng / Cfg::kStagesK) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+              issue_nt(tmem_base + kTmemS, descQb, descK + ((ks * Cfg::kTileBytes) >> 4));
+              umma_commit(s_full);
+            }
+            __syncwarp();
+            // (c) dP(g+1) into the buffer dS(g-1) just left (in-order tensor pipe: after dQ(g-1))
+            mbar_wait(&v_full[vs], (ng >> 1) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+              issue_nt(tmem_base + kTmemdP + vs * kTile, descdOb, descV + ((vs * Cfg::kTileBytes) >> 4));
+              umma_commit(&dp_full[vs]);
+              umma_commit(&v_empty[vs]);
+            }
+            __syncwarp();
+          }
         }
-        __syncwarp();
-      }
+        {
+          const uint32_t pg = g0 + num_blocks - 1, ks = pg % Cfg::kStagesK;
+          mbar_wait(&ds_full[pg & 1], (pg >> 1) & 1);
+          if (num_blocks == 1) mbar_wait(&dq_free[qb], q_phase ^ 1);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_dQ(qb, pg & 1, ks, num_blocks > 1 ? 1u : 0u);
+            umma_commit(&k_empty[ks]);
+            umma_commit(dq_final);
+            umma_commit(&q_empty[qb]);  // (every MMA that read this item's Q / dO has completed as well)
+          }
+          __syncwarp();
+        }
+        g0 += num_blocks;
+      }  // work items
     }
   }
 
@@ -527,38 +589,51 @@ struct KeyValueConfig {
   // Q(r+1) could not start before dK(r-1) had retired and S^T(r+1) waited for a TMA round trip (22 % of the elementwise
   // warps' time in the profile).  Separate rings, three stages of Q, two of dO.
   static constexpr uint32_t kStagesQ = 3, kStagesdO = 2;
+  // D <= 64: persistent CTAs with K / V double-buffered, so the next work item's tiles land and its first S^T / dP^T are
+  // computed while the elementwise warps store the current item's dV and dK (which then need a scratch tile of their
+  // own).  D = 128: no shared memory left for that; one work item per CTA, scratch overlays the dead Q ring.
+  static constexpr bool kPersistent = DPAD <= 64;
+  static constexpr uint32_t kBuffers = kPersistent ? 2 : 1;
   static constexpr uint32_t kSmemK = 0;
-  static constexpr uint32_t kSmemV = kTileBytes;
-  static constexpr uint32_t kSmemQ = 2 * kTileBytes;
+  static constexpr uint32_t kSmemV = kBuffers * kTileBytes;
+  static constexpr uint32_t kSmemQ = 2 * kBuffers * kTileBytes;
   static constexpr uint32_t kSmemdO = kSmemQ + kStagesQ * kTileBytes;
-  static constexpr uint32_t kSmemVec = kSmemdO + kStagesdO * kTileBytes;  // float L[2][128], D[2][128]
+  static constexpr uint32_t kSmemScratch = kPersistent ? kSmemdO + kStagesdO * kTileBytes : kSmemQ;  // 8 warps x 4 KB
+  static constexpr uint32_t kSmemVec = kSmemdO + kStagesdO * kTileBytes + (kPersistent ? 8 * 4096 : 0);  // float L[2][128], D[2][128]
   static constexpr uint32_t kSmemBar = kSmemVec + 4 * kTile * 4;
-  static constexpr uint32_t kNumBars = 24;
+  static constexpr uint32_t kNumBars = 32;
   static constexpr uint32_t kSmemTmemPtr = kSmemBar + kNumBars * 8;
   static constexpr uint32_t kSmemBytes = kSmemTmemPtr + 16;
   static_assert(kSmemBytes <= 232448, "shared memory over budget");
   static_assert(8 * 4096 <= kStagesQ * kTileBytes, "epilogue scratch does not fit the Q stages");
 };
 
-template <uint32_t DPAD, bool kBF16, bool kConvertDO>
+template <uint32_t DPAD, bool kBF16, bool kConvertDO, uint32_t kPoly>
 __global__ void __launch_bounds__(kThreads, 1)
     attention_backward_key_value_tcgen05(const __grid_constant__ CUtensorMap mapQ,
                                          const __grid_constant__ CUtensorMap mapdO,
                                          const __grid_constant__ CUtensorMap mapK,
                                          const __grid_constant__ CUtensorMap mapV, const BackwardArgs a) {
   using Cfg = KeyValueConfig<DPAD>;
+  constexpr uint32_t kDB = Cfg::kBuffers;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t head = blockIdx.y;
-  const uint32_t c0 = blockIdx.x * kTile;
   const uint32_t total_blocks = (a.R + kTile - 1) / kTile;
-  const uint32_t blk0 = blockIdx.z * a.blocks_per_split;  // first query block of this split (host: never empty)
-  const uint32_t num_blocks = min(a.blocks_per_split, total_blocks - blk0);
+  // work item -> (traversal split, head, 128-row tile of K / V); items blockIdx.x, blockIdx.x + gridDim.x, ...  `g0`
+  // counts the query blocks this CTA has processed before the current item: every ring stage, TMEM region and barrier
+  // phase below is a function of the global block index g = g0 + r.
+  auto decode = [&](uint32_t item, uint32_t &c0, uint32_t &head, uint32_t &split, uint32_t &blk0, uint32_t &num_blocks) {
+    c0 = (item % a.tiles) * kTile;
+    head = (item / a.tiles) % a.batch;
+    split = item / (a.tiles * a.batch);
+    blk0 = split * a.blocks_per_split;  // first query block of this split (host: never empty)
+    num_blocks = min(a.blocks_per_split, total_blocks - blk0);
+  };
   // At D <= 64 the accumulators leave room for a THIRD 128-column region: dP^T then has a region of its own (Z) and
-  // S^T / P^T / dS^T alternate between X and Y, so S^T(r+2) is issued a whole pass ahead and dP^T(r+1) in the middle of
-  // pass r -- the elementwise warps never wait for the tensor pipe in steady state (they waited 24 % of the time at
+  // S^T / P^T / dS^T alternate between X and Y, so S^T(g+2) is issued a whole pass ahead and dP^T(g+1) in the middle of
+  // pass g -- the elementwise warps never wait for the tensor pipe in steady state (they waited 24 % of the time at
   // D = 64 with two regions).  At D = 128 TMEM is full (128 + 128 + 128 + 128) and the two-region scheme above applies.
   constexpr bool kThird = DPAD <= 64;
   constexpr uint32_t kTmemX = 0, kTmemY = 128, kTmemZ = 256;
@@ -566,33 +641,36 @@ __global__ void __launch_bounds__(kThreads, 1)
   static_assert(kTmemdK + DPAD <= kTmemCols, "accumulators do not fit TMEM");
 
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kSmemBar);
-  uint64_t *kv_full = bars;           // K and V tiles landed
-  uint64_t *q_full = bars + 1;        // [3] Q(r) landed
-  uint64_t *q_empty = bars + 4;       // [3]
-  uint64_t *do_full = bars + 7;       // [2] dO(r) landed
-  uint64_t *do_empty = bars + 9;      // [2]
-  uint64_t *vec_full = bars + 11;     // [2] L(r), D(r) vectors in shared memory (32 arrivals)
-  uint64_t *vec_empty = bars + 13;    // [2] (256 arrivals)
-  uint64_t *st_full = bars + 15;      // S^T(r) in TMEM (two regions: kThird uses st_full and st_full2 = bars + 23 alternately)
-  uint64_t *st_full2 = bars + 23;
-  uint64_t *p_full = bars + 16;       // P^T(r) written (256 arrivals)
-  uint64_t *acc_final = bars + 17;
-  uint64_t *do_ready = bars + 18;     // [2] kConvertDO: staged dO(r) rewritten as FP16 (warps 10 and 11: 64 arrivals)
-  uint64_t *dpt_full = bars + 20;     // dP^T(r) in TMEM
-  uint64_t *rd_free = bars + 21;      // dP^T(r) is in registers: its region may take S^T(r+1) (256 arrivals)
-  uint64_t *ds_full = bars + 22;      // dS^T(r) written (256 arrivals)
+  uint64_t *kv_full = bars;           // [2] K and V tiles of the item landed
+  uint64_t *kv_empty = bars + 2;      // [2] every MMA of the item has completed: the buffers may be reloaded
+  uint64_t *q_full = bars + 4;        // [3] Q(g) landed
+  uint64_t *q_empty = bars + 7;       // [3]
+  uint64_t *do_full = bars + 10;      // [2] dO(g) landed
+  uint64_t *do_empty = bars + 12;     // [2]
+  uint64_t *vec_full = bars + 14;     // [2] L(g), D(g) vectors in shared memory (32 arrivals)
+  uint64_t *vec_empty = bars + 16;    // [2] (256 arrivals)
+  uint64_t *do_ready = bars + 18;     // [2] kConvertDO: staged dO(g) rewritten as FP16 (warps 10 and 11: 64 arrivals)
+  uint64_t *st_full = bars + 20;      // S^T(g) in TMEM (kThird: st_full for even g, st_full2 for odd g -- one per region)
+  uint64_t *st_full2 = bars + 21;
+  uint64_t *p_full = bars + 22;       // P^T(g) written (256 arrivals)
+  uint64_t *acc_final = bars + 23;    // one phase per item: the item's last dK += dS^T Q has completed
+  uint64_t *dpt_full = bars + 24;     // dP^T(g) in TMEM
+  uint64_t *rd_free = bars + 25;      // dP^T(g) is in registers: its region may be overwritten (256 arrivals)
+  uint64_t *ds_full = bars + 26;      // dS^T(g) written (256 arrivals)
+  uint64_t *acc_free = bars + 27;     // one phase per item: the epilogue has read dV and dK out of TMEM (256 arrivals)
   static_assert(!(kBF16 && kConvertDO), "dO is only converted when Q, K, V are FP16");
   float *vecL = reinterpret_cast<float *>(smem + Cfg::kSmemVec);  // [stage][128]
   float *vecD = vecL + 2 * kTile;
   uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem + Cfg::kSmemTmemPtr);
 
   if (threadIdx.x == 0) {
-    mbar_init(kv_full, 1);
     for (uint32_t s = 0; s < Cfg::kStagesQ; ++s) {
       mbar_init(&q_full[s], 1);
       mbar_init(&q_empty[s], 1);
     }
     for (uint32_t s = 0; s < 2; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
       mbar_init(&do_full[s], 1);
       mbar_init(&do_empty[s], 1);
       mbar_init(&vec_full[s], 32);
@@ -606,6 +684,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     mbar_init(dpt_full, 1);
     mbar_init(rd_free, kElemThreads);
     mbar_init(ds_full, kElemThreads);
+    mbar_init(acc_free, kElemThreads);
     fence_barrier_init();
   }
   if (warp == 8) {
@@ -616,7 +695,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  if (gridDim.z > 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (a.num_splits > 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp < 8) {
     // ---------------- elementwise warpgroups: thread = key row, columns = queries ----------------
@@ -624,84 +703,93 @@ __global__ void __launch_bounds__(kThreads, 1)
     const uint32_t h = warp >> 2, quarter = warp & 3;
     const uint32_t tLane = tmem_base + ((quarter * 32) << 16);
 
-    for (uint32_t r = 0; r < num_blocks; ++r) {
-      const uint32_t stage = r & 1;
-      const uint32_t rs = (r & 1) ? kTmemY : kTmemX, rd = kThird ? kTmemZ : ((r & 1) ? kTmemX : kTmemY);
-      const float *Lq = vecL + stage * kTile + h * kHalf, *Dq = vecD + stage * kTile + h * kHalf;
-      // ---- first half: P^T = exp2(S^T * log2e/sqrt(D) - L[q])   (+Softmax.swift:419-427) ----
-      if (kThird)
-        mbar_wait((r & 1) ? st_full2 : st_full, (r >> 1) & 1);  // one barrier per S^T region: two S^T can be outstanding
-      else
-        mbar_wait(st_full, r & 1);
-      mbar_wait(&vec_full[stage], (r >> 1) & 1);
-      tc_fence_after();
-      float p[kHalf];
+    uint32_t g0 = 0;
+    for (uint32_t item = blockIdx.x, it = 0; item < a.num_items; item += gridDim.x, ++it) {
+      uint32_t c0, head, split, blk0, num_blocks;
+      decode(item, c0, head, split, blk0, num_blocks);
+      for (uint32_t r = 0; r < num_blocks; ++r) {
+        const uint32_t g = g0 + r, stage = g & 1;
+        const uint32_t rs = (g & 1) ? kTmemY : kTmemX, rd = kThird ? kTmemZ : ((g & 1) ? kTmemX : kTmemY);
+        const float *Lq = vecL + stage * kTile + h * kHalf, *Dq = vecD + stage * kTile + h * kHalf;
+        // ---- first half: P^T = exp2(S^T * log2e/sqrt(D) - L[q])   (+Softmax.swift:419-427) ----
+        if (kThird)
+          mbar_wait((g & 1) ? st_full2 : st_full, (g >> 1) & 1);  // one barrier per S^T region: two S^T can be outstanding
+        else
+          mbar_wait(st_full, g & 1);
+        mbar_wait(&vec_full[stage], (g >> 1) & 1);
+        tc_fence_after();
+        float p[kHalf];
 #pragma unroll
-      for (uint32_t c = 0; c < kHalf; c += 32) tmem_ld32(tLane + rs + h * kHalf + c, *reinterpret_cast<uint32_t(*)[32]>(&p[c]));
-      tc_wait_ld();
-      // both warpgroups hold S^T(r) in registers before either overwrites the region with P^T / dS^T (warpgroup 1's
-      // P^T columns [32,64) lie inside warpgroup 0's S^T columns [0,64))
-      asm volatile("bar.sync 1, %0;" ::"n"(kElemThreads) : "memory");
-      const uint32_t q0 = (blk0 + r) * kTile + h * kHalf;
-      if (blk0 + r + 1 == total_blocks && q0 + kHalf > a.R) {  // padded query rows: P^T = 0 there
+        for (uint32_t c = 0; c < kHalf; c += 32) tmem_ld32(tLane + rs + h * kHalf + c, *reinterpret_cast<uint32_t(*)[32]>(&p[c]));
+        tc_wait_ld();
+        // both warpgroups hold S^T(g) in registers before either overwrites the region with P^T / dS^T (warpgroup 1's
+        // P^T columns [32,64) lie inside warpgroup 0's S^T columns [0,64))
+        asm volatile("bar.sync 1, %0;" ::"n"(kElemThreads) : "memory");
+        const uint32_t q0 = (blk0 + r) * kTile + h * kHalf;
+        if (blk0 + r + 1 == total_blocks && q0 + kHalf > a.R) {  // padded query rows: P^T = 0 there
 #pragma unroll
-        for (uint32_t c = 0; c < kHalf; ++c)
-          if (q0 + c >= a.R) p[c] = -INFINITY;
-      }
-#pragma unroll
-      for (uint32_t c = 0; c < kHalf; c += 32) {
-        uint32_t pp[16];
-#pragma unroll
-        for (uint32_t k = 0; k < 16; ++k) {
-          exp2_pair<kPolyPairs<DPAD>>(k, p[c + 2 * k], p[c + 2 * k + 1], a.scale_log2, Lq[c + 2 * k], Lq[c + 2 * k + 1]);
-          pp[k] = kBF16 ? pack_bf16x2(p[c + 2 * k], p[c + 2 * k + 1]) : pack_f16x2(p[c + 2 * k], p[c + 2 * k + 1]);
+          for (uint32_t c = 0; c < kHalf; ++c)
+            if (q0 + c >= a.R) p[c] = -INFINITY;
         }
-        tmem_st16(tLane + rs + h * (kHalf / 2) + (c >> 1), pp);  // P^T of queries [64h + c, +32) -> columns [32h + c/2, +16)
-      }
-      tc_wait_st();
-      tc_fence_before();
-      mbar_arrive(p_full);
-
-      // ---- second half: dS^T = P^T * (dP^T/sqrt(D) - D[q]) ----
-      mbar_wait(dpt_full, r & 1);
-      tc_fence_after();
-      uint32_t dp[kHalf];
 #pragma unroll
-      for (uint32_t c = 0; c < kHalf; c += 32) tmem_ld32(tLane + rd + h * kHalf + c, *reinterpret_cast<uint32_t(*)[32]>(&dp[c]));
-      tc_wait_ld();
-      tc_fence_before();
-      mbar_arrive(rd_free);  // S^T(r+1) may overwrite the dP^T region now
-      const float2 scale2 = make_float2(a.scale, a.scale);
+        for (uint32_t c = 0; c < kHalf; c += 32) {
+          uint32_t pp[16];
 #pragma unroll
-      for (uint32_t c = 0; c < kHalf; c += 32) {
-        uint32_t dd[16];
-#pragma unroll
-        for (uint32_t k = 0; k < 16; ++k) {
-          // (the vector loader stores -D, so the pair of D terms is one 64-bit shared-memory load and the
-          // subtraction folds into the packed FMA; see backwardQuery for why packed arithmetic)
-          const float2 negD2 = *reinterpret_cast<const float2 *>(&Dq[c + 2 * k]);
-          const float2 t = ffma2(make_float2(__uint_as_float(dp[c + 2 * k]), __uint_as_float(dp[c + 2 * k + 1])), scale2, negD2);
-          const float2 ds = fmul2(make_float2(p[c + 2 * k], p[c + 2 * k + 1]), t);
-          dd[k] = kBF16 ? pack_bf16x2(ds.x, ds.y) : pack_f16x2(ds.x, ds.y);
+          for (uint32_t k = 0; k < 16; ++k) {
+            exp2_pair<kPoly>(k, p[c + 2 * k], p[c + 2 * k + 1], a.scale_log2, Lq[c + 2 * k], Lq[c + 2 * k + 1]);
+            pp[k] = kBF16 ? pack_bf16x2(p[c + 2 * k], p[c + 2 * k + 1]) : pack_f16x2(p[c + 2 * k], p[c + 2 * k + 1]);
+          }
+          tmem_st16(tLane + rs + h * (kHalf / 2) + (c >> 1), pp);  // P^T of queries [64h + c, +32) -> columns [32h + c/2, +16)
         }
-        tmem_st16(tLane + rs + kHalf + h * (kHalf / 2) + (c >> 1), dd);  // dS^T -> columns [64 + 32h + c/2, +16)
-      }
-      tc_wait_st();
-      tc_fence_before();
-      mbar_arrive(ds_full);
-      mbar_arrive(&vec_empty[stage]);
-    }
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(p_full);
 
-    // epilogue: dV, dK -> global (FP32); warpgroup h writes columns [h D/2, (h+1) D/2) of both
-    mbar_wait(acc_final, 0);
-    tc_fence_after();
-    {
-      float4 *scratch = reinterpret_cast<float4 *>(smem + Cfg::kSmemQ) + warp * 256;  // the Q stages are dead now
-      const uint32_t warp_row0 = c0 + quarter * 32;
-      const size_t base = blockIdx.z * a.split_stride + (static_cast<size_t>(head) * a.C + warp_row0) * a.D;
-      store_accumulator_coalesced(tLane + kTmemdV, h * (DPAD / 2), DPAD / 2, scratch, a.dV + base, warp_row0, a.C, a.D, lane);
-      store_accumulator_coalesced(tLane + kTmemdK, h * (DPAD / 2), DPAD / 2, scratch, a.dK + base, warp_row0, a.C, a.D, lane);
-    }
+        // ---- second half: dS^T = P^T * (dP^T/sqrt(D) - D[q]) ----
+        mbar_wait(dpt_full, g & 1);
+        tc_fence_after();
+        uint32_t dp[kHalf];
+#pragma unroll
+        for (uint32_t c = 0; c < kHalf; c += 32) tmem_ld32(tLane + rd + h * kHalf + c, *reinterpret_cast<uint32_t(*)[32]>(&dp[c]));
+        tc_wait_ld();
+        tc_fence_before();
+        mbar_arrive(rd_free);  // the dP^T region may be overwritten now
+        const float2 scale2 = make_float2(a.scale, a.scale);
+#pragma unroll
+        for (uint32_t c = 0; c < kHalf; c += 32) {
+          uint32_t dd[16];
+#pragma unroll
+          for (uint32_t k = 0; k < 16; ++k) {
+            // (the vector loader stores -D, so the pair of D terms is one 64-bit shared-memory load and the
+            // subtraction folds into the packed FMA; see backwardQuery for why packed arithmetic)
+            const float2 negD2 = *reinterpret_cast<const float2 *>(&Dq[c + 2 * k]);
+            const float2 t = ffma2(make_float2(__uint_as_float(dp[c + 2 * k]), __uint_as_float(dp[c + 2 * k + 1])), scale2, negD2);
+            const float2 ds = fmul2(make_float2(p[c + 2 * k], p[c + 2 * k + 1]), t);
+            dd[k] = kBF16 ? pack_bf16x2(ds.x, ds.y) : pack_f16x2(ds.x, ds.y);
+          }
+          tmem_st16(tLane + rs + kHalf + h * (kHalf / 2) + (c >> 1), dd);  // dS^T -> columns [64 + 32h + c/2, +16)
+        }
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(ds_full);
+        mbar_arrive(&vec_empty[stage]);
+      }
+
+      // epilogue: dV, dK -> global (FP32); warpgroup h writes columns [h D/2, (h+1) D/2) of both
+      mbar_wait(acc_final, it & 1);
+      tc_fence_after();
+      {
+        float4 *scratch = reinterpret_cast<float4 *>(smem + Cfg::kSmemScratch) + warp * 256;
+        const uint32_t warp_row0 = c0 + quarter * 32;
+        const size_t base = split * a.split_stride + (static_cast<size_t>(head) * a.C + warp_row0) * a.D;
+        store_accumulator_coalesced(tLane + kTmemdV, h * (DPAD / 2), DPAD / 2, scratch, a.dV + base, warp_row0, a.C, a.D, lane);
+        store_accumulator_coalesced(tLane + kTmemdK, h * (DPAD / 2), DPAD / 2, scratch, a.dK + base, warp_row0, a.C, a.D, lane);
+      }
+      // the accumulators are out of TMEM: the next item's first dV / dK MMAs (accumulate off) may overwrite them
+      tc_fence_before();
+      mbar_arrive(acc_free);
+      g0 += num_blocks;
+    }  // work items
   } else {
     setmaxnreg_dec<kOtherRegs>();
     // kConvertDO: warps 10 and 11 each rewrite one half of the staged BF16 dO tile as FP16 once the TMA has landed it
@@ -715,61 +803,83 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_arrive(&do_ready[stage]);
     };
     if (warp == 9) {
-      // ---------------- TMA producer ----------------
-      if (elect_one()) {
-        mbar_arrive_expect_tx(kv_full, 2 * Cfg::kTileBytes);
-#pragma unroll
-        for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds) {
-          tma_load_3d(smem + Cfg::kSmemK + ds * kSubTileBytes, &mapK, kv_full, ds * 64, c0, head);
-          tma_load_3d(smem + Cfg::kSmemV + ds * kSubTileBytes, &mapV, kv_full, ds * 64, c0, head);
-        }
-      }
-      for (uint32_t r = 0; r < num_blocks; ++r) {
-        const uint32_t qs = r % Cfg::kStagesQ, qphase = (r / Cfg::kStagesQ) & 1;
-        const uint32_t os = r & 1, ophase = (r >> 1) & 1;
-        mbar_wait(&q_empty[qs], qphase ^ 1);
+      // ---------------- TMA producer: K, V of every item, and the Q and dO rings ----------------
+      uint32_t g0 = 0;
+      for (uint32_t item = blockIdx.x, it = 0; item < a.num_items; item += gridDim.x, ++it) {
+        uint32_t c0, head, split, blk0, num_blocks;
+        decode(item, c0, head, split, blk0, num_blocks);
+        const uint32_t kb = it % kDB;
+        mbar_wait(&kv_empty[kb], ((it / kDB) & 1) ^ 1);  // the item that used these buffers last is done with them
         if (elect_one()) {
-          mbar_arrive_expect_tx(&q_full[qs], Cfg::kTileBytes);
+          mbar_arrive_expect_tx(&kv_full[kb], 2 * Cfg::kTileBytes);
 #pragma unroll
-          for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
-            tma_load_3d(smem + Cfg::kSmemQ + qs * Cfg::kTileBytes + ds * kSubTileBytes, &mapQ, &q_full[qs], ds * 64,
-                        (blk0 + r) * kTile, head);
+          for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds) {
+            tma_load_3d(smem + Cfg::kSmemK + kb * Cfg::kTileBytes + ds * kSubTileBytes, &mapK, &kv_full[kb], ds * 64, c0, head);
+            tma_load_3d(smem + Cfg::kSmemV + kb * Cfg::kTileBytes + ds * kSubTileBytes, &mapV, &kv_full[kb], ds * 64, c0, head);
+          }
         }
-        mbar_wait(&do_empty[os], ophase ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&do_full[os], Cfg::kTileBytes);
+        for (uint32_t r = 0; r < num_blocks; ++r) {
+          const uint32_t g = g0 + r;
+          const uint32_t qs = g % Cfg::kStagesQ, qphase = (g / Cfg::kStagesQ) & 1;
+          const uint32_t os = g & 1, ophase = (g >> 1) & 1;
+          mbar_wait(&q_empty[qs], qphase ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&q_full[qs], Cfg::kTileBytes);
 #pragma unroll
-          for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
-            tma_load_3d(smem + Cfg::kSmemdO + os * Cfg::kTileBytes + ds * kSubTileBytes, &mapdO, &do_full[os], ds * 64,
-                        (blk0 + r) * kTile, head);
+            for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
+              tma_load_3d(smem + Cfg::kSmemQ + qs * Cfg::kTileBytes + ds * kSubTileBytes, &mapQ, &q_full[qs], ds * 64,
+                          (blk0 + r) * kTile, head);
+          }
+          mbar_wait(&do_empty[os], ophase ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&do_full[os], Cfg::kTileBytes);
+#pragma unroll
+            for (uint32_t ds = 0; ds < Cfg::kSubTiles; ++ds)
+              tma_load_3d(smem + Cfg::kSmemdO + os * Cfg::kTileBytes + ds * kSubTileBytes, &mapdO, &do_full[os], ds * 64,
+                          (blk0 + r) * kTile, head);
+          }
         }
+        g0 += num_blocks;
       }
     } else if (warp == 10) {
       // ---------------- L / D vector loader (values are read back in their memory precision,
       //                  AttentionKernel+Softmax.swift:356-404, 453-468) ----------------
-      for (uint32_t r = 0; r < num_blocks; ++r) {
-        const uint32_t stage = r & 1, phase = (r >> 1) & 1;
-        mbar_wait(&vec_empty[stage], phase ^ 1);
+      uint32_t g0 = 0;
+      for (uint32_t item = blockIdx.x; item < a.num_items; item += gridDim.x) {
+        uint32_t c0, head, split, blk0, num_blocks;
+        decode(item, c0, head, split, blk0, num_blocks);
+        for (uint32_t r = 0; r < num_blocks; ++r) {
+          const uint32_t g = g0 + r, stage = g & 1, phase = (g >> 1) & 1;
+          mbar_wait(&vec_empty[stage], phase ^ 1);
 #pragma unroll
-        for (uint32_t i = 0; i < kTile / 32; ++i) {
-          const uint32_t q = (blk0 + r) * kTile + i * 32 + lane;
-          const size_t idx = static_cast<size_t>(head) * a.R + min(q, a.R - 1);
-          vecL[stage * kTile + i * 32 + lane] = load_stat(a.L, idx, a.l_prec);
-          vecD[stage * kTile + i * 32 + lane] = -load_stat(a.Dterm, idx, a.d_prec);  // negated: see the dS^T pass
+          for (uint32_t i = 0; i < kTile / 32; ++i) {
+            const uint32_t q = (blk0 + r) * kTile + i * 32 + lane;
+            const size_t idx = static_cast<size_t>(head) * a.R + min(q, a.R - 1);
+            vecL[stage * kTile + i * 32 + lane] = load_stat(a.L, idx, a.l_prec);
+            vecD[stage * kTile + i * 32 + lane] = -load_stat(a.Dterm, idx, a.d_prec);  // negated: see the dS^T pass
+          }
+          mbar_arrive(&vec_full[stage]);  // release semantics order the shared-memory writes above
+          if constexpr (kConvertDO) convert_dO(stage, phase, 0);
         }
-        mbar_arrive(&vec_full[stage]);  // release semantics order the shared-memory writes above
-        if constexpr (kConvertDO) convert_dO(stage, phase, 0);
+        g0 += num_blocks;
       }
     } else if (warp == 11) {
-      if constexpr (kConvertDO)
-        for (uint32_t r = 0; r < num_blocks; ++r) convert_dO(r & 1, (r >> 1) & 1, 1);
+      if constexpr (kConvertDO) {
+        uint32_t g0 = 0;
+        for (uint32_t item = blockIdx.x; item < a.num_items; item += gridDim.x) {
+          uint32_t c0, head, split, blk0, num_blocks;
+          decode(item, c0, head, split, blk0, num_blocks);
+          for (uint32_t r = 0; r < num_blocks; ++r) convert_dO((g0 + r) & 1, ((g0 + r) >> 1) & 1, 1);
+          g0 += num_blocks;
+        }
+      }
     } else if (warp == 8) {
       // ---------------- MMA issuer ----------------
       constexpr uint32_t kFormat = kBF16 ? 1u : 0u;
       constexpr uint32_t idescNT = make_idesc_f16(kTile, kTile, kFormat, 0, 0);
       constexpr uint32_t idescAcc = make_idesc_f16(kTile, DPAD, kFormat, 0, 1);
-      const uint64_t descK = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemK), 16, 1024);
-      const uint64_t descV = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemV), 16, 1024);
+      const uint64_t descK0 = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemK), 16, 1024);
+      const uint64_t descV0 = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemV), 16, 1024);
       const uint64_t descQ = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemQ), 16, 1024);
       const uint64_t descdO = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemdO), 16, 1024);
       const uint64_t descQmn = make_smem_desc_sw128(smem_u32(smem + Cfg::kSmemQ), kSubTileBytes, 1024);
@@ -788,129 +898,149 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (uint32_t k = 0; k < kTile / 16; ++k)
           umma_ts(d_tmem, a_base + k * 8, b_desc + ((k * 2048) >> 4), idescAcc, k > 0 ? 1u : accumulate);
       };
+      auto q_at = [&](uint32_t g) { return descQ + (((g % Cfg::kStagesQ) * Cfg::kTileBytes) >> 4); };
+      auto do_at = [&](uint32_t g) { return descdO + (((g & 1) * Cfg::kTileBytes) >> 4); };
+      auto region = [&](uint32_t g) { return tmem_base + ((g & 1) ? kTmemY : kTmemX); };
 
-      // prologue: S^T(0) -> X, dP^T(0) -> Y (Z with three regions)
-      mbar_wait(kv_full, 0);
-      mbar_wait(&q_full[0], 0);
-      tc_fence_after();
-      if (elect_one()) {
-        issue_nt(tmem_base + kTmemX, descK, descQ);  // S^T = K Q^T
-        umma_commit(st_full);
-      }
-      __syncwarp();
-      mbar_wait(&do_full[0], 0);
-      if constexpr (kConvertDO) mbar_wait(&do_ready[0], 0);
-      tc_fence_after();
-      if (elect_one()) {
-        issue_nt(tmem_base + (kThird ? kTmemZ : kTmemY), descV, descdO);  // dP^T = V dO^T
-        umma_commit(dpt_full);
-      }
-      __syncwarp();
+      uint32_t g0 = 0;
+      for (uint32_t item = blockIdx.x, it = 0; item < a.num_items; item += gridDim.x, ++it) {
+        uint32_t c0, head, split, blk0, num_blocks;
+        decode(item, c0, head, split, blk0, num_blocks);
+        const uint32_t kb = it % kDB;
+        const uint64_t descK = descK0 + ((kb * Cfg::kTileBytes) >> 4), descV = descV0 + ((kb * Cfg::kTileBytes) >> 4);
 
-      if constexpr (kThird) {
-        // three regions: S^T(1) straight away, then per block  dV(r) -> dP^T(r+1) -> dK(r) -> S^T(r+2)
-        if (num_blocks > 1) {
-          mbar_wait(&q_full[1 % Cfg::kStagesQ], 0);
-          tc_fence_after();
-          if (elect_one()) {
-            issue_nt(tmem_base + kTmemY, descK, descQ + (((1 % Cfg::kStagesQ) * Cfg::kTileBytes) >> 4));
-            umma_commit(st_full2);
-          }
-          __syncwarp();
+        // prologue: S^T(g0) and dP^T(g0) (and S^T(g0 + 1) with three regions).  For every item but the first they are
+        // issued while the elementwise warps are still storing the previous item's dV / dK: the S^T regions' last readers
+        // (dK of the previous item's last two blocks) are ahead on the in-order tensor pipe, the dP^T region only needs
+        // the previous item's last dP^T to have been read out (rd_free).
+        mbar_wait(&kv_full[kb], (it / kDB) & 1);
+        mbar_wait(&q_full[g0 % Cfg::kStagesQ], (g0 / Cfg::kStagesQ) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_nt(region(g0), descK, q_at(g0));  // S^T = K Q^T
+          umma_commit(kThird && (g0 & 1) ? st_full2 : st_full);
         }
-        for (uint32_t r = 0; r < num_blocks; ++r) {
-          const uint32_t qs = r % Cfg::kStagesQ, os = r & 1;
-          const uint32_t nos = (r + 1) & 1, nophase = ((r + 1) >> 1) & 1;
-          const uint32_t nqs = (r + 2) % Cfg::kStagesQ, nqphase = ((r + 2) / Cfg::kStagesQ) & 1;
-          const uint32_t rs = tmem_base + ((r & 1) ? kTmemY : kTmemX);
-          // (a) dV += P^T(r) dO(r); dO(r) is done with after this
-          mbar_wait(p_full, r & 1);
-          tc_fence_after();
-          if (elect_one()) {
-            issue_acc(tmem_base + kTmemdV, rs, descdOmn + ((os * Cfg::kTileBytes) >> 4), r > 0 ? 1u : 0u);
-            umma_commit(&do_empty[os]);
-          }
-          __syncwarp();
-          // (b) dP^T(r+1) = V dO(r+1)^T into Z as soon as dP^T(r) has been read out of it
-          if (r + 1 < num_blocks) {
-            mbar_wait(rd_free, r & 1);
-            mbar_wait(&do_full[nos], nophase);
-            if constexpr (kConvertDO) mbar_wait(&do_ready[nos], nophase);
+        __syncwarp();
+        mbar_wait(&do_full[g0 & 1], (g0 >> 1) & 1);
+        if constexpr (kConvertDO) mbar_wait(&do_ready[g0 & 1], (g0 >> 1) & 1);
+        if (it > 0) mbar_wait(rd_free, (g0 - 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_nt(kThird ? tmem_base + kTmemZ : region(g0 + 1), descV, do_at(g0));  // dP^T = V dO^T
+          umma_commit(dpt_full);
+        }
+        __syncwarp();
+
+        if constexpr (kThird) {
+          // three regions: S^T(g0 + 1) straight away, then per block  dV(g) -> dP^T(g+1) -> dK(g) -> S^T(g+2)
+          if (num_blocks > 1) {
+            mbar_wait(&q_full[(g0 + 1) % Cfg::kStagesQ], ((g0 + 1) / Cfg::kStagesQ) & 1);
             tc_fence_after();
             if (elect_one()) {
-              issue_nt(tmem_base + kTmemZ, descV, descdO + ((nos * Cfg::kTileBytes) >> 4));
-              umma_commit(dpt_full);
+              issue_nt(region(g0 + 1), descK, q_at(g0 + 1));
+              umma_commit(((g0 + 1) & 1) ? st_full2 : st_full);
             }
             __syncwarp();
           }
-          // (c) dK += dS^T(r) Q(r); Q(r) is done with after this
-          mbar_wait(ds_full, r & 1);
-          tc_fence_after();
-          if (elect_one()) {
-            issue_acc(tmem_base + kTmemdK, rs + kHalf, descQmn + ((qs * Cfg::kTileBytes) >> 4), r > 0 ? 1u : 0u);
-            umma_commit(&q_empty[qs]);
-            if (r + 1 == num_blocks) umma_commit(acc_final);
-          }
-          __syncwarp();
-          // (d) S^T(r+2) = K Q(r+2)^T into the region P^T(r) / dS^T(r) occupied (in-order pipe: after dV(r), dK(r))
-          if (r + 2 < num_blocks) {
-            mbar_wait(&q_full[nqs], nqphase);
+          for (uint32_t r = 0; r < num_blocks; ++r) {
+            const uint32_t g = g0 + r;
+            // (a) dV += P^T(g) dO(g); dO(g) is done with after this
+            mbar_wait(p_full, g & 1);
+            if (r == 0) mbar_wait(acc_free, (it & 1) ^ 1);  // the previous item's epilogue has read the accumulators out
             tc_fence_after();
             if (elect_one()) {
-              issue_nt(rs, descK, descQ + ((nqs * Cfg::kTileBytes) >> 4));
-              umma_commit((r & 1) ? st_full2 : st_full);
+              issue_acc(tmem_base + kTmemdV, region(g), descdOmn + (((g & 1) * Cfg::kTileBytes) >> 4), r > 0 ? 1u : 0u);
+              umma_commit(&do_empty[g & 1]);
             }
             __syncwarp();
+            // (b) dP^T(g+1) = V dO(g+1)^T into Z as soon as dP^T(g) has been read out of it
+            if (r + 1 < num_blocks) {
+              mbar_wait(rd_free, g & 1);
+              mbar_wait(&do_full[(g + 1) & 1], ((g + 1) >> 1) & 1);
+              if constexpr (kConvertDO) mbar_wait(&do_ready[(g + 1) & 1], ((g + 1) >> 1) & 1);
+              tc_fence_after();
+              if (elect_one()) {
+                issue_nt(tmem_base + kTmemZ, descV, do_at(g + 1));
+                umma_commit(dpt_full);
+              }
+              __syncwarp();
+            }
+            // (c) dK += dS^T(g) Q(g); Q(g) is done with after this
+            mbar_wait(ds_full, g & 1);
+            tc_fence_after();
+            if (elect_one()) {
+              issue_acc(tmem_base + kTmemdK, region(g) + kHalf, descQmn + (((g % Cfg::kStagesQ) * Cfg::kTileBytes) >> 4),
+                        r > 0 ? 1u : 0u);
+              umma_commit(&q_empty[g % Cfg::kStagesQ]);
+              if (r + 1 == num_blocks) {
+                umma_commit(acc_final);
+                umma_commit(&kv_empty[kb]);
+              }
+            }
+            __syncwarp();
+            // (d) S^T(g+2) = K Q(g+2)^T into the region P^T(g) / dS^T(g) occupied (in-order pipe: after dV(g), dK(g))
+            if (r + 2 < num_blocks) {
+              mbar_wait(&q_full[(g + 2) % Cfg::kStagesQ], ((g + 2) / Cfg::kStagesQ) & 1);
+              tc_fence_after();
+              if (elect_one()) {
+                issue_nt(region(g), descK, q_at(g + 2));
+                umma_commit((g & 1) ? st_full2 : st_full);
+              }
+              __syncwarp();
+            }
+          }
+        } else {
+          for (uint32_t r = 0; r < num_blocks; ++r) {
+            const uint32_t g = g0 + r;
+            const bool has_next = r + 1 < num_blocks;
+            // (a) dV += P^T(g) dO(g); dO(g) is done with after this
+            mbar_wait(p_full, g & 1);
+            if (r == 0) mbar_wait(acc_free, (it & 1) ^ 1);
+            tc_fence_after();
+            if (elect_one()) {
+              issue_acc(tmem_base + kTmemdV, region(g), descdOmn + (((g & 1) * Cfg::kTileBytes) >> 4), r > 0 ? 1u : 0u);
+              umma_commit(&do_empty[g & 1]);
+            }
+            __syncwarp();
+            // (b) S^T(g+1) = K Q(g+1)^T into the region dP^T(g) has just been read out of
+            if (has_next) {
+              mbar_wait(rd_free, g & 1);
+              mbar_wait(&q_full[(g + 1) % Cfg::kStagesQ], ((g + 1) / Cfg::kStagesQ) & 1);
+              tc_fence_after();
+              if (elect_one()) {
+                issue_nt(region(g + 1), descK, q_at(g + 1));
+                umma_commit(st_full);
+              }
+              __syncwarp();
+            }
+            // (c) dK += dS^T(g) Q(g); Q(g) is done with after this
+            mbar_wait(ds_full, g & 1);
+            tc_fence_after();
+            if (elect_one()) {
+              issue_acc(tmem_base + kTmemdK, region(g) + kHalf, descQmn + (((g % Cfg::kStagesQ) * Cfg::kTileBytes) >> 4),
+                        r > 0 ? 1u : 0u);
+              umma_commit(&q_empty[g % Cfg::kStagesQ]);
+              if (!has_next) {
+                umma_commit(acc_final);
+                umma_commit(&kv_empty[kb]);
+              }
+            }
+            __syncwarp();
+            // (d) dP^T(g+1) = V dO(g+1)^T into the region P^T(g) / dS^T(g) occupied (in-order pipe: after dV(g), dK(g))
+            if (has_next) {
+              mbar_wait(&do_full[(g + 1) & 1], ((g + 1) >> 1) & 1);
+              if constexpr (kConvertDO) mbar_wait(&do_ready[(g + 1) & 1], ((g + 1) >> 1) & 1);
+              tc_fence_after();
+              if (elect_one()) {
+                issue_nt(region(g), descV, do_at(g + 1));
+                umma_commit(dpt_full);
+              }
+              __syncwarp();
+            }
           }
         }
-      } else {
-        for (uint32_t r = 0; r < num_blocks; ++r) {
-          const uint32_t qs = r % Cfg::kStagesQ, os = r & 1;
-          const uint32_t nqs = (r + 1) % Cfg::kStagesQ, nqphase = ((r + 1) / Cfg::kStagesQ) & 1;
-          const uint32_t nos = (r + 1) & 1, nophase = ((r + 1) >> 1) & 1;
-          const uint32_t rs = tmem_base + ((r & 1) ? kTmemY : kTmemX), rd = tmem_base + ((r & 1) ? kTmemX : kTmemY);
-          const bool has_next = r + 1 < num_blocks;
-          // (a) dV += P^T(r) dO(r); dO(r) is done with after this
-          mbar_wait(p_full, r & 1);
-          tc_fence_after();
-          if (elect_one()) {
-            issue_acc(tmem_base + kTmemdV, rs, descdOmn + ((os * Cfg::kTileBytes) >> 4), r > 0 ? 1u : 0u);
-            umma_commit(&do_empty[os]);
-          }
-          __syncwarp();
-          // (b) S^T(r+1) = K Q(r+1)^T into the region dP^T(r) has just been read out of
-          if (has_next) {
-            mbar_wait(rd_free, r & 1);
-            mbar_wait(&q_full[nqs], nqphase);
-            tc_fence_after();
-            if (elect_one()) {
-              issue_nt(rd, descK, descQ + ((nqs * Cfg::kTileBytes) >> 4));
-              umma_commit(st_full);
-            }
-            __syncwarp();
-          }
-          // (c) dK += dS^T(r) Q(r); Q(r) is done with after this
-          mbar_wait(ds_full, r & 1);
-          tc_fence_after();
-          if (elect_one()) {
-            issue_acc(tmem_base + kTmemdK, rs + kHalf, descQmn + ((qs * Cfg::kTileBytes) >> 4), r > 0 ? 1u : 0u);
-            umma_commit(&q_empty[qs]);
-            if (!has_next) umma_commit(acc_final);
-          }
-          __syncwarp();
-          // (d) dP^T(r+1) = V dO(r+1)^T into the region P^T(r) / dS^T(r) occupied (in-order pipe: after dV(r), dK(r))
-          if (has_next) {
-            mbar_wait(&do_full[nos], nophase);
-            if constexpr (kConvertDO) mbar_wait(&do_ready[nos], nophase);
-            tc_fence_after();
-            if (elect_one()) {
-              issue_nt(rs, descV, descdO + ((nos * Cfg::kTileBytes) >> 4));
-              umma_commit(dpt_full);
-            }
-            __syncwarp();
-          }
-        }
-      }
+        g0 += num_blocks;
+      }  // work items
     }
   }
 
@@ -951,19 +1081,23 @@ __global__ void __launch_bounds__(256)
 
 // How many ranges to cut the traversal axis into: only when the SMs would otherwise idle (a single head at N = 4096 is
 // 32 CTAs for 148 SMs), at least two blocks per range, at most 8 ranges.
-static uint32_t choose_blocks_per_split(uint32_t ctas, uint32_t total_blocks, uint32_t sm_count) {
-  if (ctas * 2 > sm_count || total_blocks < 4) return total_blocks;
+// (min_blocks and max_splits are the row's tuning columns; min_blocks = 0 turns splitting off)
+static uint32_t choose_blocks_per_split(uint32_t ctas, uint32_t total_blocks, uint32_t sm_count, uint32_t min_blocks,
+                                        uint32_t max_splits) {
+  if (ctas * 2 > sm_count || min_blocks == 0 || total_blocks < 2 * min_blocks) return total_blocks;
+  if (max_splits > 8) max_splits = 8;  // sum_splits<8>
   uint32_t splits = sm_count / ctas;
-  if (splits > 8) splits = 8;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 2) return total_blocks;
   uint32_t per = (total_blocks + splits - 1) / splits;
-  if (per < 2) per = 2;
+  if (per < min_blocks) per = min_blocks;
   return per;
 }
 
-template <uint32_t DPAD, bool kBF16, bool kConvertDO = false>
+template <uint32_t DPAD, bool kBF16, bool kConvertDO, uint32_t kPoly>
 cudaError_t launch(const AttentionParams &p, cudaStream_t stream, bool key_value) {
-  auto kernel_q = attention_backward_query_tcgen05<DPAD, kBF16, kConvertDO>;
-  auto kernel_kv = attention_backward_key_value_tcgen05<DPAD, kBF16, kConvertDO>;
+  auto kernel_q = attention_backward_query_tcgen05<DPAD, kBF16, kConvertDO, kPoly>;
+  auto kernel_kv = attention_backward_key_value_tcgen05<DPAD, kBF16, kConvertDO, kPoly>;
   const int device = current_device();
   cudaError_t e;
   if (!key_value)
@@ -997,15 +1131,24 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, bool key_value
   // parallelised dimension -> CTAs; traversed dimension -> blocks, possibly split over blockIdx.z
   const uint32_t par = key_value ? p.C : p.R, trav = key_value ? p.R : p.C;
   const uint32_t tiles = (par + kTile - 1) / kTile, total_blocks = (trav + kTile - 1) / kTile;
-  const uint32_t per = choose_blocks_per_split(tiles * p.batch, total_blocks, device_sm_count(device));
+  const uint32_t per = choose_blocks_per_split(tiles * p.batch, total_blocks, device_sm_count(device), p.split_min_blocks, p.split_max);
   const uint32_t splits = (total_blocks + per - 1) / per;
   a.blocks_per_split = per;
   a.split_stride = 0;
-  dim3 grid(tiles, p.batch, splits);
+  a.tiles = tiles;
+  a.batch = p.batch;
+  a.num_splits = splits;
+  a.num_items = tiles * p.batch * splits;
+  // both kernels walk work items (split, head, tile): persistent CTAs, one per SM, where the kernel can overlap
+  // consecutive items (D <= 64); otherwise one CTA per item
+  const uint32_t sm_count = device_sm_count(device);
+  const dim3 grid_q(QueryConfig<DPAD>::kPersistent && a.num_items > sm_count ? sm_count : a.num_items, 1, 1);
+  const dim3 grid = grid_q;
+  static_assert(QueryConfig<DPAD>::kPersistent == KeyValueConfig<DPAD>::kPersistent, "one grid rule for both kernels");
   const size_t smem = key_value ? KeyValueConfig<DPAD>::kSmemBytes : QueryConfig<DPAD>::kSmemBytes;
   if (splits == 1) {
     if (!key_value)
-      kernel_q<<<grid, kThreads, smem, stream>>>(mapQ, mapdO, mapK, mapV, a);
+      kernel_q<<<grid_q, kThreads, smem, stream>>>(mapQ, mapdO, mapK, mapV, a);
     else
       kernel_kv<<<grid, kThreads, smem, stream>>>(mapQ, mapdO, mapK, mapV, a);
     return cudaGetLastError();
@@ -1023,7 +1166,7 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, bool key_value
   a.dV = scratch;
   a.dK = scratch + tensor_elems;
   if (!key_value)
-    kernel_q<<<grid, kThreads, smem, stream>>>(mapQ, mapdO, mapK, mapV, a);
+    kernel_q<<<grid_q, kThreads, smem, stream>>>(mapQ, mapdO, mapK, mapV, a);
   else
     kernel_kv<<<grid, kThreads, smem, stream>>>(mapQ, mapdO, mapK, mapV, a);
   e = cudaGetLastError();
@@ -1069,12 +1212,24 @@ static cudaError_t launch_backward(const AttentionParams &p, cudaStream_t stream
   }
   const bool bf16 = p.prec[sQ] == BF16;
   const bool convert = p.prec[sdO] != p.prec[sQ];  // FP16 Q/K/V with BF16 dO
-  if (p.D <= 64) {
-    if (convert) return bwd::launch<64, false, true>(p, stream, key_value);
-    return bf16 ? bwd::launch<64, true>(p, stream, key_value) : bwd::launch<64, false>(p, stream, key_value);
+  // the row's exp2 column selects the instantiation (kernel creation has checked the range)
+#define MFA_BWD_MODES(DPAD_, POLY_)                                                          \
+  if (convert) return bwd::launch<DPAD_, false, true, POLY_>(p, stream, key_value);         \
+  return bf16 ? bwd::launch<DPAD_, true, false, POLY_>(p, stream, key_value)                 \
+              : bwd::launch<DPAD_, false, false, POLY_>(p, stream, key_value);
+#define MFA_BWD_DISPATCH(DPAD_)                \
+  switch (p.exp2_fma_quarters) {               \
+    case 0: { MFA_BWD_MODES(DPAD_, 0) }        \
+    case 1: { MFA_BWD_MODES(DPAD_, 1) }        \
+    case 2: { MFA_BWD_MODES(DPAD_, 2) }        \
+    default: { MFA_BWD_MODES(DPAD_, 3) }       \
   }
-  if (convert) return bwd::launch<128, false, true>(p, stream, key_value);
-  return bf16 ? bwd::launch<128, true>(p, stream, key_value) : bwd::launch<128, false>(p, stream, key_value);
+  if (p.D <= 64) {
+    MFA_BWD_DISPATCH(64)
+  }
+  MFA_BWD_DISPATCH(128)
+#undef MFA_BWD_DISPATCH
+#undef MFA_BWD_MODES
 }
 
 cudaError_t launch_tcgen05_backward_query(const AttentionParams &p, cudaStream_t stream) {
@@ -1085,11 +1240,12 @@ cudaError_t launch_tcgen05_backward_key_value(const AttentionParams &p, cudaStre
 }
 
 // 1 launch, or 2 (kernel + sum_splits) when the traversal split engages for this problem size
-uint32_t tcgen05_backward_launch_count(int type, uint32_t R, uint32_t C, uint32_t batch) {
+uint32_t tcgen05_backward_launch_count(int type, uint32_t R, uint32_t C, uint32_t batch, uint32_t min_blocks,
+                                       uint32_t max_splits) {
   const bool key_value = type == 2;  // MFA_BACKWARD_KEY_VALUE
   const uint32_t par = key_value ? C : R, trav = key_value ? R : C;
   const uint32_t tiles = (par + bwd::kTile - 1) / bwd::kTile, total_blocks = (trav + bwd::kTile - 1) / bwd::kTile;
-  return bwd::choose_blocks_per_split(tiles * batch, total_blocks, device_sm_count(current_device())) < total_blocks ? 2 : 1;
+  return bwd::choose_blocks_per_split(tiles * batch, total_blocks, device_sm_count(current_device()), min_blocks, max_splits) < total_blocks ? 2 : 1;
 }
 
 void tcgen05_backward_geometry(int type, uint32_t D, uint32_t *threads, uint32_t *smem_bytes, uint32_t *par,

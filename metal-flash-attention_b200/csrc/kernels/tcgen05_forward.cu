@@ -59,15 +59,11 @@ constexpr uint32_t kThreads = 384;
 // must not exceed the launch allocation or the second setmaxnreg.inc never returns.
 constexpr uint32_t kLaunchRegs = 168, kSoftmaxRegs = 208, kOtherRegs = 88;
 static_assert(kSoftmaxRegs * 256 + kOtherRegs * 128 <= kLaunchRegs * kThreads, "setmaxnreg over-subscribed");
-// Of every 4 element pairs, how many take exp2 on the FMA pipe (exp2_poly2) instead of the MUFU pipe.  Swept on B200
-// (TFLOP/s at N = 4096, 64 heads):  D=128: 0 -> 1258, 1 -> 1241, 2 -> 1183, 3 -> 1094;  D=64: 0 -> 729, 1 -> 765,
-// 2 -> 737, 3 -> 626.  At D = 64 the tensor pipe needs half as long per block, the MUFU pipe (16 ex2 / clk / SM) just
-// as long, so taking a quarter of the exponentials off it pays; at D = 128 it only costs issue slots.
-#ifdef MFA_POLY_PAIRS
-template <uint32_t DPAD> constexpr uint32_t kPolyPairsFor = MFA_POLY_PAIRS;
-#else
-template <uint32_t DPAD> constexpr uint32_t kPolyPairsFor = DPAD <= 64 ? 1 : 0;
-#endif
+// kPoly (template parameter, from the parameter-table row the kernel was created from): of every 4 element pairs, how
+// many take exp2 on the FMA pipe (exp2_poly2) instead of the MUFU pipe.  Swept on B200 (TFLOP/s at N = 4096, 64 heads;
+// scripts/sweep.py repeats it):  D=128: 0 -> 1258, 1 -> 1241, 2 -> 1183;  D=64: 0 -> 729, 1 -> 765, 2 -> 737.  At D = 64
+// the tensor pipe needs half as long per block, the MUFU pipe (16 ex2 / clk / SM) just as long, so taking a quarter of the
+// exponentials off it pays; at D = 128 it only costs issue slots.
 constexpr float kLazySumLimit = 256.0f;
 #ifndef MFA_FWD_WARP_ARRIVE
 #define MFA_FWD_WARP_ARRIVE 0
@@ -109,7 +105,7 @@ constexpr uint32_t kTraceSlots = 8;  // per (role, iteration)
 // item-level probes: roles 4 (tile 0 softmax), 5 (tile 1 softmax), 6 (MMA), indexed by the CTA's item counter
 #define MFA_TRACE_ITEM(role, it, slot) MFA_TRACE(role, it, slot)
 
-template <uint32_t DPAD, bool kBF16, bool kTrace = false, bool kFused = false>
+template <uint32_t DPAD, bool kBF16, uint32_t kPolyPairs, bool kTrace = false, bool kFused = false>
 __global__ void __launch_bounds__(kThreads, 1)
     attention_forward_tcgen05(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                               const __grid_constant__ CUtensorMap mapV, float *__restrict__ O, void *__restrict__ L,
@@ -122,7 +118,6 @@ __global__ void __launch_bounds__(kThreads, 1)
   // into the next item while the softmax warps drain the current one; TMEM alloc, barrier init and descriptor
   // prefetch are paid once per SM instead of once per tile.
   using Cfg = Config<DPAD>;
-  constexpr uint32_t kPolyPairs = kPolyPairsFor<DPAD>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -696,19 +691,22 @@ __global__ void __launch_bounds__(128)
 
 // how many key ranges to cut every item into: only when the SMs would otherwise idle, only into equal ranges of at
 // least four key blocks (shorter ranges are dominated by the per-item prologue / epilogue)
-static uint32_t choose_splits(uint32_t items, uint32_t total_blocks, uint32_t sm_count, uint32_t max_splits = 16) {
-  if (items * 2 > sm_count) return 1;
+// (min_blocks and max_splits are the row's tuning columns; min_blocks = 0 turns splitting off)
+static uint32_t choose_splits(uint32_t items, uint32_t total_blocks, uint32_t sm_count, uint32_t min_blocks,
+                              uint32_t max_splits) {
+  if (items * 2 > sm_count || min_blocks == 0) return 1;
+  if (max_splits > 16) max_splits = 16;
   const uint32_t target = sm_count / items;
   uint32_t best = 1;
   for (uint32_t s = 2; s <= target && s <= max_splits; ++s)
-    if (total_blocks % s == 0 && total_blocks / s >= 4) best = s;
+    if (total_blocks % s == 0 && total_blocks / s >= min_blocks) best = s;
   return best;
 }
 
-template <uint32_t DPAD, bool kBF16, bool kTrace = false>
+template <uint32_t DPAD, bool kBF16, uint32_t kPoly, bool kTrace = false>
 cudaError_t launch(const AttentionParams &p, cudaStream_t stream, long long *trace = nullptr) {
   using Cfg = Config<DPAD>;
-  auto kernel = attention_forward_tcgen05<DPAD, kBF16, kTrace, false>;
+  auto kernel = attention_forward_tcgen05<DPAD, kBF16, kPoly, kTrace, false>;
   const int device = current_device();
   cudaError_t e;
   if ((e = ensure_max_dynamic_smem(reinterpret_cast<const void *>(kernel), Cfg::kSmemBytes, device)) != cudaSuccess) return e;
@@ -724,7 +722,7 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, long long *tra
   const uint32_t total_blocks = (p.C + kBlockN - 1) / kBlockN;
   const int l_is_fp16 = p.prec[sL] == FP16 ? 1 : 0;
 
-  const uint32_t splits = choose_splits(num_items, total_blocks, sm_count);
+  const uint32_t splits = choose_splits(num_items, total_blocks, sm_count, p.split_min_blocks, p.split_max);
   if (splits == 1) {
     const uint32_t grid = num_items < sm_count ? num_items : sm_count;
     kernel<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mapQ, mapK, mapV, static_cast<float *>(p.buf[sO]), p.buf[sL],
@@ -738,7 +736,7 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, long long *tra
   constexpr uint32_t kPairRows = kTileM * kTilesPerCta;
   if (g_forward_fused_enabled && split_items <= sm_count && 2 * num_items * sizeof(uint32_t) <= kWorkspaceCounterBytes) {
     // fused form: one cooperative launch (every CTA resident, one item each); [counters | O partials | (m, l)]
-    auto fused = attention_forward_tcgen05<DPAD, kBF16, kTrace, true>;
+    auto fused = attention_forward_tcgen05<DPAD, kBF16, kPoly, kTrace, true>;
     if ((e = ensure_max_dynamic_smem(reinterpret_cast<const void *>(fused), Cfg::kSmemBytes, device)) != cudaSuccess) return e;
     const size_t slots = static_cast<size_t>(split_items) * kPairRows;
     const size_t o_bytes = slots * p.D * sizeof(float), ml_bytes = slots * sizeof(float2);
@@ -819,23 +817,34 @@ cudaError_t launch_tcgen05_forward(const AttentionParams &p, cudaStream_t stream
     return launch_tcgen05_forward_generic(p, stream);  // tcgen05_forward_d256.cu
   const bool bf16 = p.prec[sQ] == BF16;
   if (p.D > 128) return launch_tcgen05_forward_d256(p, stream);  // tcgen05_forward_d256.cu
-  if (p.D <= 64) return bf16 ? fwd::launch<64, true>(p, stream) : fwd::launch<64, false>(p, stream);
-  return bf16 ? fwd::launch<128, true>(p, stream) : fwd::launch<128, false>(p, stream);
+  // the row's exp2 column selects the instantiation (kernel creation has checked the range)
+#define MFA_FWD_DISPATCH(DPAD_)                                                                              \
+  switch (p.exp2_fma_quarters) {                                                                             \
+    case 0: return bf16 ? fwd::launch<DPAD_, true, 0>(p, stream) : fwd::launch<DPAD_, false, 0>(p, stream);  \
+    case 1: return bf16 ? fwd::launch<DPAD_, true, 1>(p, stream) : fwd::launch<DPAD_, false, 1>(p, stream);  \
+    default: return bf16 ? fwd::launch<DPAD_, true, 2>(p, stream) : fwd::launch<DPAD_, false, 2>(p, stream); \
+  }
+  if (p.D <= 64) {
+    MFA_FWD_DISPATCH(64)
+  }
+  MFA_FWD_DISPATCH(128)
+#undef MFA_FWD_DISPATCH
 }
 
 // Debug entry (not in include/mfa_b200.h): the D=128 bf16 forward with pipeline timestamps of CTA (0,0)
 // written to `trace` (3 roles x 64 iterations x 8 slots of clock64()).  Used by scripts/trace_forward.py.
 cudaError_t launch_tcgen05_forward_trace(const AttentionParams &p, cudaStream_t stream, long long *trace) {
-  return fwd::launch<128, true, true>(p, stream, trace);
+  return fwd::launch<128, true, 0, true>(p, stream, trace);
 }
 
 // 1 launch, or 2 (attention + combine) when the scratch form of split-KV engages for this problem size
-uint32_t tcgen05_forward_launch_count(uint32_t R, uint32_t C, uint32_t D, uint32_t batch) {
+uint32_t tcgen05_forward_launch_count(uint32_t R, uint32_t C, uint32_t D, uint32_t batch, uint32_t min_blocks,
+                                      uint32_t max_splits) {
   if (D > 128) return 1;
   const uint32_t sm_count = device_sm_count(current_device());
   const uint32_t pairs = (R + fwd::kTileM * fwd::kTilesPerCta - 1) / (fwd::kTileM * fwd::kTilesPerCta);
   const uint32_t blocks = (C + fwd::kBlockN - 1) / fwd::kBlockN;
-  if (fwd::choose_splits(pairs * batch, blocks, sm_count) == 1) return 1;
+  if (fwd::choose_splits(pairs * batch, blocks, sm_count, min_blocks, max_splits) == 1) return 1;
   return g_forward_fused_enabled ? 1 : 2;  // fused split-KV merges inside the attention kernel
 }
 

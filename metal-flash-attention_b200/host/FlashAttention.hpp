@@ -40,7 +40,17 @@ struct AttentionKernelDescriptor {  // AttentionKernelDescriptor.swift:7-48
   std::optional<uint16_t> headDimension() const {
     return c.has_head_dimension ? std::optional<uint16_t>(c.head_dimension) : std::nullopt;
   }
+  // B200 extension: the tuning columns of the parameter-table row (editable like every other field)
+  uint8_t &exp2FmaQuarters() { return c.exp2_fma_quarters; }
+  uint8_t &splitMinBlocks() { return c.split_min_blocks; }
+  uint8_t &splitMax() { return c.split_max; }
+  bool tensorCoreFamily() const { return c.backend == MFA_BACKEND_TCGEN05; }
 };
+
+// The parameter tables are data (AttentionDescriptor+Parameters.swift:106-285 analogue): replace one at run time.
+inline void setParameterTable(AttentionKernelType type, const char *text, bool transposedForward = false) {
+  check(mfa_set_parameter_table(static_cast<mfa_kernel_type_t>(type), transposedForward ? 1 : 0, text));
+}
 
 struct AttentionDescriptor {  // AttentionDescriptor.swift:10-27
   bool lowPrecisionInputs = false;
@@ -80,9 +90,24 @@ struct AttentionDescriptor {  // AttentionDescriptor.swift:10-27
     check(mfa_attention_descriptor_memory_precision(&d, static_cast<mfa_operand_t>(operand), &p));
     return static_cast<GEMMOperandPrecision>(p);
   }
+  GEMMOperandPrecision registerPrecision(AttentionOperand operand) const {  // +Precisions.swift:149-215
+    mfa_attention_descriptor_t d = c();
+    mfa_precision_t p;
+    check(mfa_attention_descriptor_register_precision(&d, static_cast<mfa_operand_t>(operand), &p));
+    return static_cast<GEMMOperandPrecision>(p);
+  }
+  std::string parameterFile(AttentionKernelType type) const {  // +Parameters.swift:13-39
+    mfa_attention_descriptor_t d = c();
+    return mfa_attention_descriptor_parameter_file(&d, static_cast<mfa_kernel_type_t>(type));
+  }
   void setFunctionConstants(mfa_function_constants_t &constants) const {  // AttentionDescriptor.swift:139-148
     mfa_attention_descriptor_t d = c();
     check(mfa_attention_descriptor_set_function_constants(&d, &constants));
+  }
+  // end-to-end call on HOST pointers: H2D -> kernels (fwd -> dQ -> dK/dV, SquareAttentionTest.swift:355-368) -> D2H
+  void runHost(uint32_t runMask, const std::array<void *, MFA_BUFFER_COUNT> &hostBuffers, int device = 0) const {
+    mfa_attention_descriptor_t d = c();
+    check(mfa_attention_run_host(&d, runMask, hostBuffers.data(), device));
   }
 };
 
@@ -109,6 +134,13 @@ class AttentionKernel {  // AttentionKernel.swift:11-50
   uint32_t threadgroupMemoryAllocation() const {
     uint32_t v; check(mfa_attention_kernel_threadgroup_memory_allocation(handle_, &v)); return v;
   }
+  uint32_t gridSize(const mfa_function_constants_t &constants) const {  // SquareAttentionTest.swift:328-339
+    uint32_t v; check(mfa_attention_kernel_grid_size(handle_, &constants, &v)); return v;
+  }
+  uint32_t launchCount(const mfa_function_constants_t &constants) const {
+    uint32_t v; check(mfa_attention_kernel_launch_count(handle_, &constants, &v)); return v;
+  }
+  std::string sourceName() const { return mfa_attention_kernel_source_name(handle_); }
   // compile + bind + dispatch (SquareAttentionTest.swift:240-372): device pointers by buffer binding
   void encode(const mfa_function_constants_t &constants, const std::array<void *, MFA_BUFFER_COUNT> &buffers,
               void *cudaStream = nullptr) const {

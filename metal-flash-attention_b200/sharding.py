@@ -26,36 +26,46 @@ def head_partition(total_heads: int, world_size: int, rank: int) -> Tuple[int, i
 def scatter_heads(full: Optional[torch.Tensor], total_heads: int, tail_shape, dtype, device, src: int = 0,
                   group=None) -> torch.Tensor:
     """Rank `src` holds `full` = [total_heads, *tail_shape]; every rank returns its [count, *tail_shape] shard.
-    Point-to-point sends (ncclSend/ncclRecv under NCCL), no collective on the compute path."""
+    Point-to-point sends (ncclSend/ncclRecv under NCCL, posted as ONE batch so that the transfers to all peers run
+    concurrently over NVSwitch instead of one after the other), no collective on the compute path."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     start, count = head_partition(total_heads, world, rank)
     if rank == src:
         assert full is not None and full.shape[0] == total_heads
-        requests = []
+        ops = []
         for peer in range(world):
             if peer == src:
                 continue
             ps, pc = head_partition(total_heads, world, peer)
             if pc:
-                requests.append(dist.isend(full[ps:ps + pc].contiguous(), dst=peer, group=group))
+                ops.append(dist.P2POp(dist.isend, full[ps:ps + pc], peer, group))
+        requests = dist.batch_isend_irecv(ops) if ops else []
         shard = full[start:start + count].clone()
         for r in requests:
             r.wait()
         return shard
     shard = torch.empty((count, *tail_shape), dtype=dtype, device=device)
     if count:
-        dist.recv(shard, src=src, group=group)
+        for r in dist.batch_isend_irecv([dist.P2POp(dist.irecv, shard, src, group)]):
+            r.wait()
     return shard
 
 
-def gather_heads(shard: torch.Tensor, total_heads: int, dst: int = 0, group=None) -> Optional[torch.Tensor]:
-    """Inverse of scatter_heads: rank `dst` returns [total_heads, ...], the others None."""
+def gather_heads(shard: torch.Tensor, total_heads: int, dst: int = 0, group=None,
+                 out: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """Inverse of scatter_heads: rank `dst` returns [total_heads, ...] (written into `out` when given, so that a caller
+    timing the transfer does not time a multi-gigabyte allocation), the others None.  All receives are posted as one
+    batch."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     if rank != dst:
         if shard.shape[0]:
-            dist.send(shard.contiguous(), dst=dst, group=group)
+            for r in dist.batch_isend_irecv([dist.P2POp(dist.isend, shard.contiguous(), dst, group)]):
+                r.wait()
         return None
-    full = torch.empty((total_heads, *shard.shape[1:]), dtype=shard.dtype, device=shard.device)
+    full = out if out is not None else torch.empty((total_heads, *shard.shape[1:]), dtype=shard.dtype,
+                                                   device=shard.device)
+    assert full.shape[0] == total_heads and full.shape[1:] == shard.shape[1:]
+    ops = []
     for peer in range(world):
         ps, pc = head_partition(total_heads, world, peer)
         if pc == 0:
@@ -63,7 +73,9 @@ def gather_heads(shard: torch.Tensor, total_heads: int, dst: int = 0, group=None
         if peer == dst:
             full[ps:ps + pc] = shard
         else:
-            dist.recv(full[ps:ps + pc], src=peer, group=group)
+            ops.append(dist.P2POp(dist.irecv, full[ps:ps + pc], peer, group))
+    for r in (dist.batch_isend_irecv(ops) if ops else []):
+        r.wait()
     return full
 
 

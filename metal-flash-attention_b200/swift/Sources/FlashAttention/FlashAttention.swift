@@ -281,6 +281,27 @@ public struct AttentionKernelDescriptor {
     get { AttentionBackend(rawValue: c.backend) ?? .simtFP32 }
     set { c.backend = newValue.rawValue }
   }
+  /// B200 extension: tuning columns of the parameter-table row.  Of every 4 element pairs of P, how many take exp2 on
+  /// the FMA pipe (selects the kernel instantiation); small-grid split policy (minimum blocks per range, 0 = never;
+  /// maximum ranges).
+  public var exp2FmaQuarters: UInt8 {
+    get { c.exp2_fma_quarters }
+    set { c.exp2_fma_quarters = newValue }
+  }
+  public var splitPolicy: (minimumBlocks: UInt8, maximumSplits: UInt8) {
+    get { (c.split_min_blocks, c.split_max) }
+    set { c.split_min_blocks = newValue.minimumBlocks; c.split_max = newValue.maximumSplits }
+  }
+}
+
+/// The parameter tables are data (AttentionDescriptor+Parameters.swift:106-285): replace the tensor-core family's table
+/// of `type` at run time (`nil` restores the built-in one).
+public func setParameterTable(type: AttentionKernelType, text: String?, transposedForward: Bool = false) {
+  if let text = text {
+    text.withCString { check(mfa_set_parameter_table(mfa_kernel_type_t(type.rawValue), transposedForward ? 1 : 0, $0)) }
+  } else {
+    check(mfa_set_parameter_table(mfa_kernel_type_t(type.rawValue), transposedForward ? 1 : 0, nil))
+  }
 }
 
 /// AttentionKernel.swift:11-50, 268-363

@@ -6,6 +6,7 @@ import ctypes
 import os
 import re
 import subprocess
+import sys
 
 import pytest
 
@@ -67,11 +68,12 @@ def test_memory_precisions_follow_reference_policy():
 
 
 def test_register_precisions():
-    # a descriptor the FP32 CUDA-core family serves (head % 8 != 0): the reference's policy verbatim
-    r = make(head=35, lowIn=True, lowMid=True).registerPrecisions
+    # a descriptor the FP32 CUDA-core family serves (head beyond the tensor-core kernels): the reference's policy verbatim
+    assert make(head=300, lowIn=True).kernelDescriptor(KT.forward).backend == mfa.Backend.simtFP32
+    r = make(head=300, lowIn=True, lowMid=True).registerPrecisions
     assert r[Op.O] == r[Op.dV] == r[Op.dK] == r[Op.dQ] == P.FP32            # :209-212
     assert r[Op.dS] == P.BF16 and r[Op.dP] == P.FP32 and r[Op.P] == P.FP16  # :198-200 (native BF16 branch)
-    r = make(head=35, lowIn=True, lowMid=False).registerPrecisions
+    r = make(head=300, lowIn=True, lowMid=False).registerPrecisions
     assert r[Op.P] == P.FP32 and r[Op.dS] == P.FP32                         # :203-205
     r = make().registerPrecisions
     assert all(v == P.FP32 for v in r.values())
@@ -125,7 +127,15 @@ def test_heuristic_selects_tensor_core_family_only_where_it_applies():
     assert make(4096, 4096, 128, lowIn=True, bf16=True).kernelDescriptor(KT.forward).backend == mfa.Backend.tcgen05
     assert make(4096, 4096, 64, lowIn=True).kernelDescriptor(KT.forward).backend == mfa.Backend.tcgen05
     assert make(4096, 4096, 128).kernelDescriptor(KT.forward).backend == mfa.Backend.simtFP32       # FP32 inputs
-    assert make(64, 64, 77, lowIn=True).kernelDescriptor(KT.forward).backend == mfa.Backend.simtFP32  # D % 8 != 0
+    # D % 8 != 0 with 16-bit row-major operands: tensor cores through head-dimension padding (kernels/pad_head.cu) ...
+    kd77 = make(64, 64, 77, lowIn=True).kernelDescriptor(KT.forward)
+    assert kd77.backend == mfa.Backend.tcgen05 and kd77.headDimension == 77 and kd77.blockDimensions[2] == 80
+    assert make(64, 64, 77, lowIn=True).kernelDescriptor(KT.backwardKeyValue).backend == mfa.Backend.tcgen05
+    # ... as far as the kernels reach (forward pad8(D) <= 256, backward <= 128), and not for transposed operands
+    assert make(64, 64, 199, lowIn=True).kernelDescriptor(KT.forward).backend == mfa.Backend.tcgen05
+    assert make(64, 64, 199, lowIn=True).kernelDescriptor(KT.backwardQuery).backend == mfa.Backend.simtFP32
+    assert make(64, 64, 77, lowIn=True, transposes=(True, False, False, False)).kernelDescriptor(
+        KT.forward).backend == mfa.Backend.simtFP32
     # transposed operands: the layout-generic tensor-core forward where TMA can address the transposed view (row pitch =
     # sequence length, a multiple of 8 elements); the backward kernels take row-major operands only
     tK = make(64, 64, 64, lowIn=True, transposes=(False, True, False, False))
@@ -150,7 +160,10 @@ def test_heuristic_selects_tensor_core_family_only_where_it_applies():
 def test_parameter_file_has_reference_format():
     text = make(4096, 4096, 128, lowIn=True, bf16=True).parameterFile(KT.forward)
     rows = [line for line in text.split("\n") if line.strip()]
-    assert rows and all(len([c for c in row.split("|") if c != ""]) == 5 for row in rows)   # AttentionParameterRow.swift:46-49
+    # the reference's five segments (AttentionParameterRow.swift:46-49) + three B200 tuning columns on the tcgen05 family
+    assert rows and all(len([c for c in row.split("|") if c != ""]) == 8 for row in rows)
+    simt = make(64, 64, 35).parameterFile(KT.forward)
+    assert all(len([c for c in row.split("|") if c != ""]) == 5 for row in simt.split("\n") if row.strip())
     maxima = [int(row.split("|")[1]) for row in rows]
     assert maxima == sorted(maxima)
 
@@ -285,3 +298,94 @@ int main() {
                            f"-Wl,-rpath,{libdir}"])
     out = subprocess.check_output([str(exe)], text=True).splitlines()
     assert out[0] == "256 128 128 384 384" and out[1] == "Descriptor was incomplete."
+
+
+FORWARD_TABLE = ("| 64  | 256 | 128 | 64  | Q, O | 2 | 8 | 4 |\n"
+                 "| 128 | 256 | 128 | 128 | Q, O | 1 | 2 | 16 |\n"
+                 "| 256 | 128 | 128 | 256 | Q, O | 0 | 0 | 1 |\n")
+
+
+def test_parameter_table_is_live_data():
+    """The B200 parameter table drives the kernel (AttentionDescriptor+Parameters.swift:106-285 analogue): editing a row
+    changes the kernel descriptor, the launched instantiation (source name) and the small-grid split policy; every
+    compiled variant is accepted, anything else is rejected and leaves the current table in place."""
+    d = make(4096, 4096, 128, lowIn=True, bf16=True)
+    c = mfa.FunctionConstantValues()
+    d.setFunctionConstants(c)
+    try:
+        kd = d.kernelDescriptor(KT.forward)
+        assert kd.exp2FmaQuarters == 0 and kd.splitPolicy == (4, 8)
+        k = mfa.AttentionKernel(kd)
+        assert "exp2" not in k.sourceName() and k.launchCount(c) == 2        # 32 blocks / 8 ranges of >= 4
+        cached_before = mfa.AttentionKernel.cached(d, KT.forward).sourceName()
+
+        mfa.setParameterTable(KT.forward, FORWARD_TABLE)
+        assert d.parameterFile(KT.forward) == FORWARD_TABLE
+        kd = d.kernelDescriptor(KT.forward)
+        assert kd.exp2FmaQuarters == 1 and kd.splitPolicy == (2, 16)
+        assert "exp2 on FMA pipe 1/4" in mfa.AttentionKernel(kd).sourceName()
+        assert mfa.AttentionKernel.cached(d, KT.forward).sourceName() != cached_before   # the cache follows the table
+        kd64 = make(2048, 2048, 64, lowIn=True).kernelDescriptor(KT.forward)
+        assert kd64.exp2FmaQuarters == 2 and kd64.splitPolicy == (8, 4)
+
+        # a table may turn splitting off; the descriptor is plain data and may be edited field by field as well
+        kd.splitPolicy = (0, 1)
+        assert mfa.AttentionKernel(kd).launchCount(c) == 1
+        for q in range(mfa.maxExp2FmaQuarters(KT.forward) + 1):
+            kd.exp2FmaQuarters = q
+            mfa.AttentionKernel(kd)
+        kd.exp2FmaQuarters = mfa.maxExp2FmaQuarters(KT.forward) + 1
+        with pytest.raises(mfa.MFAError, match="no compiled sm_100a kernel"):
+            mfa.AttentionKernel(kd)
+
+        # rejected tables leave the installed one untouched
+        for bad, message in ((FORWARD_TABLE.replace("| 2 | 8 | 4 |", "| 3 | 8 | 4 |"), "no compiled kernel"),
+                             (FORWARD_TABLE.replace("Q, O", "Q, dQ", 1), "Unexpected operand: dQ"),
+                             ("| 64 | 256 | 128 |\n", "Number of segments was invalid"),
+                             ("| 64 | 256 | 128 | 64 | Q, O |\n", "tuning columns")):
+            with pytest.raises(mfa.MFAError, match=message):
+                mfa.setParameterTable(KT.forward, bad)
+            assert d.parameterFile(KT.forward) == FORWARD_TABLE
+        # the backward kernels have their own tables and a wider compiled range
+        mfa.setParameterTable(KT.backwardQuery, "| 128 | 128 | 128 | 128 | Q, dO, dQ | 3 | 2 | 8 |\n")
+        assert "exp2 on FMA pipe 3/4" in mfa.AttentionKernel(d.kernelDescriptor(KT.backwardQuery)).sourceName()
+    finally:
+        for t in KT:
+            mfa.setParameterTable(t, None)
+    assert d.kernelDescriptor(KT.forward).exp2FmaQuarters == 0
+
+
+def test_parameter_file_from_the_environment(tmp_path):
+    """MFA_B200_PARAMETER_FILE: the tables scripts/sweep.py writes are picked up when the library is loaded."""
+    path = tmp_path / "tables.txt"
+    path.write_text("# comment\n[forward]\n" + FORWARD_TABLE + "[backwardKeyValue]\n"
+                    "| 64  | 128 | 128 | 64  | K, V, dV, dK | 1 | 2 | 4 |\n| 128 | 128 | 128 | 128 | K, V, dV, dK | 2 | 2 | 8 |\n")
+    code = ("import mfa_b200 as mfa\n"
+            "d = mfa.AttentionDescriptor(); d.lowPrecisionInputs = True\n"
+            "d.matrixDimensions = (512, 512, 64); d.transposeState = (False,) * 4\n"
+            "KT = mfa.AttentionKernelType\n"
+            "print([(d.kernelDescriptor(t).exp2FmaQuarters,) + d.kernelDescriptor(t).splitPolicy for t in KT])\n")
+    out = subprocess.check_output([sys.executable, "-c", code], cwd=ROOT, text=True,
+                                  env=dict(os.environ, MFA_B200_PARAMETER_FILE=str(path)))
+    assert out.strip() == "[(2, 8, 4), (1, 2, 8), (1, 2, 4)]"   # forward and dK-dV from the file, dQ built in
+
+
+def test_committed_parameter_file_matches_the_builtin_tables():
+    """metal-flash-attention_b200/parameters/b200.txt (written by scripts/sweep.py on a B200) is the source of the
+    built-in defaults: loading it must not change any table."""
+    path = os.path.join(ROOT, "metal-flash-attention_b200", "parameters", "b200.txt")
+    if not os.path.exists(path):
+        pytest.skip("no committed sweep result")
+    code = ("import mfa_b200 as mfa\n"
+            "KT = mfa.AttentionKernelType\n"
+            "for D in (64, 128, 256):\n"
+            "    d = mfa.AttentionDescriptor(); d.lowPrecisionInputs = True\n"
+            "    d.matrixDimensions = (512, 512, D); d.transposeState = (False,) * 4\n"
+            "    for t in KT:\n"
+            "        kd = d.kernelDescriptor(t)\n"
+            "        print(D, int(t), kd.backend.name, kd.blockDimensions, kd.exp2FmaQuarters, kd.splitPolicy)\n")
+    plain = subprocess.check_output([sys.executable, "-c", code], cwd=ROOT, text=True,
+                                    env={k: v for k, v in os.environ.items() if k != "MFA_B200_PARAMETER_FILE"})
+    loaded = subprocess.check_output([sys.executable, "-c", code], cwd=ROOT, text=True,
+                                     env=dict(os.environ, MFA_B200_PARAMETER_FILE=path))
+    assert plain == loaded

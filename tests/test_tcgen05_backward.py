@@ -111,3 +111,85 @@ def test_config3_fwd_bwd_n2048_d64():
     _run(2048, 2048, 64, False, seed=2, referencePolicy=True)
     _run(2048, 2048, 64, False, seed=0)
     _run(2048, 2048, 64, True, seed=1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("D", [64, 128])
+def test_every_compiled_table_variant_matches_the_oracle(D):
+    """The parameter table selects the kernel instantiation (exp2-on-the-FMA-pipe fraction) and the small-grid split
+    policy: every compiled variant of the three kernels must give the same answers.  Shapes: a grid that is split
+    (one head, 1024 x 1536) under two split policies, and ragged edges."""
+    import mfa_b200 as mfa
+    KT = mfa.AttentionKernelType
+    resident = {KT.forward: "Q, O", KT.backwardQuery: "Q, dO, dQ", KT.backwardKeyValue: "K, V, dV, dK"}
+    par = {KT.forward: 256, KT.backwardQuery: 128, KT.backwardKeyValue: 128}
+    try:
+        for q in range(4):
+            for policy in ((2, 8), (4, 3)):
+                for t in KT:
+                    qq = min(q, mfa.maxExp2FmaQuarters(t))
+                    mfa.setParameterTable(t, f"| 128 | {par[t]} | 128 | 128 | {resident[t]} | {qq} | {policy[0]} | {policy[1]} |\n")
+                _run(1024, 1536, D, True, seed=q + D)
+            _run(200, 333, D, False, seed=q + D + 1, referencePolicy=True)
+    finally:
+        for t in KT:
+            mfa.setParameterTable(t, None)
+
+
+@pytest.mark.gpu
+def test_persistent_backward_many_items_per_cta():
+    """D <= 64: both backward kernels are persistent (one CTA per SM walks the work items, barrier phases and ring stages
+    carried across items, Q / dO resp. K / V double-buffered).  More items than SMs, ragged shapes, odd block counts, so
+    that every phase pattern across an item boundary occurs."""
+    import numpy as np
+    import mfa_b200 as mfa
+    import oracle
+    from tests.attention_harness import run_attention, check
+    Op = mfa.AttentionOperand
+    for (H, R, C, D, bf16) in ((40, 640, 384, 64, True), (23, 300, 900, 40, False), (170, 128, 128, 64, True)):
+        desc = mfa.AttentionDescriptor()
+        desc.lowPrecisionInputs = True
+        desc.inputPrecisionOverride = mfa.GEMMOperandPrecision.BF16 if bf16 else mfa.GEMMOperandPrecision.FP16
+        desc.matrixDimensions = (R, C, D)
+        desc.transposeState = (False, False, False, False)
+        desc.batchCount = H
+        rounding = oracle.BF16 if bf16 else oracle.FP16
+        nets = [oracle.Network(R, C, D, seed=900 + h, threads=8).round_inputs(rounding) for h in range(H)]
+        inputs = {getattr(Op, k): np.stack([getattr(n, k) for n in nets]) for k in ("Q", "K", "V", "dO")}
+        out = run_attention(desc, None, inputs=inputs)
+        for h in sorted({0, 1, H // 2, H - 2, H - 1}):
+            ref = {"dV": nets[h].derivativeV(), "dK": nets[h].derivativeK(), "dQ": nets[h].derivativeQ()}
+            for name, expected in ref.items():
+                check(expected, out[name][h], 5e-2, f"{name}[{h}]")
+                rel = _rel_rms(out[name][h], expected)
+                assert rel <= (4e-3 if bf16 else 1.5e-3), (name, h, rel)
+        assert all(np.isfinite(out[name]).all() for name in ("D", "dQ", "dK", "dV"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("R,C,D", [(160, 160, 35), (257, 129, 77), (384, 200, 95), (64, 640, 3), (300, 300, 100)])
+@pytest.mark.parametrize("policy", ["reference", "bf16"])
+def test_head_dimensions_that_are_not_multiples_of_8_run_on_the_tensor_cores(R, C, D, policy):
+    """16-bit operands with D % 8 != 0 (the reference's own shapes: D = 35, 77, 95, ... SquareAttentionTest.swift:6-25) are
+    staged with pad8(D) zero-padded columns and run on the tcgen05 kernels (kernels/pad_head.cu); outputs come back
+    un-padded, and nothing is written past them (the harness checks the poisoned tails)."""
+    _run(R, C, D, policy == "bf16", seed=R + C + D, referencePolicy=policy == "reference")
+
+
+@pytest.mark.gpu
+def test_padded_forward_beyond_the_backward_kernels_reach():
+    """D = 199 (reference shape list): forward on the tensor-core kernel for 128 < D <= 256 through padding to 200."""
+    import mfa_b200 as mfa
+    import oracle
+    from tests.attention_harness import run_attention, check
+    desc = mfa.AttentionDescriptor()
+    desc.lowPrecisionInputs = True
+    desc.matrixDimensions = (311, 190, 199)
+    desc.transposeState = (False, False, False, False)
+    assert desc.kernelDescriptor(mfa.AttentionKernelType.forward).backend == mfa.Backend.tcgen05
+    net = oracle.Network(311, 190, 199, seed=8, threads=8).round_inputs(oracle.FP16)
+    out = run_attention(desc, net, types=[mfa.AttentionKernelType.forward])
+    O, L = net.inferenceAttention(with_L=True)
+    check(O, out["O"], 2e-3, "O")
+    check(L, out["L"], 1e-3, "L")
+    assert _rel_rms(out["O"], O) <= 1e-3
