@@ -2,7 +2,7 @@
 by tests/golden/make_golden.py), through the C ABI -- these vectors do not depend on rebuilding the oracle on the GPU
 box.  FP32 fixtures: the reference's FP32 bar, 2e-5 absolute on O, L, D, dV, dK, dQ (SquareAttentionTest.swift:547-554).
 16-bit fixtures (inputs already rounded to the memory format): the tensor-core family, relative RMS error <= 2e-3 (BF16)
-/ 1e-3 (FP16) on O and <= 4e-3 / 1.5e-3 on the gradients, L within 1e-3."""
+/ 3e-4 (FP16) on O and <= 2.5e-3 / 3e-4 on the gradients (the quantisation floors of the 16-bit MMA operands), L within 1e-3."""
 import glob
 import os
 
@@ -45,8 +45,8 @@ def test_kernels_reproduce_golden_fixture(path):
     def rel_rms(a, b):
         return float(np.sqrt(np.mean((a - b) ** 2)) / max(np.sqrt(np.mean(b ** 2)), 1e-30))
 
-    assert rel_rms(out["O"], g["O"]) <= (2e-3 if bf16 else 1e-3)
+    assert rel_rms(out["O"], g["O"]) <= (2e-3 if bf16 else 3e-4)
     check(g["L"], out["L"], 1e-3, "L")
     check(g["D"], out["D"], 2e-2, "D")
     for name in ("dV", "dK", "dQ"):
-        assert rel_rms(out[name], g[name]) <= (4e-3 if bf16 else 1.5e-3), name
+        assert rel_rms(out[name], g[name]) <= (2.5e-3 if bf16 else 3e-4), name

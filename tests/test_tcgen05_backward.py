@@ -3,8 +3,10 @@ rounded to the kernels' 16-bit memory format.  Forward runs first (it produces O
 D and dQ), then backwardKeyValue -- the reference's order (SquareAttentionTest.swift:355-368).
 
 Stated tolerances: the reference's mixed-precision bars (D 1e-1, gradients 5e-2, RectangularAttentionTest.swift:
-459-464) and, tighter, relative RMS error of every gradient <= 4e-3 for BF16 / 1.5e-3 for FP16 (P and dS are rounded
-to the 16-bit MMA input type before the accumulate GEMMs: two rounded operands per gradient)."""
+459-464) and, tighter, relative RMS error of every gradient <= 2.5e-3 for BF16 / 3e-4 for FP16: the quantisation floor
+of the 16-bit MMA operands P and dS (2^-s / sqrt(6) per rounded operand, s = 8 / 11 significant bits: 1.6e-3 / 2.0e-4;
+measured 1.64-1.71e-3 and 2.1-2.2e-4 at the BASELINE configs, profiles/r2_parity.jsonl; small shapes scatter a little
+above the asymptotic value)."""
 import numpy as np
 import pytest
 
@@ -42,9 +44,9 @@ def _run(R, C, D, bf16, seed, lowMid=False, referencePolicy=False):
     out = run_attention(desc, net)
     ref = oracle_outputs(net)
     check(ref["D"], out["D"], 1e-1 if lowMid else 2e-2, "D")
-    bound = 4e-3 if bf16 else 1.5e-3
+    bound = 2.5e-3 if bf16 else 3e-4
     if lowMid and not bf16:
-        bound = 6e-3   # L read back from FP16 (|L| ~ 8: half an ulp = 2^-8 in log2 units -> P off by up to 0.27 %)
+        bound = 2.5e-3   # L read back from FP16 (|L| ~ 8: half an ulp = 2^-8 in log2 units -> P off by up to 0.27 %)
     for name in ("dV", "dK", "dQ"):
         check(ref[name], out[name], 5e-2, name)
         rel = _rel_rms(out[name], ref[name])
@@ -162,7 +164,7 @@ def test_persistent_backward_many_items_per_cta():
             for name, expected in ref.items():
                 check(expected, out[name][h], 5e-2, f"{name}[{h}]")
                 rel = _rel_rms(out[name][h], expected)
-                assert rel <= (4e-3 if bf16 else 1.5e-3), (name, h, rel)
+                assert rel <= (2.5e-3 if bf16 else 3e-4), (name, h, rel)
         assert all(np.isfinite(out[name]).all() for name in ("D", "dQ", "dK", "dV"))
 
 

@@ -2,9 +2,11 @@
 
 The oracle runs on the inputs AFTER rounding to the kernel's 16-bit memory format, so the comparison
 isolates the kernel's own arithmetic.  Stated tolerances (north_star: "within 1e-3 relative"):
-  O : relative RMS error  rms(O - O_ref) / rms(O_ref) <= 1e-3 for FP16 and <= 2e-3 for BF16 (P, the A operand of
-      O += P V, is rounded to the MMA input type: BF16 keeps 8 significant bits, so every product carries a
-      relative error up to 2^-9 = 1.95e-3 that the row sum does not average away relative to O), and element-wise
+  O : relative RMS error  rms(O - O_ref) / rms(O_ref) <= 3e-4 for FP16 and <= 2e-3 for BF16.  These are the
+      quantisation floors of P, the A operand of O += P V, which is rounded to the MMA input type: round-to-nearest with
+      s significant bits has a relative error uniform in +-2^-s / (1 + f), rms 2^-s / sqrt(6) -- 1.99e-4 for FP16
+      (s = 11), 1.59e-3 for BF16 (s = 8) -- and the row sum does not average it away relative to O.  Measured
+      (profiles/r2_parity.jsonl): 1.98e-4 and 1.59e-3 at N = 4096, D = 128.  And element-wise
       |err| <= eps_P * max|V| + 1e-5 with eps_P = 2^-8 (bf16) or 2^-10 (fp16): P is rounded to the 16-bit MMA
       input type before O += P V, so each element carries at most half an ulp of P times the V it multiplies
       (the bound is reached when C is tiny and nothing averages out);
@@ -48,7 +50,7 @@ def check_O(O, actual, V, bf16, name="O"):
     tolO = (2.0 ** -8 if bf16 else 2.0 ** -10) * float(np.abs(V).max()) + 1e-5
     errO = check(O, actual, min(tolO, 5e-2), name)
     rel_rms = float(np.sqrt(np.mean((actual - O) ** 2)) / max(np.sqrt(np.mean(O ** 2)), 1e-30))
-    bound = 2e-3 if bf16 else 1e-3
+    bound = 2e-3 if bf16 else 3e-4
     assert rel_rms <= bound, f"{name}: relative RMS error {rel_rms:.3e} > {bound}"
     return errO
 
