@@ -43,8 +43,8 @@ METRIC = "giga-FMA-instr/sec forward attn N=4096 D=128 bf16"
 UNIT = "GINSTRS"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
 # (profiles/), for the default H; None until a capture exists.
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 299422976  # profiles/r1_fwd_ncu_summary.csv: 201.59 MB read + 97.84 MB written
-NCU_TRAFFIC_SOURCE = "profiles/r1_fwd_ncu_summary.csv (ncu --set full, one 64-head launch; not re-measured in this run)"
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 300388864  # profiles/r2_fwd_ncu_summary.csv: 202.04 MB read + 98.35 MB written
+NCU_TRAFFIC_SOURCE = "profiles/r2_fwd_ncu_summary.csv (ncu --set full, one 64-head launch of this kernel; not re-measured in this run)"
 
 
 def measured_peaks():
@@ -174,7 +174,8 @@ def run_config5(args, mfa, torch, dist, rank, world, stream, heads_per_launch):
 
     if world > 1:   # open the NCCL point-to-point connections outside the timed region
         warm = torch.zeros(world, 1024, device="cuda") if rank == 0 else None
-        scatter_heads(warm, world, (1024,), torch.float32, dev)
+        piece = scatter_heads(warm, world, (1024,), torch.float32, dev)
+        gather_heads(piece, world)   # (the peer -> rank 0 direction is a separate set of connections)
 
     if world > 1:
         shards, scatter_ms = timed(lambda: {op: scatter_heads(full.get(op), total, (N_SEQ, D_HEAD), torch.bfloat16, dev)

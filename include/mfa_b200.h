@@ -206,14 +206,14 @@ MFA_API int mfa_attention_descriptor_kernel_descriptor(const mfa_attention_descr
 MFA_API const char *mfa_attention_descriptor_parameter_file(const mfa_attention_descriptor_t *descriptor,
                                                             mfa_kernel_type_t type);
 
-/** The tables are DATA: this replaces the tcgen05-family table of `type` (`transposed_forward` != 0: the table of the
- *  layout-generic forward kernel) with `text` in the format above; NULL restores the built-in table.  The text is
+/** The tables are DATA: this replaces the tcgen05-family table of `type` (`transposed` != 0: the table used with transposed operands, i.e. of the
+ *  layout-generic kernels) with `text` in the format above; NULL restores the built-in table.  The text is
  *  parsed and validated first (unknown operand names, malformed rows, tuning values without a compiled kernel are
  *  rejected and the current table stays).  Kernels fetched from the descriptor-keyed cache afterwards follow the new
  *  table.  At load time the library also reads the file named by the environment variable MFA_B200_PARAMETER_FILE
- *  (sections "[forward]", "[forward.transposed]", "[backwardQuery]", "[backwardKeyValue]"; scripts/sweep.py writes
+ *  (sections "[forward]", "[backwardQuery]", "[backwardKeyValue]", each also as "[....transposed]"; scripts/sweep.py writes
  *  one from measurements on the current GPU).  Not thread-safe against concurrent kernelDescriptor() calls. */
-MFA_API int mfa_set_parameter_table(mfa_kernel_type_t type, int transposed_forward, const char *text);
+MFA_API int mfa_set_parameter_table(mfa_kernel_type_t type, int transposed, const char *text);
 /** Largest exp2_fma_quarters with a compiled instantiation for `type`. */
 MFA_API int mfa_max_exp2_fma_quarters(mfa_kernel_type_t type);
 

@@ -176,9 +176,9 @@ def releaseDeviceResources(device: int = 0) -> None:
     _check(_lib.mfa_release_device_resources(int(device)))
 
 
-def setParameterTable(type: "AttentionKernelType", text: Optional[str], transposedForward: bool = False) -> None:
+def setParameterTable(type: "AttentionKernelType", text: Optional[str], transposed: bool = False) -> None:
     """mfa_set_parameter_table: replace (text) or restore (None) the tcgen05-family parameter table of `type`."""
-    _check(_lib.mfa_set_parameter_table(int(type), int(bool(transposedForward)),
+    _check(_lib.mfa_set_parameter_table(int(type), int(bool(transposed)),
                                         None if text is None else text.encode()))
 
 

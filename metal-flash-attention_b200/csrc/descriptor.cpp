@@ -12,6 +12,7 @@
 #include "internal.h"
 
 namespace mfa {
+constexpr int kTableSlots = 6;  // parameter tables of the tcgen05 family (see table_slot)
 
 thread_local std::string g_last_error;
 
@@ -119,13 +120,25 @@ static const char *kForwardTcgen05Transposed =
     "| 128 | 128 | 128 | 128 | Q, O | 0 | 0 | 1 |\n"
     "| 256 | 128 | 128 | 256 | Q, O | 0 | 0 | 1 |\n"
     "\n";
+// (the 256 rows and the transposed tables: the layout-generic backward kernels, 64-row traversal blocks;
+// backwardKeyValue keeps one accumulator resident per pass -- dV, then dK)
 static const char *kBackwardQueryTcgen05 =
     "| 64  | 128 | 128 | 64  | Q, dO, dQ | 1 | 2 | 8 |\n"
     "| 128 | 128 | 128 | 128 | Q, dO, dQ | 0 | 2 | 8 |\n"
+    "| 256 | 128 | 64  | 256 | Q, dO, dQ | 0 | 2 | 8 |\n"
     "\n";
 static const char *kBackwardKeyValueTcgen05 =
     "| 64  | 128 | 128 | 64  | K, V, dV, dK | 2 | 2 | 8 |\n"
     "| 128 | 128 | 128 | 128 | K, V, dV, dK | 2 | 2 | 8 |\n"
+    "| 256 | 128 | 64  | 256 | K, V, dV, dK | 0 | 2 | 8 |\n"
+    "\n";
+static const char *kBackwardQueryTcgen05Transposed =
+    "| 128 | 128 | 64  | 128 | Q, dO, dQ | 0 | 2 | 8 |\n"
+    "| 256 | 128 | 64  | 256 | Q, dO, dQ | 0 | 2 | 8 |\n"
+    "\n";
+static const char *kBackwardKeyValueTcgen05Transposed =
+    "| 128 | 128 | 64  | 128 | K, V, dV, dK | 0 | 2 | 8 |\n"
+    "| 256 | 128 | 64  | 256 | K, V, dV, dK | 0 | 2 | 8 |\n"
     "\n";
 static const char *kForwardSimt =
     "| 512 | 64 | 64 | 32 | O |\n"
@@ -148,10 +161,13 @@ int select_backend(const mfa_attention_descriptor_t &d, int type) {
   if (!d.low_precision_inputs || d.head == 0) return MFA_BACKEND_SIMT_FP32;
   const uint32_t padded = (static_cast<uint32_t>(d.head) + 7) / 8 * 8;
   if (any_transpose(d)) {
-    // transposed operands: tensor-core forward only, and only where TMA can address the transposed view (row pitch =
-    // sequence length, a multiple of 8 elements); the backward kernels take row-major operands
-    if (type != MFA_FORWARD || !tcgen05_forward_transposes_ok(d.row, d.column, d.transpose_Q, d.transpose_K, d.transpose_V))
-      return MFA_BACKEND_SIMT_FP32;
+    // transposed operands: the layout-generic kernels, where TMA can address the transposed view (row pitch = sequence
+    // length, a multiple of 8 elements)
+    const bool ok = type == MFA_FORWARD
+                        ? tcgen05_forward_transposes_ok(d.row, d.column, d.transpose_Q, d.transpose_K, d.transpose_V)
+                        : tcgen05_backward_transposes_ok(d.row, d.column, d.transpose_Q, d.transpose_K, d.transpose_V,
+                                                         d.transpose_O);
+    if (!ok) return MFA_BACKEND_SIMT_FP32;
     if (d.head % 8 != 0) return MFA_BACKEND_SIMT_FP32;  // (head-dimension padding is implemented for row-major operands)
   }
   // D % 8 != 0 (row-major): the operands are staged with pad8(D) columns (kernels/pad_head.cu) and the tcgen05 kernels
@@ -164,9 +180,9 @@ int select_backend(const mfa_attention_descriptor_t &d, int type) {
 }
 
 // The tcgen05 tables are data: mfa_set_parameter_table() / MFA_B200_PARAMETER_FILE replace them at run time.
-// slot 0 forward, 1 forward (transposed operands), 2 backwardQuery, 3 backwardKeyValue; empty = built-in
-static std::string g_table_override[4];
-static bool g_table_overridden[4] = {false, false, false, false};
+// slot 0 forward, 2 backwardQuery, 4 backwardKeyValue; +1: the table used with transposed operands; empty = built-in
+static std::string g_table_override[kTableSlots];
+static bool g_table_overridden[kTableSlots] = {false, false, false, false, false, false};
 static unsigned g_table_generation = 0;
 unsigned parameter_table_generation() { return g_table_generation; }
 
@@ -175,17 +191,19 @@ static const char *builtin_table(int slot) {
     case 0: return kForwardTcgen05;
     case 1: return kForwardTcgen05Transposed;
     case 2: return kBackwardQueryTcgen05;
-    default: return kBackwardKeyValueTcgen05;
+    case 3: return kBackwardQueryTcgen05Transposed;
+    case 4: return kBackwardKeyValueTcgen05;
+    default: return kBackwardKeyValueTcgen05Transposed;
   }
 }
-static int table_slot(int type, bool transposed_forward) {
-  return type == MFA_FORWARD ? (transposed_forward ? 1 : 0) : (type == MFA_BACKWARD_QUERY ? 2 : 3);
+static int table_slot(int type, bool transposed) {
+  return (type == MFA_FORWARD ? 0 : (type == MFA_BACKWARD_QUERY ? 2 : 4)) + (transposed ? 1 : 0);
 }
 
 const char *parameter_file(const mfa_attention_descriptor_t &d, int type) {
   const bool tc = select_backend(d, type) == MFA_BACKEND_TCGEN05;
   if (tc) {
-    const int slot = table_slot(type, type == MFA_FORWARD && any_transpose(d));
+    const int slot = table_slot(type, any_transpose(d));
     return g_table_overridden[slot] ? g_table_override[slot].c_str() : builtin_table(slot);
   }
   switch (type) {
@@ -388,9 +406,11 @@ struct ParameterFileLoader {
       fprintf(stderr, "mfa_b200: cannot open MFA_B200_PARAMETER_FILE=%s\n", path);
       return;
     }
-    static const char *names[4] = {"[forward]", "[forward.transposed]", "[backwardQuery]", "[backwardKeyValue]"};
-    static const int types[4] = {MFA_FORWARD, MFA_FORWARD, MFA_BACKWARD_QUERY, MFA_BACKWARD_KEY_VALUE};
-    std::string text[4];
+    static const char *names[mfa::kTableSlots] = {"[forward]", "[forward.transposed]", "[backwardQuery]",
+                                             "[backwardQuery.transposed]", "[backwardKeyValue]", "[backwardKeyValue.transposed]"};
+    static const int types[mfa::kTableSlots] = {MFA_FORWARD, MFA_FORWARD, MFA_BACKWARD_QUERY, MFA_BACKWARD_QUERY,
+                                           MFA_BACKWARD_KEY_VALUE, MFA_BACKWARD_KEY_VALUE};
+    std::string text[mfa::kTableSlots];
     int current = -1;
     char line[1024];
     while (fgets(line, sizeof(line), f)) {
@@ -399,16 +419,16 @@ struct ParameterFileLoader {
       if (l.empty() || l[0] == '#') continue;
       if (l[0] == '[') {
         current = -1;
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < mfa::kTableSlots; ++i)
           if (l == names[i]) current = i;
         continue;
       }
       if (current >= 0) text[current] += l + "\n";
     }
     fclose(f);
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < mfa::kTableSlots; ++i)
       if (!text[i].empty() &&
-          mfa_set_parameter_table(static_cast<mfa_kernel_type_t>(types[i]), i == 1, text[i].c_str()) != MFA_SUCCESS)
+          mfa_set_parameter_table(static_cast<mfa_kernel_type_t>(types[i]), i & 1, text[i].c_str()) != MFA_SUCCESS)
         fprintf(stderr, "mfa_b200: section %s of %s rejected: %s\n", names[i], path, mfa_last_error());
   }
 } g_parameter_file_loader;
@@ -508,9 +528,9 @@ int mfa_max_exp2_fma_quarters(mfa_kernel_type_t type) {
   return type == MFA_FORWARD ? static_cast<int>(kMaxForwardExp2Quarters) : static_cast<int>(kMaxBackwardExp2Quarters);
 }
 
-int mfa_set_parameter_table(mfa_kernel_type_t type, int transposed_forward, const char *text) {
+int mfa_set_parameter_table(mfa_kernel_type_t type, int transposed, const char *text) {
   if (type < MFA_FORWARD || type > MFA_BACKWARD_KEY_VALUE) return fail(MFA_ERROR_INVALID_ARGUMENT, "Unrecognized kernel type.");
-  const int slot = table_slot(type, transposed_forward != 0);
+  const int slot = table_slot(type, transposed != 0);
   if (!text) {
     g_table_overridden[slot] = false;
     g_table_override[slot].clear();

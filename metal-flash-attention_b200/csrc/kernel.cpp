@@ -144,8 +144,7 @@ int mfa_attention_kernel_create(const mfa_attention_kernel_descriptor_t *kd, mfa
     bool transposed = false;
     for (int i = 0; i < n; ++i)
       if ((kd->transpose_state_mask >> ops[i]) & 1) transposed = true;
-    if (transposed && k->type != MFA_FORWARD) ok = false;  // only the forward has a layout-generic tensor-core kernel
-    if (transposed && D % 8 != 0) ok = false;              // padding is implemented for row-major operands
+    if (transposed && D % 8 != 0) ok = false;  // padding is implemented for row-major operands
     // dO: same element type, or BF16 beside FP16 Q/K/V (the reference's policy; converted on chip)
     if (k->type != MFA_FORWARD && kd->memory_precisions[MFA_dO] != pq &&
         !(pq == MFA_FP16 && kd->memory_precisions[MFA_dO] == MFA_BF16))
@@ -153,7 +152,7 @@ int mfa_attention_kernel_create(const mfa_attention_kernel_descriptor_t *kd, mfa
     if (!ok) {
       delete k;
       return fail(MFA_ERROR_UNSUPPORTED,
-                  "MFA_BACKEND_TCGEN05 needs FP16/BF16 Q,K,V (row-major for the backward kernels and for head % 8 != 0; dO of the same "
+                  "MFA_BACKEND_TCGEN05 needs FP16/BF16 Q,K,V (row-major for head % 8 != 0; dO of the same "
                   "type, or BF16 with FP16 Q,K,V) and pad8(head) <= the compiled maximum; use MFA_BACKEND_SIMT_FP32 for this "
                   "descriptor.");
     }
@@ -169,6 +168,8 @@ int mfa_attention_kernel_create(const mfa_attention_kernel_descriptor_t *kd, mfa
       tcgen05_forward_generic_geometry(D, &k->threads, &k->smem_bytes, &k->par, &k->trav, &k->head);
     else if (k->type == MFA_FORWARD)
       tcgen05_forward_geometry(Dp, &k->threads, &k->smem_bytes, &k->par, &k->trav, &k->head);
+    else if (transposed || Dp > 128)
+      tcgen05_backward_generic_geometry(k->type, Dp, &k->threads, &k->smem_bytes, &k->par, &k->trav, &k->head);
     else
       tcgen05_backward_geometry(k->type, Dp, &k->threads, &k->smem_bytes, &k->par, &k->trav, &k->head);
   } else if (k->backend == MFA_BACKEND_SIMT_FP32) {
@@ -193,7 +194,7 @@ int mfa_attention_kernel_create(const mfa_attention_kernel_descriptor_t *kd, mfa
   static const char *typeNames[] = {"forward", "backward_query", "backward_key_value"};
   k->source_name = std::string("attention_") + typeNames[k->type] +
                    (k->backend == MFA_BACKEND_TCGEN05 ? "_tcgen05" : "_simt_fp32") + "<D=" + std::to_string(D) +
-                   (k->backend == MFA_BACKEND_TCGEN05 && D <= 128 && kd->exp2_fma_quarters
+                   (k->backend == MFA_BACKEND_TCGEN05 && k->trav == 128 && D <= 128 && kd->exp2_fma_quarters
                         ? ", exp2 on FMA pipe " + std::to_string(kd->exp2_fma_quarters) + "/4"
                         : std::string()) +
                    ">";
@@ -248,9 +249,13 @@ int mfa_attention_kernel_launch_count(const mfa_attention_kernel_t *kernel, cons
     *out = tcgen05_forward_launch_count(c->row, c->column, kernel->descriptor.head_dimension,
                                         c->batch_count ? c->batch_count : 1, kernel->descriptor.split_min_blocks,
                                         kernel->descriptor.split_max);
-  if (kernel->backend == MFA_BACKEND_TCGEN05 && kernel->type != MFA_FORWARD)
-    *out = tcgen05_backward_launch_count(kernel->type, c->row, c->column, c->batch_count ? c->batch_count : 1,
-                                         kernel->descriptor.split_min_blocks, kernel->descriptor.split_max);
+  if (kernel->backend == MFA_BACKEND_TCGEN05 && kernel->type != MFA_FORWARD) {
+    const uint16_t any = kernel->descriptor.transpose_state_mask & kernel->descriptor.transpose_state_valid_mask;
+    const uint32_t Dp = (kernel->descriptor.head_dimension + 7u) / 8u * 8u;
+    *out = (any || Dp > 128 ? tcgen05_backward_generic_launch_count : tcgen05_backward_launch_count)(
+        kernel->type, c->row, c->column, c->batch_count ? c->batch_count : 1, kernel->descriptor.split_min_blocks,
+        kernel->descriptor.split_max);
+  }
   // head % 8 != 0 on the tensor-core family: one padding copy per staged input, one un-padding copy per output
   if (kernel->backend == MFA_BACKEND_TCGEN05 && kernel->descriptor.head_dimension % 8 != 0)
     *out += kernel->type == MFA_FORWARD ? 4 : (kernel->type == MFA_BACKWARD_QUERY ? 6 : 6);

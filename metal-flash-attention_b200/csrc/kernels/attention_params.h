@@ -60,6 +60,13 @@ uint32_t tcgen05_backward_launch_count(int type, uint32_t R, uint32_t C, uint32_
                                        uint32_t max_splits);
 void tcgen05_backward_geometry(int type, uint32_t D, uint32_t *threads, uint32_t *smem_bytes, uint32_t *par,
                                uint32_t *trav, uint32_t *head);
+// layout-generic backward (tcgen05_backward_generic.cu): 128 < D <= 256, and transposed operands at any D <= 256
+bool tcgen05_backward_transposes_ok(uint32_t R, uint32_t C, bool tQ, bool tK, bool tV, bool tO);
+cudaError_t launch_tcgen05_backward_generic(const AttentionParams &p, cudaStream_t stream, bool key_value);
+uint32_t tcgen05_backward_generic_launch_count(int type, uint32_t R, uint32_t C, uint32_t batch, uint32_t min_blocks,
+                                               uint32_t max_splits);
+void tcgen05_backward_generic_geometry(int type, uint32_t D, uint32_t *threads, uint32_t *smem_bytes, uint32_t *par,
+                                       uint32_t *trav, uint32_t *head);
 
 void tcgen05_forward_set_fused(int enabled);  // debug: 0 = split-KV through scratch + combine kernel (two launches)
 cudaError_t launch_tcgen05_forward_trace(const AttentionParams &p, cudaStream_t stream, long long *trace);  // debug

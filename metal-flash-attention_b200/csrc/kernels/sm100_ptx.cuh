@@ -87,16 +87,6 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const void *map, uin
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-// 3-D tiled store shared -> global (bulk async-group completion)
-__device__ __forceinline__ void tma_store_3d(const void *map, const void *smem_src, int32_t c0, int32_t c1, int32_t c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(map)),
-               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 // ---------------------------------------------------------------- tcgen05: TMEM management ----
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_result, uint32_t columns) {
@@ -385,35 +375,7 @@ __device__ __forceinline__ float softmax_exp_half(uint32_t (&v)[64], uint32_t (&
   return acc.x + acc.y;
 }
 
-// ---------------------------------------------------------------- thread-block clusters ------
-// all threads of every CTA in the cluster take part (warp-convergent); release/acquire orders shared-memory
-// writes before the barrier against distributed-shared-memory reads after it
-__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-// shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank`
-__device__ __forceinline__ uint32_t map_shared_rank(uint32_t smem_addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ float4 ld_dsmem_f32x4(uint32_t cluster_addr) {
-  float4 v;
-  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "r"(cluster_addr));
-  return v;
-}
-__device__ __forceinline__ float2 ld_dsmem_f32x2(uint32_t cluster_addr) {
-  float2 v;
-  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(cluster_addr));
-  return v;
-}
-
+// ---------------------------------------------------------------- register reallocation ------
 template <uint32_t RegCount>
 __device__ __forceinline__ void setmaxnreg_inc() {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(RegCount));

@@ -23,7 +23,9 @@
 #include <float.h>
 #include <stdint.h>
 
+#include "accumulator_store.cuh"
 #include "attention_params.h"
+#include "backward_common.cuh"
 #include "device_state.h"
 #include "sm100_ptx.cuh"
 #include "tma_host.h"
@@ -59,73 +61,6 @@ __device__ __forceinline__ void exp2_pair(uint32_t pair, float &p0, float &p1, f
   } else {
     p0 = ex2_approx(x.x);
     p1 = ex2_approx(x.y);
-  }
-}
-
-__device__ __forceinline__ float load_16bit(const void *p, size_t i, bool bf16) {
-  const uint16_t h = reinterpret_cast<const uint16_t *>(p)[i];
-  return bf16 ? __uint_as_float(static_cast<uint32_t>(h) << 16) : __half2float(__ushort_as_half(h));
-}
-// L is FP32 or FP16, D is FP32 or BF16 in memory (AttentionDescriptor+Precisions.swift:81-87)
-__device__ __forceinline__ float load_stat(const void *p, size_t i, int prec) {
-  if (prec == FP32) return reinterpret_cast<const float *>(p)[i];
-  const uint16_t h = reinterpret_cast<const uint16_t *>(p)[i];
-  return prec == FP16 ? __half2float(__ushort_as_half(h)) : __uint_as_float(static_cast<uint32_t>(h) << 16);
-}
-__device__ __forceinline__ void store_stat(void *p, size_t i, int prec, float v) {
-  if (prec == FP32) reinterpret_cast<float *>(p)[i] = v;
-  else if (prec == FP16) reinterpret_cast<uint16_t *>(p)[i] = __half_as_ushort(__float2half_rn(v));
-  else reinterpret_cast<uint16_t *>(p)[i] = static_cast<uint16_t>(__float_as_uint(v) >> 16);  // BF16 store truncates
-}
-
-// dO arrives as BF16 while Q, K, V are FP16 (the reference's own low-precision policy,
-// AttentionDescriptor+Precisions.swift:13-23); tcgen05 kind::f16 cannot mix the two element types in one MMA, so the
-// staged dO tile is rewritten in place as FP16 before any MMA reads it.  BF16 -> FP16 is exact for 2^-14 <= |x| < 65504
-// (8 significant bits fit FP16's 11); gradients outside that range would not survive FP16 Q/K/V either.
-__device__ __forceinline__ uint32_t bf16x2_to_f16x2(uint32_t w) {
-  return pack_f16x2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
-}
-__device__ __forceinline__ uint4 bf16x8_to_f16x8(uint4 v) {
-  return make_uint4(bf16x2_to_f16x2(v.x), bf16x2_to_f16x2(v.y), bf16x2_to_f16x2(v.z), bf16x2_to_f16x2(v.w));
-}
-
-// Accumulator epilogue shared by both kernels: TMEM hands every thread one row, and storing rows straight from registers
-// touches 32 different cache lines per warp store.  Each warp therefore transposes 32 x 32 chunks through a private
-// XOR-swizzled 4 KB scratch tile in shared memory (128-bit accesses, conflict-free both ways) and writes four full
-// 128 B lines per store instruction -- the forward kernel's epilogue (tcgen05_forward.cu).  `scratch` overlays the
-// staged-operand ring, which is dead once the final commit has arrived.  Columns [col0, col0 + cols) of the
-// accumulator at `t_acc` go to rows [warp_row0, warp_row0 + 32) of `out` ([rows_total][D] FP32).
-__device__ __forceinline__ void store_accumulator_coalesced(uint32_t t_acc, uint32_t col0, uint32_t cols, float4 *scratch,
-                                                            float *out_base, uint32_t warp_row0, uint32_t rows_total,
-                                                            uint32_t D, uint32_t lane) {
-  const uint32_t sub_row = lane >> 3, quad = lane & 7;  // transposed view: 4 rows x 8 float4 per warp access
-  for (uint32_t cc = 0; cc < cols; cc += 32) {
-    const uint32_t c = col0 + cc;
-    uint32_t o[32];
-    tmem_ld32(t_acc + c, o);
-    tc_wait_ld();
-#pragma unroll
-    for (uint32_t j = 0; j < 8; ++j)
-      scratch[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(o[4 * j]), __uint_as_float(o[4 * j + 1]),
-                                                          __uint_as_float(o[4 * j + 2]), __uint_as_float(o[4 * j + 3]));
-    __syncwarp();
-    // all eight values in distinct registers before the first store (a store holds its source registers until the
-    // data has left the SM)
-    float4 v[8];
-#pragma unroll
-    for (uint32_t i = 0; i < 8; ++i) {
-      const uint32_t r = 4 * i + sub_row;
-      v[i] = scratch[r * 8 + (quad ^ (r & 7))];
-    }
-    if (c + 4 * quad < D) {  // D % 8 == 0: a float4 is either fully inside or fully outside
-#pragma unroll
-      for (uint32_t i = 0; i < 8; ++i) {
-        const uint32_t r = 4 * i + sub_row;
-        if (warp_row0 + r < rows_total)
-          *reinterpret_cast<float4 *>(out_base + static_cast<size_t>(r) * D + c + 4 * quad) = v[i];
-      }
-    }
-    __syncwarp();
   }
 }
 
@@ -173,7 +108,7 @@ struct QueryConfig {
   static constexpr uint32_t kSmemV = kSmemK + kStagesK * kTileBytes;
   static constexpr uint32_t kSmemScratch = kPersistent ? kSmemV + kStagesV * kTileBytes : kSmemK;  // 8 warps x 4 KB
   static constexpr uint32_t kSmemVec = kSmemV + kStagesV * kTileBytes + (kPersistent ? 8 * 4096 : 0);  // float D[128]
-  static constexpr uint32_t kSmemBar = kSmemVec + kTile * 4;
+  static constexpr uint32_t kSmemBar = kSmemVec + 2 * kTile * 4;  // (persistent: one vector per item parity)
   static constexpr uint32_t kNumBars = 28;
   static constexpr uint32_t kSmemTmemPtr = kSmemBar + kNumBars * 8;
   static constexpr uint32_t kSmemBytes = kSmemTmemPtr + 16;
@@ -220,6 +155,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t *dq_final = bars + 20;     // one phase per item: the item's last dQ += dS K has completed
   uint64_t *do_ready = bars + 21;     // kConvertDO, one phase per item: the dO tile has been rewritten as FP16 (256)
   uint64_t *dq_free = bars + 22;      // [2] the epilogue has read this dQ accumulator out of TMEM (256 arrivals)
+  uint64_t *dterm_full = bars + 24;   // [2] persistent form: warp 11 has written the item's D vector (32 arrivals)
+  uint64_t *dterm_empty = bars + 26;  // [2] ... and every elementwise thread has read it (256 arrivals)
   static_assert(!(kBF16 && kConvertDO), "dO is only converted when Q, K, V are FP16");
   constexpr bool kDOisBF16 = kBF16 || kConvertDO;  // element type of dO in global memory
   uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem + Cfg::kSmemTmemPtr);
@@ -233,6 +170,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&dp_full[s], 1);
       mbar_init(&ds_full[s], kElemThreads);
       mbar_init(&dq_free[s], kElemThreads);
+      mbar_init(&dterm_full[s], 32);
+      mbar_init(&dterm_empty[s], kElemThreads);
     }
     for (uint32_t s = 0; s < Cfg::kStagesK; ++s) {
       mbar_init(&k_full[s], 1);
@@ -289,6 +228,13 @@ __global__ void __launch_bounds__(kThreads, 1)
       // here -- so each warp instead takes 16 rows and spreads the columns over its lanes (one 512 B line of O per load),
       // reduces with shuffles and hands the results to the row owners through shared memory.
       float Dterm;
+      if constexpr (Cfg::kPersistent) {
+        // computed off the critical path by warp 11, one item ahead (see there)
+        const uint32_t db = it & 1;
+        mbar_wait(&dterm_full[db], (it >> 1) & 1);
+        Dterm = reinterpret_cast<const float *>(smem + Cfg::kSmemVec)[db * kTile + row_in_tile];
+        mbar_arrive(&dterm_empty[db]);
+      } else
       {
         float *dvec = reinterpret_cast<float *>(smem + Cfg::kSmemVec);
         constexpr uint32_t kRowsPerWarp = kTile / 8;
@@ -328,7 +274,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       const size_t stat_idx = static_cast<size_t>(head) * a.R + row_c;
       const float Lrow = load_stat(a.L, stat_idx, a.l_prec);
-      if (h == 0 && row < a.R && split == 0) store_stat(a.Dterm, stat_idx, a.d_prec, Dterm);
+      if (!Cfg::kPersistent && h == 0 && row < a.R && split == 0) store_stat(a.Dterm, stat_idx, a.d_prec, Dterm);
 
       for (uint32_t j = 0; j < num_blocks; ++j) {
         const uint32_t g = g0 + j, bf = g & 1;
@@ -444,6 +390,55 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
         }
         g0 += num_blocks;
+      }
+    } else if (warp == 11) {
+      // ---------------- persistent form: D = rowsum(dO * O) / sqrt(D) of every item, one item ahead ----------------
+      // (computeD, AttentionKernel+Softmax.swift:32-221.)  In the one-item-per-CTA form the elementwise warps compute it
+      // while the first tiles are in flight anyway; with persistent CTAs it sat at the head of every item (global-load
+      // latency with nothing to overlap: ~2 k of the ~7 k cycles between two items' block loops), so the otherwise idle
+      // warp 11 produces the vector of item it+1 while item it is being processed.  DPAD <= 64: 16 lanes cover a row with
+      // one float4 of O and four 16-bit dO each, so a warp load covers two rows; eight loads are in flight per lane.
+      if constexpr (Cfg::kPersistent) {
+        float *dvec = reinterpret_cast<float *>(smem + Cfg::kSmemVec);
+        const uint32_t sub = lane >> 4, col = 4 * (lane & 15);
+        const bool active = col < a.D;
+        for (uint32_t item = blockIdx.x, it = 0; item < a.num_items; item += gridDim.x, ++it) {
+          uint32_t r0, head, split, blk0, num_blocks;
+          decode(item, r0, head, split, blk0, num_blocks);
+          const uint32_t db = it & 1;
+          mbar_wait(&dterm_empty[db], ((it >> 1) & 1) ^ 1);
+#pragma unroll 1
+          for (uint32_t base_row = 0; base_row < kTile; base_row += 16) {
+            float4 o4[8];
+            uint2 g4[8];
+#pragma unroll
+            for (uint32_t i = 0; i < 8; ++i) {
+              const uint32_t rr = min(r0 + base_row + 2 * i + sub, a.R - 1);
+              const size_t base = (static_cast<size_t>(head) * a.R + rr) * a.D + col;
+              o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              g4[i] = make_uint2(0u, 0u);
+              if (active) {
+                o4[i] = __ldg(reinterpret_cast<const float4 *>(a.O + base));
+                g4[i] = __ldg(reinterpret_cast<const uint2 *>(static_cast<const uint16_t *>(a.dO) + base));
+              }
+            }
+#pragma unroll
+            for (uint32_t i = 0; i < 8; ++i) {
+              const float2 lo = kDOisBF16 ? unpack_bf16x2(g4[i].x) : unpack_f16x2(g4[i].x);
+              const float2 hi = kDOisBF16 ? unpack_bf16x2(g4[i].y) : unpack_f16x2(g4[i].y);
+              float acc = fmaf(lo.x, o4[i].x, fmaf(lo.y, o4[i].y, fmaf(hi.x, o4[i].z, hi.y * o4[i].w)));
+#pragma unroll
+              for (uint32_t off = 8; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+              if ((lane & 15) == 0) {
+                const uint32_t rt = base_row + 2 * i + sub;
+                const float d = acc * a.scale;
+                dvec[db * kTile + rt] = d;
+                if (split == 0 && r0 + rt < a.R) store_stat(a.Dterm, static_cast<size_t>(head) * a.R + r0 + rt, a.d_prec, d);
+              }
+            }
+          }
+          mbar_arrive(&dterm_full[db]);  // (release: orders this lane's vector writes before the readers' acquire)
+        }
       }
     } else if (warp == 8) {
       // ---------------- MMA issuer ----------------
@@ -1052,48 +1047,6 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
 }
 
-// Sums the partial accumulators of a traversal split: out[t][i] = sum_s part[s][t][i] (t = tensor: dQ, or dV and dK).
-// The backward pass needs no softmax re-normalisation across splits (L and D are inputs), so unlike the forward's
-// split-KV merge this is a plain, deterministic sum -- still no atomics (README.md:11).  Every load of a thread is
-// issued before the first add; launched with programmatic stream serialisation.
-template <uint32_t kMaxSplits>
-__global__ void __launch_bounds__(256)
-    sum_splits(const float4 *__restrict__ part, float4 *__restrict__ out0, float4 *__restrict__ out1, size_t tensor_quads,
-               size_t split_stride_quads, uint32_t num_splits) {
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= tensor_quads) return;
-  const float4 *src = part + blockIdx.y * tensor_quads + i;
-  float4 v[kMaxSplits];
-#pragma unroll
-  for (uint32_t s = 0; s < kMaxSplits; ++s)
-    v[s] = s < num_splits ? __ldcg(src + s * split_stride_quads) : make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 acc = v[0];
-#pragma unroll
-  for (uint32_t s = 1; s < kMaxSplits; ++s) {
-    acc.x += v[s].x;
-    acc.y += v[s].y;
-    acc.z += v[s].z;
-    acc.w += v[s].w;
-  }
-  (blockIdx.y == 0 ? out0 : out1)[i] = acc;
-}
-
-// How many ranges to cut the traversal axis into: only when the SMs would otherwise idle (a single head at N = 4096 is
-// 32 CTAs for 148 SMs), at least two blocks per range, at most 8 ranges.
-// (min_blocks and max_splits are the row's tuning columns; min_blocks = 0 turns splitting off)
-static uint32_t choose_blocks_per_split(uint32_t ctas, uint32_t total_blocks, uint32_t sm_count, uint32_t min_blocks,
-                                        uint32_t max_splits) {
-  if (ctas * 2 > sm_count || min_blocks == 0 || total_blocks < 2 * min_blocks) return total_blocks;
-  if (max_splits > 8) max_splits = 8;  // sum_splits<8>
-  uint32_t splits = sm_count / ctas;
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 2) return total_blocks;
-  uint32_t per = (total_blocks + splits - 1) / splits;
-  if (per < min_blocks) per = min_blocks;
-  return per;
-}
-
 template <uint32_t DPAD, bool kBF16, bool kConvertDO, uint32_t kPoly>
 cudaError_t launch(const AttentionParams &p, cudaStream_t stream, bool key_value) {
   auto kernel_q = attention_backward_query_tcgen05<DPAD, kBF16, kConvertDO, kPoly>;
@@ -1170,29 +1123,16 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, bool key_value
   else
     kernel_kv<<<grid, kThreads, smem, stream>>>(mapQ, mapdO, mapK, mapV, a);
   e = cudaGetLastError();
-  if (e == cudaSuccess) {
-    const size_t quads = tensor_elems / 4;  // D % 8 == 0
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr.val.programmaticStreamSerializationAllowed = 1;
-    cudaLaunchConfig_t config = {};
-    config.gridDim = dim3(static_cast<uint32_t>((quads + 255) / 256), tensors, 1);
-    config.blockDim = dim3(256, 1, 1);
-    config.stream = stream;
-    config.attrs = &attr;
-    config.numAttrs = 1;
-    float4 *out0 = reinterpret_cast<float4 *>(key_value ? p.buf[sdV] : p.buf[sdQ]);
-    float4 *out1 = reinterpret_cast<float4 *>(key_value ? p.buf[sdK] : p.buf[sdQ]);
-    e = cudaLaunchKernelEx(&config, sum_splits<8>, reinterpret_cast<const float4 *>(scratch), out0, out1, quads,
-                           a.split_stride / 4, splits);
-    if (e == cudaSuccess) e = cudaGetLastError();
-  }
+  if (e == cudaSuccess)
+    e = launch_sum_splits(scratch, static_cast<float *>(key_value ? p.buf[sdV] : p.buf[sdQ]),
+                          static_cast<float *>(key_value ? p.buf[sdK] : p.buf[sdQ]), tensor_elems, tensors, a.split_stride,
+                          splits, stream);
   return e;
 }
 
 }  // namespace bwd
 
-uint32_t tcgen05_backward_max_head() { return 128; }
+uint32_t tcgen05_backward_max_head() { return 256; }  // (128, 256]: tcgen05_backward_generic.cu
 
 bool tcgen05_backward_supported(const AttentionParams &p) {
   // dO: the element type of Q/K/V, or BF16 beside FP16 Q/K/V (the reference's policy; converted on chip)
@@ -1200,9 +1140,16 @@ bool tcgen05_backward_supported(const AttentionParams &p) {
   const bool types = (p.prec[sQ] == FP16 || p.prec[sQ] == BF16) && p.prec[sK] == p.prec[sQ] &&
                      p.prec[sV] == p.prec[sQ] && dO_ok && p.prec[sO] == FP32 &&
                      p.prec[sdQ] == FP32 && p.prec[sdK] == FP32 && p.prec[sdV] == FP32;
-  const bool layout = !p.transposed[sQ] && !p.transposed[sK] && !p.transposed[sV] && !p.transposed[sO] &&
-                      !p.transposed[sdO] && !p.transposed[sdQ] && !p.transposed[sdK] && !p.transposed[sdV];
+  // derived operands follow their primal (dO ~ O, dQ ~ Q, dK ~ K, dV ~ V: AttentionKernel.swift:189-195)
+  const bool layout = tcgen05_backward_transposes_ok(p.R, p.C, p.transposed[sQ] || p.transposed[sdQ], p.transposed[sK] || p.transposed[sdK],
+                                                     p.transposed[sV] || p.transposed[sdV], p.transposed[sO] || p.transposed[sdO]);
   return types && layout && p.D % 8 == 0 && p.D <= tcgen05_backward_max_head();
+}
+
+// D > 128 or any transposed operand: the layout-generic kernels
+static bool needs_generic(const AttentionParams &p) {
+  return p.D > 128 || p.transposed[sQ] || p.transposed[sK] || p.transposed[sV] || p.transposed[sO] || p.transposed[sdO] ||
+         p.transposed[sdQ] || p.transposed[sdK] || p.transposed[sdV];
 }
 
 static cudaError_t launch_backward(const AttentionParams &p, cudaStream_t stream, bool key_value) {
@@ -1210,6 +1157,7 @@ static cudaError_t launch_backward(const AttentionParams &p, cudaStream_t stream
     set_launch_detail("descriptor is outside the tcgen05 backward kernels' domain");
     return cudaErrorInvalidValue;
   }
+  if (needs_generic(p)) return launch_tcgen05_backward_generic(p, stream, key_value);
   const bool bf16 = p.prec[sQ] == BF16;
   const bool convert = p.prec[sdO] != p.prec[sQ];  // FP16 Q/K/V with BF16 dO
   // the row's exp2 column selects the instantiation (kernel creation has checked the range)

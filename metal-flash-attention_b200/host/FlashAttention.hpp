@@ -48,8 +48,8 @@ struct AttentionKernelDescriptor {  // AttentionKernelDescriptor.swift:7-48
 };
 
 // The parameter tables are data (AttentionDescriptor+Parameters.swift:106-285 analogue): replace one at run time.
-inline void setParameterTable(AttentionKernelType type, const char *text, bool transposedForward = false) {
-  check(mfa_set_parameter_table(static_cast<mfa_kernel_type_t>(type), transposedForward ? 1 : 0, text));
+inline void setParameterTable(AttentionKernelType type, const char *text, bool transposed = false) {
+  check(mfa_set_parameter_table(static_cast<mfa_kernel_type_t>(type), transposed ? 1 : 0, text));
 }
 
 struct AttentionDescriptor {  // AttentionDescriptor.swift:10-27

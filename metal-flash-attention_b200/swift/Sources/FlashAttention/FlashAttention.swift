@@ -296,11 +296,11 @@ public struct AttentionKernelDescriptor {
 
 /// The parameter tables are data (AttentionDescriptor+Parameters.swift:106-285): replace the tensor-core family's table
 /// of `type` at run time (`nil` restores the built-in one).
-public func setParameterTable(type: AttentionKernelType, text: String?, transposedForward: Bool = false) {
+public func setParameterTable(type: AttentionKernelType, text: String?, transposed: Bool = false) {
   if let text = text {
-    text.withCString { check(mfa_set_parameter_table(mfa_kernel_type_t(type.rawValue), transposedForward ? 1 : 0, $0)) }
+    text.withCString { check(mfa_set_parameter_table(mfa_kernel_type_t(type.rawValue), transposed ? 1 : 0, $0)) }
   } else {
-    check(mfa_set_parameter_table(mfa_kernel_type_t(type.rawValue), transposedForward ? 1 : 0, nil))
+    check(mfa_set_parameter_table(mfa_kernel_type_t(type.rawValue), transposed ? 1 : 0, nil))
   }
 }
 

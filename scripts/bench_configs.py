@@ -15,12 +15,12 @@ from bench import ClockSampler   # NVML clock / throttle-reason sampler shared w
 KT, Op, P = mfa.AttentionKernelType, mfa.AttentionOperand, mfa.GEMMOperandPrecision
 
 
-def run(N, D, precision, H, steps=20):
+def run(N, D, precision, H, steps=20, transpose=(False,) * 4):
     desc = mfa.AttentionDescriptor()
     desc.lowPrecisionInputs = True
     desc.inputPrecisionOverride = precision   # None = the reference's policy: FP16 Q/K/V, BF16 dO
     desc.matrixDimensions = (N, N, D)
-    desc.transposeState = (False,) * 4
+    desc.transposeState = tuple(transpose)   # (timing only: the buffers' contents are random either way)
     desc.batchCount = H
     dt = torch.bfloat16 if precision == P.BF16 else torch.float16
     dt_dO = torch.bfloat16 if precision is None else dt
@@ -37,8 +37,6 @@ def run(N, D, precision, H, steps=20):
            "heads": H}
     work = {KT.forward: (2 * D + 5, 4), KT.backwardQuery: (3 * D + 5, 6), KT.backwardKeyValue: (4 * D + 5, 8)}
     for t in KT:
-        if D > 128 and t != KT.forward:
-            continue   # backward at D > 128 runs on the SIMT family; not part of this table
         kd = desc.kernelDescriptor(t)
         k = mfa.AttentionKernel(kd)
         for _ in range(3):
@@ -63,5 +61,12 @@ if __name__ == "__main__":
     H = int(sys.argv[1]) if len(sys.argv) > 1 else 128
     for N, D, prec, heads in ((8192, 256, P.BF16, 16), (8192, 256, P.BF16, 1), (2048, 64, None, H), (2048, 64, P.FP16, H),
                               (2048, 64, P.BF16, H), (4096, 128, None, 64), (4096, 128, P.BF16, 64), (4096, 64, P.BF16, 64),
-                              (2048, 64, P.FP16, 1), (4096, 128, P.BF16, 1)):
+                              (2048, 64, P.FP16, 1), (4096, 128, P.BF16, 1), (4096, 256, P.BF16, 16), (4096, 256, None, 16),
+                              (4096, 192, P.BF16, 16)):
         print(json.dumps(run(N, D, prec, heads)), flush=True)
+    # transposed operands (the layout-generic kernels); timing only
+    for N, D, heads, tr in ((4096, 128, 32, (True,) * 4), (4096, 128, 32, (False, True, False, False)),
+                            (2048, 64, 64, (True,) * 4), (4096, 256, 16, (True,) * 4)):
+        r = run(N, D, P.BF16, heads, transpose=tr)
+        r["transposeState(Q,K,V,O)"] = list(tr)
+        print(json.dumps(r), flush=True)

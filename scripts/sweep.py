@@ -32,9 +32,22 @@ def table_text(kind, rows):
     for bucket in (64, 128):
         q, mb, ms = rows[bucket]
         lines.append(f"| {bucket:<3d} | {PAR[kind]} | 128 | {bucket:<3d} | {RESIDENT[kind]} | {q} | {mb} | {ms} |")
+    # rows that are not swept: one compiled configuration each (the D <= 256 forward; the wide-head backward kernels,
+    # whose split policy follows the 128 row's)
     if kind == "forward":
         lines.append("| 256 | 128 | 128 | 256 | Q, O | 0 | 0 | 1 |")
+    else:
+        _, mb, ms = rows[128]
+        lines.append(f"| 256 | 128 | 64  | 256 | {RESIDENT[kind]} | 0 | {mb} | {ms} |")
     return "\n".join(lines) + "\n"
+
+
+def transposed_text(kind, rows):
+    """The layout-generic kernels' tables (transposed operands)."""
+    if kind == "forward":
+        return "| 128 | 128 | 128 | 128 | Q, O | 0 | 0 | 1 |\n| 256 | 128 | 128 | 256 | Q, O | 0 | 0 | 1 |\n"
+    _, mb, ms = rows[128]
+    return "".join(f"| {b:<3d} | 128 | 64  | {b:<3d} | {RESIDENT[kind]} | 0 | {mb} | {ms} |\n" for b in (128, 256))
 
 
 def write_file(path, tables):
@@ -44,6 +57,7 @@ def write_file(path, tables):
                 "# element pairs) | minimum blocks per split range (0 = never split) | maximum split ranges\n")
         for kind, rows in tables.items():
             f.write(SECTIONS[kind] + "\n" + table_text(kind, rows))
+            f.write(SECTIONS[kind][:-1] + ".transposed]\n" + transposed_text(kind, rows))
 
 
 def child(spec):

@@ -5,6 +5,9 @@
 //   variant 0: 64 x ex2 only (the MUFU pipe's cadence as one warp sees it)
 //   variant 1: production pattern: x = s * scale - m (FFMA2), ex2 x 2, row sum (FADD2), 16-bit pack (F2FP)
 //   variant 2: same through softmax_exp_half (in place, MFA_EXP_SKEW-pipelined)
+//   variant 3: x pair -> f16x2 (F2FP), ONE ex2.approx.ftz.f16x2 per pair; the result IS the packed FP16 P (no row sum:
+//              l would come from a ones column of V on the tensor core)
+//   variant 4: variant 3 plus an FP32 row sum of the unpacked results
 // each with kPoly = 0..4 of every 4 pairs on the FMA pipe (variant 0: ignored).
 // Build: make -C tests/gpu_probe   Run (GPU box): tests/gpu_probe/_build/exp_probe
 #include <cstdio>
@@ -49,11 +52,24 @@ __device__ __forceinline__ float step(float (&s)[64], uint32_t (&packed)[32], fl
       packed[i] = pack_bf16x2(pr.x, pr.y);
     }
     return sum2.x + sum2.y;
-  } else {
+  } else if (VARIANT == 2) {
     uint32_t v[64];
 #pragma unroll
     for (uint32_t i = 0; i < 64; ++i) v[i] = __float_as_uint(s[i]);
     return softmax_exp_half<true, POLY>(v, packed, scale_log2, m);
+  } else {
+    float2 sum2 = make_float2(0.f, 0.f);
+    const float2 scale2 = make_float2(scale_log2, scale_log2), negm2 = make_float2(-m, -m);
+#pragma unroll
+    for (uint32_t i = 0; i < 32; ++i) {
+      const float2 x = ffma2(make_float2(s[2 * i], s[2 * i + 1]), scale2, negm2);
+      const uint32_t xh = pack_f16x2(x.x, x.y);
+      uint32_t ph;
+      asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(ph) : "r"(xh));
+      packed[i] = ph;
+      if (VARIANT == 4) sum2 = fadd2(sum2, unpack_f16x2(ph));
+    }
+    return sum2.x + sum2.y;
   }
 }
 
@@ -137,5 +153,7 @@ int main() {
   both<2, 0>("softmax_exp_half (in place, skewed)");
   both<2, 1>("softmax_exp_half (in place, skewed)");
   both<2, 2>("softmax_exp_half (in place, skewed)");
+  both<3, 0>("f16x2 ex2 (one MUFU per pair), no row sum");
+  both<4, 0>("f16x2 ex2 (one MUFU per pair) + FP32 row sum");
   return 0;
 }

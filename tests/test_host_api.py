@@ -131,17 +131,28 @@ def test_heuristic_selects_tensor_core_family_only_where_it_applies():
     kd77 = make(64, 64, 77, lowIn=True).kernelDescriptor(KT.forward)
     assert kd77.backend == mfa.Backend.tcgen05 and kd77.headDimension == 77 and kd77.blockDimensions[2] == 80
     assert make(64, 64, 77, lowIn=True).kernelDescriptor(KT.backwardKeyValue).backend == mfa.Backend.tcgen05
-    # ... as far as the kernels reach (forward pad8(D) <= 256, backward <= 128), and not for transposed operands
+    # ... as far as the kernels reach (pad8(D) <= 256), and not for transposed operands
     assert make(64, 64, 199, lowIn=True).kernelDescriptor(KT.forward).backend == mfa.Backend.tcgen05
-    assert make(64, 64, 199, lowIn=True).kernelDescriptor(KT.backwardQuery).backend == mfa.Backend.simtFP32
+    kd199 = make(64, 64, 199, lowIn=True).kernelDescriptor(KT.backwardQuery)
+    assert kd199.backend == mfa.Backend.tcgen05 and kd199.blockDimensions == (128, 64, 200)   # wide-head kernels
+    assert make(64, 64, 260, lowIn=True).kernelDescriptor(KT.backwardQuery).backend == mfa.Backend.simtFP32
+    assert make(64, 64, 260, lowIn=True).kernelDescriptor(KT.forward).backend == mfa.Backend.simtFP32
     assert make(64, 64, 77, lowIn=True, transposes=(True, False, False, False)).kernelDescriptor(
         KT.forward).backend == mfa.Backend.simtFP32
-    # transposed operands: the layout-generic tensor-core forward where TMA can address the transposed view (row pitch =
-    # sequence length, a multiple of 8 elements); the backward kernels take row-major operands only
+    # transposed operands: the layout-generic tensor-core kernels where TMA can address the transposed view (row pitch =
+    # sequence length, a multiple of 8 elements)
     tK = make(64, 64, 64, lowIn=True, transposes=(False, True, False, False))
     assert tK.kernelDescriptor(KT.forward).backend == mfa.Backend.tcgen05
     assert tK.kernelDescriptor(KT.forward).blockDimensions == (128, 128, 64)
-    assert tK.kernelDescriptor(KT.backwardQuery).backend == mfa.Backend.simtFP32
+    for t in (KT.backwardQuery, KT.backwardKeyValue):
+        assert tK.kernelDescriptor(t).backend == mfa.Backend.tcgen05
+        assert tK.kernelDescriptor(t).blockDimensions == (128, 64, 64)       # 64-row traversal blocks
+        mfa.AttentionKernel(tK.kernelDescriptor(t))                           # ... and the kernel object accepts them
+    # backward: Q^T and dO^T (which follows O) are addressed through R, K^T and V^T through C
+    assert make(77, 64, 64, lowIn=True, transposes=(False, False, False, True)).kernelDescriptor(
+        KT.backwardKeyValue).backend == mfa.Backend.simtFP32
+    assert make(64, 77, 64, lowIn=True, transposes=(False, False, False, True)).kernelDescriptor(
+        KT.backwardKeyValue).backend == mfa.Backend.tcgen05
     assert make(64, 77, 64, lowIn=True, transposes=(False, True, False, False)).kernelDescriptor(
         KT.forward).backend == mfa.Backend.simtFP32                                                # C % 8 != 0
     assert make(77, 64, 64, lowIn=True, transposes=(False, True, False, True)).kernelDescriptor(
