@@ -133,10 +133,12 @@ static const char *kBackwardKeyValueTcgen05 =
     "| 256 | 128 | 64  | 256 | K, V, dV, dK | 0 | 2 | 8 |\n"
     "\n";
 static const char *kBackwardQueryTcgen05Transposed =
+    "| 64  | 128 | 64  | 64  | Q, dO, dQ | 0 | 2 | 8 |\n"
     "| 128 | 128 | 64  | 128 | Q, dO, dQ | 0 | 2 | 8 |\n"
     "| 256 | 128 | 64  | 256 | Q, dO, dQ | 0 | 2 | 8 |\n"
     "\n";
 static const char *kBackwardKeyValueTcgen05Transposed =
+    "| 64  | 128 | 64  | 64  | K, V, dV, dK | 0 | 2 | 8 |\n"
     "| 128 | 128 | 64  | 128 | K, V, dV, dK | 0 | 2 | 8 |\n"
     "| 256 | 128 | 64  | 256 | K, V, dV, dK | 0 | 2 | 8 |\n"
     "\n";

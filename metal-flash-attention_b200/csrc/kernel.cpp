@@ -252,9 +252,13 @@ int mfa_attention_kernel_launch_count(const mfa_attention_kernel_t *kernel, cons
   if (kernel->backend == MFA_BACKEND_TCGEN05 && kernel->type != MFA_FORWARD) {
     const uint16_t any = kernel->descriptor.transpose_state_mask & kernel->descriptor.transpose_state_valid_mask;
     const uint32_t Dp = (kernel->descriptor.head_dimension + 7u) / 8u * 8u;
-    *out = (any || Dp > 128 ? tcgen05_backward_generic_launch_count : tcgen05_backward_launch_count)(
-        kernel->type, c->row, c->column, c->batch_count ? c->batch_count : 1, kernel->descriptor.split_min_blocks,
-        kernel->descriptor.split_max);
+    const uint32_t b = c->batch_count ? c->batch_count : 1;
+    const bool convert = kernel->descriptor.memory_precisions[MFA_dO] != kernel->descriptor.memory_precisions[MFA_Q];
+    *out = (any || Dp > 128)
+               ? tcgen05_backward_generic_launch_count(kernel->type, c->row, c->column, Dp, b, kernel->descriptor.split_min_blocks,
+                                                       kernel->descriptor.split_max, convert)
+               : tcgen05_backward_launch_count(kernel->type, c->row, c->column, b, kernel->descriptor.split_min_blocks,
+                                               kernel->descriptor.split_max);
   }
   // head % 8 != 0 on the tensor-core family: one padding copy per staged input, one un-padding copy per output
   if (kernel->backend == MFA_BACKEND_TCGEN05 && kernel->descriptor.head_dimension % 8 != 0)

@@ -63,8 +63,8 @@ void tcgen05_backward_geometry(int type, uint32_t D, uint32_t *threads, uint32_t
 // layout-generic backward (tcgen05_backward_generic.cu): 128 < D <= 256, and transposed operands at any D <= 256
 bool tcgen05_backward_transposes_ok(uint32_t R, uint32_t C, bool tQ, bool tK, bool tV, bool tO);
 cudaError_t launch_tcgen05_backward_generic(const AttentionParams &p, cudaStream_t stream, bool key_value);
-uint32_t tcgen05_backward_generic_launch_count(int type, uint32_t R, uint32_t C, uint32_t batch, uint32_t min_blocks,
-                                               uint32_t max_splits);
+uint32_t tcgen05_backward_generic_launch_count(int type, uint32_t R, uint32_t C, uint32_t D, uint32_t batch,
+                                               uint32_t min_blocks, uint32_t max_splits, bool convert_dO);
 void tcgen05_backward_generic_geometry(int type, uint32_t D, uint32_t *threads, uint32_t *smem_bytes, uint32_t *par,
                                        uint32_t *trav, uint32_t *head);
 
@@ -74,6 +74,7 @@ cudaError_t launch_tcgen05_forward_d256_trace(const AttentionParams &p, cudaStre
 // head-dimension padding for D % 8 != 0 on the tensor-core family (pad_head.cu)
 cudaError_t launch_pad_columns(const void *src, void *dst, uint64_t rows, uint32_t D, uint32_t Dp, uint32_t element_bytes,
                                cudaStream_t stream);
+cudaError_t launch_bf16_to_f16(const void *src, void *dst, uint64_t elements, cudaStream_t stream);
 cudaError_t launch_unpad_columns(const void *src, void *dst, uint64_t rows, uint32_t D, uint32_t Dp, cudaStream_t stream);
 const char *last_launch_detail();  // thread-local detail string for MFA_ERROR_CUDA messages
 

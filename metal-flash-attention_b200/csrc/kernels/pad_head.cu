@@ -9,6 +9,7 @@
 #include <stdint.h>
 
 #include "attention_params.h"
+#include "backward_common.cuh"
 
 namespace mfa {
 namespace {
@@ -35,7 +36,20 @@ __global__ void __launch_bounds__(256) unpad_columns(const T *__restrict__ src, 
   dst[i] = src[r * Dp + c];
 }
 
+// dO (BF16) -> FP16, eight elements per thread; exact for 2^-14 <= |x| < 65504 (backward_common.cuh)
+__global__ void __launch_bounds__(256) bf16_to_f16(const uint4 *__restrict__ src, uint4 *__restrict__ dst, uint64_t vectors) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < vectors) dst[i] = bwd::bf16x8_to_f16x8(src[i]);
+}
+
 }  // namespace
+
+cudaError_t launch_bf16_to_f16(const void *src, void *dst, uint64_t elements, cudaStream_t stream) {
+  const uint64_t vectors = elements / 8;  // D % 8 == 0
+  bf16_to_f16<<<static_cast<uint32_t>((vectors + 255) / 256), 256, 0, stream>>>(static_cast<const uint4 *>(src),
+                                                                                 static_cast<uint4 *>(dst), vectors);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_pad_columns(const void *src, void *dst, uint64_t rows, uint32_t D, uint32_t Dp, uint32_t element_bytes,
                                cudaStream_t stream) {

@@ -30,6 +30,12 @@
 #include "sm100_ptx.cuh"
 #include "tma_host.h"
 
+// 1: the persistent dQ kernel's D = rowsum(dO * O) is computed one item ahead by warp 11 (0: by the elementwise warps at
+// the head of every item, as in the one-item-per-CTA form); A/B builds: make VARIANT=inlineD EXTRA=-DMFA_DQ_DTERM_OFFLOAD=0
+#ifndef MFA_DQ_DTERM_OFFLOAD
+#define MFA_DQ_DTERM_OFFLOAD 1
+#endif
+
 namespace mfa {
 namespace bwd {
 
@@ -91,7 +97,7 @@ struct BackwardArgs {
 //   Tensor-pipe order per block j:  dQ(j-1)  ->  S(j+1)  ->  dP(j+1).  The elementwise warps split their pass so that
 //   the exponentials (which need only S) run while dP is still on the pipe: measured 2310 -> see DESIGN.md.
 // ================================================================================================
-template <uint32_t DPAD>
+template <uint32_t DPAD, bool kOffload = false>
 struct QueryConfig {
   static constexpr uint32_t kSubTiles = DPAD / 64;
   static constexpr uint32_t kTileBytes = kSubTiles * kSubTileBytes;  // one 128 x DPAD 16-bit tile
@@ -107,9 +113,14 @@ struct QueryConfig {
   static constexpr uint32_t kSmemK = 2 * kBuffers * kTileBytes;
   static constexpr uint32_t kSmemV = kSmemK + kStagesK * kTileBytes;
   static constexpr uint32_t kSmemScratch = kPersistent ? kSmemV + kStagesV * kTileBytes : kSmemK;  // 8 warps x 4 KB
-  static constexpr uint32_t kSmemVec = kSmemV + kStagesV * kTileBytes + (kPersistent ? 8 * 4096 : 0);  // float D[128]
-  static constexpr uint32_t kSmemBar = kSmemVec + 2 * kTile * 4;  // (persistent: one vector per item parity)
-  static constexpr uint32_t kNumBars = 28;
+  // persistent: warp 11 stages the next item's O (FP32) and dO rows here for D = rowsum(dO * O)
+  static constexpr bool kOffloadD = kOffload;  // (its own instantiation: the staging area costs the inline form ~4 %)
+  static_assert(!kOffload || kPersistent, "the D-term is only offloaded in the persistent form");
+  static constexpr uint32_t kStageBytes = kOffloadD ? kTile * DPAD * 6 : 0;
+  static constexpr uint32_t kSmemStage = kSmemV + kStagesV * kTileBytes + (kPersistent ? 8 * 4096 : 0);
+  static constexpr uint32_t kSmemVec = kSmemStage + kStageBytes;  // float D[128] (persistent: one per item parity)
+  static constexpr uint32_t kSmemBar = kSmemVec + 2 * kTile * 4;
+  static constexpr uint32_t kNumBars = 30;
   static constexpr uint32_t kSmemTmemPtr = kSmemBar + kNumBars * 8;
   static constexpr uint32_t kSmemBytes = kSmemTmemPtr + 16;
   static_assert(kSmemBytes <= 232448, "shared memory over budget");
@@ -117,12 +128,12 @@ struct QueryConfig {
   static_assert(384 + kBuffers * DPAD <= 512, "dQ accumulators do not fit TMEM");
 };
 
-template <uint32_t DPAD, bool kBF16, bool kConvertDO, uint32_t kPoly>
+template <uint32_t DPAD, bool kBF16, bool kConvertDO, uint32_t kPoly, bool kOffload>
 __global__ void __launch_bounds__(kThreads, 1)
     attention_backward_query_tcgen05(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapdO,
                                      const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV,
                                      const BackwardArgs a) {
-  using Cfg = QueryConfig<DPAD>;
+  using Cfg = QueryConfig<DPAD, kOffload>;
   constexpr uint32_t kDB = Cfg::kBuffers;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -157,6 +168,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t *dq_free = bars + 22;      // [2] the epilogue has read this dQ accumulator out of TMEM (256 arrivals)
   uint64_t *dterm_full = bars + 24;   // [2] persistent form: warp 11 has written the item's D vector (32 arrivals)
   uint64_t *dterm_empty = bars + 26;  // [2] ... and every elementwise thread has read it (256 arrivals)
+  uint64_t *stage_full = bars + 28;   // persistent form: the item's O and dO rows have landed in the staging area
   static_assert(!(kBF16 && kConvertDO), "dO is only converted when Q, K, V are FP16");
   constexpr bool kDOisBF16 = kBF16 || kConvertDO;  // element type of dO in global memory
   uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem + Cfg::kSmemTmemPtr);
@@ -181,6 +193,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     mbar_init(s_free, kElemThreads);
     mbar_init(dq_final, 1);
     mbar_init(do_ready, kElemThreads);
+    mbar_init(stage_full, 1);
     fence_barrier_init();
   }
   if (warp == 8) {
@@ -203,6 +216,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     const uint32_t tLane = tmem_base + ((quarter * 32) << 16);
 
     uint32_t g0 = 0;
+    float Lnext = 0.f;
     for (uint32_t item = blockIdx.x, it = 0; item < a.num_items; item += gridDim.x, ++it) {
       uint32_t r0, head, split, blk0, num_blocks;
       decode(item, r0, head, split, blk0, num_blocks);
@@ -228,7 +242,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       // here -- so each warp instead takes 16 rows and spreads the columns over its lanes (one 512 B line of O per load),
       // reduces with shuffles and hands the results to the row owners through shared memory.
       float Dterm;
-      if constexpr (Cfg::kPersistent) {
+      constexpr bool offload = Cfg::kOffloadD;
+      if constexpr (offload) {
         // computed off the critical path by warp 11, one item ahead (see there)
         const uint32_t db = it & 1;
         mbar_wait(&dterm_full[db], (it >> 1) & 1);
@@ -248,8 +263,8 @@ __global__ void __launch_bounds__(kThreads, 1)
           o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           g4[i] = make_uint2(0u, 0u);
           if (active) {
-            o4[i] = __ldg(reinterpret_cast<const float4 *>(a.O + base));
-            g4[i] = __ldg(reinterpret_cast<const uint2 *>(static_cast<const uint16_t *>(a.dO) + base));
+            o4[i] = ldg_stream_f32x4(a.O + base);
+            g4[i] = ldg_stream_u32x2(static_cast<const uint16_t *>(a.dO) + base);
           }
         }
 #pragma unroll
@@ -273,8 +288,9 @@ __global__ void __launch_bounds__(kThreads, 1)
         Dterm = dvec[row_in_tile];
       }
       const size_t stat_idx = static_cast<size_t>(head) * a.R + row_c;
-      const float Lrow = load_stat(a.L, stat_idx, a.l_prec);
-      if (!Cfg::kPersistent && h == 0 && row < a.R && split == 0) store_stat(a.Dterm, stat_idx, a.d_prec, Dterm);
+      // (persistent form: fetched during the previous item's epilogue, see below)
+      const float Lrow = (Cfg::kPersistent && it > 0) ? Lnext : load_stat(a.L, stat_idx, a.l_prec);
+      if (!offload && h == 0 && row < a.R && split == 0) store_stat(a.Dterm, stat_idx, a.d_prec, Dterm);
 
       for (uint32_t j = 0; j < num_blocks; ++j) {
         const uint32_t g = g0 + j, bf = g & 1;
@@ -326,6 +342,12 @@ __global__ void __launch_bounds__(kThreads, 1)
         mbar_arrive(&ds_full[bf]);
       }
 
+      // the next item's L: issued now so that its latency hides under the wait for the last MMA and the epilogue
+      if (Cfg::kPersistent && item + gridDim.x < a.num_items) {
+        uint32_t nr0, nhead, nsplit, nblk0, nblocks;
+        decode(item + gridDim.x, nr0, nhead, nsplit, nblk0, nblocks);
+        Lnext = load_stat(a.L, static_cast<size_t>(nhead) * a.R + min(nr0 + row_in_tile, a.R - 1), a.l_prec);
+      }
       // epilogue: dQ -> global (FP32); warpgroup h writes columns [h D/2, (h+1) D/2)
       mbar_wait(dq_final, it & 1);
       tc_fence_after();
@@ -396,47 +418,56 @@ __global__ void __launch_bounds__(kThreads, 1)
       // (computeD, AttentionKernel+Softmax.swift:32-221.)  In the one-item-per-CTA form the elementwise warps compute it
       // while the first tiles are in flight anyway; with persistent CTAs it sat at the head of every item (global-load
       // latency with nothing to overlap: ~2 k of the ~7 k cycles between two items' block loops), so the otherwise idle
-      // warp 11 produces the vector of item it+1 while item it is being processed.  DPAD <= 64: 16 lanes cover a row with
-      // one float4 of O and four 16-bit dO each, so a warp load covers two rows; eight loads are in flight per lane.
-      if constexpr (Cfg::kPersistent) {
+      // warp 11 produces the vector of item it+1 while item it is being processed.  The item's rows of O and dO are one
+      // contiguous range each (row-major, leading dimension D): two bulk copies bring them into a staging area -- no
+      // registers in flight, so the whole 48 KB is outstanding at once (register-staged loads, eight per lane, took longer
+      // than an N = 2048 item lasts) -- and the warp then reduces from shared memory, four rows per lane.
+      if constexpr (Cfg::kOffloadD) {
         float *dvec = reinterpret_cast<float *>(smem + Cfg::kSmemVec);
-        const uint32_t sub = lane >> 4, col = 4 * (lane & 15);
-        const bool active = col < a.D;
+        const float *stO = reinterpret_cast<const float *>(smem + Cfg::kSmemStage);
+        const uint16_t *stG = reinterpret_cast<const uint16_t *>(smem + Cfg::kSmemStage + kTile * DPAD * 4);
+        const uint32_t chunks = a.D / 4;  // float4 chunks per row
         for (uint32_t item = blockIdx.x, it = 0; item < a.num_items; item += gridDim.x, ++it) {
           uint32_t r0, head, split, blk0, num_blocks;
           decode(item, r0, head, split, blk0, num_blocks);
           const uint32_t db = it & 1;
+          const uint32_t rows = min(kTile, a.R - r0);  // rows past R keep whatever the staging area held: never stored
+          if (elect_one()) {
+            const size_t first = (static_cast<size_t>(head) * a.R + r0) * a.D;
+            mbar_arrive_expect_tx(stage_full, rows * a.D * 6);
+            bulk_load_1d(smem + Cfg::kSmemStage, a.O + first, rows * a.D * 4, stage_full);
+            bulk_load_1d(smem + Cfg::kSmemStage + kTile * DPAD * 4, static_cast<const uint16_t *>(a.dO) + first,
+                         rows * a.D * 2, stage_full);
+          }
+          __syncwarp();
           mbar_wait(&dterm_empty[db], ((it >> 1) & 1) ^ 1);
-#pragma unroll 1
-          for (uint32_t base_row = 0; base_row < kTile; base_row += 16) {
-            float4 o4[8];
-            uint2 g4[8];
+          mbar_wait(stage_full, it & 1);
+          // lane = rows lane, lane + 32, lane + 64, lane + 96; the lanes walk their rows' chunks on a diagonal so that a
+          // warp access spreads over the banks (rows are D * 4 bytes apart).  No shuffles, no branches: the four
+          // accumulators are independent FMA chains.
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+          for (uint32_t step = 0; step < chunks; ++step) {
+            uint32_t c = step + lane;
+            c -= (c / chunks) * chunks;
 #pragma unroll
-            for (uint32_t i = 0; i < 8; ++i) {
-              const uint32_t rr = min(r0 + base_row + 2 * i + sub, a.R - 1);
-              const size_t base = (static_cast<size_t>(head) * a.R + rr) * a.D + col;
-              o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-              g4[i] = make_uint2(0u, 0u);
-              if (active) {
-                o4[i] = __ldg(reinterpret_cast<const float4 *>(a.O + base));
-                g4[i] = __ldg(reinterpret_cast<const uint2 *>(static_cast<const uint16_t *>(a.dO) + base));
-              }
-            }
-#pragma unroll
-            for (uint32_t i = 0; i < 8; ++i) {
-              const float2 lo = kDOisBF16 ? unpack_bf16x2(g4[i].x) : unpack_f16x2(g4[i].x);
-              const float2 hi = kDOisBF16 ? unpack_bf16x2(g4[i].y) : unpack_f16x2(g4[i].y);
-              float acc = fmaf(lo.x, o4[i].x, fmaf(lo.y, o4[i].y, fmaf(hi.x, o4[i].z, hi.y * o4[i].w)));
-#pragma unroll
-              for (uint32_t off = 8; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-              if ((lane & 15) == 0) {
-                const uint32_t rt = base_row + 2 * i + sub;
-                const float d = acc * a.scale;
-                dvec[db * kTile + rt] = d;
-                if (split == 0 && r0 + rt < a.R) store_stat(a.Dterm, static_cast<size_t>(head) * a.R + r0 + rt, a.d_prec, d);
-              }
+            for (uint32_t q = 0; q < 4; ++q) {
+              const uint32_t rt = lane + 32 * q;
+              const float4 o = *reinterpret_cast<const float4 *>(stO + rt * a.D + 4 * c);
+              const uint2 g = *reinterpret_cast<const uint2 *>(stG + rt * a.D + 4 * c);
+              const float2 lo = kDOisBF16 ? unpack_bf16x2(g.x) : unpack_f16x2(g.x);
+              const float2 hi = kDOisBF16 ? unpack_bf16x2(g.y) : unpack_f16x2(g.y);
+              acc[q] = fmaf(lo.x, o.x, fmaf(lo.y, o.y, fmaf(hi.x, o.z, fmaf(hi.y, o.w, acc[q]))));
             }
           }
+#pragma unroll
+          for (uint32_t q = 0; q < 4; ++q) {
+            const uint32_t rt = lane + 32 * q;
+            const float d = acc[q] * a.scale;
+            dvec[db * kTile + rt] = d;
+            if (split == 0 && r0 + rt < a.R) store_stat(a.Dterm, static_cast<size_t>(head) * a.R + r0 + rt, a.d_prec, d);
+          }
+          __syncwarp();  // every lane has read the staging area before the next item's copies overwrite it
           mbar_arrive(&dterm_full[db]);  // (release: orders this lane's vector writes before the readers' acquire)
         }
       }
@@ -1049,12 +1080,31 @@ __global__ void __launch_bounds__(kThreads, 1)
 
 template <uint32_t DPAD, bool kBF16, bool kConvertDO, uint32_t kPoly>
 cudaError_t launch(const AttentionParams &p, cudaStream_t stream, bool key_value) {
-  auto kernel_q = attention_backward_query_tcgen05<DPAD, kBF16, kConvertDO, kPoly>;
+  auto kernel_q = attention_backward_query_tcgen05<DPAD, kBF16, kConvertDO, kPoly, false>;
   auto kernel_kv = attention_backward_key_value_tcgen05<DPAD, kBF16, kConvertDO, kPoly>;
+  size_t smem_q = QueryConfig<DPAD, false>::kSmemBytes;
   const int device = current_device();
   cudaError_t e;
+
+  // parallelised dimension -> CTAs; traversed dimension -> blocks, possibly split over blockIdx.z
+  const uint32_t par = key_value ? p.C : p.R, trav = key_value ? p.R : p.C;
+  const uint32_t tiles = (par + kTile - 1) / kTile, total_blocks = (trav + kTile - 1) / kTile;
+  const uint32_t per = choose_blocks_per_split(tiles * p.batch, total_blocks, device_sm_count(device), p.split_min_blocks, p.split_max);
+  const uint32_t splits = (total_blocks + per - 1) / per;
+  // D-term of the persistent dQ kernel (D <= 64): computed one item ahead by warp 11 (kOffload) or by the elementwise
+  // warps at the head of every item.  A/B on one box (profiles/r2_sweep_dq_dterm*.jsonl, TFLOP/s, offload | inline): N=512
+  // 580 | 473, N=1024 750 | 670, N=2048 880 | 840 (reference policy 900 | 834), N=4096 915 | 955, N=8192 975 | 1030: the
+  // head of an item that the offload removes matters for short items; the 48 KB staging area it needs costs long items ~4 %
+  // (also with the offload switched off at run time, and with no-allocate loads: it is the shared-memory footprint, 225
+  // instead of 177 KB), so the two forms are separate instantiations and long items take the inline one.
+  if constexpr (QueryConfig<DPAD>::kPersistent && MFA_DQ_DTERM_OFFLOAD != 0) {
+    if (!key_value && per <= 24) {
+      kernel_q = attention_backward_query_tcgen05<DPAD, kBF16, kConvertDO, kPoly, true>;
+      smem_q = QueryConfig<DPAD, true>::kSmemBytes;
+    }
+  }
   if (!key_value)
-    e = ensure_max_dynamic_smem(reinterpret_cast<const void *>(kernel_q), QueryConfig<DPAD>::kSmemBytes, device);
+    e = ensure_max_dynamic_smem(reinterpret_cast<const void *>(kernel_q), smem_q, device);
   else
     e = ensure_max_dynamic_smem(reinterpret_cast<const void *>(kernel_kv), KeyValueConfig<DPAD>::kSmemBytes, device);
   if (e != cudaSuccess) return e;
@@ -1081,11 +1131,6 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, bool key_value
   a.l_prec = p.prec[sL];
   a.d_prec = p.prec[sD];
 
-  // parallelised dimension -> CTAs; traversed dimension -> blocks, possibly split over blockIdx.z
-  const uint32_t par = key_value ? p.C : p.R, trav = key_value ? p.R : p.C;
-  const uint32_t tiles = (par + kTile - 1) / kTile, total_blocks = (trav + kTile - 1) / kTile;
-  const uint32_t per = choose_blocks_per_split(tiles * p.batch, total_blocks, device_sm_count(device), p.split_min_blocks, p.split_max);
-  const uint32_t splits = (total_blocks + per - 1) / per;
   a.blocks_per_split = per;
   a.split_stride = 0;
   a.tiles = tiles;
@@ -1098,7 +1143,7 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, bool key_value
   const dim3 grid_q(QueryConfig<DPAD>::kPersistent && a.num_items > sm_count ? sm_count : a.num_items, 1, 1);
   const dim3 grid = grid_q;
   static_assert(QueryConfig<DPAD>::kPersistent == KeyValueConfig<DPAD>::kPersistent, "one grid rule for both kernels");
-  const size_t smem = key_value ? KeyValueConfig<DPAD>::kSmemBytes : QueryConfig<DPAD>::kSmemBytes;
+  const size_t smem = key_value ? KeyValueConfig<DPAD>::kSmemBytes : smem_q;
   if (splits == 1) {
     if (!key_value)
       kernel_q<<<grid_q, kThreads, smem, stream>>>(mapQ, mapdO, mapK, mapV, a);
@@ -1200,7 +1245,8 @@ void tcgen05_backward_geometry(int type, uint32_t D, uint32_t *threads, uint32_t
                                uint32_t *trav, uint32_t *head) {
   *threads = bwd::kThreads;
   if (type == 1)  // MFA_BACKWARD_QUERY
-    *smem_bytes = D <= 64 ? bwd::QueryConfig<64>::kSmemBytes : bwd::QueryConfig<128>::kSmemBytes;
+    *smem_bytes = D <= 64 ? bwd::QueryConfig<64, MFA_DQ_DTERM_OFFLOAD != 0>::kSmemBytes  // (the larger of its two forms)
+                          : bwd::QueryConfig<128>::kSmemBytes;
   else
     *smem_bytes = D <= 64 ? bwd::KeyValueConfig<64>::kSmemBytes : bwd::KeyValueConfig<128>::kSmemBytes;
   *par = bwd::kTile;

@@ -15,6 +15,8 @@
 //         kQuery   A1 = Q, A2 = dO, B1 = K, B2 = V      S  = A1 B1^T, dP  = A2 B2^T, dQ += dS B1
 //         kKey     A1 = K, A2 = V,  B1 = Q, B2 = dO     S^T = A1 B1^T, dP^T = A2 B2^T, dK += dS^T B1
 //         kValue   A1 = K,          B1 = Q, B2 = dO     S^T = A1 B1^T,                 dV += P^T B2
+//         kKeyValue (D <= 128, where dK and dV fit TMEM side by side: 256 + 2 D <= 512): kKey plus dV += P^T B2 -- one
+//                  pass, four GEMMs; P^T is written over S^T and dS^T over dP^T, both A operands live in TMEM at once
 //     L and D are per ROW in kQuery (registers; D is computed here, computeD +Softmax.swift:32-221) and per COLUMN in
 //     the other two (64-entry vectors staged in shared memory one block ahead).
 //
@@ -25,7 +27,7 @@
 // TMEM: S double buffer [0,128) (2 x 64 columns), dP double buffer [128,256), accumulator [256, 256 + DPAD).  P / dS
 // (16-bit) overwrite S / dP in place and feed the accumulate MMA from TMEM.  Warps 0-7: elementwise (thread = TMEM lane
 // x 32 of the block's 64 columns), warp 8: MMA issuer, warp 9: TMA producer for the resident tiles and ring 1, warp 10:
-// TMA producer for ring 2, warps 10-11 rewrite BF16 dO blocks as FP16 (kKey / kValue with the reference's mixed policy).
+// TMA producer for ring 2.  (The reference's FP16 + BF16-dO policy: the host converts dO once, see the launcher.)
 // Tensor-pipe order per block j:  dP(j+1) -> S(j+1) -> acc(j): the elementwise pass of block j runs under the first two.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -44,7 +46,6 @@ namespace mfa {
 namespace bwdg {
 
 using namespace ptx;
-using bwd::bf16x8_to_f16x8;
 using bwd::load_16bit;
 using bwd::load_stat;
 using bwd::store_stat;
@@ -55,10 +56,11 @@ constexpr uint32_t kCols = 32;    // block columns per elementwise thread
 constexpr uint32_t kThreads = 384, kElemThreads = 256;
 constexpr uint32_t kLaunchRegs = 168, kElemRegs = 208, kOtherRegs = 88;
 static_assert(kElemRegs * 256 + kOtherRegs * 128 <= kLaunchRegs * kThreads, "setmaxnreg over-subscribed");
-enum Mode : uint32_t { kQuery = 0, kKey = 1, kValue = 2 };
+enum Mode : uint32_t { kQuery = 0, kKey = 1, kValue = 2, kKeyValue = 3 };
 
 // tmask bits
-constexpr uint32_t kTransA1 = 1, kTransA2 = 2, kTransB1 = 4, kTransB2 = 8, kTransOut = 16, kTransO = 32, kTransdO = 64;
+constexpr uint32_t kTransA1 = 1, kTransA2 = 2, kTransB1 = 4, kTransB2 = 8, kTransOut = 16, kTransO = 32, kTransdO = 64,
+                   kTransOut2 = 128;
 
 struct GenericArgs {
   const void *dO;   // global dO (kQuery: for D = rowsum(dO * O))
@@ -66,6 +68,7 @@ struct GenericArgs {
   const void *L;    // [batch][R]
   void *Dterm;      // [batch][R]: written by kQuery, read by kKey
   float *out;       // dQ | dK | dV (FP32)
+  float *out2;      // kKeyValue: dV (out = dK)
   uint32_t R, C, D;
   float scale, scale_log2;
   int l_prec, d_prec;
@@ -84,6 +87,7 @@ struct Config {
   // operand, or kValue's accumulate operand.  D = 256, kQuery / kKey: 2 x 64 + 2 x 32 + 32 = 224 KB.
   static constexpr uint32_t kStages1 = 2;
   static constexpr uint32_t kStages2 = (kMode == kValue || DPAD <= 128) ? 2 : 1;
+  static_assert(kMode != kKeyValue || DPAD <= 128, "dK and dV do not fit TMEM beside S^T / dP^T");
   static constexpr uint32_t kSmemRes = 0;
   static constexpr uint32_t kSmemRing1 = kResidents * kResBytes;
   static constexpr uint32_t kSmemRing2 = kSmemRing1 + kStages1 * kBlkBytes;
@@ -95,11 +99,11 @@ struct Config {
   static constexpr uint32_t kSmemBytes = kSmemTmemPtr + 16;
   static_assert(kSmemBytes <= 232448, "shared memory over budget");
   static_assert(8 * 4096 <= (kStages1 + kStages2) * kBlkBytes, "epilogue scratch does not fit the rings");
-  static constexpr uint32_t kTmemS = 0, kTmemdP = 128, kTmemAcc = 256, kTmemCols = 512;
-  static_assert(kTmemAcc + DPAD <= kTmemCols, "accumulator does not fit TMEM");
+  static constexpr uint32_t kTmemS = 0, kTmemdP = 128, kTmemAcc = 256, kTmemAcc2 = 256 + DPAD, kTmemCols = 512;
+  static_assert(kTmemAcc + (kMode == kKeyValue ? 2 : 1) * DPAD <= kTmemCols, "accumulators do not fit TMEM");
 };
 
-template <uint32_t DPAD, bool kBF16, bool kConvertDO, uint32_t kMode>
+template <uint32_t DPAD, bool kBF16, uint32_t kMode>
 __global__ void __launch_bounds__(kThreads, 1)
     attention_backward_generic_tcgen05(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
                                        const __grid_constant__ CUtensorMap mapB1, const __grid_constant__ CUtensorMap mapB2,
@@ -132,10 +136,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t *dp_full = bars + 13;      // [2] dP(j) in TMEM
   uint64_t *ds_full = bars + 15;      // [2] dS(j) -- kValue: P(j) -- written (256 arrivals)
   uint64_t *acc_final = bars + 17;    // the last accumulate MMA has completed
-  uint64_t *do_ready = bars + 18;     // [2] kConvertDO: dO rewritten as FP16 (kQuery: resident tile, 256 arrivals;
-                                      //     kKey / kValue: ring 2 stage, 64 arrivals)
-  static_assert(!(kBF16 && kConvertDO), "dO is only converted when Q, K, V are FP16");
-  constexpr bool kDOisBF16 = kBF16 || kConvertDO;  // element type of dO in global memory
+  uint64_t *p_full = bars + 18;       // [2] kKeyValue: P(j) written over S(j) (256 arrivals)
+  constexpr bool kDOisBF16 = kBF16;  // dO has the element type of Q, K, V here (the host converts a BF16 dO beside FP16 inputs)
   uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem + Cfg::kSmemTmemPtr);
 
   if (threadIdx.x == 0) {
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&s_free[s], kElemThreads);
       mbar_init(&dp_full[s], 1);
       mbar_init(&ds_full[s], kElemThreads);
-      mbar_init(&do_ready[s], kMode == kQuery ? kElemThreads : 64);
+      mbar_init(&p_full[s], kElemThreads);
     }
     mbar_init(acc_final, 1);
     fence_barrier_init();
@@ -183,21 +185,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     auto load_column_stat = [&](uint32_t blk) -> float {
       const uint32_t t = threadIdx.x, q = blk * kBlock + (t & 63);
       if (t < 64) return q < a.R ? load_stat(a.L, static_cast<size_t>(head) * a.R + q, a.l_prec) : INFINITY;  // P = 0 there
-      if (kMode == kKey && q < a.R) return load_stat(a.Dterm, static_cast<size_t>(head) * a.R + q, a.d_prec);
+      if ((kMode == kKey || kMode == kKeyValue) && q < a.R) return load_stat(a.Dterm, static_cast<size_t>(head) * a.R + q, a.d_prec);
       return 0.f;
     };
 
     if constexpr (kMode == kQuery) {
-      if constexpr (kConvertDO) {
-        // BF16 dO tile (TMA) -> FP16 in place; elementwise, so the swizzle and the major-ness are irrelevant
-        mbar_wait(res_full, 0);
-        uint4 *tile = reinterpret_cast<uint4 *>(smem + Cfg::kSmemRes + Cfg::kResBytes);
-#pragma unroll
-        for (uint32_t i = 0; i < Cfg::kResBytes / (kElemThreads * 16); ++i)
-          tile[i * kElemThreads + threadIdx.x] = bf16x8_to_f16x8(tile[i * kElemThreads + threadIdx.x]);
-        fence_proxy_async_smem();
-        mbar_arrive(&do_ready[0]);
-      }
       // computeD: D = (sum_d dO * O) / sqrt(D)
       if ((a.tmask & (kTransO | kTransdO)) == 0) {
         // row-major: each warp takes 16 rows and spreads the columns over its lanes (full cache lines per load)
@@ -219,8 +211,8 @@ __global__ void __launch_bounds__(kThreads, 1)
               o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
               g4[i] = make_uint2(0u, 0u);
               if (active) {
-                o4[i] = __ldg(reinterpret_cast<const float4 *>(a.O + base));
-                g4[i] = __ldg(reinterpret_cast<const uint2 *>(static_cast<const uint16_t *>(a.dO) + base));
+                o4[i] = ldg_stream_f32x4(a.O + base);
+                g4[i] = ldg_stream_u32x2(static_cast<const uint16_t *>(a.dO) + base);
               }
             }
 #pragma unroll
@@ -277,7 +269,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       float p[kCols];
       tmem_ld32(tS, *reinterpret_cast<uint32_t(*)[32]>(&p[0]));
       tc_wait_ld();
-      if constexpr (kMode != kValue) {
+      if constexpr (kMode == kQuery || kMode == kKey) {
         tc_fence_before();
         mbar_arrive(&s_free[b]);  // S(j+2) may overwrite this buffer
       }
@@ -319,6 +311,16 @@ __global__ void __launch_bounds__(kThreads, 1)
           packed[k] = kBF16 ? pack_bf16x2(p[2 * k], p[2 * k + 1]) : pack_f16x2(p[2 * k], p[2 * k + 1]);
         tmem_st16(tS, packed);
       } else {
+        if constexpr (kMode == kKeyValue) {
+          // P^T over S^T first: dV += P^T dO can run while dS^T is being computed
+#pragma unroll
+          for (uint32_t k = 0; k < kCols / 2; ++k)
+            packed[k] = kBF16 ? pack_bf16x2(p[2 * k], p[2 * k + 1]) : pack_f16x2(p[2 * k], p[2 * k + 1]);
+          tmem_st16(tS, packed);
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(&p_full[b]);
+        }
         // dS = P * (dP / sqrt(D) - D), written over dP as the 16-bit A operand of the accumulate MMA
         mbar_wait(&dp_full[b], ph);
         tc_fence_after();
@@ -353,27 +355,31 @@ __global__ void __launch_bounds__(kThreads, 1)
     // ---------------- epilogue: accumulator -> global (FP32) ----------------
     mbar_wait(acc_final, 0);
     tc_fence_after();
-    float *out_head = a.out + split * a.split_stride + static_cast<size_t>(head) * par_len * a.D;
-    if (a.tmask & kTransOut) {
-      float *o_col = out_head + row;
+    auto store_accumulator = [&](uint32_t t_col, float *out, bool transposed) {
+      float *out_head = out + split * a.split_stride + static_cast<size_t>(head) * par_len * a.D;
+      if (transposed) {
+        float *o_col = out_head + row;
 #pragma unroll 1
-      for (uint32_t cc = 0; cc < DPAD / 2; cc += 32) {
-        const uint32_t c = h * (DPAD / 2) + cc;
-        uint32_t o[32];
-        tmem_ld32(tLane + Cfg::kTmemAcc + c, o);
-        tc_wait_ld();
-        if (row < par_len) {
+        for (uint32_t cc = 0; cc < DPAD / 2; cc += 32) {
+          const uint32_t c = h * (DPAD / 2) + cc;
+          uint32_t o[32];
+          tmem_ld32(tLane + t_col + c, o);
+          tc_wait_ld();
+          if (row < par_len) {
 #pragma unroll
-          for (uint32_t k = 0; k < 32; ++k)
-            if (c + k < a.D) o_col[static_cast<size_t>(c + k) * par_len] = __uint_as_float(o[k]);
+            for (uint32_t k = 0; k < 32; ++k)
+              if (c + k < a.D) o_col[static_cast<size_t>(c + k) * par_len] = __uint_as_float(o[k]);
+          }
         }
+      } else {
+        float4 *scratch = reinterpret_cast<float4 *>(smem + Cfg::kSmemScratch) + warp * 256;
+        const uint32_t warp_row0 = p0 + quarter * 32;
+        store_accumulator_coalesced(tLane + t_col, h * (DPAD / 2), DPAD / 2, scratch,
+                                    out_head + static_cast<size_t>(warp_row0) * a.D, warp_row0, par_len, a.D, lane);
       }
-    } else {
-      float4 *scratch = reinterpret_cast<float4 *>(smem + Cfg::kSmemScratch) + warp * 256;
-      const uint32_t warp_row0 = p0 + quarter * 32;
-      store_accumulator_coalesced(tLane + Cfg::kTmemAcc, h * (DPAD / 2), DPAD / 2, scratch,
-                                  out_head + static_cast<size_t>(warp_row0) * a.D, warp_row0, par_len, a.D, lane);
-    }
+    };
+    store_accumulator(Cfg::kTmemAcc, a.out, a.tmask & kTransOut);
+    if constexpr (kMode == kKeyValue) store_accumulator(Cfg::kTmemAcc2, a.out2, a.tmask & kTransOut2);
   } else {
     setmaxnreg_dec<kOtherRegs>();
     // 128-row resident tile / 64-row block -> shared memory.  Row-major: one [rows][64 columns of D] box per 64-column
@@ -411,29 +417,14 @@ __global__ void __launch_bounds__(kThreads, 1)
           load_block(smem + Cfg::kSmemRing1 + st * Cfg::kBlkBytes, &mapB1, &r1_full[st], tB1, (blk0 + j) * kBlock);
         }
       }
-    } else if (warp == 10 || warp == 11) {
-      // ---------------- TMA producer for ring 2 (warp 10); BF16 -> FP16 rewrite of its dO blocks (warps 10, 11) ----
-      constexpr bool kConvertRing = kConvertDO && kMode != kQuery;
-      if (warp == 10 || kConvertRing) {
-        for (uint32_t j = 0; j < num_blocks; ++j) {
-          const uint32_t st = j % Cfg::kStages2, ph = (j / Cfg::kStages2) & 1;
-          if (warp == 10) {
-            mbar_wait(&r2_empty[st], ph ^ 1);
-            if (elect_one()) {
-              mbar_arrive_expect_tx(&r2_full[st], Cfg::kBlkBytes);
-              load_block(smem + Cfg::kSmemRing2 + st * Cfg::kBlkBytes, &mapB2, &r2_full[st], tB2, (blk0 + j) * kBlock);
-            }
-            __syncwarp();
-          }
-          if constexpr (kConvertRing) {
-            mbar_wait(&r2_full[st], ph);
-            uint4 *tile = reinterpret_cast<uint4 *>(smem + Cfg::kSmemRing2 + st * Cfg::kBlkBytes);
-            const uint32_t t = (warp - 10) * 32 + lane;
-#pragma unroll 4
-            for (uint32_t i = 0; i < Cfg::kBlkBytes / (64 * 16); ++i) tile[i * 64 + t] = bf16x8_to_f16x8(tile[i * 64 + t]);
-            fence_proxy_async_smem();
-            mbar_arrive(&do_ready[st]);
-          }
+    } else if (warp == 10) {
+      // ---------------- TMA producer for ring 2 ----------------
+      for (uint32_t j = 0; j < num_blocks; ++j) {
+        const uint32_t st = j % Cfg::kStages2, ph = (j / Cfg::kStages2) & 1;
+        mbar_wait(&r2_empty[st], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&r2_full[st], Cfg::kBlkBytes);
+          load_block(smem + Cfg::kSmemRing2 + st * Cfg::kBlkBytes, &mapB2, &r2_full[st], tB2, (blk0 + j) * kBlock);
         }
       }
     } else if (warp == 8) {
@@ -456,20 +447,20 @@ __global__ void __launch_bounds__(kThreads, 1)
       // acc[128 x DPAD] (+)= A[128 x 64] (TMEM, 16-bit) . B[64 x DPAD].  A row-major block is an MN-major B (16 rows =
       // 2048 B, 64-column blocks 64 x 128 B apart: LBO); a transposed block ([DPAD rows of D][64]) is K-major.
       // The thread's columns [32 h, 32 h + 32) sit in 32-bit columns [32 h, 32 h + 16) of the buffer.
-      auto issue_acc = [&](uint32_t a_tmem, uint32_t b_off, bool tB, uint32_t accumulate) {
+      auto issue_acc = [&](uint32_t d_col, uint32_t a_tmem, uint32_t b_off, bool tB, uint32_t accumulate) {
         const uint32_t idesc = make_idesc_f16(kTile, DPAD, kFormat, 0, tB ? 0u : 1u);
         const uint64_t db = make_smem_desc_sw128(smem_u32(smem + b_off), tB ? 16 : kBlock * 128, 1024);
 #pragma unroll
         for (uint32_t k = 0; k < kBlock / 16; ++k) {
           const uint32_t bo = tB ? k * 32 : k * 2048;
-          umma_ts(tmem_base + Cfg::kTmemAcc, a_tmem + (k >> 1) * kCols + (k & 1) * 8, db + (bo >> 4), idesc,
+          umma_ts(tmem_base + d_col, a_tmem + (k >> 1) * kCols + (k & 1) * 8, db + (bo >> 4), idesc,
                   k > 0 ? 1u : accumulate);
         }
       };
       auto issue_S = [&](uint32_t j) {
         const uint32_t st = j & 1;
         mbar_wait(&r1_full[st], (j >> 1) & 1);
-        if (kMode != kValue && j >= 2) mbar_wait(&s_free[j & 1], ((j - 2) >> 1) & 1);
+        if ((kMode == kQuery || kMode == kKey) && j >= 2) mbar_wait(&s_free[j & 1], ((j - 2) >> 1) & 1);
         tc_fence_after();
         if (elect_one()) {
           issue_nt(tmem_base + Cfg::kTmemS + (j & 1) * kBlock, Cfg::kSmemRes, tA1, Cfg::kSmemRing1 + st * Cfg::kBlkBytes, tB1);
@@ -481,19 +472,17 @@ __global__ void __launch_bounds__(kThreads, 1)
       auto issue_dP = [&](uint32_t j) {
         const uint32_t st = j % Cfg::kStages2, ph = (j / Cfg::kStages2) & 1;
         mbar_wait(&r2_full[st], ph);
-        if (kConvertDO && kMode == kKey) mbar_wait(&do_ready[st], ph);
         tc_fence_after();
         if (elect_one()) {
           issue_nt(tmem_base + Cfg::kTmemdP + (j & 1) * kBlock, Cfg::kSmemRes + Cfg::kResBytes, tA2,
                    Cfg::kSmemRing2 + st * Cfg::kBlkBytes, tB2);
           umma_commit(&dp_full[j & 1]);
-          umma_commit(&r2_empty[st]);
+          if (kMode != kKeyValue) umma_commit(&r2_empty[st]);  // (kKeyValue: dV += P^T dO still reads the block)
         }
         __syncwarp();
       };
 
       mbar_wait(res_full, 0);
-      if (kConvertDO && kMode == kQuery) mbar_wait(&do_ready[0], 0);
       if constexpr (kMode != kValue) issue_dP(0);
       issue_S(0);
       for (uint32_t j = 0; j < num_blocks; ++j) {
@@ -503,21 +492,33 @@ __global__ void __launch_bounds__(kThreads, 1)
           if constexpr (kMode != kValue) issue_dP(j + 1);
           issue_S(j + 1);
         }
+        if constexpr (kMode == kKeyValue) {
+          // dV += P^T(j) dO(j) as soon as P^T is written; dS^T(j) is still being computed
+          const uint32_t st = j % Cfg::kStages2;
+          mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_acc(Cfg::kTmemAcc2, tmem_base + Cfg::kTmemS + (j & 1) * kBlock, Cfg::kSmemRing2 + st * Cfg::kBlkBytes, tB2,
+                      j > 0 ? 1u : 0u);
+            umma_commit(&r2_empty[st]);
+          }
+          __syncwarp();
+        }
         mbar_wait(&ds_full[j & 1], (j >> 1) & 1);
         if constexpr (kMode == kValue) {
           const uint32_t st = j % Cfg::kStages2, ph = (j / Cfg::kStages2) & 1;
           mbar_wait(&r2_full[st], ph);
-          if (kConvertDO) mbar_wait(&do_ready[st], ph);
           tc_fence_after();
           if (elect_one()) {
-            issue_acc(tmem_base + Cfg::kTmemS + (j & 1) * kBlock, Cfg::kSmemRing2 + st * Cfg::kBlkBytes, tB2, j > 0 ? 1u : 0u);
+            issue_acc(Cfg::kTmemAcc, tmem_base + Cfg::kTmemS + (j & 1) * kBlock, Cfg::kSmemRing2 + st * Cfg::kBlkBytes, tB2,
+                      j > 0 ? 1u : 0u);
             umma_commit(&r2_empty[st]);
             if (j + 1 == num_blocks) umma_commit(acc_final);
           }
         } else {
           tc_fence_after();
           if (elect_one()) {
-            issue_acc(tmem_base + Cfg::kTmemdP + (j & 1) * kBlock, Cfg::kSmemRing1 + (j & 1) * Cfg::kBlkBytes, tB1,
+            issue_acc(Cfg::kTmemAcc, tmem_base + Cfg::kTmemdP + (j & 1) * kBlock, Cfg::kSmemRing1 + (j & 1) * Cfg::kBlkBytes, tB1,
                       j > 0 ? 1u : 0u);
             umma_commit(&r1_empty[j & 1]);
             if (j + 1 == num_blocks) umma_commit(acc_final);
@@ -545,10 +546,10 @@ static cudaError_t operand_map(CUtensorMap *map, const AttentionParams &p, int s
                             : make_tensor_map_16bit(map, p.buf[slot], seq, p.D, p.batch, box_rows);
 }
 
-template <uint32_t DPAD, bool kBF16, bool kConvertDO, uint32_t kMode>
+template <uint32_t DPAD, bool kBF16, uint32_t kMode>
 cudaError_t launch_pass(const AttentionParams &p, cudaStream_t stream) {
   using Cfg = Config<DPAD, kMode>;
-  auto kernel = attention_backward_generic_tcgen05<DPAD, kBF16, kConvertDO, kMode>;
+  auto kernel = attention_backward_generic_tcgen05<DPAD, kBF16, kMode>;
   const int device = current_device();
   cudaError_t e = ensure_max_dynamic_smem(reinterpret_cast<const void *>(kernel), Cfg::kSmemBytes, device);
   if (e != cudaSuccess) return e;
@@ -556,7 +557,7 @@ cudaError_t launch_pass(const AttentionParams &p, cudaStream_t stream) {
   // (A1, A2) resident, (B1, B2) streamed -- see the table in the file header
   const int sA1 = kMode == kQuery ? sQ : sK, sA2 = kMode == kQuery ? sdO : sV;
   const int sB1 = kMode == kQuery ? sK : sQ, sB2 = kMode == kQuery ? sV : sdO;
-  const int sOut = kMode == kQuery ? sdQ : (kMode == kKey ? sdK : sdV);
+  const int sOut = kMode == kQuery ? sdQ : (kMode == kValue ? sdV : sdK);  // (kKeyValue: dK, and dV as the second output)
   const uint32_t par = kMode == kQuery ? p.R : p.C, trav = kMode == kQuery ? p.C : p.R;
   CUtensorMap mapA1, mapA2, mapB1, mapB2;
   if ((e = operand_map(&mapA1, p, sA1, par, kTile, DPAD)) != cudaSuccess) return e;
@@ -570,6 +571,7 @@ cudaError_t launch_pass(const AttentionParams &p, cudaStream_t stream) {
   a.L = p.buf[sL];
   a.Dterm = p.buf[sD];
   a.out = static_cast<float *>(p.buf[sOut]);
+  a.out2 = static_cast<float *>(p.buf[sdV]);
   a.R = p.R;
   a.C = p.C;
   a.D = p.D;
@@ -579,7 +581,7 @@ cudaError_t launch_pass(const AttentionParams &p, cudaStream_t stream) {
   a.d_prec = p.prec[sD];
   a.tmask = (p.transposed[sA1] ? kTransA1 : 0u) | (p.transposed[sA2] ? kTransA2 : 0u) | (p.transposed[sB1] ? kTransB1 : 0u) |
             (p.transposed[sB2] ? kTransB2 : 0u) | (p.transposed[sOut] ? kTransOut : 0u) | (p.transposed[sO] ? kTransO : 0u) |
-            (p.transposed[sdO] ? kTransdO : 0u);
+            (p.transposed[sdO] ? kTransdO : 0u) | (p.transposed[sdV] ? kTransOut2 : 0u);
 
   const uint32_t tiles = (par + kTile - 1) / kTile, total_blocks = (trav + kBlock - 1) / kBlock;
   // the row's split policy counts 128-row blocks
@@ -597,23 +599,29 @@ cudaError_t launch_pass(const AttentionParams &p, cudaStream_t stream) {
     return cudaGetLastError();
   }
   const size_t tensor_elems = static_cast<size_t>(p.batch) * par * p.D;
+  constexpr uint32_t tensors = kMode == kKeyValue ? 2 : 1;  // partial accumulators: [split][tensor][batch][rows][D]
   void *ws = nullptr;
-  if ((e = workspace_for(device, stream, splits * tensor_elems * sizeof(float), &ws)) != cudaSuccess) return e;
+  if ((e = workspace_for(device, stream, splits * tensors * tensor_elems * sizeof(float), &ws)) != cudaSuccess) return e;
   float *scratch = reinterpret_cast<float *>(static_cast<char *>(ws) + kWorkspaceCounterBytes);
-  a.split_stride = tensor_elems;
+  a.split_stride = tensors * tensor_elems;
   a.out = scratch;
+  a.out2 = scratch + tensor_elems;
   kernel<<<a.num_items, kThreads, Cfg::kSmemBytes, stream>>>(mapA1, mapA2, mapB1, mapB2, a);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  float *out = static_cast<float *>(p.buf[sOut]);
-  return bwd::launch_sum_splits(scratch, out, out, tensor_elems, 1, a.split_stride, splits, stream);
+  return bwd::launch_sum_splits(scratch, static_cast<float *>(p.buf[sOut]), static_cast<float *>(p.buf[sdV]), tensor_elems,
+                                tensors, a.split_stride, splits, stream);
 }
 
-template <uint32_t DPAD, bool kBF16, bool kConvertDO>
+template <uint32_t DPAD, bool kBF16>
 cudaError_t launch(const AttentionParams &p, cudaStream_t stream, bool key_value) {
-  if (!key_value) return launch_pass<DPAD, kBF16, kConvertDO, kQuery>(p, stream);
-  cudaError_t e = launch_pass<DPAD, kBF16, kConvertDO, kValue>(p, stream);
-  if (e != cudaSuccess) return e;
-  return launch_pass<DPAD, kBF16, kConvertDO, kKey>(p, stream);
+  if (!key_value) return launch_pass<DPAD, kBF16, kQuery>(p, stream);
+  if constexpr (DPAD <= 128) {
+    return launch_pass<DPAD, kBF16, kKeyValue>(p, stream);  // dK and dV fit TMEM side by side: one pass
+  } else {
+    cudaError_t e = launch_pass<DPAD, kBF16, kValue>(p, stream);
+    if (e != cudaSuccess) return e;
+    return launch_pass<DPAD, kBF16, kKey>(p, stream);
+  }
 }
 
 static uint32_t pass_launches(uint32_t par, uint32_t trav, uint32_t batch, uint32_t min_blocks, uint32_t max_splits) {
@@ -631,13 +639,28 @@ bool tcgen05_backward_transposes_ok(uint32_t R, uint32_t C, bool tQ, bool tK, bo
   return true;
 }
 
-cudaError_t launch_tcgen05_backward_generic(const AttentionParams &p, cudaStream_t stream, bool key_value) {
+cudaError_t launch_tcgen05_backward_generic(const AttentionParams &p_in, cudaStream_t stream, bool key_value) {
+  AttentionParams p = p_in;
+  // The reference's policy (FP16 Q/K/V beside BF16 dO): tcgen05 kind::f16 cannot mix the two types in one MMA.  These
+  // kernels stream dO blocks through a one- or two-stage ring with only two spare warps to rewrite them (measured: the dK
+  // pass at D = 256 fell from 762 to 533 TFLOP/s with the in-kernel rewrite), so dO is converted ONCE into the workspace
+  // (O(N D) against O(N^2 D)) and the all-FP16 instantiations run.
+  if (p.prec[sdO] != p.prec[sQ]) {
+    const uint64_t elements = static_cast<uint64_t>(p.batch) * p.R * p.D;
+    void *ws = nullptr;
+    cudaError_t e = workspace_for(current_device(), stream, elements * 2, &ws, /*slot=*/2);
+    if (e != cudaSuccess) return e;
+    void *converted = static_cast<char *>(ws) + kWorkspaceCounterBytes;
+    if ((e = launch_bf16_to_f16(p.buf[sdO], converted, elements, stream)) != cudaSuccess) return e;
+    p.buf[sdO] = converted;
+    p.prec[sdO] = p.prec[sQ];
+  }
   const bool bf16 = p.prec[sQ] == BF16;
-  const bool convert = p.prec[sdO] != p.prec[sQ];  // FP16 Q/K/V with BF16 dO
-#define MFA_BWDG_MODES(DPAD_)                                                   \
-  if (convert) return bwdg::launch<DPAD_, false, true>(p, stream, key_value);  \
-  return bf16 ? bwdg::launch<DPAD_, true, false>(p, stream, key_value)          \
-              : bwdg::launch<DPAD_, false, false>(p, stream, key_value);
+#define MFA_BWDG_MODES(DPAD_) \
+  return bf16 ? bwdg::launch<DPAD_, true>(p, stream, key_value) : bwdg::launch<DPAD_, false>(p, stream, key_value);
+  if (p.D <= 64) {
+    MFA_BWDG_MODES(64)
+  }
   if (p.D <= 128) {
     MFA_BWDG_MODES(128)
   }
@@ -645,23 +668,28 @@ cudaError_t launch_tcgen05_backward_generic(const AttentionParams &p, cudaStream
 #undef MFA_BWDG_MODES
 }
 
-// backwardQuery: 1 launch (+1 when the traversal split engages); backwardKeyValue: the dV pass and the dK pass
-uint32_t tcgen05_backward_generic_launch_count(int type, uint32_t R, uint32_t C, uint32_t batch, uint32_t min_blocks,
-                                               uint32_t max_splits) {
-  if (type == 1) return bwdg::pass_launches(R, C, batch, min_blocks, max_splits);
-  return 2 * bwdg::pass_launches(C, R, batch, min_blocks, max_splits);
+// backwardQuery: 1 launch (+1 when the traversal split engages); backwardKeyValue: one pass at D <= 128, else the dV pass
+// and the dK pass
+uint32_t tcgen05_backward_generic_launch_count(int type, uint32_t R, uint32_t C, uint32_t D, uint32_t batch,
+                                               uint32_t min_blocks, uint32_t max_splits, bool convert_dO) {
+  const uint32_t extra = convert_dO ? 1 : 0;  // the BF16 -> FP16 copy of dO
+  if (type == 1) return extra + bwdg::pass_launches(R, C, batch, min_blocks, max_splits);
+  return extra + (D <= 128 ? 1 : 2) * bwdg::pass_launches(C, R, batch, min_blocks, max_splits);
 }
 
 void tcgen05_backward_generic_geometry(int type, uint32_t D, uint32_t *threads, uint32_t *smem_bytes, uint32_t *par,
                                        uint32_t *trav, uint32_t *head) {
   *threads = bwdg::kThreads;
+  const uint32_t block = D <= 64 ? 64u : (D <= 128 ? 128u : 256u);
   if (type == 1)
-    *smem_bytes = D <= 128 ? bwdg::Config<128, bwdg::kQuery>::kSmemBytes : bwdg::Config<256, bwdg::kQuery>::kSmemBytes;
+    *smem_bytes = block == 64 ? bwdg::Config<64, bwdg::kQuery>::kSmemBytes
+                              : (block == 128 ? bwdg::Config<128, bwdg::kQuery>::kSmemBytes : bwdg::Config<256, bwdg::kQuery>::kSmemBytes);
   else  // the larger of the two passes
-    *smem_bytes = D <= 128 ? bwdg::Config<128, bwdg::kKey>::kSmemBytes : bwdg::Config<256, bwdg::kKey>::kSmemBytes;
+    *smem_bytes = block == 64 ? bwdg::Config<64, bwdg::kKeyValue>::kSmemBytes
+                              : (block == 128 ? bwdg::Config<128, bwdg::kKeyValue>::kSmemBytes : bwdg::Config<256, bwdg::kKey>::kSmemBytes);
   *par = bwdg::kTile;
   *trav = bwdg::kBlock;
-  const uint32_t padded = (D + 7) / 8 * 8, block = D <= 128 ? 128u : 256u;
+  const uint32_t padded = (D + 7) / 8 * 8;
   *head = block < padded ? block : padded;
 }
 

@@ -47,7 +47,7 @@ def transposed_text(kind, rows):
     if kind == "forward":
         return "| 128 | 128 | 128 | 128 | Q, O | 0 | 0 | 1 |\n| 256 | 128 | 128 | 256 | Q, O | 0 | 0 | 1 |\n"
     _, mb, ms = rows[128]
-    return "".join(f"| {b:<3d} | 128 | 64  | {b:<3d} | {RESIDENT[kind]} | 0 | {mb} | {ms} |\n" for b in (128, 256))
+    return "".join(f"| {b:<3d} | 128 | 64  | {b:<3d} | {RESIDENT[kind]} | 0 | {mb} | {ms} |\n" for b in (64, 128, 256))
 
 
 def write_file(path, tables):
