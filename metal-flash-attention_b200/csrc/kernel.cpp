@@ -258,7 +258,7 @@ int mfa_attention_kernel_launch_count(const mfa_attention_kernel_t *kernel, cons
                ? tcgen05_backward_generic_launch_count(kernel->type, c->row, c->column, Dp, b, kernel->descriptor.split_min_blocks,
                                                        kernel->descriptor.split_max, convert)
                : tcgen05_backward_launch_count(kernel->type, c->row, c->column, b, kernel->descriptor.split_min_blocks,
-                                               kernel->descriptor.split_max);
+                                               kernel->descriptor.split_max, convert);
   }
   // head % 8 != 0 on the tensor-core family: one padding copy per staged input, one un-padding copy per output
   if (kernel->backend == MFA_BACKEND_TCGEN05 && kernel->descriptor.head_dimension % 8 != 0)

@@ -57,7 +57,8 @@ bool tcgen05_backward_supported(const AttentionParams &p);
 cudaError_t launch_tcgen05_backward_query(const AttentionParams &p, cudaStream_t stream);
 cudaError_t launch_tcgen05_backward_key_value(const AttentionParams &p, cudaStream_t stream);
 uint32_t tcgen05_backward_launch_count(int type, uint32_t R, uint32_t C, uint32_t batch, uint32_t min_blocks,
-                                       uint32_t max_splits);
+                                       uint32_t max_splits, bool convert_dO);
+bool tcgen05_backward_converts_dO_first(uint32_t C, uint32_t batch);
 void tcgen05_backward_geometry(int type, uint32_t D, uint32_t *threads, uint32_t *smem_bytes, uint32_t *par,
                                uint32_t *trav, uint32_t *head);
 // layout-generic backward (tcgen05_backward_generic.cu): 128 < D <= 256, and transposed operands at any D <= 256

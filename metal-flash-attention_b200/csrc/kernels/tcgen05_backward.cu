@@ -1197,6 +1197,12 @@ static bool needs_generic(const AttentionParams &p) {
          p.transposed[sdQ] || p.transposed[sdK] || p.transposed[sdV];
 }
 
+// dK/dV, FP16 Q/K/V beside BF16 dO: convert dO in a pass of its own when the key tiles fill more than one wave of SMs
+bool tcgen05_backward_converts_dO_first(uint32_t C, uint32_t batch) {
+  const uint64_t tiles = static_cast<uint64_t>((C + bwd::kTile - 1) / bwd::kTile) * batch;
+  return tiles > static_cast<uint64_t>(device_sm_count(current_device()));
+}
+
 static cudaError_t launch_backward(const AttentionParams &p, cudaStream_t stream, bool key_value) {
   if (!tcgen05_backward_supported(p)) {
     set_launch_detail("descriptor is outside the tcgen05 backward kernels' domain");
@@ -1205,6 +1211,23 @@ static cudaError_t launch_backward(const AttentionParams &p, cudaStream_t stream
   if (needs_generic(p)) return launch_tcgen05_backward_generic(p, stream, key_value);
   const bool bf16 = p.prec[sQ] == BF16;
   const bool convert = p.prec[sdO] != p.prec[sQ];  // FP16 Q/K/V with BF16 dO
+  // dK/dV with the reference's policy: every streamed dO block has to be rewritten as FP16 by two helper warps before
+  // dP^T = V dO^T may start -- 15 % at config 3 (N = 2048, D = 64: 802 against 941 TFLOP/s all-FP16).  When the grid is
+  // more than one wave, dO is converted ONCE into the workspace instead (O(N D), ~3 % of the kernel) and the all-FP16
+  // instantiation runs; small grids (latency-bound, an extra launch costs more than it saves) keep the in-kernel rewrite,
+  // as does dQ, whose resident dO tile is rewritten once per item by all eight elementwise warps (2 %).
+  if (convert && key_value && tcgen05_backward_converts_dO_first(p.C, p.batch)) {
+    AttentionParams q = p;
+    const uint64_t elements = static_cast<uint64_t>(p.batch) * p.R * p.D;
+    void *ws = nullptr;
+    cudaError_t e = workspace_for(current_device(), stream, elements * 2, &ws, /*slot=*/2);
+    if (e != cudaSuccess) return e;
+    void *converted = static_cast<char *>(ws) + kWorkspaceCounterBytes;
+    if ((e = launch_bf16_to_f16(p.buf[sdO], converted, elements, stream)) != cudaSuccess) return e;
+    q.buf[sdO] = converted;
+    q.prec[sdO] = q.prec[sQ];
+    return launch_backward(q, stream, key_value);
+  }
   // the row's exp2 column selects the instantiation (kernel creation has checked the range)
 #define MFA_BWD_MODES(DPAD_, POLY_)                                                          \
   if (convert) return bwd::launch<DPAD_, false, true, POLY_>(p, stream, key_value);         \
@@ -1234,11 +1257,12 @@ cudaError_t launch_tcgen05_backward_key_value(const AttentionParams &p, cudaStre
 
 // 1 launch, or 2 (kernel + sum_splits) when the traversal split engages for this problem size
 uint32_t tcgen05_backward_launch_count(int type, uint32_t R, uint32_t C, uint32_t batch, uint32_t min_blocks,
-                                       uint32_t max_splits) {
+                                       uint32_t max_splits, bool convert_dO) {
   const bool key_value = type == 2;  // MFA_BACKWARD_KEY_VALUE
   const uint32_t par = key_value ? C : R, trav = key_value ? R : C;
   const uint32_t tiles = (par + bwd::kTile - 1) / bwd::kTile, total_blocks = (trav + bwd::kTile - 1) / bwd::kTile;
-  return bwd::choose_blocks_per_split(tiles * batch, total_blocks, device_sm_count(current_device()), min_blocks, max_splits) < total_blocks ? 2 : 1;
+  const uint32_t extra = (key_value && convert_dO && tcgen05_backward_converts_dO_first(C, batch)) ? 1 : 0;
+  return extra + (bwd::choose_blocks_per_split(tiles * batch, total_blocks, device_sm_count(current_device()), min_blocks, max_splits) < total_blocks ? 2 : 1);
 }
 
 void tcgen05_backward_geometry(int type, uint32_t D, uint32_t *threads, uint32_t *smem_bytes, uint32_t *par,

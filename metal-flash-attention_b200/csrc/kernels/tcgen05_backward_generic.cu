@@ -2,15 +2,15 @@
 // TRANSPOSED operands (stored [D][seq], AttentionKernel.swift:189-195) at any D <= 256, D % 8 == 0.  The reference serves
 // these cases by blocking the head dimension and spilling the accumulators (AttentionDescriptor+Parameters.swift:182-285,
 // the rows past D = 128; loopBackwardQuery / loopBackwardKeyValue, AttentionKernel+Source.swift:202-293); on B200 the
-// limits are 512 TMEM columns and 227 KB of shared memory, and they force three changes against tcgen05_backward.cu:
+// limits are 512 TMEM columns and 227 KB of shared memory, and they force these changes against tcgen05_backward.cu:
 //
 //   * the traversed operands come in blocks of 64 rows, not 128 (a 128 x 256 16-bit tile is 64 KB; two resident tiles
 //     plus a ring of 128-row blocks do not fit).  The S / dP MMAs are then M128 x N64, which the tensor pipe runs at
 //     the N = 128 cost (64 cycles per k-step): these kernels top out near 60 % of the MMA peak by construction;
-//   * dK and dV together would need 512 accumulator columns, leaving none for S^T / dP^T: backwardKeyValue runs as TWO
-//     passes over the query blocks -- a dV pass (S^T -> P^T -> dV += P^T dO) and a dK pass (S^T, dP^T -> dS^T ->
+//   * at D > 128, dK and dV together would need 512 accumulator columns, leaving none for S^T / dP^T: backwardKeyValue runs
+//     as TWO passes over the query blocks -- a dV pass (S^T -> P^T -> dV += P^T dO) and a dK pass (S^T, dP^T -> dS^T ->
 //     dK += dS^T Q) -- one accumulator each.  S^T is computed twice: 5 GEMMs instead of 4;
-//   * all three passes are ONE kernel template.  With (A1, A2) the resident 128-row tiles and (B1, B2) the streamed
+//   * all passes are ONE kernel template.  With (A1, A2) the resident 128-row tiles and (B1, B2) the streamed
 //     64-row blocks:
 //         kQuery   A1 = Q, A2 = dO, B1 = K, B2 = V      S  = A1 B1^T, dP  = A2 B2^T, dQ += dS B1
 //         kKey     A1 = K, A2 = V,  B1 = Q, B2 = dO     S^T = A1 B1^T, dP^T = A2 B2^T, dK += dS^T B1
@@ -18,13 +18,14 @@
 //         kKeyValue (D <= 128, where dK and dV fit TMEM side by side: 256 + 2 D <= 512): kKey plus dV += P^T B2 -- one
 //                  pass, four GEMMs; P^T is written over S^T and dS^T over dP^T, both A operands live in TMEM at once
 //     L and D are per ROW in kQuery (registers; D is computed here, computeD +Softmax.swift:32-221) and per COLUMN in
-//     the other two (64-entry vectors staged in shared memory one block ahead).
+//     the others (64-entry vectors staged in shared memory one block ahead).
 //
 // A transposed operand is fetched through a tensor map of the transposed view and consumed through the other UMMA
 // major-ness (K-major <-> MN-major), exactly as in the layout-generic forward kernel (tcgen05_forward_d256.cu); a
 // transposed output is stored straight from registers (a warp's 32 rows are contiguous in memory then).
 //
-// TMEM: S double buffer [0,128) (2 x 64 columns), dP double buffer [128,256), accumulator [256, 256 + DPAD).  P / dS
+// TMEM: S double buffer [0,128) (2 x 64 columns), dP double buffer [128,256), accumulator [256, 256 + DPAD) (kKeyValue: dK
+// there, dV behind it).  P / dS
 // (16-bit) overwrite S / dP in place and feed the accumulate MMA from TMEM.  Warps 0-7: elementwise (thread = TMEM lane
 // x 32 of the block's 64 columns), warp 8: MMA issuer, warp 9: TMA producer for the resident tiles and ring 1, warp 10:
 // TMA producer for ring 2.  (The reference's FP16 + BF16-dO policy: the host converts dO once, see the launcher.)

@@ -32,7 +32,7 @@ def error_stats(actual, expected):
             "rel_rms": float(np.sqrt(np.mean(err * err)) / max(rms_b, 1e-30)), "rms_ref": rms_b}
 
 
-def run_config(name, R, C, D, policy, backward, seed, threads, lowMid=False, f64=True):
+def run_config(name, R, C, D, policy, backward, seed, threads, lowMid=False, f64=True, transpose=(False,) * 4):
     import mfa_b200 as mfa
     import oracle
     from oracle.oracle_np import attention_f64
@@ -43,7 +43,7 @@ def run_config(name, R, C, D, policy, backward, seed, threads, lowMid=False, f64
     desc.lowPrecisionInputs = policy != "fp32"
     desc.lowPrecisionIntermediates = lowMid
     desc.matrixDimensions = (R, C, D)
-    desc.transposeState = (False, False, False, False)
+    desc.transposeState = tuple(transpose)
     if policy == "bf16":
         desc.inputPrecisionOverride = P.BF16
     elif policy == "fp16":
@@ -94,6 +94,9 @@ def main():
         ("fwd+bwd N=4096 D=128", 4096, 4096, 128, "fp16", True, 3),
         ("fwd+bwd N=2048 D=256", 2048, 2048, 256, "bf16", True, 5),
         ("fwd+bwd N=1000 D=72 ragged", 1000, 777, 72, "reference", True, 6),
+        ("fwd+bwd N=2048 D=256 reference", 2048, 2048, 256, "reference", True, 8),
+        ("fwd+bwd N=2048 D=128 Q,K,V,O transposed", 2048, 2048, 128, "fp16", True, 9),
+        ("fwd+bwd N=1024 D=64 K,O transposed", 1024, 1536, 64, "bf16", True, 10),
         ("config1 fwd+bwd N=128 D=64 fp32", 128, 128, 64, "fp32", True, 7),
     ]
     if not args.quick:
@@ -103,7 +106,9 @@ def main():
     with open(args.out, "w") as f:
         for name, R, C, D, policy, backward, seed in configs:
             try:
-                rows = run_config(name, R, C, D, policy, backward, seed, threads, f64=R <= 4096)
+                transpose = (True,) * 4 if "Q,K,V,O transposed" in name else ((False, True, False, True) if "K,O transposed" in name
+                                                                              else (False,) * 4)
+                rows = run_config(name, R, C, D, policy, backward, seed, threads, f64=R <= 4096, transpose=transpose)
             except Exception as exc:  # keep going: a failing config is a row in the table too
                 rows = [{"config": name, "policy": policy, "error": repr(exc)}]
             for row in rows:

@@ -281,3 +281,30 @@ def test_backward_wide_heads_batched():
         for name in ("dQ", "dK", "dV"):
             rel = _rel_rms(out[name][i], ref[name])
             assert rel <= 2.5e-3, f"head {i} {name}: {rel:.3e}"
+
+
+@pytest.mark.gpu
+def test_reference_policy_large_grid_converts_dO_once():
+    """FP16 Q/K/V beside BF16 dO with more key tiles than SMs: dK/dV converts dO in a pass of its own (one more launch)
+    and runs the all-FP16 kernel; dQ keeps the in-kernel rewrite."""
+    import mfa_b200 as mfa
+    import oracle
+    from tests.attention_harness import run_attention
+    Op = mfa.AttentionOperand
+    H, R, C, D = 40, 300, 640, 64
+    desc = mfa.AttentionDescriptor()
+    desc.lowPrecisionInputs = True
+    desc.matrixDimensions = (R, C, D)
+    desc.transposeState = (False, False, False, False)
+    desc.batchCount = H
+    constants = mfa.FunctionConstantValues()
+    desc.setFunctionConstants(constants)
+    assert mfa.AttentionKernel(desc.kernelDescriptor(mfa.AttentionKernelType.backwardKeyValue)).launchCount(constants) == 2
+    assert mfa.AttentionKernel(desc.kernelDescriptor(mfa.AttentionKernelType.backwardQuery)).launchCount(constants) == 1
+    nets = [oracle.Network(R, C, D, seed=300 + h, threads=8).round_inputs(oracle.FP16, oracle.BF16) for h in range(H)]
+    inputs = {getattr(Op, k): np.stack([getattr(n, k) for n in nets]) for k in ("Q", "K", "V", "dO")}
+    out = run_attention(desc, None, inputs=inputs)
+    for h in (0, 17, H - 1):
+        for name, expected in {"dV": nets[h].derivativeV(), "dK": nets[h].derivativeK(), "dQ": nets[h].derivativeQ()}.items():
+            rel = _rel_rms(out[name][h], expected)
+            assert rel <= 3e-4, (name, h, rel)
