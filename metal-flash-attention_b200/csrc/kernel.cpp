@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -498,6 +499,11 @@ void destroy_scratch(Scratch &s) {
 // (copy launch overheads), at most kMaxChunks chunks, and no chunking at all for a single problem
 uint32_t chunk_heads(uint32_t batch, size_t bytes_per_head) {
   if (batch <= 1) return 1;
+  // tuning knob (scripts/gpu_runs: chunk-count sweep of the host-buffer path): MFA_B200_HOST_CHUNKS=<n>
+  if (const char *env = getenv("MFA_B200_HOST_CHUNKS")) {
+    const uint32_t n = static_cast<uint32_t>(atoi(env));
+    if (n >= 1 && n <= kMaxChunks) return (batch + n - 1) / n;
+  }
   uint32_t heads = (batch + 15) / 16;
   const size_t kMinChunkBytes = size_t(4) << 20;
   if (bytes_per_head * heads < kMinChunkBytes)
