@@ -381,6 +381,35 @@ def test_parameter_file_from_the_environment(tmp_path):
     assert out.strip() == "[(2, 8, 4), (1, 2, 8), (1, 2, 4)]"   # forward and dK-dV from the file, dQ built in
 
 
+def test_transposed_tables_are_separate_and_live(tmp_path):
+    """Every kernel type has a second table for transposed operands (the layout-generic kernels); run-time replacement
+    and the file sections "[....transposed]" reach exactly that table."""
+    plain = make(512, 512, 64, lowIn=True)
+    trans = make(512, 512, 64, lowIn=True, transposes=(False, True, False, False))
+    assert trans.kernelDescriptor(KT.backwardKeyValue).blockDimensions == (128, 64, 64)
+    assert plain.kernelDescriptor(KT.backwardKeyValue).blockDimensions == (128, 128, 64)
+    try:
+        mfa.setParameterTable(KT.backwardKeyValue, "| 256 | 128 | 64 | 256 | K, V, dV, dK | 0 | 4 | 2 |\n", transposed=True)
+        assert trans.kernelDescriptor(KT.backwardKeyValue).splitPolicy == (4, 2)
+        assert plain.kernelDescriptor(KT.backwardKeyValue).splitPolicy == (2, 8)          # the row-major table is untouched
+        with pytest.raises(mfa.MFAError, match="Unexpected operand"):
+            mfa.setParameterTable(KT.backwardQuery, "| 256 | 128 | 64 | 256 | K, V | 0 | 2 | 8 |\n", transposed=True)
+    finally:
+        mfa.setParameterTable(KT.backwardKeyValue, None, transposed=True)
+    assert trans.kernelDescriptor(KT.backwardKeyValue).splitPolicy == (2, 8)
+    path = tmp_path / "tables.txt"
+    path.write_text("[backwardQuery.transposed]\n| 256 | 128 | 64 | 256 | Q, dO, dQ | 0 | 3 | 5 |\n")
+    code = ("import mfa_b200 as mfa\n"
+            "KT = mfa.AttentionKernelType\n"
+            "for t in ((False,) * 4, (True, False, False, False)):\n"
+            "    d = mfa.AttentionDescriptor(); d.lowPrecisionInputs = True\n"
+            "    d.matrixDimensions = (512, 512, 128); d.transposeState = t\n"
+            "    print(d.kernelDescriptor(KT.backwardQuery).splitPolicy)\n")
+    out = subprocess.check_output([sys.executable, "-c", code], cwd=ROOT, text=True,
+                                  env=dict(os.environ, MFA_B200_PARAMETER_FILE=str(path)))
+    assert out.split() == ["(2,", "8)", "(3,", "5)"]
+
+
 def test_committed_parameter_file_matches_the_builtin_tables():
     """metal-flash-attention_b200/parameters/b200.txt (written by scripts/sweep.py on a B200) is the source of the
     built-in defaults: loading it must not change any table."""

@@ -1,12 +1,13 @@
-"""Seeded random shapes through the tensor-core family (forward for D <= 256, backward for D <= 128): ragged R and C,
+"""Seeded random shapes through the tensor-core family (forward and backward for D <= 256): ragged R and C,
 every D % 8 == 0, the three 16-bit operand policies, small batches -- chosen so that the split paths (forward split-KV,
 backward traversal split, ragged last ranges), the D <= 256 kernel's masked tails and the reference-policy dO conversion
-all get exercised against the CPU oracle.  Tolerances as in test_tcgen05_forward.py / test_tcgen05_backward.py."""
+all get exercised against the CPU oracle; a second list draws random transpose states (sequence lengths rounded to
+multiples of 8, which the transposed TMA views need) for the layout-generic kernels.  Tolerances as in test_tcgen05_forward.py / test_tcgen05_backward.py."""
 import numpy as np
 import pytest
 
 
-def _cases(count, seed):
+def _cases(count, seed, transposed=False):
     rng = np.random.default_rng(seed)
     cases = []
     for i in range(count):
@@ -16,11 +17,16 @@ def _cases(count, seed):
         policy = ("bf16", "fp16", "reference")[int(rng.integers(0, 3))]
         lowMid = bool(rng.integers(0, 2))
         batch = int(rng.integers(1, 4))
-        cases.append((R, C, D, policy, lowMid, batch))
+        transpose = (False,) * 4
+        if transposed:
+            mask = int(rng.integers(1, 16))
+            transpose = tuple(bool(mask & (1 << i)) for i in range(4))
+            R, C = max(8, R // 8 * 8), max(8, C // 8 * 8)
+        cases.append((R, C, D, policy, lowMid, batch, transpose))
     return cases
 
 
-CASES = _cases(28, seed=20260923)
+CASES = _cases(28, seed=20260923) + _cases(20, seed=7, transposed=True)
 
 
 @pytest.mark.gpu
@@ -30,7 +36,7 @@ def test_random_shape(case):
     import oracle
     from tests.attention_harness import run_attention, check
 
-    R, C, D, policy, lowMid, batch = CASES[case]
+    R, C, D, policy, lowMid, batch, transpose = CASES[case]
     KT, Op, P = mfa.AttentionKernelType, mfa.AttentionOperand, mfa.GEMMOperandPrecision
     desc = mfa.AttentionDescriptor()
     desc.lowPrecisionInputs = True
@@ -38,10 +44,10 @@ def test_random_shape(case):
     if policy != "reference":
         desc.inputPrecisionOverride = P.BF16 if policy == "bf16" else P.FP16
     desc.matrixDimensions = (R, C, D)
-    desc.transposeState = (False, False, False, False)
+    desc.transposeState = transpose
     desc.batchCount = batch
-    backward = D <= 128
-    types = list(KT) if backward else [KT.forward]
+    backward = True
+    types = list(KT)
     for t in types:
         assert desc.kernelDescriptor(t).backend == mfa.Backend.tcgen05, t
     prec = desc.memoryPrecisions
