@@ -121,7 +121,7 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def host_tensor(mfa, shape, dtype, device):
+def host_tensor(mfa, shape, dtype, device, upload=False):
     """A torch view of a page-locked buffer from mfa_host_alloc (NUMA-local to `device`); returns (tensor, address)."""
     import ctypes
     import torch
@@ -129,7 +129,7 @@ def host_tensor(mfa, shape, dtype, device):
     for n in shape:
         nbytes *= int(n)
     nbytes *= torch.empty((), dtype=dtype).element_size()
-    addr = mfa.hostAlloc(nbytes, device)
+    addr = mfa.hostAlloc(nbytes, device, upload=upload)
     raw = (ctypes.c_uint8 * nbytes).from_address(addr)
     return torch.frombuffer(raw, dtype=torch.uint8).view(dtype).reshape(tuple(shape)), addr
 
@@ -380,7 +380,9 @@ def main():
     if not args.no_e2e:
         host, host_addr = {}, {}
         for op, t in sets[0].items():
-            host[op], host_addr[op] = host_tensor(mfa, t.shape, t.dtype, torch.cuda.current_device())
+            host[op], host_addr[op] = host_tensor(mfa, t.shape, t.dtype, torch.cuda.current_device(),
+                                                  upload=op in (Op.Q, Op.K, Op.V) and not os.environ.get("MFA_B200_BENCH_NO_WC"))
+            # (write-combined upload buffers: the host only writes them; MFA_B200_BENCH_NO_WC=1 is the A/B switch)
             if op in (Op.Q, Op.K, Op.V):
                 host[op].copy_(t.cpu())
         host_ptrs = dict(host_addr)
@@ -403,7 +405,8 @@ def main():
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                "ms_per_step": dt / e2e_steps * 1e3,
                "api": "mfa_attention_run_host (pinned host Q,K,V -> device, kernel, O,L -> host)",
-               "host_buffers": "mfa_host_alloc: cudaHostAlloc(portable) first-touched on the GPU's NUMA node",
+               "host_buffers": "mfa_host_alloc (O, L) / mfa_host_alloc_upload (Q, K, V: write-combined): cudaHostAlloc(portable) "
+                               "first-touched on the GPU's NUMA node",
                "numa_node": numa_node}
         # spot-check that the e2e path produced the same O as the device path.  The host path works through the batch in
         # chunks of a few heads, for which the library may split the key axis across SMs and merge; each split rounds

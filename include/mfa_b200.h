@@ -307,6 +307,14 @@ MFA_API int mfa_attention_run_host(const mfa_attention_descriptor_t *descriptor,
 /** Page-locked host buffer for mfa_attention_run_host, allocated (first-touched) on the NUMA node `device` hangs
  *  off and portable across CUDA contexts.  The calling thread's CPU affinity is unchanged on return. */
 MFA_API int mfa_host_alloc(size_t bytes, int device, void **out);
+/** The same for buffers the host only WRITES and the GPU reads (Q, K, V, dO of mfa_attention_run_host): the pages are also
+ *  write-combined, so the upload's PCIe reads are not snooped through the CPU caches and the buffers do not evict the
+ *  host's working set.  Reading such a buffer with the CPU is very slow: do not use it for outputs.  Measured
+ *  (profiles/r2_e2e_chunks.txt): with upload buffers alone the 201 MB + 135 MB step time is unchanged within the box-to-box
+ *  noise (5.7-6.5 ms on that box either way); with the OUTPUT buffers write-combined as well it was 5.10 ms in every run
+ *  against 5.3-6.5 ms -- the device-to-host writes into cacheable memory are what the host's cache hierarchy slows down --
+ *  but outputs a CPU cannot read at speed are not a configuration this library measures or recommends. */
+MFA_API int mfa_host_alloc_upload(size_t bytes, int device, void **out);
 MFA_API int mfa_host_free(void *ptr);
 /** Restricts the calling thread to the CPUs of `device`'s NUMA node (within the affinity it already has), so that
  *  memory it allocates afterwards and the copies it issues stay on the GPU's socket.  `*numa_node` (optional) receives

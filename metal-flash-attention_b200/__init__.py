@@ -134,6 +134,7 @@ def _load():
     try:
         lib.mfa_set_parameter_table.argtypes = [c.c_int, c.c_int, c.c_char_p]
         lib.mfa_host_alloc.argtypes = [c.c_size_t, c.c_int, c.POINTER(c.c_void_p)]
+        lib.mfa_host_alloc_upload.argtypes = [c.c_size_t, c.c_int, c.POINTER(c.c_void_p)]
         lib.mfa_host_free.argtypes = [c.c_void_p]
         lib.mfa_host_bind_thread_to_device.argtypes = [c.c_int, c.POINTER(c.c_int)]
         lib.mfa_release_device_resources.argtypes = [c.c_int]
@@ -152,10 +153,11 @@ def _check(status: int):
         raise MFAError(status, _lib.mfa_last_error().decode())
 
 
-def hostAlloc(nbytes: int, device: int = 0) -> int:
-    """mfa_host_alloc: page-locked host buffer on the NUMA node of `device` (for runHost); returns the address."""
+def hostAlloc(nbytes: int, device: int = 0, upload: bool = False) -> int:
+    """mfa_host_alloc: page-locked host buffer on the NUMA node of `device` (for runHost); returns the address.
+    upload=True (mfa_host_alloc_upload): write-combined pages for buffers the host only writes (Q, K, V, dO)."""
     out = ctypes.c_void_p()
-    _check(_lib.mfa_host_alloc(int(nbytes), int(device), ctypes.byref(out)))
+    _check((_lib.mfa_host_alloc_upload if upload else _lib.mfa_host_alloc)(int(nbytes), int(device), ctypes.byref(out)))
     return out.value
 
 

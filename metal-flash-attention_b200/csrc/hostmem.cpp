@@ -100,7 +100,7 @@ int mfa_host_bind_thread_to_device(int device, int *numa_node) {
   return MFA_SUCCESS;
 }
 
-int mfa_host_alloc(size_t bytes, int device, void **out) {
+static int host_alloc(size_t bytes, int device, unsigned extra_flags, void **out) {
   if (!out || bytes == 0) return mfa::fail(MFA_ERROR_INVALID_ARGUMENT, "NULL argument or zero size.");
   int node = -1;
   cpu_set_t cpus, previous;
@@ -113,11 +113,16 @@ int mfa_host_alloc(size_t bytes, int device, void **out) {
   int prior_device = -1;
   cudaGetDevice(&prior_device);
   cudaError_t e = cudaSetDevice(device);
-  if (e == cudaSuccess) e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+  if (e == cudaSuccess) e = cudaHostAlloc(out, bytes, cudaHostAllocPortable | extra_flags);
   if (prior_device >= 0 && prior_device != device) cudaSetDevice(prior_device);
   if (rebound) sched_setaffinity(0, sizeof(previous), &previous);
   if (e != cudaSuccess) return mfa::fail(MFA_ERROR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
   return MFA_SUCCESS;
+}
+
+int mfa_host_alloc(size_t bytes, int device, void **out) { return host_alloc(bytes, device, 0u, out); }
+int mfa_host_alloc_upload(size_t bytes, int device, void **out) {
+  return host_alloc(bytes, device, cudaHostAllocWriteCombined, out);
 }
 
 int mfa_host_free(void *ptr) {

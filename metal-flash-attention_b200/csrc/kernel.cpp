@@ -599,6 +599,13 @@ int mfa_attention_run_host(const mfa_attention_descriptor_t *descriptor, uint32_
     for (int i = 0; i < kHostStreams; ++i) cudaStreamSynchronize(s.stream[i]);
     return result;
   };
+  // per-row statistics (L, D: a few KB per head) are not worth one copy per chunk: they come back in ONE copy after the
+  // last chunk (the download stream is then behind every kernel)
+  uint32_t small_outputs = 0;
+  const char *stats_env = getenv("MFA_B200_HOST_BATCH_STATS");  // tuning knob: 0 = one copy per chunk, as for O
+  if (per_chunk < batch && !(stats_env && stats_env[0] == '0'))
+    for (int op = 0; op < MFA_BUFFER_COUNT; ++op)
+      if ((outputs & (1u << op)) && host_buffers[op] && head_bytes[op] * batch <= (size_t(4) << 20)) small_outputs |= 1u << op;
   uint32_t chunk_index = 0;
   for (uint32_t h0 = 0; h0 < batch; h0 += per_chunk, ++chunk_index) {
     const uint32_t heads = batch - h0 < per_chunk ? batch - h0 : per_chunk;
@@ -625,12 +632,16 @@ int mfa_attention_run_host(const mfa_attention_descriptor_t *descriptor, uint32_
         (e = cudaStreamWaitEvent(download, s.computed[chunk_index], 0)) != cudaSuccess)
       return drained(fail(MFA_ERROR_CUDA, std::string("event: ") + cudaGetErrorString(e)));
     for (int op = 0; op < MFA_BUFFER_COUNT; ++op) {
-      if (!(outputs & (1u << op)) || !host_buffers[op]) continue;
+      if (!(outputs & (1u << op)) || !host_buffers[op] || (small_outputs & (1u << op))) continue;
       char *dst = static_cast<char *>(host_buffers[op]) + head_bytes[op] * h0;
       if ((e = cudaMemcpyAsync(dst, chunk_dev[op], head_bytes[op] * heads, cudaMemcpyDeviceToHost, download)) != cudaSuccess)
         return drained(fail(MFA_ERROR_CUDA, std::string("D2H copy: ") + cudaGetErrorString(e)));
     }
   }
+  for (int op = 0; op < MFA_BUFFER_COUNT; ++op)
+    if (small_outputs & (1u << op))
+      if ((e = cudaMemcpyAsync(host_buffers[op], dev[op], head_bytes[op] * batch, cudaMemcpyDeviceToHost, download)) != cudaSuccess)
+        return drained(fail(MFA_ERROR_CUDA, std::string("D2H copy: ") + cudaGetErrorString(e)));
   // (the device scratch is reused by the next call on this thread: every stream must have drained before returning,
   // which the synchronous contract of this entry point requires anyway)
   for (int i = 0; i < kHostStreams; ++i)

@@ -151,4 +151,22 @@ class AttentionKernel {  // AttentionKernel.swift:11-50
   bool owned_ = true;
 };
 
+// Page-locked host buffers on the GPU's NUMA node for AttentionDescriptor::runHost (B200 extension; the reference's
+// buffers are Metal shared-storage buffers, MTLContext+Buffers.swift:5-45)
+struct HostMemory {
+  // upload: write-combined pages for buffers the host only writes and the GPU reads (Q, K, V, dO)
+  static void *allocate(size_t byteCount, int device = 0, bool upload = false) {
+    void *pointer = nullptr;
+    check(upload ? mfa_host_alloc_upload(byteCount, device, &pointer) : mfa_host_alloc(byteCount, device, &pointer));
+    return pointer;
+  }
+  static void free(void *pointer) { check(mfa_host_free(pointer)); }
+  static int bindThread(int device) {
+    int node = -1;
+    check(mfa_host_bind_thread_to_device(device, &node));
+    return node;
+  }
+  static void releaseResources(int device) { check(mfa_release_device_resources(device)); }
+};
+
 }  // namespace FlashAttention

@@ -145,9 +145,10 @@ public struct AttentionDescriptor {
 
 /// Page-locked host buffers on the GPU's NUMA node for `AttentionDescriptor.runHost` (B200 extension).
 public enum HostMemory {
-  public static func allocate(byteCount: Int, device: Int32 = 0) -> UnsafeMutableRawPointer {
+  /// `upload`: write-combined pages for buffers the host only writes and the GPU reads (Q, K, V, dO).
+  public static func allocate(byteCount: Int, device: Int32 = 0, upload: Bool = false) -> UnsafeMutableRawPointer {
     var pointer: UnsafeMutableRawPointer?
-    check(mfa_host_alloc(byteCount, device, &pointer))
+    check(upload ? mfa_host_alloc_upload(byteCount, device, &pointer) : mfa_host_alloc(byteCount, device, &pointer))
     return pointer!
   }
   public static func free(_ pointer: UnsafeMutableRawPointer) { check(mfa_host_free(pointer)) }

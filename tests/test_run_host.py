@@ -94,7 +94,7 @@ def test_run_host_forward_only_leaves_other_outputs_untouched():
 
 @pytest.mark.gpu
 def test_run_host_with_numa_local_buffers_and_release():
-    """mfa_host_alloc buffers (page-locked, first-touched on the GPU's NUMA node) through run_host; the caller's CPU
+    """mfa_host_alloc / mfa_host_alloc_upload buffers (page-locked, first-touched on the GPU's NUMA node) through run_host; the caller's CPU
     affinity and current device are unchanged afterwards; mfa_release_device_resources frees the scratch and the next call
     simply allocates again."""
     import ctypes
@@ -114,7 +114,8 @@ def test_run_host_with_numa_local_buffers_and_release():
     affinity = os.sched_getaffinity(0)
     device = torch.cuda.current_device()
     sizes = {Op.Q: B * R * D * 2, Op.K: B * C * D * 2, Op.V: B * C * D * 2, Op.O: B * R * D * 4, Op.L: B * R * 4}
-    addr = {op: mfa.hostAlloc(n, device) for op, n in sizes.items()}
+    # inputs in write-combined upload buffers (mfa_host_alloc_upload), outputs in cacheable ones
+    addr = {op: mfa.hostAlloc(n, device, upload=op in (Op.Q, Op.K, Op.V)) for op, n in sizes.items()}
     try:
         assert os.sched_getaffinity(0) == affinity, "mfa_host_alloc must not leave the thread re-bound"
         for op, name in ((Op.Q, "Q"), (Op.K, "K"), (Op.V, "V")):
