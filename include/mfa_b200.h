@@ -260,7 +260,11 @@ MFA_API const char *mfa_attention_kernel_source_name(const mfa_attention_kernel_
  *  kernel type does not touch may be NULL.  Asynchronous on `cuda_stream` (a cudaStream_t, NULL =
  *  default stream).  Kernel order and dependencies are the reference's: forward writes O, L;
  *  backwardQuery reads O, L, dO and writes D, dQ; backwardKeyValue reads L, D and writes dK, dV
- *  (AttentionKernelType.swift:10-22). */
+ *  (AttentionKernelType.swift:10-22).
+ *  Some launches use a library-owned workspace per (device, stream): partial results of grids split across SMs, the
+ *  zero-padded staging of head dimensions that are not multiples of 8, the FP16 copy of a BF16 dO.  It grows on demand
+ *  with cudaMalloc, which is not possible while `cuda_stream` is being captured into a CUDA graph: encode the same
+ *  problem size once outside the capture first (MFA_ERROR_CUDA with that message otherwise). */
 MFA_API int mfa_attention_kernel_encode(const mfa_attention_kernel_t *kernel,
                                         const mfa_function_constants_t *constants,
                                         void *const buffers[MFA_BUFFER_COUNT], void *cuda_stream);
