@@ -29,6 +29,11 @@
 #include "sm100_ptx.cuh"
 #include "tma_host.h"
 
+// 1: O leaves the kernel through TMA stores (0: generic-proxy stores from registers; A/B: make VARIANT=stg EXTRA=-DMFA_FWD_TMA_STORE=0)
+#ifndef MFA_FWD_TMA_STORE
+#define MFA_FWD_TMA_STORE 1
+#endif
+
 namespace mfa {
 // Split-KV has two forms (tests cover both; mfa_debug_set_forward_fused() selects):
 //   scratch -- TWO launches (default): normalised partials in the library's workspace + the combine_splits kernel,
@@ -105,10 +110,11 @@ constexpr uint32_t kTraceSlots = 8;  // per (role, iteration)
 // item-level probes: roles 4 (tile 0 softmax), 5 (tile 1 softmax), 6 (MMA), indexed by the CTA's item counter
 #define MFA_TRACE_ITEM(role, it, slot) MFA_TRACE(role, it, slot)
 
-template <uint32_t DPAD, bool kBF16, uint32_t kPolyPairs, bool kTrace = false, bool kFused = false>
+template <uint32_t DPAD, bool kBF16, uint32_t kPolyPairs, bool kTrace = false, bool kFused = false, bool kTmaStoreO = false>
 __global__ void __launch_bounds__(kThreads, 1)
     attention_forward_tcgen05(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
-                              const __grid_constant__ CUtensorMap mapV, float *__restrict__ O, void *__restrict__ L,
+                              const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapO,
+                              float *__restrict__ O, void *__restrict__ L,
                               uint32_t R, uint32_t C, uint32_t D, float scale_log2, int l_is_fp16,
                               uint32_t num_items, uint32_t pairs_per_head, uint32_t num_splits, uint32_t batch,
                               float *__restrict__ part_O, float2 *__restrict__ part_ml,
@@ -352,34 +358,57 @@ __global__ void __launch_bounds__(kThreads, 1)
                                          (t * kTileM + (warp & 3) * 32)) * D
                              : O + (static_cast<size_t>(head) * R + warp_row0) * D;
       const uint32_t sub_row = lane >> 3, quad = lane & 7;  // transposed view: 4 rows x 8 float4 per warp access
+      // Non-fused form: the transposed chunk leaves through the TMA (cp.async.bulk.tensor store from the scratch tile,
+      // whose XOR pattern IS the 128-byte swizzle of a [32 rows][32 floats] box): the warp does not wait for the global
+      // writes -- it only waits, before rewriting the scratch tile, until the previous chunk's store has READ it.  Rows past
+      // R and columns past D are clipped by the tensor map.  (Generic-proxy stores from registers, the fused form below,
+      // held the warp until every line had left the SM.)  With one scratch tile per warp the wait for the previous chunk's
+      // read is partly exposed, and at 32 blocks per item the epilogue is too small a share to matter, so the launcher picks
+      // this instantiation for short items only (A/B on one box, TFLOP/s, this build | register stores: N=512 D=64 525 | 501,
+      // N=1024 D=128 833 | 780, N=2048 D=64 FP16 712 | 702; N=4096 D=128 equal: profiles/r2_sweep_fwd_tma_store.jsonl).
+      constexpr bool kTmaStore = kTmaStoreO;  // (its own instantiation: as a run-time branch it cost the long-item case 1.8 %)
+      static_assert(!(kFused && kTmaStoreO), "the fused form keeps the register stores");
   #pragma unroll
       for (uint32_t c = 0; c < DPAD; c += 32) {
         uint32_t o[32];
         tmem_ld32(tO + c, o);
         tc_wait_ld();
+        if constexpr (kTmaStore) {
+          if (lane == 0) tma_store_wait_read_all();  // (also covers the previous item's last chunk)
+          __syncwarp();
+        }
   #pragma unroll
         for (uint32_t j = 0; j < 8; ++j)
           sts_f32x4(scratch + (lane * 8 + (j ^ (lane & 7))) * 16,
                     make_float4(__uint_as_float(o[4 * j]) * out_scale, __uint_as_float(o[4 * j + 1]) * out_scale,
                                 __uint_as_float(o[4 * j + 2]) * out_scale, __uint_as_float(o[4 * j + 3]) * out_scale));
-        __syncwarp();
-        // read the whole transposed chunk into distinct registers BEFORE the first store: a store keeps its source
-        // registers busy until the data has left the SM, so reusing a handful of registers would serialise the
-        // stores on memory latency (measured: 11k cycles per tile epilogue)
-        float4 v[8];
-  #pragma unroll
-        for (uint32_t i = 0; i < 8; ++i) {
-          const uint32_t r = 4 * i + sub_row;
-          v[i] = lds_f32x4(scratch + (r * 8 + (quad ^ (r & 7))) * 16);
-        }
-        if (c + 4 * quad < D) {  // D % 8 == 0: a float4 is either fully inside or fully outside
+        if constexpr (kTmaStore) {
+          fence_proxy_async_smem();  // this lane's writes -> visible to the async proxy
+          __syncwarp();
+          if (lane == 0 && c < D) {
+            tma_store_3d(&mapO, scratch, static_cast<int32_t>(c), static_cast<int32_t>(warp_row0), static_cast<int32_t>(head));
+            tma_store_commit();
+          }
+        } else {
+          __syncwarp();
+          // read the whole transposed chunk into distinct registers BEFORE the first store: a store keeps its source
+          // registers busy until the data has left the SM, so reusing a handful of registers would serialise the
+          // stores on memory latency (measured: 11k cycles per tile epilogue)
+          float4 v[8];
   #pragma unroll
           for (uint32_t i = 0; i < 8; ++i) {
             const uint32_t r = 4 * i + sub_row;
-            if (warp_row0 + r < row_limit) *reinterpret_cast<float4 *>(o_base + static_cast<size_t>(r) * D + c + 4 * quad) = v[i];
+            v[i] = lds_f32x4(scratch + (r * 8 + (quad ^ (r & 7))) * 16);
           }
+          if (c + 4 * quad < D) {  // D % 8 == 0: a float4 is either fully inside or fully outside
+  #pragma unroll
+            for (uint32_t i = 0; i < 8; ++i) {
+              const uint32_t r = 4 * i + sub_row;
+              if (warp_row0 + r < row_limit) *reinterpret_cast<float4 *>(o_base + static_cast<size_t>(r) * D + c + 4 * quad) = v[i];
+            }
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
       if constexpr (!kFused) {
         if (row < R && L != nullptr) {
@@ -477,6 +506,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     mbar_arrive(&b.o_free[t]);
     MFA_TRACE_ITEM(warp == 0 ? 4 : (warp == 4 ? 5 : 7), it, 3);
     }  // work items
+    if (kTmaStoreO && lane == 0) tma_store_wait_all();  // the CTA's shared memory outlives its stores
   } else {
     setmaxnreg_dec<kOtherRegs>();
     // Both producer warps run their control flow warp-wide and hand exactly one elected lane to the
@@ -706,12 +736,12 @@ static uint32_t choose_splits(uint32_t items, uint32_t total_blocks, uint32_t sm
 template <uint32_t DPAD, bool kBF16, uint32_t kPoly, bool kTrace = false>
 cudaError_t launch(const AttentionParams &p, cudaStream_t stream, long long *trace = nullptr) {
   using Cfg = Config<DPAD>;
-  auto kernel = attention_forward_tcgen05<DPAD, kBF16, kPoly, kTrace, false>;
+  auto kernel = attention_forward_tcgen05<DPAD, kBF16, kPoly, kTrace, false, false>;
   const int device = current_device();
   cudaError_t e;
   if ((e = ensure_max_dynamic_smem(reinterpret_cast<const void *>(kernel), Cfg::kSmemBytes, device)) != cudaSuccess) return e;
 
-  CUtensorMap mapQ, mapK, mapV;
+  CUtensorMap mapQ, mapK, mapV, mapO;  // mapO: FP32 [heads][R][D] in boxes of 32 columns x 32 rows (the epilogue's stores)
   if ((e = make_tensor_map_16bit(&mapQ, p.buf[sQ], p.R, p.D, p.batch, kTileM)) != cudaSuccess) return e;
   if ((e = make_tensor_map_16bit(&mapK, p.buf[sK], p.C, p.D, p.batch, kBlockN)) != cudaSuccess) return e;
   if ((e = make_tensor_map_16bit(&mapV, p.buf[sV], p.C, p.D, p.batch, kBlockN)) != cudaSuccess) return e;
@@ -723,9 +753,18 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, long long *tra
   const int l_is_fp16 = p.prec[sL] == FP16 ? 1 : 0;
 
   const uint32_t splits = choose_splits(num_items, total_blocks, sm_count, p.split_min_blocks, p.split_max);
+  // short items (many epilogues per unit of work): O leaves through TMA stores; long items keep the register stores
+  // (split single heads measured 1-2 % slower with it: one item per CTA, nothing to overlap the store with)
+  if constexpr (MFA_FWD_TMA_STORE != 0 && !kTrace) {
+    if (splits == 1 && total_blocks <= 16) {
+    kernel = attention_forward_tcgen05<DPAD, kBF16, kPoly, kTrace, false, true>;
+    if ((e = ensure_max_dynamic_smem(reinterpret_cast<const void *>(kernel), Cfg::kSmemBytes, device)) != cudaSuccess) return e;
+    }
+  }
   if (splits == 1) {
+    if ((e = make_tensor_map_f32(&mapO, p.buf[sO], p.R, p.D, p.batch, 32)) != cudaSuccess) return e;
     const uint32_t grid = num_items < sm_count ? num_items : sm_count;
-    kernel<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mapQ, mapK, mapV, static_cast<float *>(p.buf[sO]), p.buf[sL],
+    kernel<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mapQ, mapK, mapV, mapO, static_cast<float *>(p.buf[sO]), p.buf[sL],
                                                         p.R, p.C, p.D, p.scale_log2, l_is_fp16, num_items,
                                                         pairs_per_head, 1u, p.batch, nullptr, nullptr, nullptr, trace);
     return cudaGetLastError();
@@ -755,7 +794,8 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, long long *tra
     config.stream = stream;
     config.attrs = &attr;
     config.numAttrs = 1;
-    e = cudaLaunchKernelEx(&config, fused, mapQ, mapK, mapV, static_cast<float *>(p.buf[sO]), p.buf[sL], p.R, p.C, p.D,
+    mapO = mapQ;  // (unused by the fused form)
+    e = cudaLaunchKernelEx(&config, fused, mapQ, mapK, mapV, mapO, static_cast<float *>(p.buf[sO]), p.buf[sL], p.R, p.C, p.D,
                            p.scale_log2, l_is_fp16, split_items, pairs_per_head, splits, p.batch, part_O, part_ml,
                            counters, trace);
     if (e == cudaSuccess) return cudaGetLastError();
@@ -770,8 +810,10 @@ cudaError_t launch(const AttentionParams &p, cudaStream_t stream, long long *tra
   if ((e = workspace_for(device, stream, o_bytes + l_bytes, &ws)) != cudaSuccess) return e;
   float *scratch = reinterpret_cast<float *>(static_cast<char *>(ws) + kWorkspaceCounterBytes);
   float *L_part = scratch + static_cast<size_t>(splits) * rows_total * p.D;
+  // partials are laid out [split][head][row][D]: one tensor map over splits x batch "heads"
+  if ((e = make_tensor_map_f32(&mapO, scratch, p.R, p.D, p.batch * splits, 32)) != cudaSuccess) return e;
   const uint32_t grid = split_items < sm_count ? split_items : sm_count;
-  kernel<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mapQ, mapK, mapV, scratch, L_part, p.R, p.C, p.D, p.scale_log2,
+  kernel<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mapQ, mapK, mapV, mapO, scratch, L_part, p.R, p.C, p.D, p.scale_log2,
                                                       0, split_items, pairs_per_head, splits, p.batch, nullptr, nullptr,
                                                       nullptr, trace);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
