@@ -366,6 +366,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       // read is partly exposed, and at 32 blocks per item the epilogue is too small a share to matter, so the launcher picks
       // this instantiation for short items only (A/B on one box, TFLOP/s, this build | register stores: N=512 D=64 525 | 501,
       // N=1024 D=128 833 | 780, N=2048 D=64 FP16 712 | 702; N=4096 D=128 equal: profiles/r2_sweep_fwd_tma_store.jsonl).
+      // (A second scratch tile per warp at D <= 64, so that the two chunks never wait for each other, measured the same
+      // within 0.5 %: profiles/r2_sweep_fwd_two_tiles.jsonl -- not kept.)
       constexpr bool kTmaStore = kTmaStoreO;  // (its own instantiation: as a run-time branch it cost the long-item case 1.8 %)
       static_assert(!(kFused && kTmaStoreO), "the fused form keeps the register stores");
   #pragma unroll
