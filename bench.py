@@ -43,7 +43,7 @@ METRIC = "giga-FMA-instr/sec forward attn N=4096 D=128 bf16"
 UNIT = "GINSTRS"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
 # (profiles/), for the default H; None until a capture exists.
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 300388864  # profiles/r2_fwd_ncu_summary.csv: 202.04 MB read + 98.35 MB written
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 298728960  # profiles/r2_fwd_ncu_summary.csv: 201.77 MB read + 96.96 MB written
 NCU_TRAFFIC_SOURCE = "profiles/r2_fwd_ncu_summary.csv (ncu --set full, one 64-head launch of this kernel; not re-measured in this run)"
 
 
