@@ -30,6 +30,12 @@
 #include "tma_host.h"
 
 // 1: O leaves the kernel through TMA stores (0: generic-proxy stores from registers; A/B: make VARIANT=stg EXTRA=-DMFA_FWD_TMA_STORE=0)
+// K / V ring depth at D <= 64.  A/B on one box (profiles/r2_sweep_fwd_stages_d64.jsonl, TFLOP/s, 4 | 3 | 2 stages): N=4096
+// 757 | 767 | 757, N=2048 714 | 716 | 713, N=512 532 | 541 | 530: depth barely matters (the softmax warps set the pace), three
+// stages are never worse and free 32 KB of shared memory.
+#ifndef MFA_FWD_STAGES_D64
+#define MFA_FWD_STAGES_D64 3
+#endif
 #ifndef MFA_FWD_TMA_STORE
 #define MFA_FWD_TMA_STORE 1
 #endif
@@ -79,7 +85,7 @@ template <uint32_t DPAD>
 struct Config {
   static constexpr uint32_t kSubTiles = DPAD / 64;                 // 64-element sub-tiles along D
   static constexpr uint32_t kTileBytes = kSubTiles * kSubTileBytes;  // one 128 x DPAD operand tile
-  static constexpr uint32_t kStages = DPAD <= 64 ? 4 : 2;
+  static constexpr uint32_t kStages = DPAD <= 64 ? MFA_FWD_STAGES_D64 : 2;
   static constexpr uint32_t kSmemQ = 0;
   static constexpr uint32_t kSmemK = kSmemQ + kTilesPerCta * kTileBytes;
   static constexpr uint32_t kSmemV = kSmemK + kStages * kTileBytes;
